@@ -1,0 +1,569 @@
+/* oracle/zo_deflate.c -- TEST INFRASTRUCTURE ONLY (see zo_oracle.h).
+ *
+ * CPU restatement of the reference's chunk compressor for the frozen parameters
+ * (windowBits 15, memLevel 8, Z_DEFAULT_STRATEGY, one zng_deflate(flush) call per <= 65536-byte
+ * chunk on a stream whose hash state is empty):
+ *
+ *   level 1  deflate_quick            deflate_quick.c:47-130
+ *   level 2  deflate_fast             deflate_fast.c:19-104
+ *            longest_match            match_tpl.h:26-280 (non-SLOW; nice 8, chain 4: deflate.c:142-168)
+ *   hashing  quick_insert_string      insert_string_tpl.h:58-75, insert_string.c:13
+ *   emission zng_emit_lit/_dist       trees_emit.h:102-164
+ *   blocks   zng_tr_flush_block &co   trees.c:106-120,151-173,185-270,280-312,322-405,411-587,625-741
+ *   framing  deflate() flush handling deflate.c:1061-1083, zng_tr_stored_block trees.c:592-609
+ *
+ * The window is NOT slid: positions are kept in original chunk coordinates, which
+ * SURVEY.md section 8(a8) shows is equivalent for match finding.  What the slide changes is
+ * modelled explicitly: (i) bytes read past the end of the data ("virtual bytes")
+ * come from the 64 KiB window image W (W[pos] below 65536, W[pos-32768] above), and
+ * (ii) a block that started below 32768 when the slide happened cannot be stored
+ * (deflate_p.h:104-112 buf == NULL, trees.c:673).
+ *
+ * The static code tables are generated from RFC 1951 section 3.2.5/3.2.6 (they are what
+ * tools/maketrees.c writes to trees_tbl.h).
+ */
+#include "zo_oracle.h"
+#include <pthread.h>
+#include <stdatomic.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ZO_WSIZE     32768u
+#define ZO_MAX_DIST  (ZO_WSIZE - 262u)        /* deflate.h:410-415: w_size - MIN_LOOKAHEAD */
+#define ZO_MAX_MATCH 258u
+#define ZO_WANT_MIN  4u                        /* WANT_MIN_MATCH */
+#define ZO_CHUNK_MAX 65536u
+#define ZO_SYM_END   16383u                    /* deflate.c:400-403 with memLevel 8, LIT_MEM */
+#define ZO_SLIDE_AT  (ZO_WSIZE + ZO_MAX_DIST) /* deflate.c:1285 */
+
+#define L_CODES 286
+#define D_CODES 30
+#define BL_CODES 19
+#define HEAP_SZ (2 * L_CODES + 1)
+#define MAX_BITS 15
+
+/* ------------------------------------------------------------------ static tables */
+static uint16_t fx_lcode[288]; static uint8_t fx_llen[288];
+static uint16_t fx_dcode[30];
+static uint8_t  len_sym[256];              /* len-3 -> length code 0..28 (zng_length_code) */
+static uint16_t len_base[29]; static uint8_t len_xbits[29];
+static uint16_t dst_base[30]; static uint8_t dst_xbits[30];
+static uint8_t  dst_sym_lo[256], dst_sym_hi[256];   /* zng_dist_code split in its two halves */
+static const uint8_t bl_order_[BL_CODES] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};  /* RFC 1951 3.2.7 */
+static const uint8_t bl_xbits[BL_CODES] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,2,3,7};
+static pthread_once_t tbl_once = PTHREAD_ONCE_INIT;
+
+static unsigned rev_bits(unsigned v, int n) {          /* trees.c:811-818 bi_reverse */
+    unsigned r = 0;
+    for (int i = 0; i < n; i++) { r = (r << 1) | (v & 1); v >>= 1; }
+    return r;
+}
+
+static void build_static_tables(void) {
+    for (int v = 0; v < 288; v++) {                    /* RFC 1951 3.2.6 */
+        unsigned code; int n;
+        if (v < 144)      { n = 8; code = 0x30 + v; }
+        else if (v < 256) { n = 9; code = 0x190 + (v - 144); }
+        else if (v < 280) { n = 7; code = v - 256; }
+        else              { n = 8; code = 0xC0 + (v - 280); }
+        fx_llen[v] = (uint8_t)n; fx_lcode[v] = (uint16_t)rev_bits(code, n);
+    }
+    for (int d = 0; d < 30; d++) fx_dcode[d] = (uint16_t)rev_bits((unsigned)d, 5);
+    /* length codes: 8 codes without extra bits, then groups of 4 with 1..5 extra bits, then 258 */
+    unsigned l = 0;
+    for (int c = 0; c < 28; c++) {
+        int xb = c < 8 ? 0 : (c - 4) / 4;
+        len_base[c] = (uint16_t)l; len_xbits[c] = (uint8_t)xb;
+        for (unsigned k = 0; k < (1u << xb); k++) len_sym[l++] = (uint8_t)c;
+    }
+    len_sym[255] = 28; len_base[28] = 0; len_xbits[28] = 0;     /* trees.c tr_static_init analogue */
+    /* distance codes: 4 without extra bits, then pairs with 1..13 extra bits */
+    unsigned d = 0;
+    for (int c = 0; c < 30; c++) {
+        int xb = c < 4 ? 0 : (c - 2) / 2;
+        dst_base[c] = (uint16_t)d; dst_xbits[c] = (uint8_t)xb;
+        for (unsigned k = 0; k < (1u << xb); k++, d++) {
+            if (d < 256) dst_sym_lo[d] = (uint8_t)c;
+            if ((d & 127) == 0 && d >= 256) dst_sym_hi[d >> 7] = (uint8_t)c;
+        }
+    }
+}
+
+static inline unsigned dist_sym(unsigned dm1) {        /* deflate.h:436 d_code */
+    return dm1 < 256 ? dst_sym_lo[dm1] : dst_sym_hi[dm1 >> 7];
+}
+
+/* ------------------------------------------------------------------ bit writer */
+typedef struct { uint8_t *p; size_t cap, n; uint64_t acc; unsigned cnt; int ovf; } bitw;
+
+static void bw_put(bitw *b, uint64_t v, unsigned nb) { /* LSB-first, trees_emit.h:42-61 semantics */
+    b->acc |= v << b->cnt; b->cnt += nb;
+    while (b->cnt >= 8) {
+        if (b->n < b->cap) b->p[b->n] = (uint8_t)b->acc; else b->ovf = 1;
+        b->n++; b->acc >>= 8; b->cnt -= 8;
+    }
+}
+static void bw_align(bitw *b) { if (b->cnt) bw_put(b, 0, 8 - b->cnt); }   /* bi_windup */
+static void bw_raw(bitw *b, const uint8_t *s, size_t k) {
+    if (b->n + k <= b->cap) memcpy(b->p + b->n, s, k); else b->ovf = 1;
+    b->n += k;
+}
+
+/* one literal/length/distance symbol with the given code tables (trees_emit.h:102-164) */
+static void emit_lit(bitw *b, const uint16_t *lc, const uint8_t *ll, unsigned c) { bw_put(b, lc[c], ll[c]); }
+static void emit_match(bitw *b, const uint16_t *lc, const uint8_t *ll, const uint16_t *dc, const uint8_t *dl,
+                       unsigned len, unsigned dist) {
+    unsigned lm3 = len - 3, ls = len_sym[lm3];
+    uint64_t v = lc[257 + ls]; unsigned nb = ll[257 + ls];
+    if (len_xbits[ls]) { v |= (uint64_t)(lm3 - len_base[ls]) << nb; nb += len_xbits[ls]; }
+    unsigned dm1 = dist - 1, ds = dist_sym(dm1);
+    v |= (uint64_t)dc[ds] << nb; nb += dl[ds];
+    if (dst_xbits[ds]) { v |= (uint64_t)(dm1 - dst_base[ds]) << nb; nb += dst_xbits[ds]; }
+    bw_put(b, v, nb);
+}
+static const uint8_t fx_dlen[30] = {5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5};
+
+/* ------------------------------------------------------------------ window model */
+typedef struct {
+    uint8_t  W[ZO_CHUNK_MAX + 8];   /* window image: data, then zeros or the previous chunk's stale bytes */
+    uint32_t len;
+    uint16_t head[65536];
+    uint16_t prev[ZO_WSIZE];
+} lzstate;
+
+static inline uint8_t vb(const lzstate *s, uint32_t pos) {  /* virtual byte, SURVEY 0.6 / deflate.c:1286 */
+    return pos < ZO_CHUNK_MAX ? s->W[pos] : s->W[pos - ZO_WSIZE];
+}
+static inline uint32_t hash4(const lzstate *s, uint32_t pos) {   /* insert_string.c:13 */
+    uint32_t v = (uint32_t)vb(s, pos) | ((uint32_t)vb(s, pos + 1) << 8) | ((uint32_t)vb(s, pos + 2) << 16) | ((uint32_t)vb(s, pos + 3) << 24);
+    return (v * 2654435761u) >> 16;
+}
+static inline uint32_t quick_insert(lzstate *s, uint32_t pos) { /* insert_string_tpl.h:58-75 */
+    uint32_t h = hash4(s, pos), old = s->head[h];
+    if (old != (uint16_t)pos) { s->prev[pos & (ZO_WSIZE - 1)] = (uint16_t)old; s->head[h] = (uint16_t)pos; }
+    return old;
+}
+static inline uint32_t match_run(const lzstate *s, uint32_t a, uint32_t b) { /* compare256(a+2,b+2)+2 */
+    uint32_t k = 0;
+    while (k < 256 && vb(s, a + 2 + k) == vb(s, b + 2 + k)) k++;
+    return k + 2;
+}
+
+static void lz_reset(lzstate *s, const uint8_t *in, uint32_t len, const uint8_t *stale) {
+    memcpy(s->W, in, len);
+    if (len < ZO_CHUNK_MAX) {
+        if (stale) { for (uint32_t p = len; p < ZO_CHUNK_MAX; p++) s->W[p] = stale[p & (ZO_WSIZE - 1)]; }
+        else memset(s->W + len, 0, ZO_CHUNK_MAX - len);
+    }
+    memset(s->W + ZO_CHUNK_MAX, 0, 8);
+    s->len = len;
+    memset(s->head, 0, sizeof(s->head));     /* deflate.c:182-184 CLEAR_HASH: empty slot == position 0 */
+    memset(s->prev, 0, sizeof(s->prev));
+}
+
+/* ------------------------------------------------------------------ level 1 */
+typedef void (*tok_sink)(void *ctx, uint32_t tok);
+
+static void quick_parse(lzstate *s, bitw *b, tok_sink sink, void *ctx) {   /* deflate_quick.c:65-120 */
+    uint32_t pos = 0, n = s->len;
+    while (pos < n) {
+        uint32_t left = n - pos;
+        if (left >= ZO_WANT_MIN) {
+            uint32_t cand = quick_insert(s, pos);
+            uint32_t dist = pos - cand;
+            if (dist > 0 && dist <= ZO_MAX_DIST && cand < pos &&
+                s->W[pos] == s->W[cand] && s->W[pos + 1] == s->W[cand + 1]) {
+                uint32_t ml = match_run(s, pos, cand);
+                if (ml >= ZO_WANT_MIN) {
+                    if (ml > left) ml = left;
+                    if (ml > ZO_MAX_MATCH) ml = ZO_MAX_MATCH;
+                    if (b) emit_match(b, fx_lcode, fx_llen, fx_dcode, fx_dlen, ml, dist);
+                    if (sink) sink(ctx, 0x80000000u | (ml << 16) | dist);
+                    pos += ml;
+                    continue;
+                }
+            }
+        }
+        if (b) emit_lit(b, fx_lcode, fx_llen, s->W[pos]);
+        if (sink) sink(ctx, s->W[pos]);
+        pos++;
+    }
+}
+
+/* ------------------------------------------------------------------ level 2: trees.c restated */
+typedef struct {
+    uint16_t freq[HEAP_SZ], code[HEAP_SZ], len[HEAP_SZ], dad[HEAP_SZ];
+    int elems, max_len, max_code;
+    const uint8_t *stat_len;      /* static lengths or NULL */
+    const uint8_t *xbits; int xbase;
+} hufftree;
+
+typedef struct {
+    hufftree lt, dt, bt;
+    int heap[HEAP_SZ]; int heap_len, heap_max; uint8_t depth[HEAP_SZ];
+    uint16_t bl_count[MAX_BITS + 1];
+    uint64_t opt_len, static_len;
+    uint16_t d_buf[ZO_SYM_END + 1]; uint8_t l_buf[ZO_SYM_END + 1]; uint32_t sym_next;
+} blockstate;
+
+#define NODE_LESS(t, n, m, dep) ((t)->freq[n] < (t)->freq[m] || ((t)->freq[n] == (t)->freq[m] && (dep)[n] <= (dep)[m]))
+
+static void sift_down(blockstate *bs, hufftree *t, int k) {      /* trees.c:151-173 */
+    int v = bs->heap[k], j = k << 1;
+    while (j <= bs->heap_len) {
+        if (j < bs->heap_len && NODE_LESS(t, bs->heap[j + 1], bs->heap[j], bs->depth)) j++;
+        if (NODE_LESS(t, v, bs->heap[j], bs->depth)) break;
+        bs->heap[k] = bs->heap[j]; k = j; j <<= 1;
+    }
+    bs->heap[k] = v;
+}
+
+static void assign_lengths(blockstate *bs, hufftree *t) {        /* trees.c:185-270 gen_bitlen */
+    int overflow = 0;
+    for (int i = 0; i <= MAX_BITS; i++) bs->bl_count[i] = 0;
+    t->len[bs->heap[bs->heap_max]] = 0;
+    int h;
+    for (h = bs->heap_max + 1; h < HEAP_SZ; h++) {
+        int n = bs->heap[h];
+        unsigned bits = t->len[t->dad[n]] + 1u;
+        if (bits > (unsigned)t->max_len) { bits = (unsigned)t->max_len; overflow++; }
+        t->len[n] = (uint16_t)bits;
+        if (n > t->max_code) continue;
+        bs->bl_count[bits]++;
+        int xb = (n >= t->xbase) ? t->xbits[n - t->xbase] : 0;
+        bs->opt_len += (uint64_t)t->freq[n] * (bits + (unsigned)xb);
+        if (t->stat_len) bs->static_len += (uint64_t)t->freq[n] * ((unsigned)t->stat_len[n] + (unsigned)xb);
+    }
+    if (!overflow) return;
+    do {
+        unsigned bits = (unsigned)t->max_len - 1;
+        while (bs->bl_count[bits] == 0) bits--;
+        bs->bl_count[bits]--; bs->bl_count[bits + 1] += 2; bs->bl_count[t->max_len]--;
+        overflow -= 2;
+    } while (overflow > 0);
+    for (unsigned bits = (unsigned)t->max_len; bits != 0; bits--) {
+        int n = bs->bl_count[bits];
+        while (n != 0) {
+            int m = bs->heap[--h];
+            if (m > t->max_code) continue;
+            if (t->len[m] != bits) {
+                bs->opt_len += (uint64_t)bits * t->freq[m];
+                bs->opt_len -= (uint64_t)t->len[m] * t->freq[m];
+                t->len[m] = (uint16_t)bits;
+            }
+            n--;
+        }
+    }
+}
+
+static void assign_codes(blockstate *bs, hufftree *t) {          /* trees.c:280-312 gen_codes */
+    uint16_t next[MAX_BITS + 1]; unsigned c = 0;
+    for (int bits = 1; bits <= MAX_BITS; bits++) { c = (c + bs->bl_count[bits - 1]) << 1; next[bits] = (uint16_t)c; }
+    for (int n = 0; n <= t->max_code; n++) {
+        int l = t->len[n];
+        if (l) t->code[n] = (uint16_t)rev_bits(next[l]++, l);
+    }
+}
+
+static void build_huffman(blockstate *bs, hufftree *t) {         /* trees.c:322-405 build_tree */
+    int max_code = -1, node;
+    bs->heap_len = 0; bs->heap_max = HEAP_SZ;
+    for (int n = 0; n < t->elems; n++) {
+        if (t->freq[n]) { bs->heap[++bs->heap_len] = max_code = n; bs->depth[n] = 0; }
+        else t->len[n] = 0;
+    }
+    while (bs->heap_len < 2) {
+        node = bs->heap[++bs->heap_len] = (max_code < 2 ? ++max_code : 0);
+        t->freq[node] = 1; bs->depth[node] = 0;
+        bs->opt_len--;
+        if (t->stat_len) bs->static_len -= t->stat_len[node];
+    }
+    t->max_code = max_code;
+    for (int n = bs->heap_len / 2; n >= 1; n--) sift_down(bs, t, n);
+    node = t->elems;
+    do {
+        int n = bs->heap[1];
+        bs->heap[1] = bs->heap[bs->heap_len--];
+        sift_down(bs, t, 1);
+        int m = bs->heap[1];
+        bs->heap[--bs->heap_max] = n;
+        bs->heap[--bs->heap_max] = m;
+        t->freq[node] = (uint16_t)(t->freq[n] + t->freq[m]);
+        bs->depth[node] = (uint8_t)((bs->depth[n] >= bs->depth[m] ? bs->depth[n] : bs->depth[m]) + 1);
+        t->dad[n] = t->dad[m] = (uint16_t)node;
+        bs->heap[1] = node++;
+        sift_down(bs, t, 1);
+    } while (bs->heap_len >= 2);
+    bs->heap[--bs->heap_max] = bs->heap[1];
+    assign_lengths(bs, t);
+    assign_codes(bs, t);
+}
+
+/* trees.c:411-519: run-length walk over a code-length array; emit==NULL counts into bt.freq */
+static void rle_lengths(blockstate *bs, hufftree *t, int max_code, bitw *emit) {
+    int prevlen = -1, nextlen = t->len[0], count = 0, max_count = 7, min_count = 4;
+    if (nextlen == 0) { max_count = 138; min_count = 3; }
+    if (!emit) t->len[max_code + 1] = 0xffff;       /* guard (scan_tree) */
+    for (int n = 0; n <= max_code; n++) {
+        int curlen = nextlen; nextlen = t->len[n + 1];
+        if (++count < max_count && curlen == nextlen) continue;
+        if (count < min_count) {
+            if (emit) { do bw_put(emit, bs->bt.code[curlen], bs->bt.len[curlen]); while (--count); }
+            else bs->bt.freq[curlen] = (uint16_t)(bs->bt.freq[curlen] + count);
+        } else if (curlen != 0) {
+            if (curlen != prevlen) {
+                if (emit) { bw_put(emit, bs->bt.code[curlen], bs->bt.len[curlen]); count--; }
+                else bs->bt.freq[curlen]++;
+            }
+            if (emit) { bw_put(emit, bs->bt.code[16], bs->bt.len[16]); bw_put(emit, (uint64_t)(count - 3), 2); }
+            else bs->bt.freq[16]++;
+        } else if (count <= 10) {
+            if (emit) { bw_put(emit, bs->bt.code[17], bs->bt.len[17]); bw_put(emit, (uint64_t)(count - 3), 3); }
+            else bs->bt.freq[17]++;
+        } else {
+            if (emit) { bw_put(emit, bs->bt.code[18], bs->bt.len[18]); bw_put(emit, (uint64_t)(count - 11), 7); }
+            else bs->bt.freq[18]++;
+        }
+        count = 0; prevlen = curlen;
+        if (nextlen == 0) { max_count = 138; min_count = 3; }
+        else if (curlen == nextlen) { max_count = 6; min_count = 3; }
+        else { max_count = 7; min_count = 4; }
+    }
+}
+
+static void block_reset(blockstate *bs) {                        /* trees.c:106-120 init_block */
+    memset(bs->lt.freq, 0, sizeof(uint16_t) * L_CODES);
+    memset(bs->dt.freq, 0, sizeof(uint16_t) * D_CODES);
+    memset(bs->bt.freq, 0, sizeof(uint16_t) * BL_CODES);
+    bs->lt.freq[256] = 1;
+    bs->opt_len = bs->static_len = 0; bs->sym_next = 0;
+}
+
+static void block_init(blockstate *bs) {
+    memset(bs, 0, sizeof(*bs));
+    bs->lt.elems = L_CODES; bs->lt.max_len = 15; bs->lt.stat_len = fx_llen; bs->lt.xbits = len_xbits; bs->lt.xbase = 257;
+    bs->dt.elems = D_CODES; bs->dt.max_len = 15; bs->dt.stat_len = fx_dlen; bs->dt.xbits = dst_xbits; bs->dt.xbase = 0;
+    bs->bt.elems = BL_CODES; bs->bt.max_len = 7; bs->bt.stat_len = NULL; bs->bt.xbits = bl_xbits; bs->bt.xbase = 0;
+    block_reset(bs);
+}
+
+static void write_symbols(blockstate *bs, bitw *b, const uint16_t *lc, const uint8_t *ll,
+                          const uint16_t *dc, const uint8_t *dl) {        /* trees.c:708-741 compress_block */
+    for (uint32_t i = 0; i < bs->sym_next; i++) {
+        if (bs->d_buf[i] == 0) emit_lit(b, lc, ll, bs->l_buf[i]);
+        else emit_match(b, lc, ll, dc, dl, bs->l_buf[i] + 3u, bs->d_buf[i]);
+    }
+    bw_put(b, lc[256], ll[256]);
+}
+
+/* trees.c:625-703 zng_tr_flush_block.  raw == NULL means "buf == NULL" (block too old to store). */
+static void flush_block(blockstate *bs, bitw *b, const uint8_t *raw, uint32_t stored_len, int last) {
+    uint64_t opt_lenb, static_lenb; int max_blindex = 0;
+    if (bs->sym_next == 0) {
+        opt_lenb = static_lenb = 0; bs->static_len = 7;
+    } else {
+        build_huffman(bs, &bs->lt);
+        build_huffman(bs, &bs->dt);
+        rle_lengths(bs, &bs->lt, bs->lt.max_code, NULL);          /* trees.c:525-552 build_bl_tree */
+        rle_lengths(bs, &bs->dt, bs->dt.max_code, NULL);
+        build_huffman(bs, &bs->bt);
+        for (max_blindex = BL_CODES - 1; max_blindex >= 3; max_blindex--)
+            if (bs->bt.len[bl_order_[max_blindex]] != 0) break;
+        bs->opt_len += 3 * ((uint64_t)max_blindex + 1) + 5 + 5 + 4;
+        opt_lenb = (bs->opt_len + 3 + 7) >> 3;
+        static_lenb = (bs->static_len + 3 + 7) >> 3;
+        if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+    }
+    if ((uint64_t)stored_len + 4 <= opt_lenb && raw != NULL) {
+        bw_put(b, (uint64_t)(0 << 1) + (unsigned)last, 3);         /* trees.c:592-609 */
+        bw_align(b);
+        bw_put(b, stored_len & 0xffff, 16); bw_put(b, (~stored_len) & 0xffff, 16);
+        bw_raw(b, raw, stored_len);
+    } else if (static_lenb == opt_lenb) {
+        bw_put(b, (uint64_t)(1 << 1) + (unsigned)last, 3);
+        write_symbols(bs, b, fx_lcode, fx_llen, fx_dcode, fx_dlen);
+    } else {
+        uint8_t ll8[L_CODES], dl8[D_CODES];
+        bw_put(b, (uint64_t)(2 << 1) + (unsigned)last, 3);
+        int lcodes = bs->lt.max_code + 1, dcodes = bs->dt.max_code + 1, blcodes = max_blindex + 1;
+        bw_put(b, (uint64_t)(lcodes - 257), 5); bw_put(b, (uint64_t)(dcodes - 1), 5); bw_put(b, (uint64_t)(blcodes - 4), 4);
+        for (int r = 0; r < blcodes; r++) bw_put(b, bs->bt.len[bl_order_[r]], 3);
+        rle_lengths(bs, &bs->lt, lcodes - 1, b);
+        rle_lengths(bs, &bs->dt, dcodes - 1, b);
+        for (int i = 0; i < L_CODES; i++) ll8[i] = (uint8_t)bs->lt.len[i];
+        for (int i = 0; i < D_CODES; i++) dl8[i] = (uint8_t)bs->dt.len[i];
+        write_symbols(bs, b, bs->lt.code, ll8, bs->dt.code, dl8);
+    }
+    block_reset(bs);
+    if (last) bw_align(b);
+}
+
+/* match_tpl.h:26-280 restated for level 2 (best_len starts at 2, nice 8, chain 4, level<5).
+ * The pre-filter at best_len 2..7 is exactly "bytes 0..best_len equal" (SURVEY 8(a6)). */
+static uint32_t longest_match_l2(const lzstate *s, uint32_t pos, uint32_t cand, uint32_t lookahead, uint32_t *mstart) {
+    uint32_t best = 2, chain = 4;
+    uint32_t limit = pos > ZO_MAX_DIST ? pos - ZO_MAX_DIST : 0;
+    for (;;) {
+        if (cand >= pos) break;
+        int ok = 1;
+        for (uint32_t k = 0; k <= best; k++) if (vb(s, cand + k) != vb(s, pos + k)) { ok = 0; break; }
+        if (ok) {
+            uint32_t len = match_run(s, pos, cand);
+            if (len > best) {
+                *mstart = cand;
+                if (len > lookahead) return lookahead;
+                best = len;
+                if (best >= 8) return best;
+            } else break;   /* early_exit (unreachable here, kept for fidelity: match_tpl.h:261-266) */
+        }
+        if (--chain == 0) break;
+        cand = s->prev[cand & (ZO_WSIZE - 1)];
+        if (cand <= limit) break;
+    }
+    return best;
+}
+
+typedef struct { lzstate lz; blockstate bs; } deflater;
+
+static void fast_parse(deflater *d, bitw *b, int last, tok_sink sink, void *ctx) {   /* deflate_fast.c:25-103 */
+    lzstate *s = &d->lz; blockstate *bs = &d->bs;
+    uint32_t pos = 0, n = s->len, block_start = 0; int slid = 0;
+    block_init(bs);
+    for (;;) {
+        if (!slid && pos >= ZO_SLIDE_AT && n - (pos < n ? pos : n) < 262) slid = 1;   /* fill_window runs at lookahead < 262 and slides at strstart >= 65274 (deflate.c:1285) */
+        if (pos >= n) break;
+        uint32_t left = n - pos, ml = 0, mstart = 0;
+        if (left >= ZO_WANT_MIN) {
+            uint32_t cand = quick_insert(s, pos);
+            uint32_t dist = pos - cand;
+            if (dist > 0 && dist <= ZO_MAX_DIST && cand != 0 && cand < pos)
+                ml = longest_match_l2(s, pos, cand, left, &mstart);
+        }
+        int full;
+        if (ml >= ZO_WANT_MIN) {
+            uint32_t dist = pos - mstart;
+            bs->d_buf[bs->sym_next] = (uint16_t)dist; bs->l_buf[bs->sym_next++] = (uint8_t)(ml - 3);
+            bs->lt.freq[257 + len_sym[ml - 3]]++; bs->dt.freq[dist_sym(dist - 1)]++;
+            if (sink) sink(ctx, 0x80000000u | (ml << 16) | dist);
+            left -= ml;
+            if (ml <= 4 && left >= ZO_WANT_MIN) {        /* max_insert_length = max_lazy = 4 at level 2 */
+                for (uint32_t k = 1; k < ml; k++) quick_insert(s, pos + k);
+                pos += ml;
+            } else {
+                pos += ml;
+                quick_insert(s, pos - 1);               /* deflate_fast.c:80 (may hash virtual bytes) */
+            }
+        } else {
+            bs->d_buf[bs->sym_next] = 0; bs->l_buf[bs->sym_next++] = s->W[pos];
+            bs->lt.freq[s->W[pos]]++;
+            if (sink) sink(ctx, s->W[pos]);
+            pos++;
+        }
+        full = (bs->sym_next == ZO_SYM_END);
+        if (full) {
+            if (b) flush_block(bs, b, (slid && block_start < ZO_WSIZE) ? NULL : s->W + block_start, pos - block_start, 0);
+            else block_reset(bs);
+            block_start = pos;
+        }
+    }
+    if (!b) return;
+    const uint8_t *raw = (slid && block_start < ZO_WSIZE) ? NULL : s->W + block_start;
+    if (last) flush_block(bs, b, raw, pos - block_start, 1);
+    else if (bs->sym_next) flush_block(bs, b, raw, pos - block_start, 0);
+}
+
+/* ------------------------------------------------------------------ public */
+size_t zo_deflate_bound(size_t n) { return n + (n >> 3) + 64; }
+
+static size_t deflate_one(deflater *d, const uint8_t *in, uint32_t len, int level, int flush,
+                          const uint8_t *stale, uint8_t *out, size_t cap) {
+    pthread_once(&tbl_once, build_static_tables);
+    if (len > ZO_CHUNK_MAX || (level != 1 && level != 2)) return (size_t)-1;
+    if (flush != ZO_SYNC_FLUSH && flush != ZO_FULL_FLUSH && flush != ZO_FINISH) return (size_t)-1;
+    int last = (flush == ZO_FINISH);
+    bitw b = {out, cap, 0, 0, 0, 0};
+    lz_reset(&d->lz, in, len, stale);
+    if (level == 1) {
+        /* deflate_quick.c:53-63,123-128: a block is opened only if there is input, or for Z_FINISH */
+        if (len > 0 || last) {
+            bw_put(&b, (uint64_t)(1 << 1) + (unsigned)last, 3);
+            quick_parse(&d->lz, &b, NULL, NULL);
+            bw_put(&b, fx_lcode[256], fx_llen[256]);
+            if (last) bw_align(&b);
+        }
+    } else {
+        fast_parse(d, &b, last, NULL, NULL);
+    }
+    if (!last) {                         /* deflate.c:1064-1065: empty stored block for SYNC/FULL flush */
+        bw_put(&b, 0, 3); bw_align(&b); bw_put(&b, 0x0000, 16); bw_put(&b, 0xffff, 16);
+    }
+    return b.ovf ? (size_t)-1 : b.n;
+}
+
+size_t zo_deflate_chunk(const uint8_t *in, uint32_t len, int level, int flush, uint8_t *out, size_t cap) {
+    deflater *d = (deflater *)malloc(sizeof(deflater));
+    if (!d) return (size_t)-1;
+    size_t r = deflate_one(d, in, len, level, flush, NULL, out, cap);
+    free(d);
+    return r;
+}
+
+typedef struct { uint32_t *t; size_t cap, n; } tokbuf;
+static void tok_push(void *ctx, uint32_t tok) { tokbuf *tb = (tokbuf *)ctx; if (tb->n < tb->cap) tb->t[tb->n] = tok; tb->n++; }
+
+size_t zo_deflate_tokens(const uint8_t *in, uint32_t len, int level, uint32_t *tokens, size_t cap) {
+    pthread_once(&tbl_once, build_static_tables);
+    if (len > ZO_CHUNK_MAX || (level != 1 && level != 2)) return (size_t)-1;
+    deflater *d = (deflater *)malloc(sizeof(deflater));
+    if (!d) return (size_t)-1;
+    tokbuf tb = {tokens, cap, 0};
+    lz_reset(&d->lz, in, len, NULL);
+    if (level == 1) quick_parse(&d->lz, NULL, tok_push, &tb);
+    else fast_parse(d, NULL, 0, tok_push, &tb);
+    free(d);
+    return tb.n;
+}
+
+/* ---- chunk batch with a tiny pthread pool (mirrors refdrv_deflate_chunks) ---- */
+typedef struct {
+    const uint8_t *in; size_t n; uint32_t chunk; int level, flush;
+    uint8_t *out; size_t out_stride; uint32_t *sizes, *crcs, *adlers;
+    size_t units; atomic_size_t next; atomic_int err;
+} zjob;
+
+static void *zworker(void *arg) {
+    zjob *j = (zjob *)arg;
+    deflater *d = (deflater *)malloc(sizeof(deflater));
+    if (!d) { atomic_store(&j->err, 1); return NULL; }
+    for (;;) {
+        size_t u = atomic_fetch_add(&j->next, 1);
+        if (u >= j->units) break;
+        size_t off = u * (size_t)j->chunk;
+        uint32_t len = (uint32_t)((j->n - off < j->chunk) ? (j->n - off) : j->chunk);
+        /* a short chunk that follows a full one sees the previous chunk's stale upper half */
+        const uint8_t *stale = (len < ZO_CHUNK_MAX && u > 0 && j->chunk == ZO_CHUNK_MAX) ? j->in + off - ZO_WSIZE : NULL;
+        size_t r = deflate_one(d, j->in + off, len, j->level, j->flush, stale, j->out + u * j->out_stride, j->out_stride);
+        if (r == (size_t)-1) { atomic_store(&j->err, 2); r = 0; }
+        j->sizes[u] = (uint32_t)r;
+        if (j->crcs) j->crcs[u] = zo_crc32(0, j->in + off, len);
+        if (j->adlers) j->adlers[u] = zo_adler32(1, j->in + off, len);
+    }
+    free(d);
+    return NULL;
+}
+
+int zo_deflate_chunks(const uint8_t *in, size_t n, uint32_t chunk, int level, int flush,
+                      uint8_t *out, size_t out_stride, uint32_t *sizes,
+                      uint32_t *crcs, uint32_t *adlers, int nthreads) {
+    if (chunk == 0 || chunk > ZO_CHUNK_MAX) return -2;
+    zjob j = {in, n, chunk, level, flush, out, out_stride, sizes, crcs, adlers, (n + chunk - 1) / chunk, 0, 0};
+    atomic_store(&j.next, 0); atomic_store(&j.err, 0);
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    if (nthreads == 1) { zworker(&j); return atomic_load(&j.err); }
+    pthread_t t[256]; int started = 0;
+    for (int i = 0; i < nthreads; i++) { if (pthread_create(&t[i], NULL, zworker, &j) == 0) started++; else break; }
+    if (!started) zworker(&j);
+    for (int i = 0; i < started; i++) pthread_join(t[i], NULL);
+    return atomic_load(&j.err);
+}
