@@ -1,0 +1,351 @@
+#!/usr/bin/env python3
+"""bench.py -- level-1 chunked deflate throughput on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # zlib-ng's own CPU path, all host cores
+
+Workload (BASELINE.json configs[0], the configuration the metric is quoted on): per GPU a 1 GiB
+synthetic mixed text/binary buffer = 16,384 independent 64 KiB chunks, deflate_quick (level 1) raw
+deflate with Z_FULL_FLUSH chunk ends + per-chunk CRC-32, then the output-offset scan, the gather
+into one contiguous raw-deflate stream and the crc32_combine fold.  With N > 1 each rank owns its
+own 1 GiB shard (weak scaling, contiguous chunk ranges) and the only collective is an NCCL
+allgather of the per-chunk (size, crc32) pairs.
+
+A "step" is one pass over the batch.  `value` is device-resident throughput (inputs already in
+HBM); `e2e` is the same work through the host-buffer C-ABI call (zng_b200_deflate_host, what
+zng_deflate of the host library calls) with pinned host buffers, H2D and D2H inside the timing.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHUNK = 65536
+SEED = 0x9E3779B97F4A7C15
+METRIC = "level1_deflate_input_throughput"
+UNIT = "GB/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mib-per-gpu", type=int, default=1024, help="input MiB per GPU (default: the 1 GiB BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def cpu_reference_run(n_bytes: int, steps: int, warmup: int):
+    """Time the reference's CPU implementation (oracle/_ref when it was built from /root/reference,
+    else the oracle port) on the same workload: one zng_stream per worker thread, zng_deflateReset +
+    zng_deflate(Z_FULL_FLUSH) + zng_crc32 per 64 KiB chunk, all host cores."""
+    import numpy as np
+    from __graft_entry__ import load_oracle, load_package
+    pkg = load_package()
+    zo = load_oracle()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    kind = "reference" if zo.have_ref() else "port"
+    fn = zo.ref().refdrv_deflate_chunks if kind == "reference" else zo.port().zo_deflate_chunks
+    if kind == "port":
+        cores = min(cores, 256)
+    data = pkg.synth(n_bytes, SEED)
+    nch = (n_bytes + CHUNK - 1) // CHUNK
+    stride = pkg.deflate_bound(CHUNK)
+    out = np.empty(nch * stride, dtype=np.uint8)
+    sizes = np.zeros(nch, dtype=np.uint32)
+    crcs = np.zeros(nch, dtype=np.uint32)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = fn(data.ctypes.data, n_bytes, CHUNK, 1, 3, out.ctypes.data, stride, sizes.ctypes.data, crcs.ctypes.data, None, cores)
+        t1 = time.perf_counter()
+        if r != 0:
+            raise RuntimeError(f"reference deflate failed: {r}")
+        if it >= warmup:
+            times.append(t1 - t0)
+    total = sum(times)
+    return {"value": n_bytes * len(times) / total / 1e9, "ms_per_step": 1e3 * total / len(times), "cores": cores, "kind": kind,
+            "ratio": float(sizes.sum()) / n_bytes,
+            "sample": f"{n_bytes >> 20} MiB of the same synthetic workload per step ({nch} chunks), {len(times)} timed steps, wall clock"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_bytes = args.mib_per_gpu << 20
+    # bounded sample: the CPU runs ~0.1 GB/s per core; keep the whole run within a few minutes
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    budget_bytes = int(0.08e9 * cores * 120 / max(1, args.steps + args.warmup))     # ~2 min in total
+    sample = min(n_bytes, max(64 << 20, (budget_bytes >> 26) << 26))
+    res = cpu_reference_run(sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"deflate_quick level 1, {args.mib_per_gpu} MiB per GPU as 64 KiB raw-deflate chunks + per-chunk crc32 (BASELINE configs[0])",
+                   "chunk_bytes": CHUNK, "level": 1, "flush": "Z_FULL_FLUSH", "sharding": f"chunks x{args.gpus}"},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "compression_ratio": res["ratio"],
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+
+    pkg = load_package()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    ngpu = world
+
+    n = args.mib_per_gpu << 20
+    nch = n // CHUNK
+    ctx = pkg.Context(local_rank)
+    stride = pkg.deflate_bound(CHUNK)
+
+    # this rank's shard of the synthetic stream (pinned, so the e2e leg can copy from it)
+    h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    r = pkg.lib().zng_b200_synth_fill(h_in.data_ptr(), n, SEED, rank * n)
+    assert r == 0
+    d_in = h_in.to(dev, non_blocking=True)
+    slots = torch.empty(nch * stride, dtype=torch.uint8, device=dev)
+    meta = torch.zeros(2, nch, dtype=torch.int32, device=dev)              # row 0 sizes, row 1 crc32
+    sizes, crcs = meta[0], meta[1]
+    offsets = torch.zeros(nch + 1, dtype=torch.int64, device=dev)
+    packed = torch.empty(nch * stride, dtype=torch.uint8, device=dev)
+    res = torch.zeros(4, dtype=torch.int32, device=dev)
+    if ngpu > 1:
+        gathered = torch.zeros(ngpu, 2, nch, dtype=torch.int32, device=dev)
+        offsets_all = torch.zeros(ngpu * nch + 1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+
+    k1_start = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k1_stop = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches = {"n": 0}
+
+    def step(i_timed=None):
+        if i_timed is not None:
+            k1_start[i_timed].record()
+        ctx.deflate_chunks(d_in, n, CHUNK, 1, pkg.Z_FULL_FLUSH, slots, stride, sizes, crcs, None)
+        if i_timed is not None:
+            k1_stop[i_timed].record()
+        launches["n"] += 1
+        if ngpu > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), meta.view(-1))
+            allm = gathered.permute(1, 0, 2).contiguous()                 # [2, ngpu*nch] in global chunk order
+            ctx.chunk_offsets(allm[0].view(-1), ngpu * nch, 0, offsets_all)     # global byte offsets of every chunk
+            ctx.crc32_fold(allm[1].view(-1), ngpu * nch, CHUNK, ngpu * n, 0, res[0:1])
+            launches["n"] += 2
+        else:
+            ctx.crc32_fold(crcs, nch, CHUNK, n, 0, res[0:1])
+            launches["n"] += 1
+        ctx.chunk_offsets(sizes, nch, 0, offsets)                          # local packing offsets
+        ctx.gather_chunks(slots, stride, sizes, offsets, nch, packed)
+        launches["n"] += 2
+
+    def barrier():
+        if ngpu > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # parity spot check outside the timed region (rank 0): a sample of chunks against the oracle
+    parity = None
+    if rank == 0:
+        try:
+            from __graft_entry__ import load_oracle
+            zo = load_oracle()
+            hs = sizes.cpu().numpy().view(np.uint32)
+            hslots = slots.view(-1, stride)
+            pick = np.random.default_rng(0).choice(nch, size=min(64, nch), replace=False)
+            hin = h_in.numpy()
+            ok = True
+            for ci in pick:
+                exp, es, ec, _ = zo.port_deflate_chunks(hin[ci * CHUNK:(ci + 1) * CHUNK], CHUNK, 1, 3, stride, nthreads=1)
+                got = hslots[ci, : int(es[0])].cpu().numpy()
+                ok &= bool(es[0] == hs[ci]) and bool(np.array_equal(got, exp[0, : es[0]]))
+            parity = "bit-exact vs oracle on 64 sampled chunks" if ok else "MISMATCH vs oracle"
+        except Exception as e:  # oracle not built: say so, do not guess
+            parity = f"not checked ({e})"
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    k1_ms = sum(a.elapsed_time(b) for a, b in zip(k1_start, k1_stop)) / args.steps
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if ngpu > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = ngpu * n / (ms_step * 1e-3) / 1e9
+    out_bytes = int(offsets[nch].item())
+
+    # ---- e2e: host buffers through the C-ABI host call, H2D/D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        cap = nch * stride
+        h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        for _ in range(2):
+            ctx.deflate_host(h_in, n, CHUNK, 1, False, h_out, cap)
+        barrier()
+        e_steps = max(3, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            out_len, crc_e2e, _ = ctx.deflate_host(h_in, n, CHUNK, 1, False, h_out, cap)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if ngpu > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": ngpu * n * e_steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(out_len),
+               "steps": e_steps, "api": "zng_b200_deflate_host (pinned host in/out, pipelined 32 MiB slabs)"}
+
+    if rank != 0:
+        if ngpu > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    alg_bytes = n + out_bytes                       # in + out per chunk, x chunks per launch
+    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "deflate_quick_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": k1_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "serial-per-chunk LZ77 parse: latency/issue bound, not HBM bound (see DESIGN.md)"}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        roofline["traffic"] = tr.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    cpu = None
+    if not args.no_cpu_baseline and ngpu == 1:
+        try:
+            cores = len(os.sched_getaffinity(0))
+            sample = min(n, max(64 << 20, (int(0.08e9 * cores * 20 / 4) >> 26) << 26))     # ~20 s of wall clock at most
+            rr = cpu_reference_run(sample, 3, 1)
+            cpu = {"value": rr["value"], "unit": UNIT, "cores": rr["cores"], "kind": rr["kind"], "sample": rr["sample"]}
+        except Exception as e:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpu, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"deflate_quick level 1, {args.mib_per_gpu} MiB per GPU as {nch} x 64 KiB raw-deflate chunks + per-chunk crc32, offset scan + gather + crc32_combine fold (BASELINE configs[0])",
+                   "chunk_bytes": CHUNK, "level": 1, "flush": "Z_FULL_FLUSH", "sharding": f"contiguous chunk ranges x{ngpu}",
+                   "collective": "nccl allgather of (size, crc32) per chunk" if ngpu > 1 else "none",
+                   "l2": "input 1 GiB per step >> 126 MB L2, no flush needed"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["n"], "clocks": clocks,
+        "compression_ratio": out_bytes / n, "parity": parity,
+        "pct_hbm_peak_input_only": 100.0 * (value / ngpu) / peak,
+    }
+    print(json.dumps(line), flush=True)
+    if ngpu > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,128 @@
+/* zng_b200.h -- C ABI of the B200 (sm_100a) implementation of zlib-ng's chunked-DEFLATE hot path.
+ *
+ * This is the shim the C11 host library (include/zlib-ng-b200.h: zng_deflateInit2 / zng_deflate /
+ * zng_crc32 ...) calls, and what a maintainer of the reference would bind at the accelerator seam
+ * the reference already has for IBM Z DFLTCC (deflate.c:72-106 hook macros; DEFLATE_HOOK at
+ * deflate.c:1039 replaces the whole strategy call).  Plain pointers and sizes only; `stream` is a
+ * cudaStream_t passed as void* (NULL = the legacy default stream).  All `d_` pointers are device
+ * memory on the context's device, all `h_` pointers are host memory.
+ *
+ * Return values are zlib-ng's (zlib-ng.h.in:180-188): 0 = Z_OK, negative = error; CUDA failures
+ * map to ZNG_B200_CUDA_ERROR and zng_b200_last_error() names them.  There is no CPU fallback:
+ * every entry point fails when the device or the kernels are unavailable.
+ *
+ * Frozen parameters: windowBits 15, memLevel 8, Z_DEFAULT_STRATEGY,
+ * chunk <= 65536 bytes, levels 1 (deflate_quick) and 2 (deflate_fast).
+ */
+#ifndef ZNG_B200_H
+#define ZNG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZNG_B200_OK             0
+#define ZNG_B200_STREAM_ERROR (-2)   /* bad / unsupported parameters (Z_STREAM_ERROR) */
+#define ZNG_B200_DATA_ERROR   (-3)
+#define ZNG_B200_MEM_ERROR    (-4)   /* allocation failed (Z_MEM_ERROR) */
+#define ZNG_B200_BUF_ERROR    (-5)   /* output capacity too small (Z_BUF_ERROR) */
+#define ZNG_B200_CUDA_ERROR   (-100) /* a CUDA call failed; see zng_b200_last_error() */
+
+#define ZNG_B200_CHUNK_MAX 65536u
+
+/* flush modes accepted for chunk compression (zlib-ng.h.in:165-171) */
+#define ZNG_B200_SYNC_FLUSH 2
+#define ZNG_B200_FULL_FLUSH 3
+#define ZNG_B200_FINISH     4
+
+typedef struct zng_b200_ctx zng_b200_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int         zng_b200_device_count(void);
+/* device < 0: the calling thread's current device.  One context per host thread (like one
+ * zng_stream per thread, README of the reference); contexts are independent. */
+int         zng_b200_ctx_create(zng_b200_ctx **ctx, int device);
+void        zng_b200_ctx_destroy(zng_b200_ctx *ctx);
+int         zng_b200_ctx_device(const zng_b200_ctx *ctx);
+int         zng_b200_ctx_sm_count(const zng_b200_ctx *ctx);
+const char *zng_b200_last_error(const zng_b200_ctx *ctx);
+int         zng_b200_sync(zng_b200_ctx *ctx, void *stream);
+
+/* pinned host memory for the host-buffer entry points (cudaHostAlloc / cudaFreeHost) */
+void       *zng_b200_host_alloc(size_t bytes);
+void        zng_b200_host_free(void *p);
+
+/* ---- K1/K2: chunk compression, device resident ------------------------------------------- */
+/* Size of one chunk's output slot: an upper bound of what zng_deflate can emit for `chunk_len`
+ * input bytes at levels 1-2 (deflate.c:709-781 zng_deflateBound: 9 bits per literal + block and
+ * flush overhead), rounded so that slots stay 16-byte aligned with read slack for the gather. */
+size_t      zng_b200_deflate_bound(size_t chunk_len);
+
+/* Replaces: configuration_table[level].func(s, flush) called from zng_deflate (deflate.c:1036-1043)
+ * for ceil(n/chunk) independent chunks, each on a stream whose window and hash state are empty --
+ * i.e. the byte output of "zng_deflateReset; zng_deflate(Z_FULL_FLUSH)" per chunk (flush = 3; also
+ * 2), or of "zng_deflate(Z_FINISH)" per chunk (flush = 4: BFINAL set, no trailing stored block).
+ *   d_in        n input bytes
+ *   d_out       ceil(n/chunk) slots of out_stride bytes (out_stride >= zng_b200_deflate_bound(chunk),
+ *               multiple of 16; d_out 16-byte aligned); slot i receives chunk i's raw-deflate bytes
+ *   d_sizes[i]  compressed size of chunk i
+ *   d_crcs[i]   zng_crc32(0, chunk i)    (may be NULL)       crc32.c:27-41
+ *   d_adlers[i] zng_adler32(1, chunk i)  (may be NULL)       adler32.c:15-28
+ * level 1 = deflate_quick (deflate_quick.c:47-130), level 2 = deflate_fast (deflate_fast.c:19-104). */
+int zng_b200_deflate_chunks(zng_b200_ctx *ctx, const void *d_in, size_t n, uint32_t chunk, int level, int flush,
+                            void *d_out, size_t out_stride, uint32_t *d_sizes, uint32_t *d_crcs,
+                            uint32_t *d_adlers, void *stream);
+
+/* Debug aid (ZLIB_DEBUG's Tracevv token trace analogue, deflate_p.h:39-44,72): as above for level 1,
+ * additionally writing the LZ77 token stream of chunk i to d_tokens[i*tok_stride ...]: a literal is
+ * its byte value, a match is 0x80000000 | len << 16 | dist, the list ends with 0x40000000. */
+int zng_b200_deflate_chunks_trace(zng_b200_ctx *ctx, const void *d_in, size_t n, uint32_t chunk, int level, int flush,
+                                  void *d_out, size_t out_stride, uint32_t *d_sizes, uint32_t *d_tokens,
+                                  uint32_t tok_stride, void *stream);
+
+/* ---- stream assembly ---------------------------------------------------------------------- */
+/* d_offsets[i] = base + sum_{j<i} d_sizes[j] for i in 0..nchunks (nchunks+1 entries). */
+int zng_b200_chunk_offsets(zng_b200_ctx *ctx, const uint32_t *d_sizes, uint32_t nchunks, uint64_t base,
+                           uint64_t *d_offsets, void *stream);
+/* Copy chunk i's d_sizes[i] bytes from its slot to d_dst + d_offsets[i] (the concatenation is the
+ * raw-deflate stream; what flush_pending (deflate.c:789-807) does one chunk at a time). */
+int zng_b200_gather_chunks(zng_b200_ctx *ctx, const void *d_slots, size_t out_stride, const uint32_t *d_sizes,
+                           const uint64_t *d_offsets, uint32_t nchunks, void *d_dst, void *stream);
+
+/* ---- K3: checksums ------------------------------------------------------------------------ */
+/* Per-tile zng_crc32(0, .) / zng_adler32(1, .) of consecutive tile_bytes-sized pieces (<= 65536). */
+int zng_b200_checksum_chunks(zng_b200_ctx *ctx, const void *d_in, size_t n, uint32_t tile_bytes,
+                             uint32_t *d_crcs, uint32_t *d_adlers, void *stream);
+/* *d_result = crc32_combine-fold of per-tile CRCs of an n-byte buffer onto `init`
+ * (crc32_braid_comb.c:16-24; equals zng_crc32_z(init, buf, n)). */
+int zng_b200_crc32_fold(zng_b200_ctx *ctx, const uint32_t *d_crcs, uint32_t ntiles, uint32_t tile_bytes, size_t n,
+                        uint32_t init, uint32_t *d_result, void *stream);
+/* adler32_combine-fold (adler32.c:32-54; equals zng_adler32_z(init, buf, n)). */
+int zng_b200_adler32_fold(zng_b200_ctx *ctx, const uint32_t *d_adlers, uint32_t ntiles, uint32_t tile_bytes, size_t n,
+                          uint32_t init, uint32_t *d_result, void *stream);
+/* Replaces functable.crc32 / functable.adler32 (functable.h:27,33) for a device buffer:
+ * *d_result = zng_crc32_z(init, buf, n) / zng_adler32_z(init, buf, n). */
+int zng_b200_crc32(zng_b200_ctx *ctx, const void *d_buf, size_t n, uint32_t init, uint32_t *d_result, void *stream);
+int zng_b200_adler32(zng_b200_ctx *ctx, const void *d_buf, size_t n, uint32_t init, uint32_t *d_result, void *stream);
+
+/* ---- host-buffer entry points (what zng_deflate / zng_crc32 of the host library call) ----- */
+/* Compress h_in[0..n) as ceil(n/chunk) chunks and write the concatenated raw-deflate stream to
+ * h_out.  final != 0: the last chunk is compressed with Z_FINISH semantics (BFINAL block, no
+ * stored block); otherwise every chunk ends with the Z_FULL_FLUSH marker.  *crc32 / *adler32
+ * (optional) receive zng_crc32_z(0,...) / zng_adler32_z(1,...) of the whole input.  Host<->device
+ * copies are pipelined with the kernels; pinned buffers (zng_b200_host_alloc) avoid staging. */
+int zng_b200_deflate_host(zng_b200_ctx *ctx, const void *h_in, size_t n, uint32_t chunk, int level, int final,
+                          void *h_out, size_t out_cap, size_t *out_len, uint32_t *crc32, uint32_t *adler32);
+int zng_b200_crc32_host(zng_b200_ctx *ctx, const void *h_buf, size_t n, uint32_t init, uint32_t *result);
+int zng_b200_adler32_host(zng_b200_ctx *ctx, const void *h_buf, size_t n, uint32_t init, uint32_t *result);
+
+/* ---- synthetic workload (bench / tests; BASELINE.json "synthetic mixed text/binary") ------- */
+int zng_b200_synth_fill(void *h_buf, size_t n, uint64_t seed, uint64_t offset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZNG_B200_H */

@@ -1,0 +1,95 @@
+"""K3 parity: CRC-32 / Adler-32 kernels and the combine folds, through the C ABI, against the
+reference's known-answer vectors and the CPU oracle."""
+import zlib as pyzlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_crc32_kats_through_host_entry(pkg, ctx, golden):
+    for v in golden("kat_crc32.json")["vectors"]:
+        if v["data_hex"] is None or v["len"] == 0:
+            continue                                   # NULL / empty: host-library argument handling (test_host_api)
+        d = np.frombuffer(bytes.fromhex(v["data_hex"]), dtype=np.uint8)
+        assert ctx.crc32_host(d, d.size, v["init"]) == v["expect"], v
+
+
+def test_adler32_kats_through_host_entry(pkg, ctx, golden):
+    for v in golden("kat_adler32.json")["vectors"]:
+        if v["data_hex"] is None:
+            continue
+        d = np.frombuffer(bytes.fromhex(v["data_hex"]), dtype=np.uint8)
+        assert ctx.adler32_host(d, d.size, v["init"]) == v["expect"], v
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 255, 256, 257, 511, 512, 513, 5552, 65535, 65536, 65537, 3 * 65536 + 17, (8 << 20) + 3])
+def test_flat_checksums_vs_oracle(pkg, ctx, zo, n):
+    import torch
+    rng = np.random.default_rng(n)
+    data = rng.integers(0, 256, size=n, dtype=np.uint8)
+    d = torch.from_numpy(data).to(f"cuda:{ctx.device}") if n else torch.zeros(16, dtype=torch.uint8, device=f"cuda:{ctx.device}")
+    res = torch.zeros(2, dtype=torch.int32, device=d.device)
+    for ci, ai in ((0, 1), (0xdeadbeef, 0x12345678 % (65521 << 16 | 65520))):
+        ai = ((ai >> 16) % 65521) << 16 | (ai & 0xffff) % 65521
+        ctx.crc32(d, n, ci, res[0:1])
+        ctx.adler32(d, n, ai, res[1:2])
+        torch.cuda.synchronize()
+        r = res.cpu().numpy().view(np.uint32)
+        assert int(r[0]) == zo.port_crc32(data, ci)
+        assert int(r[1]) == zo.port_adler32(data, ai)
+
+
+def test_unaligned_device_pointer(pkg, ctx, zo):
+    import torch
+    data = pkg.synth(4 * 65536, seed=77)
+    d = torch.from_numpy(data).to(f"cuda:{ctx.device}")
+    res = torch.zeros(1, dtype=torch.int32, device=d.device)
+    for off in (1, 2, 3, 5, 15):
+        ctx.crc32(d[off:], data.size - off, 0, res)
+        torch.cuda.synchronize()
+        assert int(res.cpu().numpy().view(np.uint32)[0]) == zo.port_crc32(data[off:])
+
+
+def test_chunk_checksums_and_folds(pkg, ctx, zo):
+    import torch
+    n = 37 * 65536 + 1234
+    data = pkg.synth(n, seed=88)
+    dev = f"cuda:{ctx.device}"
+    d = torch.from_numpy(data).to(dev)
+    for tile in (65536, 4096, 1000):
+        nt = (n + tile - 1) // tile
+        crcs = torch.zeros(nt, dtype=torch.int32, device=dev)
+        adlers = torch.zeros(nt, dtype=torch.int32, device=dev)
+        ctx.checksum_chunks(d, n, tile, crcs, adlers)
+        res = torch.zeros(2, dtype=torch.int32, device=dev)
+        ctx.crc32_fold(crcs, nt, tile, n, 0, res[0:1])
+        ctx.adler32_fold(adlers, nt, tile, n, 1, res[1:2])
+        torch.cuda.synchronize()
+        hc = crcs.cpu().numpy().view(np.uint32); ha = adlers.cpu().numpy().view(np.uint32)
+        for i in (0, 1, nt // 2, nt - 1):
+            piece = data[i * tile:(i + 1) * tile]
+            assert int(hc[i]) == zo.port_crc32(piece) and int(ha[i]) == zo.port_adler32(piece)
+        r = res.cpu().numpy().view(np.uint32)
+        assert int(r[0]) == zo.port_crc32(data) and int(r[1]) == zo.port_adler32(data)
+
+
+def test_crc_of_1GiB_property(pkg, ctx):
+    """Checksum of checksums at BASELINE size: the device CRC-32/Adler-32 of a 1 GiB buffer equals
+    the fold of its two halves and an independent host computation."""
+    import torch
+    n = 1 << 30
+    data = pkg.synth(n, seed=404)
+    d = torch.from_numpy(data).to(f"cuda:{ctx.device}")
+    res = torch.zeros(4, dtype=torch.int32, device=d.device)
+    ctx.crc32(d, n, 0, res[0:1])
+    ctx.adler32(d, n, 1, res[1:2])
+    ctx.crc32(d[: n // 2], n // 2, 0, res[2:3])
+    torch.cuda.synchronize()
+    half = int(res.cpu().numpy().view(np.uint32)[2])
+    ctx.crc32(d[n // 2:], n // 2, half, res[3:4])       # chaining through `init` == combine
+    torch.cuda.synchronize()
+    r = res.cpu().numpy().view(np.uint32)
+    assert int(r[0]) == pyzlib.crc32(data) == int(r[3])
+    assert int(r[1]) == pyzlib.adler32(data)

@@ -1,0 +1,85 @@
+"""The oracle's deflate restatement (oracle/zo_deflate.c) against
+  * the committed digests of the unmodified reference's output (tests/golden/deflate_digests.json,
+    produced by tests/golden/make_golden.py from oracle/_ref), and
+  * the unmodified reference itself, live, when oracle/_ref is present."""
+import zlib as pyzlib   # only to digest byte strings (crc32) and to round-trip through an independent inflater
+
+import numpy as np
+import pytest
+
+
+def _case_input(pkg, name):
+    """Rebuild the input of a golden case from its name (mirrors make_golden.deflate_digests)."""
+    rng = np.random.default_rng(20261018)
+    base = name.rsplit("_l", 1)[0]
+    if base == "synth_2MiB":
+        return pkg.synth(32 * 65536)
+    if base == "synth_ragged":
+        return pkg.synth(10 * 65536 + 777, seed=12345)
+    if base == "synth_finish":
+        return pkg.synth(4 * 65536 + 4097, seed=99)
+    if base == "synth_4k_members":
+        return pkg.synth(64 * 4096, seed=7)
+    if base == "zeros":
+        return np.zeros(3 * 65536 + 5, dtype=np.uint8)
+    if base == "random":
+        lvl = int(name.rsplit("_l", 1)[1])
+        first = rng.integers(0, 256, size=2 * 65536 + 100, dtype=np.uint8)
+        if lvl == 1:
+            return first
+        # level 2 drew after the level-1 cases from the same generator: replay the draws
+        return rng.integers(0, 256, size=2 * 65536 + 100, dtype=np.uint8)
+    if base == "tiny_sizes":
+        return pkg.synth(65536, seed=3)[:257 * 40]
+    if base.startswith("short_"):
+        n = int(base.split("_")[1])
+        return pkg.synth(65536, seed=5)[:n]
+    raise KeyError(name)
+
+
+def golden_cases(pkg, golden):
+    for c in golden("deflate_digests.json")["cases"]:
+        yield c, _case_input(pkg, c["name"])
+
+
+def test_port_matches_golden_digests(pkg, zo, golden):
+    ncase = 0
+    for c, data in golden_cases(pkg, golden):
+        assert data.size == c["n"], c["name"]
+        out, sizes, crcs, adlers = zo.port_deflate_chunks(data, c["chunk"], c["level"], c["flush"])
+        assert [int(x) for x in sizes] == c["sizes"], c["name"]
+        assert [int(pyzlib.crc32(out[i, : sizes[i]].tobytes())) for i in range(len(sizes))] == c["comp_crc32"], c["name"]
+        assert [int(x) for x in crcs] == c["crc32"], c["name"]
+        assert [int(x) for x in adlers] == c["adler32"], c["name"]
+        ncase += 1
+    assert ncase >= 60
+
+
+def test_port_matches_reference_live(pkg, zo):
+    if not zo.have_ref():
+        pytest.skip("oracle/_ref not built")
+    for seed, n, chunk, flush in ((11, 48 * 65536, 65536, 3), (12, 5 * 65536 + 31000, 65536, 4), (13, 200 * 1000, 1000, 3)):
+        data = pkg.synth(n, seed=seed)
+        for level in (1, 2):
+            a = zo.port_deflate_chunks(data, chunk, level, flush)
+            b = zo.ref_deflate_chunks(data, chunk, level, flush)
+            assert np.array_equal(a[1], b[1]), (seed, level)
+            for i in range(len(a[1])):
+                assert np.array_equal(a[0][i, : a[1][i]], b[0][i, : b[1][i]]), (seed, level, i)
+            assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+
+
+def test_port_output_inflates(pkg, zo):
+    # independent check of validity: CPython's zlib inflates the concatenated chunk stream
+    data = pkg.synth(6 * 65536 + 999, seed=21)
+    for level in (1, 2):
+        out, sizes, _, _ = zo.port_deflate_chunks(data, 65536, level, 3)
+        stream = b"".join(out[i, : sizes[i]].tobytes() for i in range(len(sizes))) + b"\x03\x00"
+        assert pyzlib.decompress(stream, wbits=-15) == data.tobytes()
+
+
+def test_synth_is_deterministic_and_shardable(pkg):
+    a = pkg.synth(20 * 65536)
+    b = pkg.synth(8 * 65536, offset=12 * 65536)
+    assert np.array_equal(a[12 * 65536:], b)
+    assert not np.array_equal(pkg.synth(65536, seed=1), pkg.synth(65536, seed=2))

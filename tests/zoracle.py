@@ -1,0 +1,161 @@
+"""ctypes bindings of the CPU oracle -- TEST INFRASTRUCTURE ONLY.
+
+`port_*`  : oracle/libzng_oracle.so, our plain-C restatement of the reference algorithms
+            (oracle/zo_*.c), always available (built by __graft_entry__.build()).
+`ref_*`   : oracle/_ref/libzng_ref.so, the UNMODIFIED reference compiled from /root/reference by
+            oracle/Makefile, present when it was built in the authoring container (it travels to
+            the GPU box as a built .so).  `have_ref()` says whether it is there.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product (zlib-ng_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PORT_PATH = os.path.join(ROOT, "oracle", "libzng_oracle.so")
+REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libzng_ref.so")
+
+_port = None
+_ref = None
+
+
+def port():
+    global _port
+    if _port is None:
+        if not os.path.exists(PORT_PATH):
+            raise ImportError(f"{PORT_PATH} missing: run `make -C oracle port`")
+        L = ctypes.CDLL(PORT_PATH)
+        L.zo_crc32.restype = c_uint32; L.zo_crc32.argtypes = [c_uint32, c_void_p, c_size_t]
+        L.zo_adler32.restype = c_uint32; L.zo_adler32.argtypes = [c_uint32, c_void_p, c_size_t]
+        L.zo_crc32_combine.restype = c_uint32; L.zo_crc32_combine.argtypes = [c_uint32, c_uint32, c_int64]
+        L.zo_crc32_combine_gen.restype = c_uint32; L.zo_crc32_combine_gen.argtypes = [c_int64]
+        L.zo_crc32_combine_op.restype = c_uint32; L.zo_crc32_combine_op.argtypes = [c_uint32, c_uint32, c_uint32]
+        L.zo_adler32_combine.restype = c_uint32; L.zo_adler32_combine.argtypes = [c_uint32, c_uint32, c_int64]
+        L.zo_compare256.restype = c_uint32; L.zo_compare256.argtypes = [c_void_p, c_void_p]
+        L.zo_deflate_bound.restype = c_size_t; L.zo_deflate_bound.argtypes = [c_size_t]
+        L.zo_deflate_chunk.restype = c_size_t; L.zo_deflate_chunk.argtypes = [c_void_p, c_uint32, c_int, c_int, c_void_p, c_size_t]
+        L.zo_deflate_chunks.restype = c_int
+        L.zo_deflate_chunks.argtypes = [c_void_p, c_size_t, c_uint32, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int]
+        L.zo_deflate_tokens.restype = c_size_t; L.zo_deflate_tokens.argtypes = [c_void_p, c_uint32, c_int, c_void_p, c_size_t]
+        if hasattr(L, "zo_inflate"):
+            L.zo_inflate.restype = c_int
+            L.zo_inflate.argtypes = [c_void_p, c_size_t, c_int, c_void_p, c_size_t, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_uint32), POINTER(c_char_p)]
+            L.zo_inflate_members.restype = c_int
+            L.zo_inflate_members.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]
+        _port = L
+    return _port
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_PATH)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        if not have_ref():
+            raise ImportError(f"{REF_PATH} missing (built from /root/reference by `make -C oracle ref`)")
+        L = ctypes.CDLL(REF_PATH)
+        L.refdrv_deflate_chunks.restype = c_int
+        L.refdrv_deflate_chunks.argtypes = [c_void_p, c_size_t, c_uint32, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int]
+        L.refdrv_checksum_chunks.restype = c_int
+        L.refdrv_checksum_chunks.argtypes = [c_void_p, c_size_t, c_uint32, c_void_p, c_void_p, c_int]
+        L.refdrv_checksum_flat.restype = c_int
+        L.refdrv_checksum_flat.argtypes = [c_void_p, c_size_t, c_uint32, c_int, POINTER(c_uint32), POINTER(c_uint32)]
+        L.refdrv_inflate_members.restype = c_int
+        L.refdrv_inflate_members.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]
+        L.refdrv_gzip_members.restype = c_int
+        L.refdrv_gzip_members.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_int]
+        L.refdrv_inflate_stream.restype = c_int
+        L.refdrv_inflate_stream.argtypes = [c_void_p, c_size_t, c_int, c_void_p, c_size_t, POINTER(c_uint64), POINTER(c_uint32)]
+        L.refdrv_now.restype = c_double
+        for name, res, args in (
+            ("zng_crc32", c_uint32, [c_uint32, c_void_p, c_uint32]),
+            ("zng_crc32_z", c_uint32, [c_uint32, c_void_p, c_size_t]),
+            ("zng_adler32", c_uint32, [c_uint32, c_void_p, c_uint32]),
+            ("zng_adler32_z", c_uint32, [c_uint32, c_void_p, c_size_t]),
+            ("zng_crc32_combine", c_uint32, [c_uint32, c_uint32, c_int64]),
+            ("zng_crc32_combine_gen", c_uint32, [c_int64]),
+            ("zng_crc32_combine_op", c_uint32, [c_uint32, c_uint32, c_uint32]),
+            ("zng_adler32_combine", c_uint32, [c_uint32, c_uint32, c_int64]),
+        ):
+            f = getattr(L, name); f.restype = res; f.argtypes = args
+        _ref = L
+    return _ref
+
+
+def _u8(a) -> np.ndarray:
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(bytes(a), dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _ptr(a: np.ndarray):
+    return c_void_p(a.ctypes.data) if a.size else c_void_p(0)
+
+
+def _deflate_chunks(fn, data, chunk, level, flush, stride, nthreads):
+    data = _u8(data)
+    n = data.size
+    nch = (n + chunk - 1) // chunk
+    out = np.zeros((max(nch, 1), stride), dtype=np.uint8)
+    sizes = np.zeros(max(nch, 1), dtype=np.uint32)
+    crcs = np.zeros(max(nch, 1), dtype=np.uint32)
+    adlers = np.zeros(max(nch, 1), dtype=np.uint32)
+    r = fn(_ptr(data), n, chunk, level, flush, out.ctypes.data, stride, sizes.ctypes.data, crcs.ctypes.data, adlers.ctypes.data, nthreads)
+    if r != 0:
+        raise RuntimeError(f"oracle deflate_chunks failed: {r}")
+    return out[:nch], sizes[:nch], crcs[:nch], adlers[:nch]
+
+
+def port_deflate_chunks(data, chunk=65536, level=1, flush=3, stride=None, nthreads=None):
+    stride = stride or int(port().zo_deflate_bound(chunk))
+    return _deflate_chunks(port().zo_deflate_chunks, data, chunk, level, flush, stride, nthreads or min(os.cpu_count() or 1, 32))
+
+
+def ref_deflate_chunks(data, chunk=65536, level=1, flush=3, stride=None, nthreads=None):
+    stride = stride or int(port().zo_deflate_bound(chunk))
+    return _deflate_chunks(ref().refdrv_deflate_chunks, data, chunk, level, flush, stride, nthreads or min(os.cpu_count() or 1, 32))
+
+
+def port_tokens(chunk_bytes, level=1) -> np.ndarray:
+    d = _u8(chunk_bytes)
+    tok = np.zeros(d.size + 8, dtype=np.uint32)
+    k = port().zo_deflate_tokens(_ptr(d), d.size, level, tok.ctypes.data, tok.size)
+    return tok[:k]
+
+
+def port_crc32(data, init=0) -> int:
+    d = _u8(data)
+    return int(port().zo_crc32(init, _ptr(d), d.size))
+
+
+def port_adler32(data, init=1) -> int:
+    d = _u8(data)
+    return int(port().zo_adler32(init, _ptr(d), d.size))
+
+
+def ref_crc32(data, init=0) -> int:
+    d = _u8(data)
+    return int(ref().zng_crc32_z(init, _ptr(d), d.size))
+
+
+def ref_adler32(data, init=1) -> int:
+    d = _u8(data)
+    return int(ref().zng_adler32_z(init, _ptr(d), d.size))
+
+
+def ref_inflate_stream(stream, window_bits, expect=None):
+    s = _u8(stream)
+    e = _u8(expect) if expect is not None else None
+    total = c_uint64(0)
+    crc = c_uint32(0)
+    r = ref().refdrv_inflate_stream(_ptr(s), s.size, window_bits, _ptr(e) if e is not None else c_void_p(0),
+                                    e.size if e is not None else 0, byref(total), byref(crc))
+    return int(r), int(total.value), int(crc.value)

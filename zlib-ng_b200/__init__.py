@@ -1,0 +1,187 @@
+"""zlib-ng_b200 -- Python (ctypes) harness over libzng_b200.so.
+
+The product is the shared library: hand-written sm_100a kernels behind the C ABI of
+``include/zng_b200.h`` plus the C11 host library that mirrors zlib-ng's own API
+(``include/zlib-ng-b200.h``).  This module only binds those C symbols for the tests and
+``bench.py``; PyTorch is used for device memory, streams and ``torch.distributed`` plumbing.
+There is no fallback: importing works without a GPU (so the symbol table can be checked), but
+every compute entry point fails loudly when the library or the device is missing.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_int, c_int32, c_size_t, c_uint32, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzng_b200.so")
+
+Z_OK, Z_STREAM_END, Z_NEED_DICT = 0, 1, 2
+Z_STREAM_ERROR, Z_DATA_ERROR, Z_MEM_ERROR, Z_BUF_ERROR, Z_VERSION_ERROR = -2, -3, -4, -5, -6
+Z_NO_FLUSH, Z_SYNC_FLUSH, Z_FULL_FLUSH, Z_FINISH = 0, 2, 3, 4
+CHUNK_MAX = 65536
+
+_lib = None
+
+
+class ZngB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"zng_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib() -> ctypes.CDLL:
+    """Load libzng_b200.so (built in-tree by ``make -C zlib-ng_b200``); no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `make -C {_HERE}` (or __graft_entry__.build()); there is no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u32p, u64p = c_void_p, c_void_p, c_void_p
+    sigs = {
+        "zng_b200_device_count": (c_int, []),
+        "zng_b200_ctx_create": (c_int, [POINTER(c_void_p), c_int]),
+        "zng_b200_ctx_destroy": (None, [vp]),
+        "zng_b200_ctx_device": (c_int, [vp]),
+        "zng_b200_ctx_sm_count": (c_int, [vp]),
+        "zng_b200_last_error": (c_char_p, [vp]),
+        "zng_b200_sync": (c_int, [vp, vp]),
+        "zng_b200_host_alloc": (c_void_p, [c_size_t]),
+        "zng_b200_host_free": (None, [vp]),
+        "zng_b200_deflate_bound": (c_size_t, [c_size_t]),
+        "zng_b200_deflate_chunks": (c_int, [vp, vp, c_size_t, c_uint32, c_int, c_int, vp, c_size_t, u32p, u32p, u32p, vp]),
+        "zng_b200_deflate_chunks_trace": (c_int, [vp, vp, c_size_t, c_uint32, c_int, c_int, vp, c_size_t, u32p, u32p, c_uint32, vp]),
+        "zng_b200_chunk_offsets": (c_int, [vp, u32p, c_uint32, c_uint64, u64p, vp]),
+        "zng_b200_gather_chunks": (c_int, [vp, vp, c_size_t, u32p, u64p, c_uint32, vp, vp]),
+        "zng_b200_checksum_chunks": (c_int, [vp, vp, c_size_t, c_uint32, u32p, u32p, vp]),
+        "zng_b200_crc32_fold": (c_int, [vp, u32p, c_uint32, c_uint32, c_size_t, c_uint32, u32p, vp]),
+        "zng_b200_adler32_fold": (c_int, [vp, u32p, c_uint32, c_uint32, c_size_t, c_uint32, u32p, vp]),
+        "zng_b200_crc32": (c_int, [vp, vp, c_size_t, c_uint32, u32p, vp]),
+        "zng_b200_adler32": (c_int, [vp, vp, c_size_t, c_uint32, u32p, vp]),
+        "zng_b200_deflate_host": (c_int, [vp, vp, c_size_t, c_uint32, c_int, c_int, vp, c_size_t, POINTER(c_size_t), POINTER(c_uint32), POINTER(c_uint32)]),
+        "zng_b200_crc32_host": (c_int, [vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
+        "zng_b200_adler32_host": (c_int, [vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
+        "zng_b200_synth_fill": (c_int, [vp, c_size_t, c_uint64, c_uint64]),
+    }
+    for name, (res, args) in sigs.items():
+        f = getattr(L, name)          # AttributeError = a declared symbol is not exported: fail loudly
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+def deflate_bound(chunk_len: int) -> int:
+    return int(lib().zng_b200_deflate_bound(chunk_len))
+
+
+def synth(n: int, seed: int = 0x9E3779B97F4A7C15, offset: int = 0):
+    """n bytes of the synthetic mixed text/binary workload (host numpy array)."""
+    import numpy as np
+    buf = np.empty(n, dtype=np.uint8)
+    r = lib().zng_b200_synth_fill(buf.ctypes.data, n, seed, offset)
+    if r != 0:
+        raise ZngB200Error(r, "synth_fill")
+    return buf
+
+
+def _ptr(t) -> int:
+    """Device/host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return 0
+    if hasattr(t, "data_ptr"):
+        return int(t.data_ptr())
+    return int(t.ctypes.data)
+
+
+class Context:
+    """One zng_b200_ctx (one per host thread / device), with tensor-friendly wrappers."""
+
+    def __init__(self, device: int = -1):
+        self._h = c_void_p()
+        r = lib().zng_b200_ctx_create(byref(self._h), device)
+        if r != 0:
+            raise ZngB200Error(r, "zng_b200_ctx_create failed (no sm_100 device? there is no CPU fallback)")
+        self.device = int(lib().zng_b200_ctx_device(self._h))
+        self.sm_count = int(lib().zng_b200_ctx_sm_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().zng_b200_ctx_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, r: int):
+        if r != 0:
+            raise ZngB200Error(r, lib().zng_b200_last_error(self._h).decode())
+
+    @staticmethod
+    def _stream():
+        import torch
+        return int(torch.cuda.current_stream().cuda_stream)
+
+    # ---- device-resident entry points (torch uint8 CUDA tensors) -------------------------
+    def alloc_chunk_outputs(self, n: int, chunk: int = CHUNK_MAX, adler: bool = True):
+        import torch
+        dev = torch.device("cuda", self.device)
+        nchunks = (n + chunk - 1) // chunk
+        stride = deflate_bound(chunk)
+        slots = torch.empty(max(nchunks, 1) * stride, dtype=torch.uint8, device=dev)
+        sizes = torch.zeros(max(nchunks, 1), dtype=torch.int32, device=dev)
+        crcs = torch.zeros(max(nchunks, 1), dtype=torch.int32, device=dev)
+        adlers = torch.zeros(max(nchunks, 1), dtype=torch.int32, device=dev) if adler else None
+        return slots, stride, sizes, crcs, adlers
+
+    def deflate_chunks(self, d_in, n: int, chunk: int, level: int, flush: int, slots, stride: int, sizes, crcs=None, adlers=None):
+        self._check(lib().zng_b200_deflate_chunks(self._h, _ptr(d_in), n, chunk, level, flush, _ptr(slots), stride,
+                                                  _ptr(sizes), _ptr(crcs), _ptr(adlers), self._stream()))
+
+    def deflate_chunks_trace(self, d_in, n: int, chunk: int, level: int, flush: int, slots, stride: int, sizes, tokens, tok_stride: int):
+        self._check(lib().zng_b200_deflate_chunks_trace(self._h, _ptr(d_in), n, chunk, level, flush, _ptr(slots), stride,
+                                                        _ptr(sizes), _ptr(tokens), tok_stride, self._stream()))
+
+    def chunk_offsets(self, sizes, nchunks: int, base: int, offsets):
+        self._check(lib().zng_b200_chunk_offsets(self._h, _ptr(sizes), nchunks, base, _ptr(offsets), self._stream()))
+
+    def gather_chunks(self, slots, stride: int, sizes, offsets, nchunks: int, dst):
+        self._check(lib().zng_b200_gather_chunks(self._h, _ptr(slots), stride, _ptr(sizes), _ptr(offsets), nchunks, _ptr(dst), self._stream()))
+
+    def checksum_chunks(self, d_in, n: int, tile: int, crcs=None, adlers=None):
+        self._check(lib().zng_b200_checksum_chunks(self._h, _ptr(d_in), n, tile, _ptr(crcs), _ptr(adlers), self._stream()))
+
+    def crc32_fold(self, crcs, ntiles: int, tile: int, n: int, init: int, result):
+        self._check(lib().zng_b200_crc32_fold(self._h, _ptr(crcs), ntiles, tile, n, init, _ptr(result), self._stream()))
+
+    def adler32_fold(self, adlers, ntiles: int, tile: int, n: int, init: int, result):
+        self._check(lib().zng_b200_adler32_fold(self._h, _ptr(adlers), ntiles, tile, n, init, _ptr(result), self._stream()))
+
+    def crc32(self, d_buf, n: int, init: int, result):
+        self._check(lib().zng_b200_crc32(self._h, _ptr(d_buf), n, init, _ptr(result), self._stream()))
+
+    def adler32(self, d_buf, n: int, init: int, result):
+        self._check(lib().zng_b200_adler32(self._h, _ptr(d_buf), n, init, _ptr(result), self._stream()))
+
+    # ---- host-buffer entry points (numpy arrays / pinned tensors) ------------------------
+    def deflate_host(self, h_in, n: int, chunk: int, level: int, final: bool, h_out, out_cap: int):
+        out_len = c_size_t(0)
+        crc = c_uint32(0)
+        adler = c_uint32(0)
+        self._check(lib().zng_b200_deflate_host(self._h, _ptr(h_in), n, chunk, level, 1 if final else 0, _ptr(h_out), out_cap,
+                                                byref(out_len), byref(crc), byref(adler)))
+        return int(out_len.value), int(crc.value), int(adler.value)
+
+    def crc32_host(self, h_buf, n: int, init: int = 0) -> int:
+        res = c_uint32(0)
+        self._check(lib().zng_b200_crc32_host(self._h, _ptr(h_buf), n, init, byref(res)))
+        return int(res.value)
+
+    def adler32_host(self, h_buf, n: int, init: int = 1) -> int:
+        res = c_uint32(0)
+        self._check(lib().zng_b200_adler32_host(self._h, _ptr(h_buf), n, init, byref(res)))
+        return int(res.value)

@@ -1,0 +1,460 @@
+// capi.cu -- the C ABI declared in include/zng_b200.h: context management, argument validation
+// (mirroring the order of checks in deflateInit2 / deflate, deflate.c:292-323,823-863, for the
+// frozen parameter set), kernel launches and the pipelined host-buffer entry points.
+// No CPU fallback lives here: a missing device or a failed launch is an error.
+#include "../../include/zng_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+using namespace zb;
+
+namespace {
+constexpr int kCounters = 64;
+constexpr int kPipe = 3;                       // slabs in flight on the host path
+constexpr uint32_t kSlabChunks = 512;          // 32 MiB of input per slab at 64 KiB chunks
+
+struct Slab {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t* d_in = nullptr;
+    uint8_t* d_slots = nullptr;
+    uint8_t* d_packed = nullptr;
+    uint32_t* d_sizes = nullptr;               // sizes | crcs | adlers, kSlabChunks each
+    uint64_t* d_offsets = nullptr;             // kSlabChunks + 1
+    uint32_t* d_res = nullptr;                 // [0] crc fold, [1] adler fold
+    uint64_t* h_meta = nullptr;                // pinned: [0] total bytes, [1] crc | adler << 32
+    size_t in_bytes = 0;                       // bytes of input in flight (0 = idle)
+    uint32_t nchunks = 0;
+};
+}  // namespace
+
+struct zng_b200_ctx {
+    int device = 0;
+    int sms = 0;
+    char err[256] = {0};
+    uint32_t* counters = nullptr;
+    int next_counter = 0;
+    uint32_t* ck_scratch = nullptr;            // per-tile crcs | adlers for the flat checksum calls
+    size_t ck_tiles = 0;
+    uint32_t* d_result = nullptr;              // small result area
+    uint32_t* h_result = nullptr;              // pinned
+    // host path
+    Slab slab[kPipe];
+    bool slabs_ready = false;
+    size_t slab_stride = 0;
+    uint8_t* d_hostbuf = nullptr;              // staging for *_host checksums
+    size_t hostbuf_cap = 0;
+    uint32_t x2n[32];
+};
+
+namespace {
+
+int fail(zng_b200_ctx* c, cudaError_t e, const char* what) {
+    if (c) snprintf(c->err, sizeof(c->err), "%s: %s", what, cudaGetErrorString(e));
+    return ZNG_B200_CUDA_ERROR;
+}
+int bad(zng_b200_ctx* c, const char* what) {
+    if (c) snprintf(c->err, sizeof(c->err), "%s", what);
+    return ZNG_B200_STREAM_ERROR;
+}
+
+#define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, e_, what); } while (0)
+
+struct DeviceGuard {
+    int prev = -1; bool ok = false;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) == cudaSuccess) { ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess; } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+uint32_t* next_counter(zng_b200_ctx* ctx) {
+    uint32_t* p = ctx->counters + ctx->next_counter;
+    ctx->next_counter = (ctx->next_counter + 1) % kCounters;
+    return p;
+}
+
+int ensure_ck_scratch(zng_b200_ctx* ctx, size_t tiles) {
+    if (tiles <= ctx->ck_tiles) return 0;
+    if (ctx->ck_scratch) cudaFree(ctx->ck_scratch);
+    ctx->ck_scratch = nullptr; ctx->ck_tiles = 0;
+    size_t want = tiles < 4096 ? 4096 : tiles;
+    CK(cudaMalloc(&ctx->ck_scratch, want * 2 * sizeof(uint32_t)), "cudaMalloc(checksum scratch)");
+    ctx->ck_tiles = want;
+    return 0;
+}
+
+int ensure_slabs(zng_b200_ctx* ctx) {
+    if (ctx->slabs_ready) return 0;
+    const size_t stride = zng_b200_deflate_bound(ZNG_B200_CHUNK_MAX);
+    ctx->slab_stride = stride;
+    for (int i = 0; i < kPipe; i++) {
+        Slab& s = ctx->slab[i];
+        CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreate");
+        CK(cudaMalloc(&s.d_in, (size_t)kSlabChunks * ZNG_B200_CHUNK_MAX), "cudaMalloc(slab in)");
+        CK(cudaMalloc(&s.d_slots, (size_t)kSlabChunks * stride), "cudaMalloc(slab slots)");
+        CK(cudaMalloc(&s.d_packed, (size_t)kSlabChunks * stride), "cudaMalloc(slab packed)");
+        CK(cudaMalloc(&s.d_sizes, (size_t)kSlabChunks * 3 * sizeof(uint32_t)), "cudaMalloc(slab sizes)");
+        CK(cudaMalloc(&s.d_offsets, ((size_t)kSlabChunks + 1) * sizeof(uint64_t)), "cudaMalloc(slab offsets)");
+        CK(cudaMalloc(&s.d_res, 4 * sizeof(uint32_t)), "cudaMalloc(slab res)");
+        CK(cudaHostAlloc(&s.h_meta, 4 * sizeof(uint64_t), cudaHostAllocDefault), "cudaHostAlloc(slab meta)");
+    }
+    ctx->slabs_ready = true;
+    return 0;
+}
+
+int check_chunk_args(zng_b200_ctx* ctx, const void* d_in, size_t n, uint32_t chunk, int level, int flush,
+                     const void* d_out, size_t out_stride, const uint32_t* d_sizes) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (level != 1 && level != 2) return bad(ctx, "level must be 1 (deflate_quick) or 2 (deflate_fast)");
+    if (flush != ZNG_B200_SYNC_FLUSH && flush != ZNG_B200_FULL_FLUSH && flush != ZNG_B200_FINISH)
+        return bad(ctx, "flush must be Z_SYNC_FLUSH, Z_FULL_FLUSH or Z_FINISH");
+    if (chunk == 0 || chunk > ZNG_B200_CHUNK_MAX) return bad(ctx, "chunk must be in 1..65536");
+    if (n && !d_in) return bad(ctx, "d_in is NULL");
+    if (n && (!d_out || !d_sizes)) return bad(ctx, "d_out / d_sizes is NULL");
+    if (n && (out_stride < zng_b200_deflate_bound(chunk) || (out_stride & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))) {
+        snprintf(ctx->err, sizeof(ctx->err), "out_stride must be >= zng_b200_deflate_bound(chunk), a multiple of 16, d_out 16-byte aligned");
+        return ZNG_B200_BUF_ERROR;
+    }
+    if ((n + chunk - 1) / chunk > 0xffffffffull) return bad(ctx, "too many chunks");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zng_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
+    if (!out) return ZNG_B200_STREAM_ERROR;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ZNG_B200_CUDA_ERROR;
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return ZNG_B200_CUDA_ERROR; }
+    if (device >= ndev) return ZNG_B200_STREAM_ERROR;
+    zng_b200_ctx* ctx = new (std::nothrow) zng_b200_ctx();
+    if (!ctx) return ZNG_B200_MEM_ERROR;
+    ctx->device = device;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ZNG_B200_CUDA_ERROR; }
+    ctx->sms = prop.multiProcessorCount;
+    if (prop.major < 10) { delete ctx; return ZNG_B200_STREAM_ERROR; }       // sm_100a kernels only
+    if (cudaMalloc(&ctx->counters, kCounters * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_result, 16 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaHostAlloc(&ctx->h_result, 16 * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) {
+        zng_b200_ctx_destroy(ctx);
+        return ZNG_B200_MEM_ERROR;
+    }
+    build_x2n(ctx->x2n);
+    *out = ctx;
+    return ZNG_B200_OK;
+}
+
+void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < kPipe; i++) {
+        Slab& s = ctx->slab[i];
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_slots) cudaFree(s.d_slots);
+        if (s.d_packed) cudaFree(s.d_packed);
+        if (s.d_sizes) cudaFree(s.d_sizes);
+        if (s.d_offsets) cudaFree(s.d_offsets);
+        if (s.d_res) cudaFree(s.d_res);
+        if (s.h_meta) cudaFreeHost(s.h_meta);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->ck_scratch) cudaFree(ctx->ck_scratch);
+    if (ctx->d_result) cudaFree(ctx->d_result);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    if (ctx->d_hostbuf) cudaFree(ctx->d_hostbuf);
+    delete ctx;
+}
+
+int zng_b200_ctx_device(const zng_b200_ctx* ctx) { return ctx ? ctx->device : -1; }
+int zng_b200_ctx_sm_count(const zng_b200_ctx* ctx) { return ctx ? ctx->sms : 0; }
+const char* zng_b200_last_error(const zng_b200_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+
+int zng_b200_sync(zng_b200_ctx* ctx, void* stream) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    DeviceGuard g(ctx->device);
+    CK(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+    return 0;
+}
+
+void* zng_b200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void zng_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+size_t zng_b200_deflate_bound(size_t chunk_len) {
+    // 9 bits per literal + 3-bit header + 7-bit EOB + 5-byte flush marker, + 36 bytes of read slack
+    // for the gather's word reads; rounded up to 16.
+    size_t b = chunk_len + ((chunk_len + 7) >> 3) + 16 + 36;
+    return (b + 15) & ~(size_t)15;
+}
+
+int zng_b200_deflate_chunks_trace(zng_b200_ctx* ctx, const void* d_in, size_t n, uint32_t chunk, int level, int flush,
+                                  void* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_tokens,
+                                  uint32_t tok_stride, void* stream) {
+    int r = check_chunk_args(ctx, d_in, n, chunk, level, flush, d_out, out_stride, d_sizes);
+    if (r) return r;
+    if (level != 1) return bad(ctx, "token trace is implemented for level 1");
+    if (!d_tokens || tok_stride < chunk + 1u) return bad(ctx, "d_tokens / tok_stride");
+    DeviceGuard g(ctx->device);
+    const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
+    CK(launch_deflate_quick((const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
+                            d_sizes, nullptr, nullptr, next_counter(ctx), ctx->sms, (cudaStream_t)stream, d_tokens, tok_stride),
+       "deflate_quick launch");
+    return 0;
+}
+
+int zng_b200_deflate_chunks(zng_b200_ctx* ctx, const void* d_in, size_t n, uint32_t chunk, int level, int flush,
+                            void* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs,
+                            uint32_t* d_adlers, void* stream) {
+    int r = check_chunk_args(ctx, d_in, n, chunk, level, flush, d_out, out_stride, d_sizes);
+    if (r) return r;
+    DeviceGuard g(ctx->device);
+    const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
+    if (level == 1) {
+        CK(launch_deflate_quick((const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
+                                d_sizes, d_crcs, d_adlers, next_counter(ctx), ctx->sms, (cudaStream_t)stream, nullptr, 0),
+           "deflate_quick launch");
+        return 0;
+    }
+    return bad(ctx, "level 2 (deflate_fast) kernel is not built in this version");
+}
+
+int zng_b200_chunk_offsets(zng_b200_ctx* ctx, const uint32_t* d_sizes, uint32_t nchunks, uint64_t base,
+                           uint64_t* d_offsets, void* stream) {
+    if (!ctx || !d_offsets || (nchunks && !d_sizes)) return ZNG_B200_STREAM_ERROR;
+    DeviceGuard g(ctx->device);
+    CK(launch_offsets(d_sizes, nchunks, base, d_offsets, (cudaStream_t)stream), "offsets launch");
+    return 0;
+}
+
+int zng_b200_gather_chunks(zng_b200_ctx* ctx, const void* d_slots, size_t out_stride, const uint32_t* d_sizes,
+                           const uint64_t* d_offsets, uint32_t nchunks, void* d_dst, void* stream) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (nchunks && (!d_slots || !d_sizes || !d_offsets || !d_dst)) return bad(ctx, "NULL argument");
+    if ((out_stride & 15u) || (reinterpret_cast<uintptr_t>(d_slots) & 15u)) return bad(ctx, "slots must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    CK(launch_gather((const uint8_t*)d_slots, out_stride, d_sizes, d_offsets, nchunks, (uint8_t*)d_dst, ctx->sms, (cudaStream_t)stream),
+       "gather launch");
+    return 0;
+}
+
+int zng_b200_checksum_chunks(zng_b200_ctx* ctx, const void* d_in, size_t n, uint32_t tile_bytes,
+                             uint32_t* d_crcs, uint32_t* d_adlers, void* stream) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (tile_bytes == 0 || tile_bytes > ZNG_B200_CHUNK_MAX) return bad(ctx, "tile_bytes must be in 1..65536");
+    if (n && !d_in) return bad(ctx, "d_in is NULL");
+    const size_t ntiles = (n + tile_bytes - 1) / tile_bytes;
+    if (ntiles > 0xffffffffull) return bad(ctx, "too many tiles");
+    DeviceGuard g(ctx->device);
+    CK(launch_checksum_tiles((const uint8_t*)d_in, n, tile_bytes, (uint32_t)ntiles, d_crcs, d_adlers, ctx->sms, (cudaStream_t)stream),
+       "checksum launch");
+    return 0;
+}
+
+int zng_b200_crc32_fold(zng_b200_ctx* ctx, const uint32_t* d_crcs, uint32_t ntiles, uint32_t tile_bytes, size_t n,
+                        uint32_t init, uint32_t* d_result, void* stream) {
+    if (!ctx || !d_result || (ntiles && !d_crcs)) return ZNG_B200_STREAM_ERROR;
+    if ((size_t)ntiles != (tile_bytes ? (n + tile_bytes - 1) / tile_bytes : 0)) return bad(ctx, "ntiles does not match n / tile_bytes");
+    DeviceGuard g(ctx->device);
+    CK(launch_crc32_fold(d_crcs, ntiles, tile_bytes, n, init, d_result, (cudaStream_t)stream), "crc32 fold launch");
+    return 0;
+}
+
+int zng_b200_adler32_fold(zng_b200_ctx* ctx, const uint32_t* d_adlers, uint32_t ntiles, uint32_t tile_bytes, size_t n,
+                          uint32_t init, uint32_t* d_result, void* stream) {
+    if (!ctx || !d_result || (ntiles && !d_adlers)) return ZNG_B200_STREAM_ERROR;
+    if ((size_t)ntiles != (tile_bytes ? (n + tile_bytes - 1) / tile_bytes : 0)) return bad(ctx, "ntiles does not match n / tile_bytes");
+    DeviceGuard g(ctx->device);
+    CK(launch_adler32_fold(d_adlers, ntiles, tile_bytes, n, init, d_result, (cudaStream_t)stream), "adler32 fold launch");
+    return 0;
+}
+
+int zng_b200_crc32(zng_b200_ctx* ctx, const void* d_buf, size_t n, uint32_t init, uint32_t* d_result, void* stream) {
+    if (!ctx || !d_result) return ZNG_B200_STREAM_ERROR;
+    const size_t ntiles = (n + ZNG_B200_CHUNK_MAX - 1) / ZNG_B200_CHUNK_MAX;
+    if (ntiles > 0xffffffffull) return bad(ctx, "buffer too large");
+    DeviceGuard g(ctx->device);
+    int r = ensure_ck_scratch(ctx, ntiles);
+    if (r) return r;
+    CK(launch_checksum_tiles((const uint8_t*)d_buf, n, ZNG_B200_CHUNK_MAX, (uint32_t)ntiles, ctx->ck_scratch, nullptr, ctx->sms, (cudaStream_t)stream),
+       "checksum launch");
+    CK(launch_crc32_fold(ctx->ck_scratch, (uint32_t)ntiles, ZNG_B200_CHUNK_MAX, n, init, d_result, (cudaStream_t)stream), "crc32 fold launch");
+    return 0;
+}
+
+int zng_b200_adler32(zng_b200_ctx* ctx, const void* d_buf, size_t n, uint32_t init, uint32_t* d_result, void* stream) {
+    if (!ctx || !d_result) return ZNG_B200_STREAM_ERROR;
+    const size_t ntiles = (n + ZNG_B200_CHUNK_MAX - 1) / ZNG_B200_CHUNK_MAX;
+    if (ntiles > 0xffffffffull) return bad(ctx, "buffer too large");
+    DeviceGuard g(ctx->device);
+    int r = ensure_ck_scratch(ctx, ntiles);
+    if (r) return r;
+    uint32_t* ad = ctx->ck_scratch + ctx->ck_tiles;
+    CK(launch_checksum_tiles((const uint8_t*)d_buf, n, ZNG_B200_CHUNK_MAX, (uint32_t)ntiles, nullptr, ad, ctx->sms, (cudaStream_t)stream),
+       "checksum launch");
+    CK(launch_adler32_fold(ad, (uint32_t)ntiles, ZNG_B200_CHUNK_MAX, n, init, d_result, (cudaStream_t)stream), "adler32 fold launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------- host-buffer entry points
+static int host_checksum(zng_b200_ctx* ctx, const void* h_buf, size_t n, uint32_t init, uint32_t* result, bool crc) {
+    if (!ctx || !result) return ZNG_B200_STREAM_ERROR;
+    if (n && !h_buf) return bad(ctx, "h_buf is NULL");
+    DeviceGuard g(ctx->device);
+    // slabs of <= 256 MiB through one staging buffer; partial results chain through `init`
+    const size_t slab = (size_t)256 << 20;
+    if (ctx->hostbuf_cap < (n < slab ? n : slab)) {
+        if (ctx->d_hostbuf) cudaFree(ctx->d_hostbuf);
+        ctx->d_hostbuf = nullptr; ctx->hostbuf_cap = 0;
+        size_t want = n < slab ? n : slab;
+        if (want < (1u << 20)) want = 1u << 20;
+        CK(cudaMalloc(&ctx->d_hostbuf, want), "cudaMalloc(host staging)");
+        ctx->hostbuf_cap = want;
+    }
+    uint32_t cur = init;
+    size_t off = 0;
+    do {
+        const size_t take = (n - off) < slab ? (n - off) : slab;
+        if (take) CK(cudaMemcpyAsync(ctx->d_hostbuf, (const uint8_t*)h_buf + off, take, cudaMemcpyHostToDevice, 0), "H2D");
+        int r = crc ? zng_b200_crc32(ctx, ctx->d_hostbuf, take, cur, ctx->d_result, nullptr)
+                    : zng_b200_adler32(ctx, ctx->d_hostbuf, take, cur, ctx->d_result, nullptr);
+        if (r) return r;
+        CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0), "D2H");
+        CK(cudaStreamSynchronize(0), "sync");
+        cur = ctx->h_result[0];
+        off += take;
+    } while (off < n);
+    *result = cur;
+    return 0;
+}
+
+int zng_b200_crc32_host(zng_b200_ctx* ctx, const void* h_buf, size_t n, uint32_t init, uint32_t* result) {
+    return host_checksum(ctx, h_buf, n, init, result, true);
+}
+int zng_b200_adler32_host(zng_b200_ctx* ctx, const void* h_buf, size_t n, uint32_t init, uint32_t* result) {
+    return host_checksum(ctx, h_buf, n, init, result, false);
+}
+
+// drain one slab: wait for its kernels, copy the packed bytes out
+static int drain_slab(zng_b200_ctx* ctx, Slab& s, uint8_t* h_out, size_t out_cap, size_t& out_pos,
+                      uint32_t& crc, uint32_t& adler) {
+    if (s.in_bytes == 0) return 0;
+    CK(cudaEventSynchronize(s.done), "cudaEventSynchronize");
+    const size_t total = (size_t)s.h_meta[0];
+    const uint32_t scrc = (uint32_t)s.h_meta[1], sadler = (uint32_t)(s.h_meta[1] >> 32);
+    if (out_pos + total > out_cap) { s.in_bytes = 0; snprintf(ctx->err, sizeof(ctx->err), "output buffer too small"); return ZNG_B200_BUF_ERROR; }
+    CK(cudaMemcpyAsync(h_out + out_pos, s.d_packed, total, cudaMemcpyDeviceToHost, s.stream), "D2H packed");
+    out_pos += total;
+    crc = crc32_combine_dev(ctx->x2n, crc, scrc, s.in_bytes);
+    adler = adler32_combine_dev(adler, sadler, s.in_bytes);
+    s.in_bytes = 0;
+    return 0;
+}
+
+int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_t chunk, int level, int final,
+                          void* h_out, size_t out_cap, size_t* out_len, uint32_t* crc32, uint32_t* adler32) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (level != 1 && level != 2) return bad(ctx, "level must be 1 or 2");
+    if (chunk == 0 || chunk > ZNG_B200_CHUNK_MAX) return bad(ctx, "chunk must be in 1..65536");
+    if (!out_len || (n && !h_in) || !h_out) return bad(ctx, "NULL argument");
+    DeviceGuard g(ctx->device);
+    int r = ensure_slabs(ctx);
+    if (r) return r;
+    const size_t stride = ctx->slab_stride;
+    const size_t slab_in = (size_t)kSlabChunks * chunk;
+    uint8_t* out = (uint8_t*)h_out;
+    size_t out_pos = 0, off = 0;
+    uint32_t crc = 0, adler = 1;
+    int k = 0;
+    // n == 0 with final: one empty Z_FINISH chunk ("03 00"); n == 0 without final: nothing to emit
+    bool emitted_final = false;
+    while (off < n || (final && !emitted_final)) {
+        Slab& s = ctx->slab[k];
+        r = drain_slab(ctx, s, out, out_cap, out_pos, crc, adler);     // reuse: previous occupant must be out
+        if (r) return r;
+        const size_t take = (n - off) < slab_in ? (n - off) : slab_in;
+        const bool is_last = (off + take == n);
+        CK(cudaStreamSynchronize(s.stream), "sync slab stream");      // the D2H of the previous occupant
+        if (take) CK(cudaMemcpyAsync(s.d_in, (const uint8_t*)h_in + off, take, cudaMemcpyHostToDevice, s.stream), "H2D");
+        uint32_t nch = (uint32_t)((take + chunk - 1) / chunk);
+        uint32_t* d_sizes = s.d_sizes; uint32_t* d_crcs = s.d_sizes + kSlabChunks; uint32_t* d_adlers = s.d_sizes + 2 * kSlabChunks;
+        if (final && is_last) {
+            // all but the last chunk end with the full-flush marker; the last one is the Z_FINISH chunk
+            const uint32_t body = nch ? nch - 1 : 0;
+            const size_t body_bytes = (size_t)body * chunk;
+            if (body) { r = zng_b200_deflate_chunks(ctx, s.d_in, body_bytes, chunk, level, ZNG_B200_FULL_FLUSH, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream); if (r) return r; }
+            // the final chunk (possibly empty)
+            const size_t tail = take - body_bytes;
+            if (tail) {
+                r = zng_b200_deflate_chunks(ctx, s.d_in + body_bytes, tail, chunk, level, ZNG_B200_FINISH, s.d_slots + (size_t)body * stride, stride,
+                                            d_sizes + body, d_crcs + body, d_adlers + body, s.stream);
+                if (r) return r;
+            } else {
+                // zng_deflate(Z_FINISH) with no input: "03 00" (empty static block, BFINAL) -- deflate_quick.c:53-58
+                static const uint8_t fin[2] = {0x03, 0x00};
+                static const uint32_t meta[3] = {2u, 0u, 1u};
+                CK(cudaMemcpyAsync(s.d_slots + (size_t)body * stride, fin, 2, cudaMemcpyHostToDevice, s.stream), "H2D fin");
+                CK(cudaMemcpyAsync(d_sizes + body, &meta[0], 4, cudaMemcpyHostToDevice, s.stream), "H2D fin size");
+                CK(cudaMemcpyAsync(d_crcs + body, &meta[1], 4, cudaMemcpyHostToDevice, s.stream), "H2D fin crc");
+                CK(cudaMemcpyAsync(d_adlers + body, &meta[2], 4, cudaMemcpyHostToDevice, s.stream), "H2D fin adler");
+                nch = body + 1;
+            }
+            emitted_final = true;
+        } else {
+            r = zng_b200_deflate_chunks(ctx, s.d_in, take, chunk, level, ZNG_B200_FULL_FLUSH, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream);
+            if (r) return r;
+        }
+        CK(launch_offsets(d_sizes, nch, 0, s.d_offsets, s.stream), "offsets launch");
+        CK(launch_gather(s.d_slots, stride, d_sizes, s.d_offsets, nch, s.d_packed, ctx->sms, s.stream), "gather launch");
+        const uint32_t ntiles = (uint32_t)((take + chunk - 1) / chunk);
+        CK(launch_crc32_fold(d_crcs, ntiles, chunk, take, 0, s.d_res, s.stream), "crc fold");
+        CK(launch_adler32_fold(d_adlers, ntiles, chunk, take, 1, s.d_res + 1, s.stream), "adler fold");
+        CK(cudaMemcpyAsync(&s.h_meta[0], s.d_offsets + nch, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream), "D2H total");
+        CK(cudaMemcpyAsync(&s.h_meta[1], s.d_res, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream), "D2H checks");
+        CK(cudaEventRecord(s.done, s.stream), "event record");
+        s.in_bytes = take ? take : (size_t)0;
+        s.nchunks = nch;
+        if (!take) {   // empty final chunk: still has to be drained (in_bytes == 0 means idle) -> drain now
+            CK(cudaEventSynchronize(s.done), "cudaEventSynchronize");
+            const size_t total = (size_t)s.h_meta[0];
+            if (out_pos + total > out_cap) { snprintf(ctx->err, sizeof(ctx->err), "output buffer too small"); return ZNG_B200_BUF_ERROR; }
+            CK(cudaMemcpyAsync(out + out_pos, s.d_packed, total, cudaMemcpyDeviceToHost, s.stream), "D2H packed");
+            out_pos += total;
+        }
+        off += take;
+        k = (k + 1) % kPipe;
+    }
+    // drain in issue order
+    for (int i = 0; i < kPipe; i++) {
+        r = drain_slab(ctx, ctx->slab[(k + i) % kPipe], out, out_cap, out_pos, crc, adler);
+        if (r) return r;
+    }
+    for (int i = 0; i < kPipe; i++) CK(cudaStreamSynchronize(ctx->slab[i].stream), "final sync");
+    *out_len = out_pos;
+    if (crc32) *crc32 = crc;
+    if (adler32) *adler32 = adler;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,30 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (internal to the shared library;
+// the public C ABI is include/zng_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace zb {
+
+// K1: level-1 chunk deflate (deflate_quick.cu)
+size_t deflate_quick_smem_bytes();
+cudaError_t launch_deflate_quick(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
+                                 uint8_t* out, size_t out_stride, uint32_t* sizes, uint32_t* crcs,
+                                 uint32_t* adlers, uint32_t* counter, int num_sms, cudaStream_t stream,
+                                 uint32_t* dbg_tokens, uint32_t dbg_stride);
+
+// K3: checksums (checksum.cu)
+cudaError_t launch_checksum_tiles(const uint8_t* in, size_t n, uint32_t tile_bytes, uint32_t ntiles,
+                                  uint32_t* crcs, uint32_t* adlers, int num_sms, cudaStream_t stream);
+cudaError_t launch_crc32_fold(const uint32_t* crcs, uint32_t ntiles, uint32_t tile_bytes, size_t n, uint32_t init,
+                              uint32_t* result, cudaStream_t stream);
+cudaError_t launch_adler32_fold(const uint32_t* adlers, uint32_t ntiles, uint32_t tile_bytes, size_t n, uint32_t init,
+                                uint32_t* result, cudaStream_t stream);
+
+// stream assembly (assemble.cu)
+cudaError_t launch_offsets(const uint32_t* sizes, uint32_t n, uint64_t base, uint64_t* offsets, cudaStream_t stream);
+cudaError_t launch_gather(const uint8_t* slots, size_t stride, const uint32_t* sizes, const uint64_t* offsets,
+                          uint32_t nchunks, uint8_t* dst, int num_sms, cudaStream_t stream);
+
+}  // namespace zb
