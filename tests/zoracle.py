@@ -96,8 +96,12 @@ def _u8(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.uint8)
 
 
+_ONE = np.zeros(16, dtype=np.uint8)
+
+
 def _ptr(a: np.ndarray):
-    return c_void_p(a.ctypes.data) if a.size else c_void_p(0)
+    # an empty array still gets a valid (non-NULL) pointer: NULL means "no buffer" to zng_crc32
+    return c_void_p(a.ctypes.data) if a.size else c_void_p(_ONE.ctypes.data)
 
 
 def _deflate_chunks(fn, data, chunk, level, flush, stride, nthreads):
