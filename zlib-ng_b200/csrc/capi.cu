@@ -38,7 +38,15 @@ struct zng_b200_ctx {
     int sms = 0;
     char err[256] = {0};
     uint32_t* counters = nullptr;
+    uint8_t* tails = nullptr;                  // kCounters scratch buffers for the padded last chunks
     int next_counter = 0;
+    // K1 scratch: one 128 KiB hash-head slab per resident chain (CTA); launches that share it are
+    // ordered through k1_done
+    uint16_t* heads = nullptr;
+    uint32_t heads_grid = 0;
+    int chains_per_sm = 4;
+    cudaEvent_t k1_done = nullptr;
+    bool k1_pending = false;
     uint32_t* ck_scratch = nullptr;            // per-tile crcs | adlers for the flat checksum calls
     size_t ck_tiles = 0;
     uint32_t* d_result = nullptr;              // small result area
@@ -71,10 +79,34 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-uint32_t* next_counter(zng_b200_ctx* ctx) {
-    uint32_t* p = ctx->counters + ctx->next_counter;
+int next_slot(zng_b200_ctx* ctx) {
+    int k = ctx->next_counter;
     ctx->next_counter = (ctx->next_counter + 1) % kCounters;
-    return p;
+    return k;
+}
+
+// Launch K1 for level 1 (+ the K3 tile kernel when per-chunk checksums are wanted).
+int run_deflate_quick(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
+                      uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers,
+                      cudaStream_t stream, uint32_t* d_tokens, uint32_t tok_stride) {
+    if (nchunks == 0) return 0;
+    const uint32_t full_grid = (uint32_t)ctx->sms * (uint32_t)ctx->chains_per_sm;
+    if (ctx->heads_grid < full_grid) {
+        if (ctx->heads) { cudaDeviceSynchronize(); cudaFree(ctx->heads); ctx->heads = nullptr; ctx->heads_grid = 0; }
+        CK(cudaMalloc(&ctx->heads, deflate_quick_head_bytes(full_grid)), "cudaMalloc(hash-head slabs)");
+        ctx->heads_grid = full_grid;
+    }
+    const uint32_t grid = deflate_quick_grid(nchunks, ctx->sms, ctx->chains_per_sm);
+    const int slot = next_slot(ctx);
+    if (ctx->k1_pending) CK(cudaStreamWaitEvent(stream, ctx->k1_done, 0), "cudaStreamWaitEvent");   // slabs are shared
+    CK(launch_deflate_quick(d_in, n, chunk, nchunks, last, d_out, out_stride, d_sizes, ctx->counters + slot, ctx->heads, grid,
+                            ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream, d_tokens, tok_stride),
+       "deflate_quick launch");
+    CK(cudaEventRecord(ctx->k1_done, stream), "cudaEventRecord");
+    ctx->k1_pending = true;
+    if (d_crcs || d_adlers)
+        CK(launch_checksum_tiles(d_in, n, chunk, nchunks, d_crcs, d_adlers, ctx->sms, stream), "checksum launch");
+    return 0;
 }
 
 int ensure_ck_scratch(zng_b200_ctx* ctx, size_t tiles) {
@@ -149,7 +181,10 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ZNG_B200_CUDA_ERROR; }
     ctx->sms = prop.multiProcessorCount;
     if (prop.major < 10) { delete ctx; return ZNG_B200_STREAM_ERROR; }       // sm_100a kernels only
+    if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->chains_per_sm = v; }
     if (cudaMalloc(&ctx->counters, kCounters * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->tails, (size_t)kCounters * deflate_quick_tail_bytes()) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->k1_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaMalloc(&ctx->d_result, 16 * sizeof(uint32_t)) != cudaSuccess ||
         cudaHostAlloc(&ctx->h_result, 16 * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) {
         zng_b200_ctx_destroy(ctx);
@@ -177,6 +212,9 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->tails) cudaFree(ctx->tails);
+    if (ctx->heads) cudaFree(ctx->heads);
+    if (ctx->k1_done) cudaEventDestroy(ctx->k1_done);
     if (ctx->ck_scratch) cudaFree(ctx->ck_scratch);
     if (ctx->d_result) cudaFree(ctx->d_result);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -218,10 +256,8 @@ int zng_b200_deflate_chunks_trace(zng_b200_ctx* ctx, const void* d_in, size_t n,
     if (!d_tokens || tok_stride < chunk + 1u) return bad(ctx, "d_tokens / tok_stride");
     DeviceGuard g(ctx->device);
     const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
-    CK(launch_deflate_quick((const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
-                            d_sizes, nullptr, nullptr, next_counter(ctx), ctx->sms, (cudaStream_t)stream, d_tokens, tok_stride),
-       "deflate_quick launch");
-    return 0;
+    return run_deflate_quick(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
+                             d_sizes, nullptr, nullptr, (cudaStream_t)stream, d_tokens, tok_stride);
 }
 
 int zng_b200_deflate_chunks(zng_b200_ctx* ctx, const void* d_in, size_t n, uint32_t chunk, int level, int flush,
@@ -231,12 +267,9 @@ int zng_b200_deflate_chunks(zng_b200_ctx* ctx, const void* d_in, size_t n, uint3
     if (r) return r;
     DeviceGuard g(ctx->device);
     const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
-    if (level == 1) {
-        CK(launch_deflate_quick((const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
-                                d_sizes, d_crcs, d_adlers, next_counter(ctx), ctx->sms, (cudaStream_t)stream, nullptr, 0),
-           "deflate_quick launch");
-        return 0;
-    }
+    if (level == 1)
+        return run_deflate_quick(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
+                                 d_sizes, d_crcs, d_adlers, (cudaStream_t)stream, nullptr, 0);
     return bad(ctx, "level 2 (deflate_fast) kernel is not built in this version");
 }
 
