@@ -17,6 +17,7 @@ namespace {
 constexpr int kCounters = 64;
 constexpr int kPipe = 3;                       // slabs in flight on the host path
 constexpr uint32_t kSlabChunks = 512;          // 32 MiB of input per slab at 64 KiB chunks
+constexpr uint32_t kBatchChunks = 16384;       // chunks per K1a/K1b launch pair (token scratch: 4 GiB at 64 KiB chunks)
 
 struct Slab {
     cudaStream_t stream = nullptr;
@@ -44,9 +45,13 @@ struct zng_b200_ctx {
     // ordered through k1_done
     uint16_t* heads = nullptr;
     uint32_t heads_grid = 0;
-    int chains_per_sm = 4;
+    int chains_per_sm = 32;
     cudaEvent_t k1_done = nullptr;
     bool k1_pending = false;
+    uint32_t* tokens = nullptr;                // LZ77 token lists of one batch (K1a -> K1b)
+    size_t tok_words = 0;
+    uint32_t* ntok = nullptr;
+    uint32_t ntok_cap = 0;
     uint32_t* ck_scratch = nullptr;            // per-tile crcs | adlers for the flat checksum calls
     size_t ck_tiles = 0;
     uint32_t* d_result = nullptr;              // small result area
@@ -85,23 +90,48 @@ int next_slot(zng_b200_ctx* ctx) {
     return k;
 }
 
-// Launch K1 for level 1 (+ the K3 tile kernel when per-chunk checksums are wanted).
+// K1 for level 1: K1a parse -> token lists in ctx scratch, K1b static emit (+ the K3 tile kernel when
+// per-chunk checksums are wanted).  Inputs larger than kBatchChunks chunks run as several batches
+// that reuse the token scratch (4 B per input byte).
 int run_deflate_quick(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
                       uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers,
                       cudaStream_t stream, uint32_t* d_tokens, uint32_t tok_stride) {
     if (nchunks == 0) return 0;
-    const uint32_t full_grid = (uint32_t)ctx->sms * (uint32_t)ctx->chains_per_sm;
+    const uint32_t full_grid = deflate_quick_grid(0xffffffffu, ctx->sms, ctx->chains_per_sm);
     if (ctx->heads_grid < full_grid) {
         if (ctx->heads) { cudaDeviceSynchronize(); cudaFree(ctx->heads); ctx->heads = nullptr; ctx->heads_grid = 0; }
         CK(cudaMalloc(&ctx->heads, deflate_quick_head_bytes(full_grid)), "cudaMalloc(hash-head slabs)");
         ctx->heads_grid = full_grid;
     }
-    const uint32_t grid = deflate_quick_grid(nchunks, ctx->sms, ctx->chains_per_sm);
-    const int slot = next_slot(ctx);
-    if (ctx->k1_pending) CK(cudaStreamWaitEvent(stream, ctx->k1_done, 0), "cudaStreamWaitEvent");   // slabs are shared
-    CK(launch_deflate_quick(d_in, n, chunk, nchunks, last, d_out, out_stride, d_sizes, ctx->counters + slot, ctx->heads, grid,
-                            ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream, d_tokens, tok_stride),
-       "deflate_quick launch");
+    const uint32_t own_stride = (chunk + 32u) & ~31u;                 // tokens per chunk incl. end marker, 128-byte rows
+    const uint32_t batch = nchunks < kBatchChunks ? nchunks : kBatchChunks;
+    if (!d_tokens && ctx->tok_words < (size_t)batch * own_stride) {
+        if (ctx->tokens) { cudaDeviceSynchronize(); cudaFree(ctx->tokens); ctx->tokens = nullptr; ctx->tok_words = 0; }
+        CK(cudaMalloc(&ctx->tokens, (size_t)batch * own_stride * sizeof(uint32_t)), "cudaMalloc(token scratch)");
+        ctx->tok_words = (size_t)batch * own_stride;
+    }
+    if (ctx->ntok_cap < nchunks) {
+        if (ctx->ntok) { cudaDeviceSynchronize(); cudaFree(ctx->ntok); ctx->ntok = nullptr; ctx->ntok_cap = 0; }
+        const uint32_t want = nchunks < 4096u ? 4096u : nchunks;
+        CK(cudaMalloc(&ctx->ntok, (size_t)want * sizeof(uint32_t)), "cudaMalloc(token counts)");
+        ctx->ntok_cap = want;
+    }
+    if (ctx->k1_pending) CK(cudaStreamWaitEvent(stream, ctx->k1_done, 0), "cudaStreamWaitEvent");   // scratch is shared
+    for (uint32_t c0 = 0; c0 < nchunks; c0 += batch) {
+        const uint32_t nb = (nchunks - c0) < batch ? (nchunks - c0) : batch;
+        const size_t off = (size_t)c0 * chunk;
+        const size_t nbytes = (c0 + nb == nchunks) ? n - off : (size_t)nb * chunk;
+        uint32_t* toks = d_tokens ? d_tokens + (size_t)c0 * tok_stride : ctx->tokens;
+        const uint32_t stride = d_tokens ? tok_stride : own_stride;
+        const uint32_t grid = deflate_quick_grid(nb, ctx->sms, ctx->chains_per_sm);
+        const int slot = next_slot(ctx);
+        CK(launch_quick_parse(d_in + off, nbytes, chunk, nb, toks, stride, ctx->ntok + c0, ctx->counters + slot, ctx->heads, grid,
+                              ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream),
+           "quick_parse launch");
+        CK(launch_static_emit(toks, stride, ctx->ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
+                              d_sizes + c0, ctx->sms, stream),
+           "static_emit launch");
+    }
     CK(cudaEventRecord(ctx->k1_done, stream), "cudaEventRecord");
     ctx->k1_pending = true;
     if (d_crcs || d_adlers)
@@ -181,7 +211,7 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ZNG_B200_CUDA_ERROR; }
     ctx->sms = prop.multiProcessorCount;
     if (prop.major < 10) { delete ctx; return ZNG_B200_STREAM_ERROR; }       // sm_100a kernels only
-    if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->chains_per_sm = v; }
+    if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm = v; }
     if (cudaMalloc(&ctx->counters, kCounters * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->tails, (size_t)kCounters * deflate_quick_tail_bytes()) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->k1_done, cudaEventDisableTiming) != cudaSuccess ||
@@ -214,6 +244,8 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->tails) cudaFree(ctx->tails);
     if (ctx->heads) cudaFree(ctx->heads);
+    if (ctx->tokens) cudaFree(ctx->tokens);
+    if (ctx->ntok) cudaFree(ctx->ntok);
     if (ctx->k1_done) cudaEventDestroy(ctx->k1_done);
     if (ctx->ck_scratch) cudaFree(ctx->ck_scratch);
     if (ctx->d_result) cudaFree(ctx->d_result);

@@ -7,15 +7,18 @@
 
 namespace zb {
 
-// K1: level-1 chunk deflate (deflate_quick.cu).  `heads` = grid slabs of 128 KiB (L2-resident hash-head
-// tables), `tail` = deflate_quick_tail_bytes() of scratch for the padded copy of the last chunks.
+// K1: level-1 chunk deflate (deflate_quick.cu): K1a parse (one warp per chain) -> token lists, K1b
+// static-Huffman emit.  `heads` = 128 KiB hash-head slab per warp of the parse grid, `tail` =
+// deflate_quick_tail_bytes() of scratch for the padded copy of the last chunks.
 size_t deflate_quick_head_bytes(uint32_t grid);
 size_t deflate_quick_tail_bytes();
 uint32_t deflate_quick_grid(uint32_t nchunks, int num_sms, int chains_per_sm);
-cudaError_t launch_deflate_quick(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
-                                 uint8_t* out, size_t out_stride, uint32_t* sizes, uint32_t* counter,
-                                 uint16_t* heads, uint32_t grid, uint8_t* tail, cudaStream_t stream,
-                                 uint32_t* dbg_tokens, uint32_t dbg_stride);
+cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
+                               uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
+                               uint16_t* heads, uint32_t grid, uint8_t* tail, cudaStream_t stream);
+cudaError_t launch_static_emit(const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n, uint32_t chunk,
+                               uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
+                               int num_sms, cudaStream_t stream);
 
 // K3: checksums (checksum.cu)
 cudaError_t launch_checksum_tiles(const uint8_t* in, size_t n, uint32_t tile_bytes, uint32_t ntiles,
