@@ -274,8 +274,8 @@ size_t deflate_quick_tail_bytes() { return 2u * kChunkMax + 4u * kWinPad; }
 uint32_t deflate_quick_grid(uint32_t nchunks, int num_sms, int chains_per_sm) {
     uint32_t ctas_per_sm = ((uint32_t)chains_per_sm + kParseWarps - 1u) / kParseWarps;
     uint32_t grid = (uint32_t)num_sms * ctas_per_sm;
-    uint32_t need = (nchunks + kParseWarps - 1u) / kParseWarps;
-    return need < grid ? need : grid;
+    uint64_t need = ((uint64_t)nchunks + kParseWarps - 1u) / kParseWarps;
+    return need < grid ? (uint32_t)need : grid;
 }
 
 cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
