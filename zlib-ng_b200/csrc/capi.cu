@@ -45,7 +45,8 @@ struct zng_b200_ctx {
     // ordered through k1_done
     uint16_t* heads = nullptr;
     uint32_t heads_grid = 0;
-    int chains_per_sm = 32;
+    int chains_per_sm = 24;
+    uint32_t k1_flags = 8;                     // parser tuning switches (deflate_quick.cu), env ZNG_B200_FLAGS
     cudaEvent_t k1_done = nullptr;
     bool k1_pending = false;
     uint32_t* tokens = nullptr;                // LZ77 token lists of one batch (K1a -> K1b)
@@ -126,7 +127,7 @@ int run_deflate_quick(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_t
         const uint32_t grid = deflate_quick_grid(nb, ctx->sms, ctx->chains_per_sm);
         const int slot = next_slot(ctx);
         CK(launch_quick_parse(d_in + off, nbytes, chunk, nb, toks, stride, ctx->ntok + c0, ctx->counters + slot, ctx->heads, grid,
-                              ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream),
+                              ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), ctx->k1_flags, stream),
            "quick_parse launch");
         CK(launch_static_emit(toks, stride, ctx->ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
                               d_sizes + c0, ctx->sms, stream),
@@ -212,6 +213,7 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     ctx->sms = prop.multiProcessorCount;
     if (prop.major < 10) { delete ctx; return ZNG_B200_STREAM_ERROR; }       // sm_100a kernels only
     if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm = v; }
+    if (const char* e = getenv("ZNG_B200_FLAGS")) ctx->k1_flags = (uint32_t)atoi(e);
     if (cudaMalloc(&ctx->counters, kCounters * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->tails, (size_t)kCounters * deflate_quick_tail_bytes()) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->k1_done, cudaEventDisableTiming) != cudaSuccess ||
