@@ -15,9 +15,17 @@ using namespace zb;
 
 namespace {
 constexpr int kCounters = 64;
-constexpr int kPipe = 3;                       // slabs in flight on the host path
-constexpr uint32_t kSlabChunks = 512;          // 32 MiB of input per slab at 64 KiB chunks
+constexpr int kPipe = 6;                       // slabs in flight on the host path
+constexpr uint32_t kSlabChunks = 1024;         // 64 MiB of input per slab at 64 KiB chunks
 constexpr uint32_t kBatchChunks = 16384;       // chunks per K1a/K1b launch pair (token scratch: 4 GiB at 64 KiB chunks)
+
+// K1a -> K1b hand-over: LZ77 token lists (4 B per input byte) + token counts
+struct Scratch {
+    uint32_t* tokens = nullptr;
+    size_t tok_words = 0;
+    uint32_t* ntok = nullptr;
+    uint32_t ntok_cap = 0;
+};
 
 struct Slab {
     cudaStream_t stream = nullptr;
@@ -29,8 +37,9 @@ struct Slab {
     uint64_t* d_offsets = nullptr;             // kSlabChunks + 1
     uint32_t* d_res = nullptr;                 // [0] crc fold, [1] adler fold
     uint64_t* h_meta = nullptr;                // pinned: [0] total bytes, [1] crc | adler << 32
-    size_t in_bytes = 0;                       // bytes of input in flight (0 = idle)
-    uint32_t nchunks = 0;
+    Scratch scratch;
+    size_t in_bytes = 0;
+    bool busy = false;
 };
 }  // namespace
 
@@ -41,18 +50,15 @@ struct zng_b200_ctx {
     uint32_t* counters = nullptr;
     uint8_t* tails = nullptr;                  // kCounters scratch buffers for the padded last chunks
     int next_counter = 0;
-    // K1 scratch: one 128 KiB hash-head slab per resident chain (CTA); launches that share it are
-    // ordered through k1_done
+    // K1 hash-head slab pool: nsmid x 64 slabs of 128 KiB, handed out per SM by the kernel itself
     uint16_t* heads = nullptr;
-    uint32_t heads_grid = 0;
+    unsigned long long* sm_slots = nullptr;
+    uint32_t nsmid = 0;
     int chains_per_sm = 24;
     uint32_t k1_flags = 8;                     // parser tuning switches (deflate_quick.cu), env ZNG_B200_FLAGS
+    Scratch scratch;                           // for the device-resident entry points; users are ordered by k1_done
     cudaEvent_t k1_done = nullptr;
     bool k1_pending = false;
-    uint32_t* tokens = nullptr;                // LZ77 token lists of one batch (K1a -> K1b)
-    size_t tok_words = 0;
-    uint32_t* ntok = nullptr;
-    uint32_t ntok_cap = 0;
     uint32_t* ck_scratch = nullptr;            // per-tile crcs | adlers for the flat checksum calls
     size_t ck_tiles = 0;
     uint32_t* d_result = nullptr;              // small result area
@@ -91,52 +97,74 @@ int next_slot(zng_b200_ctx* ctx) {
     return k;
 }
 
-// K1 for level 1: K1a parse -> token lists in ctx scratch, K1b static emit (+ the K3 tile kernel when
-// per-chunk checksums are wanted).  Inputs larger than kBatchChunks chunks run as several batches
-// that reuse the token scratch (4 B per input byte).
-int run_deflate_quick(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
+int ensure_heads(zng_b200_ctx* ctx) {
+    if (ctx->heads) return 0;
+    CK(query_nsmid(ctx->d_result, &ctx->nsmid), "query nsmid");
+    CK(cudaMalloc(&ctx->sm_slots, (size_t)ctx->nsmid * sizeof(unsigned long long)), "cudaMalloc(sm slots)");
+    CK(cudaMemset(ctx->sm_slots, 0, (size_t)ctx->nsmid * sizeof(unsigned long long)), "cudaMemset(sm slots)");
+    CK(cudaMalloc(&ctx->heads, deflate_quick_head_bytes(ctx->nsmid)), "cudaMalloc(hash-head slab pool)");
+    return 0;
+}
+
+int ensure_scratch(zng_b200_ctx* ctx, Scratch& sc, uint32_t batch, uint32_t stride, uint32_t nchunks, bool need_tokens) {
+    if (need_tokens && sc.tok_words < (size_t)batch * stride) {
+        if (sc.tokens) { cudaDeviceSynchronize(); cudaFree(sc.tokens); sc.tokens = nullptr; sc.tok_words = 0; }
+        CK(cudaMalloc(&sc.tokens, (size_t)batch * stride * sizeof(uint32_t)), "cudaMalloc(token scratch)");
+        sc.tok_words = (size_t)batch * stride;
+    }
+    if (sc.ntok_cap < nchunks) {
+        if (sc.ntok) { cudaDeviceSynchronize(); cudaFree(sc.ntok); sc.ntok = nullptr; sc.ntok_cap = 0; }
+        const uint32_t want = nchunks < 4096u ? 4096u : nchunks;
+        CK(cudaMalloc(&sc.ntok, (size_t)want * sizeof(uint32_t)), "cudaMalloc(token counts)");
+        sc.ntok_cap = want;
+    }
+    return 0;
+}
+
+// K1 for level 1: K1a parse -> token lists in `sc`, K1b static emit (+ the K3 tile kernel when per-chunk
+// checksums are wanted).  Inputs larger than kBatchChunks chunks run as several batches that reuse
+// the token scratch (4 B per input byte).
+int run_deflate_quick(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
                       uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers,
                       cudaStream_t stream, uint32_t* d_tokens, uint32_t tok_stride) {
     if (nchunks == 0) return 0;
-    const uint32_t full_grid = deflate_quick_grid(0xffffffffu, ctx->sms, ctx->chains_per_sm);
-    if (ctx->heads_grid < full_grid) {
-        if (ctx->heads) { cudaDeviceSynchronize(); cudaFree(ctx->heads); ctx->heads = nullptr; ctx->heads_grid = 0; }
-        CK(cudaMalloc(&ctx->heads, deflate_quick_head_bytes(full_grid)), "cudaMalloc(hash-head slabs)");
-        ctx->heads_grid = full_grid;
-    }
+    int r = ensure_heads(ctx);
+    if (r) return r;
     const uint32_t own_stride = (chunk + 32u) & ~31u;                 // tokens per chunk incl. end marker, 128-byte rows
     const uint32_t batch = nchunks < kBatchChunks ? nchunks : kBatchChunks;
-    if (!d_tokens && ctx->tok_words < (size_t)batch * own_stride) {
-        if (ctx->tokens) { cudaDeviceSynchronize(); cudaFree(ctx->tokens); ctx->tokens = nullptr; ctx->tok_words = 0; }
-        CK(cudaMalloc(&ctx->tokens, (size_t)batch * own_stride * sizeof(uint32_t)), "cudaMalloc(token scratch)");
-        ctx->tok_words = (size_t)batch * own_stride;
-    }
-    if (ctx->ntok_cap < nchunks) {
-        if (ctx->ntok) { cudaDeviceSynchronize(); cudaFree(ctx->ntok); ctx->ntok = nullptr; ctx->ntok_cap = 0; }
-        const uint32_t want = nchunks < 4096u ? 4096u : nchunks;
-        CK(cudaMalloc(&ctx->ntok, (size_t)want * sizeof(uint32_t)), "cudaMalloc(token counts)");
-        ctx->ntok_cap = want;
-    }
-    if (ctx->k1_pending) CK(cudaStreamWaitEvent(stream, ctx->k1_done, 0), "cudaStreamWaitEvent");   // scratch is shared
+    r = ensure_scratch(ctx, sc, batch, own_stride, nchunks, d_tokens == nullptr);
+    if (r) return r;
     for (uint32_t c0 = 0; c0 < nchunks; c0 += batch) {
         const uint32_t nb = (nchunks - c0) < batch ? (nchunks - c0) : batch;
         const size_t off = (size_t)c0 * chunk;
         const size_t nbytes = (c0 + nb == nchunks) ? n - off : (size_t)nb * chunk;
-        uint32_t* toks = d_tokens ? d_tokens + (size_t)c0 * tok_stride : ctx->tokens;
+        uint32_t* toks = d_tokens ? d_tokens + (size_t)c0 * tok_stride : sc.tokens;
         const uint32_t stride = d_tokens ? tok_stride : own_stride;
         const uint32_t grid = deflate_quick_grid(nb, ctx->sms, ctx->chains_per_sm);
         const int slot = next_slot(ctx);
-        CK(launch_quick_parse(d_in + off, nbytes, chunk, nb, toks, stride, ctx->ntok + c0, ctx->counters + slot, ctx->heads, grid,
-                              ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), ctx->k1_flags, stream),
+        CK(launch_quick_parse(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->sm_slots,
+                              grid, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), ctx->k1_flags, stream),
            "quick_parse launch");
-        CK(launch_static_emit(toks, stride, ctx->ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
+        CK(launch_static_emit(toks, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
                               d_sizes + c0, ctx->sms, stream),
            "static_emit launch");
     }
-    CK(cudaEventRecord(ctx->k1_done, stream), "cudaEventRecord");
-    ctx->k1_pending = true;
     if (d_crcs || d_adlers)
         CK(launch_checksum_tiles(d_in, n, chunk, nchunks, d_crcs, d_adlers, ctx->sms, stream), "checksum launch");
+    return 0;
+}
+
+// the ctx-level scratch is shared by all device-resident calls: order them
+int run_deflate_quick_shared(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
+                             uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers,
+                             cudaStream_t stream, uint32_t* d_tokens, uint32_t tok_stride) {
+    if (nchunks == 0) return 0;
+    if (ctx->k1_pending) CK(cudaStreamWaitEvent(stream, ctx->k1_done, 0), "cudaStreamWaitEvent");
+    int r = run_deflate_quick(ctx, ctx->scratch, d_in, n, chunk, nchunks, last, d_out, out_stride, d_sizes, d_crcs, d_adlers, stream,
+                              d_tokens, tok_stride);
+    if (r) return r;
+    CK(cudaEventRecord(ctx->k1_done, stream), "cudaEventRecord");
+    ctx->k1_pending = true;
     return 0;
 }
 
@@ -240,14 +268,17 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
         if (s.d_offsets) cudaFree(s.d_offsets);
         if (s.d_res) cudaFree(s.d_res);
         if (s.h_meta) cudaFreeHost(s.h_meta);
+        if (s.scratch.tokens) cudaFree(s.scratch.tokens);
+        if (s.scratch.ntok) cudaFree(s.scratch.ntok);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->tails) cudaFree(ctx->tails);
     if (ctx->heads) cudaFree(ctx->heads);
-    if (ctx->tokens) cudaFree(ctx->tokens);
-    if (ctx->ntok) cudaFree(ctx->ntok);
+    if (ctx->sm_slots) cudaFree(ctx->sm_slots);
+    if (ctx->scratch.tokens) cudaFree(ctx->scratch.tokens);
+    if (ctx->scratch.ntok) cudaFree(ctx->scratch.ntok);
     if (ctx->k1_done) cudaEventDestroy(ctx->k1_done);
     if (ctx->ck_scratch) cudaFree(ctx->ck_scratch);
     if (ctx->d_result) cudaFree(ctx->d_result);
@@ -290,8 +321,8 @@ int zng_b200_deflate_chunks_trace(zng_b200_ctx* ctx, const void* d_in, size_t n,
     if (!d_tokens || tok_stride < chunk + 1u) return bad(ctx, "d_tokens / tok_stride");
     DeviceGuard g(ctx->device);
     const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
-    return run_deflate_quick(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
-                             d_sizes, nullptr, nullptr, (cudaStream_t)stream, d_tokens, tok_stride);
+    return run_deflate_quick_shared(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
+                                    d_sizes, nullptr, nullptr, (cudaStream_t)stream, d_tokens, tok_stride);
 }
 
 int zng_b200_deflate_chunks(zng_b200_ctx* ctx, const void* d_in, size_t n, uint32_t chunk, int level, int flush,
@@ -302,8 +333,8 @@ int zng_b200_deflate_chunks(zng_b200_ctx* ctx, const void* d_in, size_t n, uint3
     DeviceGuard g(ctx->device);
     const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
     if (level == 1)
-        return run_deflate_quick(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
-                                 d_sizes, d_crcs, d_adlers, (cudaStream_t)stream, nullptr, 0);
+        return run_deflate_quick_shared(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
+                                        d_sizes, d_crcs, d_adlers, (cudaStream_t)stream, nullptr, 0);
     return bad(ctx, "level 2 (deflate_fast) kernel is not built in this version");
 }
 
@@ -426,16 +457,24 @@ int zng_b200_adler32_host(zng_b200_ctx* ctx, const void* h_buf, size_t n, uint32
 // drain one slab: wait for its kernels, copy the packed bytes out
 static int drain_slab(zng_b200_ctx* ctx, Slab& s, uint8_t* h_out, size_t out_cap, size_t& out_pos,
                       uint32_t& crc, uint32_t& adler) {
-    if (s.in_bytes == 0) return 0;
+    if (!s.busy) return 0;
+    s.busy = false;
     CK(cudaEventSynchronize(s.done), "cudaEventSynchronize");
     const size_t total = (size_t)s.h_meta[0];
     const uint32_t scrc = (uint32_t)s.h_meta[1], sadler = (uint32_t)(s.h_meta[1] >> 32);
-    if (out_pos + total > out_cap) { s.in_bytes = 0; snprintf(ctx->err, sizeof(ctx->err), "output buffer too small"); return ZNG_B200_BUF_ERROR; }
+    if (out_pos + total > out_cap) { snprintf(ctx->err, sizeof(ctx->err), "output buffer too small"); return ZNG_B200_BUF_ERROR; }
     CK(cudaMemcpyAsync(h_out + out_pos, s.d_packed, total, cudaMemcpyDeviceToHost, s.stream), "D2H packed");
     out_pos += total;
     crc = crc32_combine_dev(ctx->x2n, crc, scrc, s.in_bytes);
     adler = adler32_combine_dev(adler, sadler, s.in_bytes);
-    s.in_bytes = 0;
+    return 0;
+}
+
+static int sync_slabs(zng_b200_ctx* ctx) {
+    for (int i = 0; i < kPipe; i++) {
+        ctx->slab[i].busy = false;
+        if (ctx->slab[i].stream) cudaStreamSynchronize(ctx->slab[i].stream);
+    }
     return 0;
 }
 
@@ -443,6 +482,7 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
                           void* h_out, size_t out_cap, size_t* out_len, uint32_t* crc32, uint32_t* adler32) {
     if (!ctx) return ZNG_B200_STREAM_ERROR;
     if (level != 1 && level != 2) return bad(ctx, "level must be 1 or 2");
+    if (level != 1) return bad(ctx, "level 2 (deflate_fast) kernel is not built in this version");
     if (chunk == 0 || chunk > ZNG_B200_CHUNK_MAX) return bad(ctx, "chunk must be in 1..65536");
     if (!out_len || (n && !h_in) || !h_out) return bad(ctx, "NULL argument");
     DeviceGuard g(ctx->device);
@@ -454,15 +494,15 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
     size_t out_pos = 0, off = 0;
     uint32_t crc = 0, adler = 1;
     int k = 0;
-    // n == 0 with final: one empty Z_FINISH chunk ("03 00"); n == 0 without final: nothing to emit
+    // n == 0 with final: one empty Z_FINISH chunk ("03 00"); n == 0 without final: nothing to emit.
+    // Slabs run on their own streams: H2D, K1a/K1b, K3, gather and D2H of different slabs overlap.
     bool emitted_final = false;
     while (off < n || (final && !emitted_final)) {
         Slab& s = ctx->slab[k];
-        r = drain_slab(ctx, s, out, out_cap, out_pos, crc, adler);     // reuse: previous occupant must be out
-        if (r) return r;
+        r = drain_slab(ctx, s, out, out_cap, out_pos, crc, adler);     // the previous occupant's bytes leave first
+        if (r) { sync_slabs(ctx); return r; }
         const size_t take = (n - off) < slab_in ? (n - off) : slab_in;
         const bool is_last = (off + take == n);
-        CK(cudaStreamSynchronize(s.stream), "sync slab stream");      // the D2H of the previous occupant
         if (take) CK(cudaMemcpyAsync(s.d_in, (const uint8_t*)h_in + off, take, cudaMemcpyHostToDevice, s.stream), "H2D");
         uint32_t nch = (uint32_t)((take + chunk - 1) / chunk);
         uint32_t* d_sizes = s.d_sizes; uint32_t* d_crcs = s.d_sizes + kSlabChunks; uint32_t* d_adlers = s.d_sizes + 2 * kSlabChunks;
@@ -470,13 +510,15 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
             // all but the last chunk end with the full-flush marker; the last one is the Z_FINISH chunk
             const uint32_t body = nch ? nch - 1 : 0;
             const size_t body_bytes = (size_t)body * chunk;
-            if (body) { r = zng_b200_deflate_chunks(ctx, s.d_in, body_bytes, chunk, level, ZNG_B200_FULL_FLUSH, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream); if (r) return r; }
-            // the final chunk (possibly empty)
+            if (body) {
+                r = run_deflate_quick(ctx, s.scratch, s.d_in, body_bytes, chunk, body, 0, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream, nullptr, 0);
+                if (r) { sync_slabs(ctx); return r; }
+            }
             const size_t tail = take - body_bytes;
             if (tail) {
-                r = zng_b200_deflate_chunks(ctx, s.d_in + body_bytes, tail, chunk, level, ZNG_B200_FINISH, s.d_slots + (size_t)body * stride, stride,
-                                            d_sizes + body, d_crcs + body, d_adlers + body, s.stream);
-                if (r) return r;
+                r = run_deflate_quick(ctx, s.scratch, s.d_in + body_bytes, tail, chunk, 1, 1, s.d_slots + (size_t)body * stride, stride,
+                                      d_sizes + body, d_crcs + body, d_adlers + body, s.stream, nullptr, 0);
+                if (r) { sync_slabs(ctx); return r; }
             } else {
                 // zng_deflate(Z_FINISH) with no input: "03 00" (empty static block, BFINAL) -- deflate_quick.c:53-58
                 static const uint8_t fin[2] = {0x03, 0x00};
@@ -489,8 +531,8 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
             }
             emitted_final = true;
         } else {
-            r = zng_b200_deflate_chunks(ctx, s.d_in, take, chunk, level, ZNG_B200_FULL_FLUSH, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream);
-            if (r) return r;
+            r = run_deflate_quick(ctx, s.scratch, s.d_in, take, chunk, nch, 0, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream, nullptr, 0);
+            if (r) { sync_slabs(ctx); return r; }
         }
         CK(launch_offsets(d_sizes, nch, 0, s.d_offsets, s.stream), "offsets launch");
         CK(launch_gather(s.d_slots, stride, d_sizes, s.d_offsets, nch, s.d_packed, ctx->sms, s.stream), "gather launch");
@@ -500,22 +542,23 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
         CK(cudaMemcpyAsync(&s.h_meta[0], s.d_offsets + nch, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream), "D2H total");
         CK(cudaMemcpyAsync(&s.h_meta[1], s.d_res, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream), "D2H checks");
         CK(cudaEventRecord(s.done, s.stream), "event record");
-        s.in_bytes = take ? take : (size_t)0;
-        s.nchunks = nch;
-        if (!take) {   // empty final chunk: still has to be drained (in_bytes == 0 means idle) -> drain now
-            CK(cudaEventSynchronize(s.done), "cudaEventSynchronize");
-            const size_t total = (size_t)s.h_meta[0];
-            if (out_pos + total > out_cap) { snprintf(ctx->err, sizeof(ctx->err), "output buffer too small"); return ZNG_B200_BUF_ERROR; }
-            CK(cudaMemcpyAsync(out + out_pos, s.d_packed, total, cudaMemcpyDeviceToHost, s.stream), "D2H packed");
-            out_pos += total;
-        }
+        s.in_bytes = take;
+        s.busy = true;
         off += take;
         k = (k + 1) % kPipe;
+        // eager drain, oldest first (output order is slab order): start the D2H of finished slabs now
+        for (int i = 0; i < kPipe; i++) {
+            Slab& o = ctx->slab[(k + i) % kPipe];
+            if (!o.busy) continue;
+            if (cudaEventQuery(o.done) != cudaSuccess) break;
+            r = drain_slab(ctx, o, out, out_cap, out_pos, crc, adler);
+            if (r) { sync_slabs(ctx); return r; }
+        }
     }
     // drain in issue order
     for (int i = 0; i < kPipe; i++) {
         r = drain_slab(ctx, ctx->slab[(k + i) % kPipe], out, out_cap, out_pos, crc, adler);
-        if (r) return r;
+        if (r) { sync_slabs(ctx); return r; }
     }
     for (int i = 0; i < kPipe; i++) CK(cudaStreamSynchronize(ctx->slab[i].stream), "final sync");
     *out_len = out_pos;

@@ -251,18 +251,39 @@ __device__ uint32_t static_emit_warp(uint32_t* stage, const uint32_t* __restrict
 }
 
 // ---------------------------------------------------------------- kernels
-// heads: one 65536 x u16 slab per warp of the grid.  tail: a zero-padded private copy of the chunks
+// Hash-head slabs are handed out per SM: slab (smid, b) belongs to the warp that holds bit b of
+// sm_slots[smid].  This lets any number of parse kernels (different streams, different batches) run
+// concurrently on one pool, sized nsmid x 64 (a resident warp always finds a free bit).
+__device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+
+__device__ __forceinline__ uint32_t slot_acquire(unsigned long long* word) {
+    for (;;) {
+        const unsigned long long m = *(volatile unsigned long long*)word;
+        const int b = __ffsll((long long)~m) - 1;
+        if (b >= 0) {
+            const unsigned long long bit = 1ull << b;
+            if (!(atomicOr(word, bit) & bit)) return (uint32_t)b;
+        }
+    }
+}
+
+__global__ void nsmid_kernel(uint32_t* out) { uint32_t r; asm volatile("mov.u32 %0, %%nsmid;" : "=r"(r)); *out = r; }
+
+// heads: the slab pool.  tail: a zero-padded private copy of the chunks
 // from `tail_first` on -- those whose read-ahead (<= kWinPad bytes past the chunk) could leave the
 // caller's allocation; every other chunk reads ahead into its successors, whose bytes cannot
 // influence the result (lengths are clipped to the chunk).
 __global__ void __launch_bounds__(kParseWarps * 32, 12)
 quick_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint32_t nchunks,
                    uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
-                   uint32_t* __restrict__ counter, uint16_t* __restrict__ heads, const uint8_t* __restrict__ tail,
-                   uint32_t tail_first, uint32_t flags) {
+                   uint32_t* __restrict__ counter, uint16_t* __restrict__ heads, unsigned long long* __restrict__ sm_slots,
+                   const uint8_t* __restrict__ tail, uint32_t tail_first, uint32_t flags) {
     const unsigned lane = lane_id();
-    const unsigned gw = blockIdx.x * kParseWarps + (threadIdx.x >> 5);
-    uint16_t* head = heads + (size_t)gw * 65536u;
+    const uint32_t sm = smid();
+    uint32_t slot = 0;
+    if (lane == 0) slot = slot_acquire(sm_slots + sm);
+    slot = __shfl_sync(ZB_FULL, slot, 0);
+    uint16_t* head = heads + ((size_t)sm * 64u + slot) * 65536u;
     for (;;) {
         uint32_t ci = 0;
         if (lane == 0) ci = atomicAdd(counter, 1u);
@@ -284,6 +305,8 @@ quick_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uin
         const uint32_t cnt = quick_parse_warp(W, len, head, tokens + (size_t)ci * tok_stride, flags);
         if (lane == 0) ntok[ci] = cnt;
     }
+    __syncwarp();
+    if (lane == 0) atomicAnd(sm_slots + sm, ~(1ull << slot));
 }
 
 __global__ void __launch_bounds__(kEmitWarps * 32)
@@ -304,7 +327,14 @@ static_emit_kernel(const uint32_t* __restrict__ tokens, uint32_t tok_stride, con
     }
 }
 
-size_t deflate_quick_head_bytes(uint32_t grid) { return (size_t)grid * kParseWarps * 65536u * sizeof(uint16_t); }
+size_t deflate_quick_head_bytes(uint32_t nsmid) { return (size_t)nsmid * 64u * 65536u * sizeof(uint16_t); }
+
+cudaError_t query_nsmid(uint32_t* d_scratch, uint32_t* nsmid) {
+    nsmid_kernel<<<1, 1>>>(d_scratch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(nsmid, d_scratch, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+}
 size_t deflate_quick_tail_bytes() { return 2u * kChunkMax + 4u * kWinPad; }
 
 // grid (CTAs of kParseWarps chains) for `chains_per_sm` chains on each SM
@@ -317,7 +347,8 @@ uint32_t deflate_quick_grid(uint32_t nchunks, int num_sms, int chains_per_sm) {
 
 cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                                uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
-                               uint16_t* heads, uint32_t grid, uint8_t* tail, uint32_t flags, cudaStream_t stream) {
+                               uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, uint32_t flags,
+                               cudaStream_t stream) {
     if (grid == 0 || nchunks == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
@@ -328,7 +359,7 @@ cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(tail + tail_bytes, 0, 2u * kWinPad, stream);
     if (e != cudaSuccess) return e;
-    quick_parse_kernel<<<grid, kParseWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, tail, tail_first, flags);
+    quick_parse_kernel<<<grid, kParseWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, tail, tail_first, flags);
     return cudaGetLastError();
 }
 

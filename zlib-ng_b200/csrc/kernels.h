@@ -10,12 +10,14 @@ namespace zb {
 // K1: level-1 chunk deflate (deflate_quick.cu): K1a parse (one warp per chain) -> token lists, K1b
 // static-Huffman emit.  `heads` = 128 KiB hash-head slab per warp of the parse grid, `tail` =
 // deflate_quick_tail_bytes() of scratch for the padded copy of the last chunks.
-size_t deflate_quick_head_bytes(uint32_t grid);
+size_t deflate_quick_head_bytes(uint32_t nsmid);       // pool of nsmid x 64 slabs, handed out per SM via sm_slots[nsmid]
+cudaError_t query_nsmid(uint32_t* d_scratch, uint32_t* nsmid);
 size_t deflate_quick_tail_bytes();
 uint32_t deflate_quick_grid(uint32_t nchunks, int num_sms, int chains_per_sm);
 cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                                uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
-                               uint16_t* heads, uint32_t grid, uint8_t* tail, uint32_t flags, cudaStream_t stream);
+                               uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, uint32_t flags,
+                               cudaStream_t stream);
 cudaError_t launch_static_emit(const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n, uint32_t chunk,
                                uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
                                int num_sms, cudaStream_t stream);
