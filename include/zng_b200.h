@@ -108,6 +108,25 @@ int zng_b200_adler32_fold(zng_b200_ctx *ctx, const uint32_t *d_adlers, uint32_t 
 int zng_b200_crc32(zng_b200_ctx *ctx, const void *d_buf, size_t n, uint32_t init, uint32_t *d_result, void *stream);
 int zng_b200_adler32(zng_b200_ctx *ctx, const void *d_buf, size_t n, uint32_t init, uint32_t *d_result, void *stream);
 
+/* ---- K4: batched inflate of independent members -------------------------------------------- */
+/* Replaces: zng_inflateInit2(&s, window_bits); zng_inflate(&s, Z_FINISH) (inflate.c:219-255, :476-1201, with
+ * inflate_fast inffast_tpl.h:53-318 and zng_inflate_table inftrees.c:30-295 underneath) for n_members
+ * independent members, each on a fresh stream.  window_bits as in zng_inflateInit2: -15 raw, 15 zlib,
+ * 31 gzip, 47 auto-detect.
+ *   d_in / d_in_off     member i occupies d_in[d_in_off[i] .. d_in_off[i+1])   (n_members + 1 offsets)
+ *   d_out / d_out_off   member i's output goes to d_out[d_out_off[i] ..], capacity d_out_off[i+1]-d_out_off[i]
+ *   d_sizes[i]          bytes produced (strm.total_out)
+ *   d_checks[i]         strm.adler after the call: crc32 (gzip) / adler32 (zlib) of the output (may be NULL)
+ *   d_status[i]         what zng_inflate returns: Z_STREAM_END 1, Z_NEED_DICT 2, Z_DATA_ERROR -3, Z_BUF_ERROR -5
+ *   d_in_used[i]        bytes consumed (strm.total_in) for members that reached Z_STREAM_END (may be NULL)
+ *   d_detail[i]         low byte: id of strm->msg (zng_b200_inflate_msg), 0x100: output capacity reached,
+ *                       0x200: input exhausted (may be NULL) */
+int zng_b200_inflate_members(zng_b200_ctx *ctx, const void *d_in, const uint64_t *d_in_off, uint32_t n_members,
+                             int window_bits, void *d_out, const uint64_t *d_out_off, uint32_t *d_sizes,
+                             uint32_t *d_checks, int32_t *d_status, uint32_t *d_in_used, uint32_t *d_detail, void *stream);
+/* the reference's strm->msg string for a detail value (NULL when there is none) */
+const char *zng_b200_inflate_msg(uint32_t detail);
+
 /* ---- host-buffer entry points (what zng_deflate / zng_crc32 of the host library call) ----- */
 /* Compress h_in[0..n) as ceil(n/chunk) chunks and write the concatenated raw-deflate stream to
  * h_out.  final != 0: the last chunk is compressed with Z_FINISH semantics (BFINAL block, no
@@ -116,6 +135,11 @@ int zng_b200_adler32(zng_b200_ctx *ctx, const void *d_buf, size_t n, uint32_t in
  * copies are pipelined with the kernels; pinned buffers (zng_b200_host_alloc) avoid staging. */
 int zng_b200_deflate_host(zng_b200_ctx *ctx, const void *h_in, size_t n, uint32_t chunk, int level, int final,
                           void *h_out, size_t out_cap, size_t *out_len, uint32_t *crc32, uint32_t *adler32);
+/* Host-buffer form of zng_b200_inflate_members (same arrays, all in host memory; offsets are copied to the
+ * device with the data, results come back in the h_ arrays). */
+int zng_b200_inflate_members_host(zng_b200_ctx *ctx, const void *h_in, const uint64_t *h_in_off, uint32_t n_members,
+                                  int window_bits, void *h_out, const uint64_t *h_out_off, uint32_t *h_sizes,
+                                  uint32_t *h_checks, int32_t *h_status, uint32_t *h_in_used, uint32_t *h_detail);
 int zng_b200_crc32_host(zng_b200_ctx *ctx, const void *h_buf, size_t n, uint32_t init, uint32_t *result);
 int zng_b200_adler32_host(zng_b200_ctx *ctx, const void *h_buf, size_t n, uint32_t init, uint32_t *result);
 

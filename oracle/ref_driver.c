@@ -214,6 +214,47 @@ REFDRV_EXPORT int refdrv_inflate_stream(const uint8_t *in, size_t n, int window_
     return r;
 }
 
+/* One zng_inflate(Z_FINISH) call on a fresh stream: what zo_inflate restates.  msg (>= 64 bytes) receives
+ * strm->msg or an empty string.  Returns the zng_inflate code, or the zng_inflateInit2 code if that failed. */
+REFDRV_EXPORT int refdrv_inflate_oneshot(const uint8_t *in, size_t n, int window_bits, uint8_t *out, size_t cap,
+                                         size_t *out_len, size_t *in_used, uint32_t *check, char *msg) {
+    zng_stream s; memset(&s, 0, sizeof(s));
+    if (msg) msg[0] = 0;
+    int r = zng_inflateInit2(&s, window_bits);
+    if (r != Z_OK) return r;
+    s.next_in = in; s.avail_in = (uint32_t)n; s.next_out = out; s.avail_out = (uint32_t)cap;
+    r = zng_inflate(&s, Z_FINISH);
+    if (out_len) *out_len = s.total_out;
+    if (in_used) *in_used = s.total_in;
+    if (check) *check = s.adler;
+    if (msg && s.msg) { strncpy(msg, s.msg, 63); msg[63] = 0; }
+    zng_inflateEnd(&s);
+    return r;
+}
+
+/* One whole gzip/zlib/raw stream through the reference's deflate with the pigz-style call sequence the
+ * host library promises to reproduce: Z_FULL_FLUSH after every `piece` bytes, Z_FINISH on the last piece. */
+REFDRV_EXPORT int refdrv_deflate_stream(const uint8_t *in, size_t n, uint32_t piece, int level, int window_bits,
+                                        uint8_t *out, size_t cap, size_t *out_len) {
+    zng_stream s; memset(&s, 0, sizeof(s));
+    int r = zng_deflateInit2(&s, level, Z_DEFLATED, window_bits, 8, Z_DEFAULT_STRATEGY);
+    if (r != Z_OK) return r;
+    s.next_out = out; s.avail_out = (uint32_t)(cap > 0xffffffffu ? 0xffffffffu : cap);
+    size_t off = 0;
+    do {
+        size_t take = n - off < piece ? n - off : piece;
+        int fin = (off + take == n);
+        s.next_in = in + off; s.avail_in = (uint32_t)take;
+        r = zng_deflate(&s, fin ? Z_FINISH : Z_FULL_FLUSH);
+        off += take;
+        if (fin) break;
+        if (r != Z_OK) break;
+    } while (1);
+    if (out_len) *out_len = s.total_out;
+    zng_deflateEnd(&s);
+    return r;
+}
+
 REFDRV_EXPORT double refdrv_now(void) {
     struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;

@@ -1,0 +1,212 @@
+"""The C11 host library (zlib-ng's own API names, include/zlib-ng.h) on the GPU: the call sequences of the
+reference's example.c / minigzip.c for this path -- zng_deflateInit2 + zng_deflate(Z_FULL_FLUSH ... Z_FINISH),
+zng_inflateInit2 + zng_inflate(Z_FINISH), zng_compress2 / zng_uncompress, zng_crc32 / zng_adler32 / combine --
+compared with the oracle (and with the unmodified reference when oracle/_ref is present)."""
+import ctypes
+import struct
+import zlib as pyzlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L(pkg, ctx):
+    return pkg.lib()
+
+
+def expected_stream(zo, data, level, wb):
+    """raw / zlib / gzip stream for the pigz-style call sequence (64 KiB pieces, Z_FULL_FLUSH, Z_FINISH last)."""
+    if zo.have_ref():
+        return zo.ref_deflate_stream(data, 65536, level, wb).tobytes()
+    n = data.size
+    nch = (n + 65535) // 65536
+    body = (nch - 1) * 65536 if nch else 0
+    parts = []
+    if body:
+        out, sizes, _, _ = zo.port_deflate_chunks(data[:body], 65536, level, 3)
+        parts += [out[i, : sizes[i]].tobytes() for i in range(len(sizes))]
+    if n - body:
+        out, sizes, _, _ = zo.port_deflate_chunks(data[body:], 65536, level, 4)
+        parts.append(out[0, : sizes[0]].tobytes())
+    else:
+        parts.append(b"\x03\x00")
+    raw = b"".join(parts)
+    if wb < 0:
+        return raw
+    if wb == 15:
+        return bytes([0x78, 0x01 if level < 2 else 0x5e]) + raw + struct.pack(">I", pyzlib.adler32(data.tobytes()))
+    return bytes([31, 139, 8, 0, 0, 0, 0, 0, 4 if level < 2 else 0, 3]) + raw + struct.pack("<II", pyzlib.crc32(data.tobytes()), n & 0xffffffff)
+
+
+def deflate_via_api(pkg, L, data, level, wb, pieces, out_room=None):
+    """Feed `data` through zng_deflate; pieces = list of (nbytes, flush).  Returns (bytes, strm)."""
+    s = pkg.ZngStream()
+    assert L.zng_deflateInit2(ctypes.byref(s), level, 8, wb, 8, 0) == 0
+    bound = int(L.zng_deflateBound(ctypes.byref(s), data.size)) + 64
+    out = np.zeros(bound, dtype=np.uint8)
+    got = bytearray()
+    pos = 0
+    for nbytes, flush in pieces:
+        s.next_in = data.ctypes.data + pos
+        s.avail_in = nbytes
+        pos += nbytes
+        while True:
+            room = out_room or bound
+            s.next_out = out.ctypes.data
+            s.avail_out = room
+            r = L.zng_deflate(ctypes.byref(s), flush)
+            got += out[: room - s.avail_out].tobytes()
+            assert r in (0, 1), (r, s.msg)
+            if r == 1 or (s.avail_out != 0 and s.avail_in == 0):
+                break
+        assert s.avail_in == 0
+    assert s.total_in == data.size and s.total_out == len(got)
+    adler = s.adler
+    assert L.zng_deflateEnd(ctypes.byref(s)) == 0
+    return bytes(got), adler
+
+
+@pytest.mark.parametrize("wb", [-15, 15, 31])
+@pytest.mark.parametrize("n", [0, 1, 65536, 3 * 65536 + 777, (8 << 20) + 5])
+def test_zng_deflate_one_call_equals_reference_piecewise(pkg, L, zo, n, wb):
+    data = pkg.synth(n, seed=n % 97 + 2)
+    got, adler = deflate_via_api(pkg, L, data, 1, wb, [(n, pkg.Z_FINISH)])
+    assert got == expected_stream(zo, data, 1, wb)
+    assert pyzlib.decompress(got, wbits=wb) == data.tobytes()
+    if wb == 15:
+        assert adler == pyzlib.adler32(data.tobytes())
+    if wb == 31:
+        assert adler == pyzlib.crc32(data.tobytes())
+
+
+def test_zng_deflate_piecewise_and_small_output_windows(pkg, L, zo):
+    n = 5 * 65536 + 1234
+    data = pkg.synth(n, seed=11)
+    exp = expected_stream(zo, data, 1, 31)
+    # the reference's own call sequence: one 64 KiB piece per Z_FULL_FLUSH call, Z_FINISH on the tail
+    pieces = [(65536, pkg.Z_FULL_FLUSH)] * 5 + [(1234, pkg.Z_FINISH)]
+    assert deflate_via_api(pkg, L, data, 1, 31, pieces)[0] == exp
+    # several pieces per call, and Z_NO_FLUSH buffering in between
+    pieces = [(2 * 65536, pkg.Z_FULL_FLUSH), (65536, pkg.Z_NO_FLUSH), (2 * 65536, pkg.Z_FULL_FLUSH), (1234, pkg.Z_FINISH)]
+    assert deflate_via_api(pkg, L, data, 1, 31, pieces)[0] == exp
+    # output handed out through a 1000-byte window (pending output like the reference's pending_buf)
+    assert deflate_via_api(pkg, L, data, 1, 31, [(n, pkg.Z_FINISH)], out_room=1000)[0] == exp
+
+
+def test_zng_deflate_argument_errors(pkg, L):
+    s = pkg.ZngStream()
+    assert L.zng_deflateInit2(None, 1, 8, 15, 8, 0) == pkg.Z_STREAM_ERROR
+    for args in ((1, 7, 15, 8, 0), (10, 8, 15, 8, 0), (1, 8, 16 + 16, 8, 0), (1, 8, 15, 10, 0), (1, 8, 15, 8, 5), (6, 8, 15, 8, 0), (1, 8, 12, 8, 0)):
+        assert L.zng_deflateInit2(ctypes.byref(s), *args) == pkg.Z_STREAM_ERROR, args
+    assert L.zng_deflateInit2(ctypes.byref(s), 1, 8, 15, 8, 0) == 0
+    buf = np.zeros(64, dtype=np.uint8)
+    s.next_in = buf.ctypes.data; s.avail_in = 4; s.next_out = None; s.avail_out = 64
+    assert L.zng_deflate(ctypes.byref(s), pkg.Z_FINISH) == pkg.Z_STREAM_ERROR           # next_out NULL (deflate.c:823)
+    s.next_out = buf.ctypes.data; s.avail_out = 0
+    assert L.zng_deflate(ctypes.byref(s), pkg.Z_FINISH) == pkg.Z_BUF_ERROR              # avail_out == 0 (deflate.c:831)
+    assert L.zng_deflate(ctypes.byref(s), 9) == pkg.Z_STREAM_ERROR
+    assert L.zng_deflateEnd(ctypes.byref(s)) in (0, pkg.Z_DATA_ERROR)
+    assert L.zng_deflateEnd(ctypes.byref(s)) == pkg.Z_STREAM_ERROR                      # already ended
+
+
+def inflate_once(pkg, L, stream, wb, cap):
+    s = pkg.ZngStream()
+    assert L.zng_inflateInit2(ctypes.byref(s), wb) == 0
+    src = np.frombuffer(stream + b"\0", dtype=np.uint8).copy()
+    out = np.zeros(cap + 1, dtype=np.uint8)
+    s.next_in = src.ctypes.data; s.avail_in = len(stream); s.next_out = out.ctypes.data; s.avail_out = cap
+    r = L.zng_inflate(ctypes.byref(s), pkg.Z_FINISH)
+    res = (r, out[: s.total_out].copy(), int(s.total_in), int(s.adler), s.msg.decode() if s.msg else None, int(s.avail_in))
+    assert L.zng_inflateEnd(ctypes.byref(s)) == 0
+    return res
+
+
+def test_zng_inflate_oneshot_matches_oracle(pkg, L, zo):
+    rng = np.random.default_rng(5)
+    for trial in range(24):
+        size = int(rng.integers(0, 200000))
+        data = pkg.synth(size + 10, seed=trial + 3)[:size].tobytes()
+        wb = [-15, 15, 31][trial % 3]
+        co = pyzlib.compressobj(int(rng.choice([1, 6])), pyzlib.DEFLATED, wb)
+        st = co.compress(data) + co.flush()
+        variants = [(st, size + 10), (st, max(size - 3, 0)), (st[: len(st) // 2], size + 10), (st + b"next member", size)]
+        s2 = bytearray(st); s2[len(s2) // 2] ^= 4
+        variants.append((bytes(s2), size + 10))
+        for stream, cap in variants:
+            g = inflate_once(pkg, L, stream, wb, cap)
+            e = zo.port_inflate(stream, wb, cap)
+            assert g[0] == e[0] and g[4] == e[4], (trial, wb, cap, g[0], g[4], e[0], e[4])
+            if e[0] == 1:
+                assert np.array_equal(g[1], e[1]) and g[2] == e[2] and g[3] == e[3]
+                assert g[5] == len(stream) - e[2]                       # unused input stays with the caller
+
+
+def test_zng_inflate_incremental(pkg, L):
+    data = pkg.synth(300000, seed=8).tobytes()
+    st = pyzlib.compress(data, 6)
+    src = np.frombuffer(st, dtype=np.uint8).copy()
+    s = pkg.ZngStream()
+    assert L.zng_inflateInit2(ctypes.byref(s), 15) == 0
+    out = np.zeros(70000, dtype=np.uint8)
+    got = bytearray()
+    pos, r = 0, 0
+    while r != 1:
+        take = min(50000, len(st) - pos)
+        s.next_in = src.ctypes.data + pos; s.avail_in = take
+        s.next_out = out.ctypes.data; s.avail_out = out.size
+        r = L.zng_inflate(ctypes.byref(s), pkg.Z_NO_FLUSH)
+        assert r in (0, 1), (r, s.msg)
+        pos += take - s.avail_in
+        got += out[: out.size - s.avail_out].tobytes()
+    assert bytes(got) == data and s.total_out == len(data) and s.total_in == len(st) and s.adler == pyzlib.adler32(data)
+    assert L.zng_inflateEnd(ctypes.byref(s)) == 0
+
+
+def test_compress_uncompress_roundtrip(pkg, L, zo):
+    data = pkg.synth(5 * 65536 + 321, seed=21)
+    cap = int(L.zng_compressBound(data.size))
+    comp = np.zeros(cap, dtype=np.uint8)
+    clen = ctypes.c_size_t(cap)
+    assert L.zng_compress2(comp.ctypes.data, ctypes.byref(clen), data.ctypes.data, data.size, 1) == 0
+    assert comp[: clen.value].tobytes() == expected_stream(zo, data, 1, 15)
+    back = np.zeros(data.size, dtype=np.uint8)
+    blen = ctypes.c_size_t(data.size)
+    assert L.zng_uncompress(back.ctypes.data, ctypes.byref(blen), comp.ctypes.data, clen.value) == 0
+    assert blen.value == data.size and np.array_equal(back, data)
+    blen = ctypes.c_size_t(1000)                                        # too small: Z_BUF_ERROR (uncompr.c)
+    assert L.zng_uncompress(back.ctypes.data, ctypes.byref(blen), comp.ctypes.data, clen.value) == pkg.Z_BUF_ERROR
+    blen = ctypes.c_size_t(data.size)                                   # truncated input: Z_DATA_ERROR
+    assert L.zng_uncompress(back.ctypes.data, ctypes.byref(blen), comp.ctypes.data, clen.value // 2) == pkg.Z_DATA_ERROR
+
+
+def test_checksum_api(pkg, L, zo, golden):
+    seen = 0
+    for v in golden("kat_crc32.json")["vectors"]:
+        if v["data_hex"] is None:                          # the reference's NULL-buffer vectors (test_crc32.cc:30-35)
+            assert L.zng_crc32_z(v["init"], None, v["len"]) == v["expect"], v
+            continue
+        buf = np.frombuffer(bytes.fromhex(v["data_hex"]) + b"\0", dtype=np.uint8).copy()
+        assert L.zng_crc32_z(v["init"], buf.ctypes.data, buf.size - 1) == v["expect"], v
+        assert L.zng_crc32(v["init"], buf.ctypes.data, buf.size - 1) == v["expect"], v
+        seen += 1
+    assert seen >= 50
+    for v in golden("kat_adler32.json")["vectors"]:
+        if v["data_hex"] is None:
+            if v["len"] != 1:
+                assert L.zng_adler32_z(v["init"], None, v["len"]) == v["expect"], v
+            continue
+        buf = np.frombuffer(bytes.fromhex(v["data_hex"]) + b"\0", dtype=np.uint8).copy()
+        assert L.zng_adler32_z(v["init"], buf.ctypes.data, buf.size - 1) == v["expect"], v
+    assert L.zng_crc32_z(123, None, 10) == 0 and L.zng_adler32_z(123, None, 10) == 1      # crc32.c:28, adler32_c.c
+    data = pkg.synth(3_000_001, seed=5)
+    a, b = data[:1_234_567], data[1_234_567:]
+    ca, cb = L.zng_crc32_z(0, a.ctypes.data, a.size), L.zng_crc32_z(0, b.ctypes.data, b.size)
+    assert ca == pyzlib.crc32(a.tobytes()) and L.zng_crc32_combine(ca, cb, b.size) == pyzlib.crc32(data.tobytes())
+    assert L.zng_crc32_combine_op(ca, cb, L.zng_crc32_combine_gen(b.size)) == pyzlib.crc32(data.tobytes())
+    aa, ab = L.zng_adler32_z(1, a.ctypes.data, a.size), L.zng_adler32_z(1, b.ctypes.data, b.size)
+    assert L.zng_adler32_combine(aa, ab, b.size) == pyzlib.adler32(data.tobytes())
+    assert L.zng_crc32_z(ca, b.ctypes.data, b.size) == pyzlib.crc32(data.tobytes())         # running value continues
+    assert L.zng_adler32_z(aa, b.ctypes.data, b.size) == pyzlib.adler32(data.tobytes())

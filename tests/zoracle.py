@@ -75,6 +75,10 @@ def ref():
         L.refdrv_inflate_stream.restype = c_int
         L.refdrv_inflate_stream.argtypes = [c_void_p, c_size_t, c_int, c_void_p, c_size_t, POINTER(c_uint64), POINTER(c_uint32)]
         L.refdrv_now.restype = c_double
+        L.refdrv_inflate_oneshot.restype = c_int
+        L.refdrv_inflate_oneshot.argtypes = [c_void_p, c_size_t, c_int, c_void_p, c_size_t, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_uint32), c_char_p]
+        L.refdrv_deflate_stream.restype = c_int
+        L.refdrv_deflate_stream.argtypes = [c_void_p, c_size_t, c_uint32, c_int, c_int, c_void_p, c_size_t, POINTER(c_size_t)]
         for name, res, args in (
             ("zng_crc32", c_uint32, [c_uint32, c_void_p, c_uint32]),
             ("zng_crc32_z", c_uint32, [c_uint32, c_void_p, c_size_t]),
@@ -163,3 +167,38 @@ def ref_inflate_stream(stream, window_bits, expect=None):
     r = ref().refdrv_inflate_stream(_ptr(s), s.size, window_bits, _ptr(e) if e is not None else c_void_p(0),
                                     e.size if e is not None else 0, byref(total), byref(crc))
     return int(r), int(total.value), int(crc.value)
+
+
+def _inflate(fn_kind, stream, window_bits, out_cap):
+    s = _u8(stream)
+    out = np.zeros(max(out_cap, 1), dtype=np.uint8)
+    ol, iu, chk = c_size_t(0), c_size_t(0), c_uint32(0)
+    if fn_kind == "ref":
+        msg = ctypes.create_string_buffer(64)
+        r = ref().refdrv_inflate_oneshot(_ptr(s), s.size, window_bits, out.ctypes.data, out_cap, byref(ol), byref(iu), byref(chk), msg)
+        m = msg.value.decode() or None
+    else:
+        mp = c_char_p()
+        r = port().zo_inflate(_ptr(s), s.size, window_bits, out.ctypes.data, out_cap, byref(ol), byref(iu), byref(chk), byref(mp))
+        m = mp.value.decode() if mp.value else None
+    return int(r), out[: ol.value], int(iu.value), int(chk.value), m
+
+
+def port_inflate(stream, window_bits, out_cap):
+    """(ret, output, in_used, check, msg) of the oracle restatement of one zng_inflate(Z_FINISH)."""
+    return _inflate("port", stream, window_bits, out_cap)
+
+
+def ref_inflate(stream, window_bits, out_cap):
+    return _inflate("ref", stream, window_bits, out_cap)
+
+
+def ref_deflate_stream(data, piece, level, window_bits):
+    d = _u8(data)
+    cap = d.size + d.size // 8 + (d.size // max(piece, 1) + 2) * 16 + 64
+    out = np.zeros(cap, dtype=np.uint8)
+    ol = c_size_t(0)
+    r = ref().refdrv_deflate_stream(_ptr(d), d.size, piece, level, window_bits, out.ctypes.data, cap, byref(ol))
+    if r != 1:
+        raise RuntimeError(f"reference deflate stream failed: {r}")
+    return out[: ol.value]

@@ -63,6 +63,32 @@ def lib() -> ctypes.CDLL:
         "zng_b200_crc32_host": (c_int, [vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
         "zng_b200_adler32_host": (c_int, [vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
         "zng_b200_synth_fill": (c_int, [vp, c_size_t, c_uint64, c_uint64]),
+        "zng_b200_inflate_members": (c_int, [vp, vp, u64p, c_uint32, c_int, vp, u64p, u32p, u32p, vp, u32p, u32p, vp]),
+        "zng_b200_inflate_members_host": (c_int, [vp, vp, u64p, c_uint32, c_int, vp, u64p, u32p, u32p, vp, u32p, u32p]),
+        "zng_b200_inflate_msg": (c_char_p, [c_uint32]),
+        # the C11 host library: zlib-ng's own API (include/zlib-ng.h)
+        "zlibng_version": (c_char_p, []),
+        "zng_deflateInit2": (c_int32, [vp, c_int32, c_int32, c_int32, c_int32, c_int32]),
+        "zng_deflate": (c_int32, [vp, c_int32]),
+        "zng_deflateReset": (c_int32, [vp]),
+        "zng_deflateEnd": (c_int32, [vp]),
+        "zng_deflateBound": (ctypes.c_ulong, [vp, ctypes.c_ulong]),
+        "zng_inflateInit2": (c_int32, [vp, c_int32]),
+        "zng_inflate": (c_int32, [vp, c_int32]),
+        "zng_inflateReset": (c_int32, [vp]),
+        "zng_inflateEnd": (c_int32, [vp]),
+        "zng_compress2": (c_int32, [vp, POINTER(c_size_t), vp, c_size_t, c_int32]),
+        "zng_compressBound": (c_size_t, [c_size_t]),
+        "zng_uncompress": (c_int32, [vp, POINTER(c_size_t), vp, c_size_t]),
+        "zng_uncompress2": (c_int32, [vp, POINTER(c_size_t), vp, POINTER(c_size_t)]),
+        "zng_crc32": (c_uint32, [c_uint32, vp, c_uint32]),
+        "zng_crc32_z": (c_uint32, [c_uint32, vp, c_size_t]),
+        "zng_adler32": (c_uint32, [c_uint32, vp, c_uint32]),
+        "zng_adler32_z": (c_uint32, [c_uint32, vp, c_size_t]),
+        "zng_crc32_combine": (c_uint32, [c_uint32, c_uint32, ctypes.c_int64]),
+        "zng_crc32_combine_gen": (c_uint32, [ctypes.c_int64]),
+        "zng_crc32_combine_op": (c_uint32, [c_uint32, c_uint32, c_uint32]),
+        "zng_adler32_combine": (c_uint32, [c_uint32, c_uint32, ctypes.c_int64]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)          # AttributeError = a declared symbol is not exported: fail loudly
@@ -70,6 +96,19 @@ def lib() -> ctypes.CDLL:
         f.argtypes = args
     _lib = L
     return L
+
+
+class ZngStream(ctypes.Structure):
+    """zng_stream (include/zlib-ng.h; same layout as the reference's, zlib-ng.h.in:99-119)."""
+    _fields_ = [("next_in", c_void_p), ("avail_in", c_uint32), ("total_in", c_size_t), ("next_out", c_void_p),
+                ("avail_out", c_uint32), ("total_out", c_size_t), ("msg", c_char_p), ("state", c_void_p),
+                ("zalloc", c_void_p), ("zfree", c_void_p), ("opaque", c_void_p), ("data_type", c_int),
+                ("adler", c_uint32), ("reserved", ctypes.c_ulong)]
+
+
+def inflate_msg(detail: int):
+    m = lib().zng_b200_inflate_msg(detail & 0xff)
+    return m.decode() if m else None
 
 
 def deflate_bound(chunk_len: int) -> int:
@@ -166,6 +205,22 @@ class Context:
 
     def adler32(self, d_buf, n: int, init: int, result):
         self._check(lib().zng_b200_adler32(self._h, _ptr(d_buf), n, init, _ptr(result), self._stream()))
+
+    def inflate_members(self, d_in, in_off, n_members: int, window_bits: int, d_out, out_off, sizes, checks, status, in_used=None, detail=None):
+        self._check(lib().zng_b200_inflate_members(self._h, _ptr(d_in), _ptr(in_off), n_members, window_bits, _ptr(d_out), _ptr(out_off),
+                                                   _ptr(sizes), _ptr(checks), _ptr(status), _ptr(in_used), _ptr(detail), self._stream()))
+
+    def inflate_members_host(self, h_in, in_off, window_bits: int, h_out, out_off):
+        """numpy in/out; returns (sizes, checks, status, in_used, detail) as numpy arrays."""
+        import numpy as np
+        n = len(in_off) - 1
+        io = np.ascontiguousarray(in_off, dtype=np.uint64)
+        oo = np.ascontiguousarray(out_off, dtype=np.uint64)
+        sizes = np.zeros(max(n, 1), dtype=np.uint32); checks = np.zeros(max(n, 1), dtype=np.uint32)
+        status = np.zeros(max(n, 1), dtype=np.int32); used = np.zeros(max(n, 1), dtype=np.uint32); detail = np.zeros(max(n, 1), dtype=np.uint32)
+        self._check(lib().zng_b200_inflate_members_host(self._h, _ptr(h_in), _ptr(io), n, window_bits, _ptr(h_out), _ptr(oo),
+                                                        _ptr(sizes), _ptr(checks), _ptr(status), _ptr(used), _ptr(detail)))
+        return sizes[:n], checks[:n], status[:n], used[:n], detail[:n]
 
     # ---- host-buffer entry points (numpy arrays / pinned tensors) ------------------------
     def deflate_host(self, h_in, n: int, chunk: int, level: int, final: bool, h_out, out_cap: int):

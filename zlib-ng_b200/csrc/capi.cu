@@ -41,6 +41,24 @@ struct Slab {
     size_t in_bytes = 0;
     bool busy = false;
 };
+// one in-flight batch of the host-buffer inflate path
+struct InfSlab {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t* d_in = nullptr;  size_t in_cap = 0;
+    uint8_t* d_out = nullptr; size_t out_cap = 0;
+    uint64_t* d_off = nullptr;                 // in offsets (cnt+1) | out offsets (cnt+1), relative to the slab
+    uint32_t* d_res = nullptr;                 // sizes | checks | status | in_used | detail, cnt_cap each
+    uint64_t* h_off = nullptr;                 // pinned staging of d_off
+    uint32_t* h_res = nullptr;                 // pinned staging of d_res
+    uint32_t cnt_cap = 0;
+    uint32_t first = 0, cnt = 0;
+    size_t out_lo = 0, out_bytes = 0;
+    bool busy = false;
+};
+constexpr int kInfPipe = 3;
+constexpr uint32_t kInfSlabMembers = 32768;
+constexpr size_t kInfSlabIn = (size_t)96 << 20, kInfSlabOut = (size_t)160 << 20;
 }  // namespace
 
 struct zng_b200_ctx {
@@ -67,6 +85,7 @@ struct zng_b200_ctx {
     Slab slab[kPipe];
     bool slabs_ready = false;
     size_t slab_stride = 0;
+    InfSlab inf[kInfPipe];
     uint8_t* d_hostbuf = nullptr;              // staging for *_host checksums
     size_t hostbuf_cap = 0;
     uint32_t x2n[32];
@@ -273,6 +292,17 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
+    for (int i = 0; i < kInfPipe; i++) {
+        InfSlab& s = ctx->inf[i];
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.d_off) cudaFree(s.d_off);
+        if (s.d_res) cudaFree(s.d_res);
+        if (s.h_off) cudaFreeHost(s.h_off);
+        if (s.h_res) cudaFreeHost(s.h_res);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->tails) cudaFree(ctx->tails);
     if (ctx->heads) cudaFree(ctx->heads);
@@ -413,6 +443,124 @@ int zng_b200_adler32(zng_b200_ctx* ctx, const void* d_buf, size_t n, uint32_t in
        "checksum launch");
     CK(launch_adler32_fold(ad, (uint32_t)ntiles, ZNG_B200_CHUNK_MAX, n, init, d_result, (cudaStream_t)stream), "adler32 fold launch");
     return 0;
+}
+
+// ---------------------------------------------------------------- K4 inflate
+int zng_b200_inflate_members(zng_b200_ctx* ctx, const void* d_in, const uint64_t* d_in_off, uint32_t n_members, int window_bits,
+                             void* d_out, const uint64_t* d_out_off, uint32_t* d_sizes, uint32_t* d_checks, int32_t* d_status,
+                             uint32_t* d_in_used, uint32_t* d_detail, void* stream) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    // zng_inflateInit2's own windowBits rules (inflate.c:232-251)
+    int wb = window_bits;
+    if (wb < 0) { if (wb < -15) return bad(ctx, "windowBits out of range"); wb = -wb; }
+    else if (wb < 48) wb &= 15;
+    if (wb && (wb < 8 || wb > 15)) return bad(ctx, "windowBits out of range");
+    if (n_members && (!d_in || !d_in_off || !d_out || !d_out_off || !d_sizes || !d_status)) return bad(ctx, "NULL argument");
+    DeviceGuard g(ctx->device);
+    const int slot = next_slot(ctx);
+    CK(launch_inflate_members((const uint8_t*)d_in, d_in_off, n_members, window_bits, (uint8_t*)d_out, d_out_off, d_sizes, d_checks,
+                              d_status, d_in_used, d_detail, ctx->counters + slot, ctx->sms, (cudaStream_t)stream),
+       "inflate launch");
+    return 0;
+}
+
+const char* zng_b200_inflate_msg(uint32_t detail) { return inflate_msg(detail & 0xffu); }
+
+static int inf_slab_reserve(zng_b200_ctx* ctx, InfSlab& s, uint32_t cnt, size_t in_bytes, size_t out_bytes) {
+    if (!s.stream) {
+        CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreate");
+    }
+    if (s.in_cap < in_bytes + 16) {
+        if (s.d_in) cudaFree(s.d_in);
+        s.d_in = nullptr; s.in_cap = 0;
+        const size_t want = in_bytes + 16 > kInfSlabIn ? in_bytes + 16 : kInfSlabIn;
+        CK(cudaMalloc(&s.d_in, want), "cudaMalloc(inflate in)");
+        s.in_cap = want;
+    }
+    if (s.out_cap < out_bytes + 16) {
+        if (s.d_out) cudaFree(s.d_out);
+        s.d_out = nullptr; s.out_cap = 0;
+        const size_t want = out_bytes + 16 > kInfSlabOut ? out_bytes + 16 : kInfSlabOut;
+        CK(cudaMalloc(&s.d_out, want), "cudaMalloc(inflate out)");
+        s.out_cap = want;
+    }
+    if (s.cnt_cap < cnt) {
+        if (s.d_off) cudaFree(s.d_off);
+        if (s.d_res) cudaFree(s.d_res);
+        if (s.h_off) cudaFreeHost(s.h_off);
+        if (s.h_res) cudaFreeHost(s.h_res);
+        s.d_off = nullptr; s.d_res = nullptr; s.h_off = nullptr; s.h_res = nullptr; s.cnt_cap = 0;
+        const uint32_t want = cnt > kInfSlabMembers ? cnt : kInfSlabMembers;
+        CK(cudaMalloc(&s.d_off, 2 * ((size_t)want + 1) * sizeof(uint64_t)), "cudaMalloc(inflate offsets)");
+        CK(cudaMalloc(&s.d_res, 5 * (size_t)want * sizeof(uint32_t)), "cudaMalloc(inflate results)");
+        CK(cudaHostAlloc(&s.h_off, 2 * ((size_t)want + 1) * sizeof(uint64_t), cudaHostAllocDefault), "cudaHostAlloc(inflate offsets)");
+        CK(cudaHostAlloc(&s.h_res, 5 * (size_t)want * sizeof(uint32_t), cudaHostAllocDefault), "cudaHostAlloc(inflate results)");
+        s.cnt_cap = want;
+    }
+    return 0;
+}
+
+static int inf_slab_drain(zng_b200_ctx* ctx, InfSlab& s, uint32_t* h_sizes, uint32_t* h_checks, int32_t* h_status,
+                          uint32_t* h_in_used, uint32_t* h_detail) {
+    if (!s.busy) return 0;
+    s.busy = false;
+    CK(cudaEventSynchronize(s.done), "cudaEventSynchronize");
+    const size_t c = s.cnt, cap = s.cnt_cap;
+    memcpy(h_sizes + s.first, s.h_res, c * 4);
+    if (h_checks) memcpy(h_checks + s.first, s.h_res + cap, c * 4);
+    memcpy(h_status + s.first, s.h_res + 2 * cap, c * 4);
+    if (h_in_used) memcpy(h_in_used + s.first, s.h_res + 3 * cap, c * 4);
+    if (h_detail) memcpy(h_detail + s.first, s.h_res + 4 * cap, c * 4);
+    return 0;
+}
+
+int zng_b200_inflate_members_host(zng_b200_ctx* ctx, const void* h_in, const uint64_t* h_in_off, uint32_t n_members, int window_bits,
+                                  void* h_out, const uint64_t* h_out_off, uint32_t* h_sizes, uint32_t* h_checks, int32_t* h_status,
+                                  uint32_t* h_in_used, uint32_t* h_detail) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (n_members && (!h_in || !h_in_off || !h_out || !h_out_off || !h_sizes || !h_status)) return bad(ctx, "NULL argument");
+    DeviceGuard g(ctx->device);
+    int k = 0, r = 0;
+    uint32_t m = 0;
+    while (m < n_members) {
+        InfSlab& s = ctx->inf[k];
+        r = inf_slab_drain(ctx, s, h_sizes, h_checks, h_status, h_in_used, h_detail);
+        if (r) break;
+        // greedy batch: as many consecutive members as fit the slab limits (at least one)
+        uint32_t cnt = 0;
+        const uint64_t i0 = h_in_off[m], o0 = h_out_off[m];
+        while (m + cnt < n_members && cnt < kInfSlabMembers) {
+            const uint64_t i1 = h_in_off[m + cnt + 1], o1 = h_out_off[m + cnt + 1];
+            if (i1 < h_in_off[m + cnt] || o1 < h_out_off[m + cnt] || i1 - h_in_off[m + cnt] > 0xffffffffull || o1 - h_out_off[m + cnt] > 0xffffffffull) {
+                for (int i = 0; i < kInfPipe; i++) { ctx->inf[i].busy = false; if (ctx->inf[i].stream) cudaStreamSynchronize(ctx->inf[i].stream); }
+                return bad(ctx, "offsets must be non-decreasing, members < 4 GiB");
+            }
+            if (cnt && (i1 - i0 > kInfSlabIn || o1 - o0 > kInfSlabOut)) break;
+            cnt++;
+        }
+        const size_t in_bytes = (size_t)(h_in_off[m + cnt] - i0), out_bytes = (size_t)(h_out_off[m + cnt] - o0);
+        r = inf_slab_reserve(ctx, s, cnt, in_bytes, out_bytes);
+        if (r) break;
+        uint64_t* hi = s.h_off; uint64_t* ho = s.h_off + (cnt + 1);
+        for (uint32_t j = 0; j <= cnt; j++) { hi[j] = h_in_off[m + j] - i0; ho[j] = h_out_off[m + j] - o0; }
+        if (in_bytes) CK(cudaMemcpyAsync(s.d_in, (const uint8_t*)h_in + i0, in_bytes, cudaMemcpyHostToDevice, s.stream), "H2D members");
+        CK(cudaMemcpyAsync(s.d_off, s.h_off, 2 * ((size_t)cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream), "H2D offsets");
+        const size_t cap = s.cnt_cap;
+        const int slot = next_slot(ctx);
+        CK(launch_inflate_members(s.d_in, s.d_off, cnt, window_bits, s.d_out, s.d_off + (cnt + 1), s.d_res, s.d_res + cap,
+                                  (int32_t*)(s.d_res + 2 * cap), s.d_res + 3 * cap, s.d_res + 4 * cap, ctx->counters + slot, ctx->sms, s.stream),
+           "inflate launch");
+        if (out_bytes) CK(cudaMemcpyAsync((uint8_t*)h_out + o0, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream), "D2H output");
+        CK(cudaMemcpyAsync(s.h_res, s.d_res, 5 * cap * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream), "D2H results");
+        CK(cudaEventRecord(s.done, s.stream), "event record");
+        s.first = m; s.cnt = cnt; s.busy = true;
+        m += cnt;
+        k = (k + 1) % kInfPipe;
+    }
+    for (int i = 0; i < kInfPipe && !r; i++) r = inf_slab_drain(ctx, ctx->inf[(k + i) % kInfPipe], h_sizes, h_checks, h_status, h_in_used, h_detail);
+    for (int i = 0; i < kInfPipe; i++) { ctx->inf[i].busy = false; if (ctx->inf[i].stream) cudaStreamSynchronize(ctx->inf[i].stream); }
+    return r;
 }
 
 // ---------------------------------------------------------------- host-buffer entry points

@@ -30,6 +30,12 @@ cudaError_t launch_crc32_fold(const uint32_t* crcs, uint32_t ntiles, uint32_t ti
 cudaError_t launch_adler32_fold(const uint32_t* adlers, uint32_t ntiles, uint32_t tile_bytes, size_t n, uint32_t init,
                                 uint32_t* result, cudaStream_t stream);
 
+// K4: batched inflate (inflate.cu), one warp per member
+cudaError_t launch_inflate_members(const uint8_t* in, const uint64_t* in_off, uint32_t n_members, int window_bits,
+                                   uint8_t* out, const uint64_t* out_off, uint32_t* sizes, uint32_t* checks, int32_t* status,
+                                   uint32_t* in_used, uint32_t* detail, uint32_t* counter, int num_sms, cudaStream_t stream);
+const char* inflate_msg(uint32_t id);
+
 // stream assembly (assemble.cu)
 cudaError_t launch_offsets(const uint32_t* sizes, uint32_t n, uint64_t base, uint64_t* offsets, cudaStream_t stream);
 cudaError_t launch_gather(const uint8_t* slots, size_t stride, const uint32_t* sizes, const uint64_t* offsets,
