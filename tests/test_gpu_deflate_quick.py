@@ -23,15 +23,15 @@ def gpu_deflate(pkg, ctx, data, chunk=65536, level=1, flush=3, want_adler=True):
     return slots.cpu().numpy().reshape(-1, stride)[:nch], u32(sizes), u32(crcs), (u32(adlers) if want_adler else None), stride
 
 
-def explain_mismatch(pkg, ctx, zo, data, chunk, ci):
+def explain_mismatch(pkg, ctx, zo, data, chunk, ci, level=1):
     """Token-level diff of chunk ci (the ZLIB_DEBUG trace analogue) for the assertion message."""
     import torch
     piece = np.ascontiguousarray(data[ci * chunk:(ci + 1) * chunk])
-    exp = zo.port_tokens(piece, 1)
+    exp = zo.port_tokens(piece, level)
     d_in = torch.from_numpy(piece).to(f"cuda:{ctx.device}")
     slots, stride, sizes, _, _ = ctx.alloc_chunk_outputs(piece.size, chunk)
     toks = torch.zeros(chunk + 8, dtype=torch.int32, device=d_in.device)
-    ctx.deflate_chunks_trace(d_in, piece.size, chunk, 1, 3, slots, stride, sizes, toks, chunk + 8)
+    ctx.deflate_chunks_trace(d_in, piece.size, chunk, level, 3, slots, stride, sizes, toks, chunk + 8)
     torch.cuda.synchronize()
     got = toks.cpu().numpy().view(np.uint32)
     end = np.nonzero(got == 0x40000000)[0]
@@ -44,12 +44,12 @@ def explain_mismatch(pkg, ctx, zo, data, chunk, ci):
             f"gpu {fmt(int(got[k])) if k < len(got) else 'END'} vs oracle {fmt(int(exp[k])) if k < len(exp) else 'END'}")
 
 
-def assert_parity(pkg, ctx, zo, data, chunk=65536, flush=3):
-    got, sizes, crcs, adlers, stride = gpu_deflate(pkg, ctx, data, chunk, 1, flush)
-    exp, esizes, ecrcs, eadlers = zo.port_deflate_chunks(data, chunk, 1, flush, stride)
+def assert_parity(pkg, ctx, zo, data, chunk=65536, flush=3, level=1):
+    got, sizes, crcs, adlers, stride = gpu_deflate(pkg, ctx, data, chunk, level, flush)
+    exp, esizes, ecrcs, eadlers = zo.port_deflate_chunks(data, chunk, level, flush, stride)
     bad = [i for i in range(len(esizes)) if sizes[i] != esizes[i] or not np.array_equal(got[i, : esizes[i]], exp[i, : esizes[i]])]
     if bad:
-        pytest.fail(f"{len(bad)} of {len(esizes)} chunks differ; " + explain_mismatch(pkg, ctx, zo, data, chunk, bad[0]))
+        pytest.fail(f"{len(bad)} of {len(esizes)} chunks differ; " + explain_mismatch(pkg, ctx, zo, data, chunk, bad[0], level))
     assert np.array_equal(crcs, ecrcs)
     assert np.array_equal(adlers, eadlers)
     return got, sizes
@@ -166,7 +166,7 @@ def test_argument_errors(pkg, ctx):
     import torch
     d = torch.zeros(65536, dtype=torch.uint8, device=f"cuda:{ctx.device}")
     slots, stride, sizes, crcs, adlers = ctx.alloc_chunk_outputs(65536)
-    for kwargs in (dict(level=0), dict(level=3), dict(flush=0), dict(flush=5), dict(chunk=0), dict(chunk=65537), dict(stride=stride - 16), dict(stride=stride + 8)):
+    for kwargs in (dict(level=0), dict(level=3), dict(level=9), dict(flush=0), dict(flush=5), dict(chunk=0), dict(chunk=65537), dict(stride=stride - 16), dict(stride=stride + 8)):
         a = dict(chunk=65536, level=1, flush=3, stride=stride)
         a.update(kwargs)
         with pytest.raises(pkg.ZngB200Error) as ei:

@@ -30,6 +30,7 @@ struct Scratch {
 struct Slab {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
+    uint8_t* d_in_alloc = nullptr;
     uint8_t* d_in = nullptr;
     uint8_t* d_slots = nullptr;
     uint8_t* d_packed = nullptr;
@@ -72,7 +73,10 @@ struct zng_b200_ctx {
     uint16_t* heads = nullptr;
     unsigned long long* sm_slots = nullptr;
     uint32_t nsmid = 0;
+    uint16_t* prevs = nullptr;                 // K2: prev[] slab pool and stale-window images, same (sm, slot) indexing
+    uint32_t* vtails = nullptr;
     int chains_per_sm = 24;
+    int chains_per_sm_l2 = 16;
     uint32_t k1_flags = 8;                     // parser tuning switches (deflate_quick.cu), env ZNG_B200_FLAGS
     Scratch scratch;                           // for the device-resident entry points; users are ordered by k1_done
     cudaEvent_t k1_done = nullptr;
@@ -125,6 +129,13 @@ int ensure_heads(zng_b200_ctx* ctx) {
     return 0;
 }
 
+int ensure_prevs(zng_b200_ctx* ctx) {
+    if (ctx->prevs) return 0;
+    CK(cudaMalloc(&ctx->prevs, deflate_fast_prev_bytes(ctx->nsmid)), "cudaMalloc(prev slab pool)");
+    CK(cudaMalloc(&ctx->vtails, deflate_fast_tail_bytes(ctx->nsmid)), "cudaMalloc(window tail images)");
+    return 0;
+}
+
 int ensure_scratch(zng_b200_ctx* ctx, Scratch& sc, uint32_t batch, uint32_t stride, uint32_t nchunks, bool need_tokens) {
     if (need_tokens && sc.tok_words < (size_t)batch * stride) {
         if (sc.tokens) { cudaDeviceSynchronize(); cudaFree(sc.tokens); sc.tokens = nullptr; sc.tok_words = 0; }
@@ -143,12 +154,14 @@ int ensure_scratch(zng_b200_ctx* ctx, Scratch& sc, uint32_t batch, uint32_t stri
 // K1 for level 1: K1a parse -> token lists in `sc`, K1b static emit (+ the K3 tile kernel when per-chunk
 // checksums are wanted).  Inputs larger than kBatchChunks chunks run as several batches that reuse
 // the token scratch (4 B per input byte).
+// level 2: K2a parse (hash chains) -> token lists, K2b block writer.  have_prev: see kernels.h.
 int run_deflate_quick(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
                       uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers,
-                      cudaStream_t stream, uint32_t* d_tokens, uint32_t tok_stride) {
+                      cudaStream_t stream, uint32_t* d_tokens, uint32_t tok_stride, int level = 1, int have_prev = 0) {
     if (nchunks == 0) return 0;
     int r = ensure_heads(ctx);
     if (r) return r;
+    if (level == 2) { r = ensure_prevs(ctx); if (r) return r; }
     const uint32_t own_stride = (chunk + 32u) & ~31u;                 // tokens per chunk incl. end marker, 128-byte rows
     const uint32_t batch = nchunks < kBatchChunks ? nchunks : kBatchChunks;
     r = ensure_scratch(ctx, sc, batch, own_stride, nchunks, d_tokens == nullptr);
@@ -161,6 +174,15 @@ int run_deflate_quick(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size_
         const uint32_t stride = d_tokens ? tok_stride : own_stride;
         const uint32_t grid = deflate_quick_grid(nb, ctx->sms, ctx->chains_per_sm);
         const int slot = next_slot(ctx);
+        if (level == 2) {
+            CK(launch_fast_parse(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->prevs,
+                                 ctx->vtails, ctx->sm_slots, ctx->sms, ctx->chains_per_sm_l2, (c0 > 0 || have_prev) ? 1 : 0, stream),
+               "fast_parse launch");
+            CK(launch_block_emit(d_in + off, toks, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
+                                 d_sizes + c0, ctx->sms, stream),
+               "block_emit launch");
+            continue;
+        }
         CK(launch_quick_parse(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->sm_slots,
                               grid, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), ctx->k1_flags, stream),
            "quick_parse launch");
@@ -176,11 +198,11 @@ int run_deflate_quick(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size_
 // the ctx-level scratch is shared by all device-resident calls: order them
 int run_deflate_quick_shared(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
                              uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers,
-                             cudaStream_t stream, uint32_t* d_tokens, uint32_t tok_stride) {
+                             cudaStream_t stream, uint32_t* d_tokens, uint32_t tok_stride, int level) {
     if (nchunks == 0) return 0;
     if (ctx->k1_pending) CK(cudaStreamWaitEvent(stream, ctx->k1_done, 0), "cudaStreamWaitEvent");
     int r = run_deflate_quick(ctx, ctx->scratch, d_in, n, chunk, nchunks, last, d_out, out_stride, d_sizes, d_crcs, d_adlers, stream,
-                              d_tokens, tok_stride);
+                              d_tokens, tok_stride, level, 0);
     if (r) return r;
     CK(cudaEventRecord(ctx->k1_done, stream), "cudaEventRecord");
     ctx->k1_pending = true;
@@ -205,7 +227,9 @@ int ensure_slabs(zng_b200_ctx* ctx) {
         Slab& s = ctx->slab[i];
         CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
         CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreate");
-        CK(cudaMalloc(&s.d_in, (size_t)kSlabChunks * ZNG_B200_CHUNK_MAX), "cudaMalloc(slab in)");
+        // 32 KiB in front of the slab hold the stream bytes that precede it (level 2: stale-window image of a short last chunk)
+        CK(cudaMalloc(&s.d_in_alloc, (size_t)kSlabChunks * ZNG_B200_CHUNK_MAX + kWSize), "cudaMalloc(slab in)");
+        s.d_in = s.d_in_alloc + kWSize;
         CK(cudaMalloc(&s.d_slots, (size_t)kSlabChunks * stride), "cudaMalloc(slab slots)");
         CK(cudaMalloc(&s.d_packed, (size_t)kSlabChunks * stride), "cudaMalloc(slab packed)");
         CK(cudaMalloc(&s.d_sizes, (size_t)kSlabChunks * 3 * sizeof(uint32_t)), "cudaMalloc(slab sizes)");
@@ -260,6 +284,7 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     ctx->sms = prop.multiProcessorCount;
     if (prop.major < 10) { delete ctx; return ZNG_B200_STREAM_ERROR; }       // sm_100a kernels only
     if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm = v; }
+    if (const char* e = getenv("ZNG_B200_CHAINS_L2")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm_l2 = v; }
     if (const char* e = getenv("ZNG_B200_FLAGS")) ctx->k1_flags = (uint32_t)atoi(e);
     if (cudaMalloc(&ctx->counters, kCounters * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->tails, (size_t)kCounters * deflate_quick_tail_bytes()) != cudaSuccess ||
@@ -280,7 +305,7 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i < kPipe; i++) {
         Slab& s = ctx->slab[i];
-        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_in_alloc) cudaFree(s.d_in_alloc);
         if (s.d_slots) cudaFree(s.d_slots);
         if (s.d_packed) cudaFree(s.d_packed);
         if (s.d_sizes) cudaFree(s.d_sizes);
@@ -306,6 +331,8 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->tails) cudaFree(ctx->tails);
     if (ctx->heads) cudaFree(ctx->heads);
+    if (ctx->prevs) cudaFree(ctx->prevs);
+    if (ctx->vtails) cudaFree(ctx->vtails);
     if (ctx->sm_slots) cudaFree(ctx->sm_slots);
     if (ctx->scratch.tokens) cudaFree(ctx->scratch.tokens);
     if (ctx->scratch.ntok) cudaFree(ctx->scratch.ntok);
@@ -347,12 +374,11 @@ int zng_b200_deflate_chunks_trace(zng_b200_ctx* ctx, const void* d_in, size_t n,
                                   uint32_t tok_stride, void* stream) {
     int r = check_chunk_args(ctx, d_in, n, chunk, level, flush, d_out, out_stride, d_sizes);
     if (r) return r;
-    if (level != 1) return bad(ctx, "token trace is implemented for level 1");
     if (!d_tokens || tok_stride < chunk + 1u) return bad(ctx, "d_tokens / tok_stride");
     DeviceGuard g(ctx->device);
     const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
     return run_deflate_quick_shared(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
-                                    d_sizes, nullptr, nullptr, (cudaStream_t)stream, d_tokens, tok_stride);
+                                    d_sizes, nullptr, nullptr, (cudaStream_t)stream, d_tokens, tok_stride, level);
 }
 
 int zng_b200_deflate_chunks(zng_b200_ctx* ctx, const void* d_in, size_t n, uint32_t chunk, int level, int flush,
@@ -362,10 +388,8 @@ int zng_b200_deflate_chunks(zng_b200_ctx* ctx, const void* d_in, size_t n, uint3
     if (r) return r;
     DeviceGuard g(ctx->device);
     const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
-    if (level == 1)
-        return run_deflate_quick_shared(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
-                                        d_sizes, d_crcs, d_adlers, (cudaStream_t)stream, nullptr, 0);
-    return bad(ctx, "level 2 (deflate_fast) kernel is not built in this version");
+    return run_deflate_quick_shared(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
+                                    d_sizes, d_crcs, d_adlers, (cudaStream_t)stream, nullptr, 0, level);
 }
 
 int zng_b200_chunk_offsets(zng_b200_ctx* ctx, const uint32_t* d_sizes, uint32_t nchunks, uint64_t base,
@@ -630,7 +654,6 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
                           void* h_out, size_t out_cap, size_t* out_len, uint32_t* crc32, uint32_t* adler32) {
     if (!ctx) return ZNG_B200_STREAM_ERROR;
     if (level != 1 && level != 2) return bad(ctx, "level must be 1 or 2");
-    if (level != 1) return bad(ctx, "level 2 (deflate_fast) kernel is not built in this version");
     if (chunk == 0 || chunk > ZNG_B200_CHUNK_MAX) return bad(ctx, "chunk must be in 1..65536");
     if (!out_len || (n && !h_in) || !h_out) return bad(ctx, "NULL argument");
     DeviceGuard g(ctx->device);
@@ -651,7 +674,9 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
         if (r) { sync_slabs(ctx); return r; }
         const size_t take = (n - off) < slab_in ? (n - off) : slab_in;
         const bool is_last = (off + take == n);
-        if (take) CK(cudaMemcpyAsync(s.d_in, (const uint8_t*)h_in + off, take, cudaMemcpyHostToDevice, s.stream), "H2D");
+        const size_t pre = (level == 2) ? (off < kWSize ? off : (size_t)kWSize) : 0;
+        const int have_prev = off > 0 ? 1 : 0;
+        if (take) CK(cudaMemcpyAsync(s.d_in - pre, (const uint8_t*)h_in + off - pre, take + pre, cudaMemcpyHostToDevice, s.stream), "H2D");
         uint32_t nch = (uint32_t)((take + chunk - 1) / chunk);
         uint32_t* d_sizes = s.d_sizes; uint32_t* d_crcs = s.d_sizes + kSlabChunks; uint32_t* d_adlers = s.d_sizes + 2 * kSlabChunks;
         if (final && is_last) {
@@ -659,13 +684,14 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
             const uint32_t body = nch ? nch - 1 : 0;
             const size_t body_bytes = (size_t)body * chunk;
             if (body) {
-                r = run_deflate_quick(ctx, s.scratch, s.d_in, body_bytes, chunk, body, 0, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream, nullptr, 0);
+                r = run_deflate_quick(ctx, s.scratch, s.d_in, body_bytes, chunk, body, 0, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream, nullptr, 0,
+                                      level, have_prev);
                 if (r) { sync_slabs(ctx); return r; }
             }
             const size_t tail = take - body_bytes;
             if (tail) {
                 r = run_deflate_quick(ctx, s.scratch, s.d_in + body_bytes, tail, chunk, 1, 1, s.d_slots + (size_t)body * stride, stride,
-                                      d_sizes + body, d_crcs + body, d_adlers + body, s.stream, nullptr, 0);
+                                      d_sizes + body, d_crcs + body, d_adlers + body, s.stream, nullptr, 0, level, (body || have_prev) ? 1 : 0);
                 if (r) { sync_slabs(ctx); return r; }
             } else {
                 // zng_deflate(Z_FINISH) with no input: "03 00" (empty static block, BFINAL) -- deflate_quick.c:53-58
@@ -679,7 +705,8 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
             }
             emitted_final = true;
         } else {
-            r = run_deflate_quick(ctx, s.scratch, s.d_in, take, chunk, nch, 0, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream, nullptr, 0);
+            r = run_deflate_quick(ctx, s.scratch, s.d_in, take, chunk, nch, 0, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream, nullptr, 0,
+                                  level, have_prev);
             if (r) { sync_slabs(ctx); return r; }
         }
         CK(launch_offsets(d_sizes, nch, 0, s.d_offsets, s.stream), "offsets launch");

@@ -106,6 +106,24 @@ __device__ __forceinline__ uint32_t crc_table_entry(uint32_t i, int slice) {
     return c;
 }
 
+// ---------------------------------------------------------------- hash-table slab pool (K1 / K2 parse kernels)
+// Hash-head slabs are handed out per SM: slab (smid, b) belongs to the warp that holds bit b of
+// sm_slots[smid].  This lets any number of parse kernels (different streams, different batches) run
+// concurrently on one pool, sized nsmid x 64 (a resident warp always finds a free bit).
+__device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+
+__device__ __forceinline__ uint32_t slot_acquire(unsigned long long* word) {
+    for (;;) {
+        const unsigned long long m = *(volatile unsigned long long*)word;
+        const int b = __ffsll((long long)~m) - 1;
+        if (b >= 0) {
+            const unsigned long long bit = 1ull << b;
+            if (!(atomicOr(word, bit) & bit)) return (uint32_t)b;
+        }
+    }
+}
+
+
 // ---------------------------------------------------------------- static Huffman symbol coding
 // RFC 1951 3.2.5/3.2.6; the same values tools/maketrees.c writes to trees_tbl.h.  Returns the
 // LSB-first bit string of one token under the fixed code (trees_emit.h:102-164 semantics).

@@ -251,22 +251,6 @@ __device__ uint32_t static_emit_warp(uint32_t* stage, const uint32_t* __restrict
 }
 
 // ---------------------------------------------------------------- kernels
-// Hash-head slabs are handed out per SM: slab (smid, b) belongs to the warp that holds bit b of
-// sm_slots[smid].  This lets any number of parse kernels (different streams, different batches) run
-// concurrently on one pool, sized nsmid x 64 (a resident warp always finds a free bit).
-__device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
-
-__device__ __forceinline__ uint32_t slot_acquire(unsigned long long* word) {
-    for (;;) {
-        const unsigned long long m = *(volatile unsigned long long*)word;
-        const int b = __ffsll((long long)~m) - 1;
-        if (b >= 0) {
-            const unsigned long long bit = 1ull << b;
-            if (!(atomicOr(word, bit) & bit)) return (uint32_t)b;
-        }
-    }
-}
-
 __global__ void nsmid_kernel(uint32_t* out) { uint32_t r; asm volatile("mov.u32 %0, %%nsmid;" : "=r"(r)); *out = r; }
 
 // heads: the slab pool.  tail: a zero-padded private copy of the chunks

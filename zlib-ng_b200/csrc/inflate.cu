@@ -127,8 +127,9 @@ __device__ __forceinline__ int decode_sym(uint64_t hold, uint32_t bits, const Co
 struct Reader {
     const uint32_t* w; uint32_t wi, e; uint64_t hold; uint32_t bits;
     __device__ __forceinline__ void init(const uint32_t* w_, uint32_t bp, uint32_t e_) {
-        w = w_; e = e_; hold = 0; bits = 0; wi = bp >> 2;
+        w = w_; e = e_; hold = 0; bits = 0; wi = (e + 3u) >> 2;     // bp >= e: nothing left, pos() == e
         if (bp < e) {
+            wi = bp >> 2;
             const uint32_t sk = bp & 3u;
             uint32_t valid = e - 4u * wi; if (valid > 4u) valid = 4u;
             uint32_t x = __ldg(w + wi);

@@ -22,6 +22,19 @@ cudaError_t launch_static_emit(const uint32_t* tokens, uint32_t tok_stride, cons
                                uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
                                int num_sms, cudaStream_t stream);
 
+// K2: level-2 chunk deflate (deflate_fast.cu): K2a parse with hash chains -> token lists, K2b block writer
+// (dynamic / static / stored blocks).  Shares the head slab pool and sm_slots with K1; prevs / tails are the
+// per-slab prev[] tables and stale-window images.  have_prev: chunk 0 of this launch is preceded in memory by
+// the 32 KiB of input that came before it in the stream (what a short last chunk's over-reads see).
+size_t deflate_fast_prev_bytes(uint32_t nsmid);
+size_t deflate_fast_tail_bytes(uint32_t nsmid);
+cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t* tokens, uint32_t tok_stride,
+                              uint32_t* ntok, uint32_t* counter, uint16_t* heads, uint16_t* prevs, uint32_t* tails,
+                              unsigned long long* sm_slots, int num_sms, int chains_per_sm, int have_prev, cudaStream_t stream);
+cudaError_t launch_block_emit(const uint8_t* in, const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n,
+                              uint32_t chunk, uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
+                              int num_sms, cudaStream_t stream);
+
 // K3: checksums (checksum.cu)
 cudaError_t launch_checksum_tiles(const uint8_t* in, size_t n, uint32_t tile_bytes, uint32_t ntiles,
                                   uint32_t* crcs, uint32_t* adlers, int num_sms, cudaStream_t stream);
