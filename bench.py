@@ -1,19 +1,20 @@
 #!/usr/bin/env python3
-"""bench.py -- level-1 chunked deflate throughput on B200 (BASELINE.json metric), one JSON line.
+"""bench.py -- chunked-DEFLATE hot path on B200, one JSON line per run.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (BASELINE metric: level 1)
     python bench.py --impl reference --gpus N --steps K ...  # zlib-ng's own CPU path, all host cores
+    python bench.py --workload deflate2|checksum|inflate     # the other BASELINE configs (same JSON contract)
 
-Workload (BASELINE.json configs[0], the configuration the metric is quoted on): per GPU a 1 GiB
-synthetic mixed text/binary buffer = 16,384 independent 64 KiB chunks, deflate_quick (level 1) raw
-deflate with Z_FULL_FLUSH chunk ends + per-chunk CRC-32, then the output-offset scan, the gather
-into one contiguous raw-deflate stream and the crc32_combine fold.  With N > 1 each rank owns its
-own 1 GiB shard (weak scaling, contiguous chunk ranges) and the only collective is an NCCL
-allgather of the per-chunk (size, crc32) pairs.
+Default workload (BASELINE.json configs[0], the configuration the metric is quoted on): per GPU a 1 GiB synthetic
+mixed text/binary buffer = 16,384 independent 64 KiB chunks, deflate_quick (level 1) raw deflate with Z_FULL_FLUSH
+chunk ends + per-chunk CRC-32, then the output-offset scan, the gather into one contiguous raw-deflate stream and
+the crc32_combine fold.  With N > 1 each rank owns its own 1 GiB shard (weak scaling, contiguous chunk ranges) and
+the only collective is an NCCL allgather of the per-chunk (size, crc32) pairs.
 
-A "step" is one pass over the batch.  `value` is device-resident throughput (inputs already in
-HBM); `e2e` is the same work through the host-buffer C-ABI call (zng_b200_deflate_host, what
-zng_deflate of the host library calls) with pinned host buffers, H2D and D2H inside the timing.
+A "step" is one pass over the batch.  `value` is device-resident throughput (inputs already in HBM, CUDA events,
+max over ranks); `e2e` is the same work through the host-buffer C-ABI call (what zng_deflate / zng_inflate /
+zng_crc32 of the host library call) with pinned host buffers, H2D and D2H inside the timing.  `roofline` is the
+dominant kernel's algorithmic bytes / its own CUDA-event time against the measured HBM peak.
 """
 from __future__ import annotations
 
@@ -21,6 +22,7 @@ import argparse
 import json
 import os
 import statistics
+import struct
 import subprocess
 import sys
 import threading
@@ -30,9 +32,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CHUNK = 65536
+MEMBER = 4096
 SEED = 0x9E3779B97F4A7C15
-METRIC = "level1_deflate_input_throughput"
 UNIT = "GB/s"
+METRICS = {"deflate1": "level1_deflate_input_throughput", "deflate2": "level2_deflate_input_throughput",
+           "checksum": "crc32_adler32_input_throughput", "inflate": "inflate_output_throughput"}
 
 
 def parse_args():
@@ -41,10 +45,23 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mib-per-gpu", type=int, default=1024, help="input MiB per GPU (default: the 1 GiB BASELINE config)")
+    ap.add_argument("--workload", default="deflate1", choices=list(METRICS))
+    ap.add_argument("--mib-per-gpu", type=int, default=1024, help="input (inflate: output) MiB per GPU; default = the 1 GiB BASELINE config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
+
+
+def workload_text(w, mib, ngpu):
+    n = mib << 20
+    if w in ("deflate1", "deflate2"):
+        lvl, fn, cfg = (1, "deflate_quick", "configs[0]") if w == "deflate1" else (2, "deflate_fast", "configs[2] at 1 GiB per GPU")
+        return (f"{fn} level {lvl}, {mib} MiB per GPU as {n // CHUNK} x 64 KiB raw-deflate chunks + per-chunk crc32, offset scan + gather + "
+                f"crc32_combine fold (BASELINE {cfg})")
+    if w == "checksum":
+        return f"zng_crc32 + zng_adler32 of a flat {mib} MiB buffer per GPU, 64 KiB tiles + combine folds (BASELINE configs[1])"
+    return (f"batched inflate of {n // MEMBER} independent 4 KiB gzip members per GPU (bodies = level-1 Z_FINISH streams, minigzip -1 framing), "
+            f"output + CRC-32 + ISIZE checked on device (BASELINE configs[3] at {mib} MiB of output per GPU)")
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -60,7 +77,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -93,57 +110,158 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------ synthetic members (inflate workload)
+def make_members(pkg, n_bytes, seed_offset=0):
+    """config 3: every 4096-byte slice of the synthetic stream as one gzip member whose body is the level-1 Z_FINISH
+    stream of the slice (what minigzip -1 writes: header 1f 8b 08 00 00000000 04 03, raw deflate, CRC32, ISIZE).
+    Built with this repo's own GPU compressor (bit-exact with the reference, tests/test_gpu_deflate_quick.py) so that
+    setup stays fast; returns (members bytes, in_off u64[n+1], raw data)."""
+    import numpy as np
+    import torch
+    ctx = pkg.Context(torch.cuda.current_device())
+    n_members = n_bytes // MEMBER
+    data = np.empty(n_bytes, dtype=np.uint8)
+    assert pkg.lib().zng_b200_synth_fill(data.ctypes.data, n_bytes, SEED, seed_offset) == 0
+    stride = pkg.deflate_bound(MEMBER)
+    parts_sizes = np.zeros(n_members, dtype=np.int64)
+    bodies = []
+    batch = 65536
+    for m0 in range(0, n_members, batch):
+        m1 = min(m0 + batch, n_members)
+        d_in = torch.from_numpy(data[m0 * MEMBER:m1 * MEMBER]).cuda()
+        slots = torch.empty((m1 - m0) * stride, dtype=torch.uint8, device="cuda")
+        sizes = torch.zeros(m1 - m0, dtype=torch.int32, device="cuda")
+        crcs = torch.zeros(m1 - m0, dtype=torch.int32, device="cuda")
+        ctx.deflate_chunks(d_in, (m1 - m0) * MEMBER, MEMBER, 1, pkg.Z_FINISH, slots, stride, sizes, crcs, None)
+        torch.cuda.synchronize()
+        bodies.append((slots.cpu().numpy().reshape(-1, stride), sizes.cpu().numpy().astype(np.int64), crcs.cpu().numpy().view(np.uint32)))
+        parts_sizes[m0:m1] = bodies[-1][1] + 18
+    ctx.close()
+    in_off = np.zeros(n_members + 1, dtype=np.uint64)
+    in_off[1:] = np.cumsum(parts_sizes).astype(np.uint64)
+    total = int(in_off[-1])
+    members = np.zeros(total + 16, dtype=np.uint8)
+    hdr = np.frombuffer(bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 4, 3]), dtype=np.uint8)
+    isize = np.frombuffer(struct.pack("<I", MEMBER), dtype=np.uint8)
+    m = 0
+    for rows, sizes, crcs in bodies:
+        for i in range(len(sizes)):
+            o = int(in_off[m]); s = int(sizes[i])
+            members[o:o + 10] = hdr
+            members[o + 10:o + 10 + s] = rows[i, :s]
+            members[o + 10 + s:o + 14 + s] = np.frombuffer(struct.pack("<I", int(crcs[i])), dtype=np.uint8)
+            members[o + 14 + s:o + 18 + s] = isize
+            m += 1
+    return members, in_off, data
+
+
+def make_members_cpu(zo, pkg, n_bytes):
+    """Same members from the CPU side (reference arm: no GPU needed): refdrv_gzip_members / oracle port."""
+    import numpy as np
+    n_members = n_bytes // MEMBER
+    data = pkg.synth(n_bytes, SEED)
+    out, sizes, crcs, _ = (zo.ref_deflate_chunks if zo.have_ref() else zo.port_deflate_chunks)(data, MEMBER, 1, 4)
+    in_off = np.zeros(n_members + 1, dtype=np.uint64)
+    in_off[1:] = np.cumsum(sizes.astype(np.int64) + 18).astype(np.uint64)
+    members = np.zeros(int(in_off[-1]) + 16, dtype=np.uint8)
+    hdr = np.frombuffer(bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 4, 3]), dtype=np.uint8)
+    for i in range(n_members):
+        o = int(in_off[i]); s = int(sizes[i])
+        members[o:o + 10] = hdr
+        members[o + 10:o + 10 + s] = out[i, :s]
+        members[o + 10 + s:o + 18 + s] = np.frombuffer(struct.pack("<II", int(crcs[i]), MEMBER), dtype=np.uint8)
+    return members, in_off, data
+
+
 # ------------------------------------------------------------------------------------ reference arm
-def cpu_reference_run(n_bytes: int, steps: int, warmup: int):
-    """Time the reference's CPU implementation (oracle/_ref when it was built from /root/reference,
-    else the oracle port) on the same workload: one zng_stream per worker thread, zng_deflateReset +
-    zng_deflate(Z_FULL_FLUSH) + zng_crc32 per 64 KiB chunk, all host cores."""
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def cpu_reference_run(workload: str, n_bytes: int, steps: int, warmup: int):
+    """Time the reference's CPU implementation (oracle/_ref when it was built from /root/reference, else the oracle
+    port) on the same workload with every host core: one zng_stream per worker thread, one chunk / member per task."""
     import numpy as np
     from __graft_entry__ import load_oracle, load_package
     pkg = load_package()
     zo = load_oracle()
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = host_cores()
     kind = "reference" if zo.have_ref() else "port"
-    fn = zo.ref().refdrv_deflate_chunks if kind == "reference" else zo.port().zo_deflate_chunks
     if kind == "port":
         cores = min(cores, 256)
-    data = pkg.synth(n_bytes, SEED)
-    nch = (n_bytes + CHUNK - 1) // CHUNK
-    stride = pkg.deflate_bound(CHUNK)
-    out = np.empty(nch * stride, dtype=np.uint8)
-    sizes = np.zeros(nch, dtype=np.uint32)
-    crcs = np.zeros(nch, dtype=np.uint32)
+    ratio = None
+    if workload in ("deflate1", "deflate2"):
+        level = 1 if workload == "deflate1" else 2
+        fn = zo.ref().refdrv_deflate_chunks if kind == "reference" else zo.port().zo_deflate_chunks
+        data = pkg.synth(n_bytes, SEED)
+        nch = (n_bytes + CHUNK - 1) // CHUNK
+        stride = pkg.deflate_bound(CHUNK)
+        out = np.empty(nch * stride, dtype=np.uint8)
+        sizes = np.zeros(nch, dtype=np.uint32)
+        crcs = np.zeros(nch, dtype=np.uint32)
+        call = lambda: fn(data.ctypes.data, n_bytes, CHUNK, level, 3, out.ctypes.data, stride, sizes.ctypes.data, crcs.ctypes.data, None, cores)
+        what = f"{n_bytes >> 20} MiB of the same synthetic workload per step ({nch} chunks; zng_deflateReset + zng_deflate(Z_FULL_FLUSH) + zng_crc32 per chunk)"
+    elif workload == "checksum":
+        data = pkg.synth(n_bytes, SEED)
+        if kind == "reference":
+            c, a = ctypes_u32(), ctypes_u32()
+            call = lambda: zo.ref().refdrv_checksum_flat(data.ctypes.data, n_bytes, 1 << 20, cores, c, a)
+        else:
+            call = lambda: (zo.port().zo_crc32(0, data.ctypes.data, n_bytes), zo.port().zo_adler32(1, data.ctypes.data, n_bytes)) and 0
+            cores = 1
+        what = f"{n_bytes >> 20} MiB flat buffer per step, 1 MiB pieces per thread + combine (zng_crc32_z + zng_adler32_z + *_combine)"
+    else:
+        members, in_off, data = make_members_cpu(zo, pkg, n_bytes)
+        nm = len(in_off) - 1
+        out = np.empty(n_bytes, dtype=np.uint8)
+        out_off = (np.arange(nm + 1, dtype=np.uint64) * MEMBER)
+        sizes = np.zeros(nm, dtype=np.uint32); crcs = np.zeros(nm, dtype=np.uint32); status = np.zeros(nm, dtype=np.int32)
+        fn = zo.ref().refdrv_inflate_members if kind == "reference" else zo.port().zo_inflate_members
+        call = lambda: fn(members.ctypes.data, in_off.ctypes.data, nm, out.ctypes.data, out_off.ctypes.data, sizes.ctypes.data, crcs.ctypes.data, status.ctypes.data, cores)
+        what = f"{nm} gzip members of 4 KiB per step (zng_inflateInit2(31) / zng_inflateReset + zng_inflate(Z_FINISH) per member)"
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        r = fn(data.ctypes.data, n_bytes, CHUNK, 1, 3, out.ctypes.data, stride, sizes.ctypes.data, crcs.ctypes.data, None, cores)
+        r = call()
         t1 = time.perf_counter()
-        if r != 0:
-            raise RuntimeError(f"reference deflate failed: {r}")
+        if r not in (0, None):
+            raise RuntimeError(f"reference {workload} failed: {r}")
         if it >= warmup:
             times.append(t1 - t0)
+    if workload in ("deflate1", "deflate2"):
+        ratio = float(sizes.sum()) / n_bytes
+    if workload == "inflate" and not (status == 1).all():
+        raise RuntimeError("reference inflate: a member did not reach Z_STREAM_END")
     total = sum(times)
-    return {"value": n_bytes * len(times) / total / 1e9, "ms_per_step": 1e3 * total / len(times), "cores": cores, "kind": kind,
-            "ratio": float(sizes.sum()) / n_bytes,
-            "sample": f"{n_bytes >> 20} MiB of the same synthetic workload per step ({nch} chunks), {len(times)} timed steps, wall clock"}
+    return {"value": n_bytes * len(times) / total / 1e9, "ms_per_step": 1e3 * total / len(times), "cores": cores, "kind": kind, "ratio": ratio,
+            "sample": f"{what}, {len(times)} timed steps, wall clock, {cores} threads"}
+
+
+def ctypes_u32():
+    import ctypes
+    return ctypes.pointer(ctypes.c_uint32(0))
+
+
+def cpu_sample_bytes(workload, n, seconds, reps):
+    """Bounded sample of the workload for the CPU arm: about `seconds` of wall clock over `reps` passes."""
+    cores = host_cores()
+    per_core = {"deflate1": 0.10e9, "deflate2": 0.06e9, "checksum": 5e9, "inflate": 0.5e9}[workload]
+    budget = int(per_core * cores * seconds / max(1, reps))
+    return min(n, max(64 << 20, (budget >> 26) << 26))
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     n_bytes = args.mib_per_gpu << 20
-    # bounded sample: the CPU runs ~0.1 GB/s per core; keep the whole run within a few minutes
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    budget_bytes = int(0.08e9 * cores * 120 / max(1, args.steps + args.warmup))     # ~2 min in total
-    sample = min(n_bytes, max(64 << 20, (budget_bytes >> 26) << 26))
-    res = cpu_reference_run(sample, args.steps, args.warmup)
+    sample = cpu_sample_bytes(args.workload, n_bytes, 120, args.steps + args.warmup)       # ~2 min in total
+    res = cpu_reference_run(args.workload, sample, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRICS[args.workload], "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"deflate_quick level 1, {args.mib_per_gpu} MiB per GPU as 64 KiB raw-deflate chunks + per-chunk crc32 (BASELINE configs[0])",
-                   "chunk_bytes": CHUNK, "level": 1, "flush": "Z_FULL_FLUSH", "sharding": f"chunks x{args.gpus}"},
+        "config": {"workload": workload_text(args.workload, args.mib_per_gpu, args.gpus), "chunk_bytes": CHUNK,
+                   "sharding": f"chunks x{args.gpus}"},
         "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "compression_ratio": res["ratio"],
@@ -172,65 +290,61 @@ def run_b200(args):
     if args.gpus != world and rank == 0:
         print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
     ngpu = world
-
+    wl = args.workload
     n = args.mib_per_gpu << 20
-    nch = n // CHUNK
     ctx = pkg.Context(local_rank)
-    stride = pkg.deflate_bound(CHUNK)
-
-    # this rank's shard of the synthetic stream (pinned, so the e2e leg can copy from it)
-    h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-    r = pkg.lib().zng_b200_synth_fill(h_in.data_ptr(), n, SEED, rank * n)
-    assert r == 0
-    d_in = h_in.to(dev, non_blocking=True)
-    slots = torch.empty(nch * stride, dtype=torch.uint8, device=dev)
-    meta = torch.zeros(2, nch, dtype=torch.int32, device=dev)              # row 0 sizes, row 1 crc32
-    sizes, crcs = meta[0], meta[1]
-    offsets = torch.zeros(nch + 1, dtype=torch.int64, device=dev)
-    packed = torch.empty(nch * stride, dtype=torch.uint8, device=dev)
-    res = torch.zeros(4, dtype=torch.int32, device=dev)
-    if ngpu > 1:
-        gathered = torch.zeros(ngpu, 2, nch, dtype=torch.int32, device=dev)
-        offsets_all = torch.zeros(ngpu * nch + 1, dtype=torch.int64, device=dev)
-    torch.cuda.synchronize()
-
-    k1_start = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    k1_stop = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    steps = args.steps
+    k_start = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    k_stop = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     launches = {"n": 0}
-
-    def step(i_timed=None):
-        if i_timed is not None:
-            k1_start[i_timed].record()
-        ctx.deflate_chunks(d_in, n, CHUNK, 1, pkg.Z_FULL_FLUSH, slots, stride, sizes, crcs, None)
-        if i_timed is not None:
-            k1_stop[i_timed].record()
-        launches["n"] += 1
-        if ngpu > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), meta.view(-1))
-            allm = gathered.permute(1, 0, 2).contiguous()                 # [2, ngpu*nch] in global chunk order
-            ctx.chunk_offsets(allm[0].view(-1), ngpu * nch, 0, offsets_all)     # global byte offsets of every chunk
-            ctx.crc32_fold(allm[1].view(-1), ngpu * nch, CHUNK, ngpu * n, 0, res[0:1])
-            launches["n"] += 2
-        else:
-            ctx.crc32_fold(crcs, nch, CHUNK, n, 0, res[0:1])
-            launches["n"] += 1
-        ctx.chunk_offsets(sizes, nch, 0, offsets)                          # local packing offsets
-        ctx.gather_chunks(slots, stride, sizes, offsets, nch, packed)
-        launches["n"] += 2
+    parity = None
+    out_bytes = 0
+    e2e_fn = None
 
     def barrier():
         if ngpu > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    if wl in ("deflate1", "deflate2"):
+        level = 1 if wl == "deflate1" else 2
+        nch = n // CHUNK
+        stride = pkg.deflate_bound(CHUNK)
+        h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)        # this rank's shard of the synthetic stream
+        assert pkg.lib().zng_b200_synth_fill(h_in.data_ptr(), n, SEED, rank * n) == 0
+        d_in = h_in.to(dev, non_blocking=True)
+        slots = torch.empty(nch * stride, dtype=torch.uint8, device=dev)
+        meta = torch.zeros(2, nch, dtype=torch.int32, device=dev)          # row 0 sizes, row 1 crc32
+        sizes, crcs = meta[0], meta[1]
+        offsets = torch.zeros(nch + 1, dtype=torch.int64, device=dev)
+        packed = torch.empty(nch * stride, dtype=torch.uint8, device=dev)
+        res = torch.zeros(4, dtype=torch.int32, device=dev)
+        if ngpu > 1:
+            gathered = torch.zeros(ngpu, 2, nch, dtype=torch.int32, device=dev)
+            offsets_all = torch.zeros(ngpu * nch + 1, dtype=torch.int64, device=dev)
+        k_per_step = 3 if level == 1 else 3                                # parse, emit, checksum tiles
 
-    # parity spot check outside the timed region (rank 0): a sample of chunks against the oracle
-    parity = None
-    if rank == 0:
-        try:
+        def step(i_timed=None):
+            if i_timed is not None:
+                k_start[i_timed].record()
+            ctx.deflate_chunks(d_in, n, CHUNK, level, pkg.Z_FULL_FLUSH, slots, stride, sizes, crcs, None)
+            if i_timed is not None:
+                k_stop[i_timed].record()
+            launches["n"] += k_per_step
+            if ngpu > 1:
+                dist.all_gather_into_tensor(gathered.view(-1), meta.view(-1))
+                allm = gathered.permute(1, 0, 2).contiguous()             # [2, ngpu*nch] in global chunk order
+                ctx.chunk_offsets(allm[0].view(-1), ngpu * nch, 0, offsets_all)     # global byte offsets of every chunk
+                ctx.crc32_fold(allm[1].view(-1), ngpu * nch, CHUNK, ngpu * n, 0, res[0:1])
+                launches["n"] += 2
+            else:
+                ctx.crc32_fold(crcs, nch, CHUNK, n, 0, res[0:1])
+                launches["n"] += 1
+            ctx.chunk_offsets(sizes, nch, 0, offsets)                      # local packing offsets
+            ctx.gather_chunks(slots, stride, sizes, offsets, nch, packed)
+            launches["n"] += 2
+
+        def parity_check():
             from __graft_entry__ import load_oracle
             zo = load_oracle()
             hs = sizes.cpu().numpy().view(np.uint32)
@@ -239,10 +353,115 @@ def run_b200(args):
             hin = h_in.numpy()
             ok = True
             for ci in pick:
-                exp, es, ec, _ = zo.port_deflate_chunks(hin[ci * CHUNK:(ci + 1) * CHUNK], CHUNK, 1, 3, stride, nthreads=1)
+                exp, es, ec, _ = zo.port_deflate_chunks(hin[ci * CHUNK:(ci + 1) * CHUNK], CHUNK, level, 3, stride, nthreads=1)
                 got = hslots[ci, : int(es[0])].cpu().numpy()
                 ok &= bool(es[0] == hs[ci]) and bool(np.array_equal(got, exp[0, : es[0]]))
-            parity = "bit-exact vs oracle on 64 sampled chunks" if ok else "MISMATCH vs oracle"
+            return "bit-exact vs oracle on 64 sampled chunks" if ok else "MISMATCH vs oracle"
+
+        def finish():
+            return int(offsets[nch].item())
+
+        cap = nch * stride
+
+        def make_e2e():
+            h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            state = {}
+
+            def call():
+                state["out_len"], _, _ = ctx.deflate_host(h_in, n, CHUNK, level, False, h_out, cap)
+            return call, (lambda: (n, int(state["out_len"]))), "zng_b200_deflate_host (pinned host in/out, 6 x 64 MiB slabs in flight on separate streams)"
+        e2e_fn = make_e2e
+        alg_bytes = lambda ob: n + ob                                     # in + out per chunk, x chunks per launch
+        kernel_name = "quick_parse_kernel + static_emit_kernel (+ checksum_tiles_kernel)" if level == 1 else "fast_parse_kernel + block_emit_kernel (+ checksum_tiles_kernel)"
+        note = "serial-per-chunk LZ77 parse: latency/issue bound, not HBM bound (see DESIGN.md)"
+
+    elif wl == "checksum":
+        h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        assert pkg.lib().zng_b200_synth_fill(h_in.data_ptr(), n, SEED, rank * n) == 0
+        d_in = h_in.to(dev, non_blocking=True)
+        res = torch.zeros(4, dtype=torch.int32, device=dev)
+        if ngpu > 1:
+            gath = torch.zeros(ngpu * 4, dtype=torch.int32, device=dev)
+
+        def step(i_timed=None):
+            if i_timed is not None:
+                k_start[i_timed].record()
+            ctx.crc32(d_in, n, 0, res[0:1])
+            ctx.adler32(d_in, n, 1, res[1:2])
+            if i_timed is not None:
+                k_stop[i_timed].record()
+            launches["n"] += 4
+            if ngpu > 1:
+                dist.all_gather_into_tensor(gath, res)                    # G x (crc, adler) -> combined on the host (G values)
+
+        def parity_check():
+            import zlib as pyzlib
+            r = res.cpu().numpy().view(np.uint32)
+            b = h_in.numpy().tobytes()
+            return "crc32/adler32 equal to an independent CPU implementation" if (int(r[0]) == pyzlib.crc32(b) and int(r[1]) == pyzlib.adler32(b)) else "MISMATCH"
+
+        def finish():
+            return 0
+
+        def make_e2e():
+            def call():
+                ctx.crc32_host(h_in, n, 0)
+                ctx.adler32_host(h_in, n, 1)
+            return call, (lambda: (2 * n, 8)), "zng_b200_crc32_host + zng_b200_adler32_host (what zng_crc32_z / zng_adler32_z call)"
+        e2e_fn = make_e2e
+        alg_bytes = lambda ob: 2 * n                                      # two passes (crc32, adler32), each reads the buffer once
+        kernel_name = "checksum_tiles_kernel x2 (+ folds)"
+        note = "table-driven CRC-32 without carry-less multiply: shared-memory lookup bound"
+
+    else:  # inflate
+        members, in_off, data = make_members(pkg, n, rank * n)
+        nm = len(in_off) - 1
+        h_members = torch.from_numpy(members).pin_memory()
+        d_members = h_members.to(dev)
+        d_io = torch.from_numpy(in_off.astype(np.int64)).to(dev)
+        out_off = np.arange(nm + 1, dtype=np.int64) * MEMBER
+        d_oo = torch.from_numpy(out_off).to(dev)
+        d_out = torch.empty(n, dtype=torch.uint8, device=dev)
+        sizes = torch.zeros(nm, dtype=torch.int32, device=dev); checks = torch.zeros_like(sizes)
+        status = torch.zeros_like(sizes)
+        comp_bytes = int(in_off[-1])
+
+        def step(i_timed=None):
+            if i_timed is not None:
+                k_start[i_timed].record()
+            ctx.inflate_members(d_members, d_io, nm, 31, d_out, d_oo, sizes, checks, status, None, None)
+            if i_timed is not None:
+                k_stop[i_timed].record()
+            launches["n"] += 1
+
+        def parity_check():
+            ok = bool((status == 1).all()) and bool((sizes == MEMBER).all())
+            ok &= bool(torch.equal(d_out.cpu(), torch.from_numpy(data)))
+            return "every member Z_STREAM_END (CRC-32 + ISIZE verified on device), output identical to the original buffer" if ok else "MISMATCH"
+
+        def finish():
+            return comp_bytes
+
+        def make_e2e():
+            h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            uin_off = in_off.astype(np.uint64); uout_off = out_off.astype(np.uint64)
+
+            def call():
+                _, _, st, _, _ = ctx.inflate_members_host(h_members, uin_off, 31, h_out, uout_off)
+                assert int(st.min()) == 1
+            return call, (lambda: (comp_bytes, n)), "zng_b200_inflate_members_host (pinned host in/out, 3 slabs of 32768 members in flight)"
+        e2e_fn = make_e2e
+        alg_bytes = lambda ob: ob + n                                     # compressed in + raw out
+        kernel_name = "inflate_members_kernel"
+        note = "serial symbol decode per member (one warp each): latency/issue bound"
+
+    torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    if rank == 0:
+        try:
+            parity = parity_check()
         except Exception as e:  # oracle not built: say so, do not guess
             parity = f"not checked ({e})"
 
@@ -253,41 +472,40 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         step(i)
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
-    k1_ms = sum(a.elapsed_time(b) for a, b in zip(k1_start, k1_stop)) / args.steps
+    k_ms = sum(a.elapsed_time(b) for a, b in zip(k_start, k_stop)) / steps
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if ngpu > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     value = ngpu * n / (ms_step * 1e-3) / 1e9
-    out_bytes = int(offsets[nch].item())
+    out_bytes = finish()
 
     # ---- e2e: host buffers through the C-ABI host call, H2D/D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        cap = nch * stride
-        h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        call, bytes_fn, api = e2e_fn()
         for _ in range(2):
-            ctx.deflate_host(h_in, n, CHUNK, 1, False, h_out, cap)
+            call()
         barrier()
-        e_steps = max(3, min(args.steps, 5))
+        e_steps = max(3, min(steps, 5))
         t0 = time.perf_counter()
         for _ in range(e_steps):
-            out_len, crc_e2e, _ = ctx.deflate_host(h_in, n, CHUNK, 1, False, h_out, cap)
+            call()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if ngpu > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        e2e = {"value": ngpu * n * e_steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(out_len),
-               "steps": e_steps, "api": "zng_b200_deflate_host (pinned host in/out, 6 x 64 MiB slabs in flight on separate streams)"}
+        h2d, d2h = bytes_fn()
+        e2e = {"value": ngpu * n * e_steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps, "api": api}
 
     if rank != 0:
         if ngpu > 1:
@@ -300,38 +518,36 @@ def run_b200(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    alg_bytes = n + out_bytes                       # in + out per chunk, x chunks per launch
-    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "deflate_quick_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "6650 GB/s (B200_PROFILING.md fallback)"
+    ab = alg_bytes(out_bytes)
+    achieved = ab / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel_ms": k1_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "serial-per-chunk LZ77 parse: latency/issue bound, not HBM bound (see DESIGN.md)"}
+                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ab, "note": note}
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
-        roofline["traffic"] = tr.get("dram_bytes_per_launch")
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        roofline["traffic"] = tr.get(wl, {}).get("dram_bytes_per_launch")
+        roofline["traffic_source"] = tr.get(wl, {}).get("source")
     except Exception:
         pass
 
     cpu = None
     if not args.no_cpu_baseline and ngpu == 1:
         try:
-            cores = len(os.sched_getaffinity(0))
-            sample = min(n, max(64 << 20, (int(0.08e9 * cores * 20 / 4) >> 26) << 26))     # ~20 s of wall clock at most
-            rr = cpu_reference_run(sample, 3, 1)
+            rr = cpu_reference_run(wl, cpu_sample_bytes(wl, n, 20, 4), 3, 1)     # ~20 s of wall clock
             cpu = {"value": rr["value"], "unit": UNIT, "cores": rr["cores"], "kind": rr["kind"], "sample": rr["sample"]}
         except Exception as e:
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpu, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRICS[wl], "value": value, "unit": UNIT, "n_gpus": ngpu, "steps": steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"deflate_quick level 1, {args.mib_per_gpu} MiB per GPU as {nch} x 64 KiB raw-deflate chunks + per-chunk crc32, offset scan + gather + crc32_combine fold (BASELINE configs[0])",
-                   "chunk_bytes": CHUNK, "level": 1, "flush": "Z_FULL_FLUSH", "sharding": f"contiguous chunk ranges x{ngpu}",
-                   "collective": "nccl allgather of (size, crc32) per chunk" if ngpu > 1 else "none",
-                   "l2": "input 1 GiB per step >> 126 MB L2, no flush needed"},
+        "config": {"workload": workload_text(wl, args.mib_per_gpu, ngpu), "chunk_bytes": CHUNK,
+                   "sharding": f"contiguous chunk ranges x{ngpu}",
+                   "collective": ("nccl allgather of (size, crc32) per chunk" if wl.startswith("deflate") else ("nccl allgather of (crc32, adler32) per rank" if wl == "checksum" else "none")) if ngpu > 1 else "none",
+                   "l2": f"input {args.mib_per_gpu} MiB per step >> 126 MB L2, no flush needed"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["n"], "clocks": clocks,
-        "compression_ratio": out_bytes / n, "parity": parity,
+        "compression_ratio": (out_bytes / n) if wl != "checksum" else None, "parity": parity,
         "pct_hbm_peak_input_only": 100.0 * (value / ngpu) / peak,
     }
     print(json.dumps(line), flush=True)
