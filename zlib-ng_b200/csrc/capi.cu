@@ -294,6 +294,13 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
         zng_b200_ctx_destroy(ctx);
         return ZNG_B200_MEM_ERROR;
     }
+    // The hash-head / prev tables are hit with random 2-byte accesses; the default L2 fetch granularity pulls more
+    // than one 32-byte sector per miss (measured: ~58 B of DRAM reads per lookup).  Ask for sector-sized fetches.
+    {
+        size_t gran = 32;
+        if (const char* e = getenv("ZNG_B200_L2FETCH")) gran = (size_t)atoi(e);
+        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    }
     build_x2n(ctx->x2n);
     *out = ctx;
     return ZNG_B200_OK;

@@ -6,114 +6,184 @@
 //   arch/generic/adler32_c.c:11-54, adler32_p.h:11-12      zng_adler32: BASE 65521
 //   adler32.c:32-54                                        adler32_combine
 //
-// Tile kernel: one CTA stages a tile (<= 64 KiB; a deflate chunk when called per chunk) in shared
-// memory with coalesced 128-bit loads; 256 threads each run a table-driven CRC over a 256-byte
-// slice (initial value 0) and multiply the slice remainder by x^(8 * bytes-after-slice) so that a
-// plain XOR over the slices is the CRC of the tile; Adler-32 is the pair (sum b, sum b*(n-j)).
-// Fold kernels: per-tile values -> one value, using crc32_combine's algebra (associative, so every
-// tile is shifted by the byte count that follows it and XOR-reduced) and adler32_combine's sums.
+// Tile kernel (v2).  The SM has no carry-less multiply, so CRC-32 is table driven: one shared-memory lookup per
+// input byte.  To run those lookups at the full 32 lanes / clock, the four byte tables are stored ONCE PER LANE
+// (address = table + byte*128 + lane*4: lane l only ever touches bank l -- conflict free; 4 x 32 KiB), and the data
+// never passes through shared memory at all: one warp owns one tile (<= 64 KiB) and streams it with coalesced
+// 128-bit loads, 512 bytes per row.  Lane l keeps four accumulators, one per 32-bit word of its 16 bytes; the
+// words of one accumulator are 512 bytes apart in the stream, so its tables advance the CRC state by 512 bytes
+// instead of 4 (T_k[b] = (b << 8k) * x^(8*512) mod P) -- same number of lookups as slicing-by-4, but coalesced loads
+// and 4 independent dependency chains per lane.  After the last row each accumulator is multiplied by
+// x^(8 * bytes between its word and the end of the rows) and the 128 accumulators are XORed.  Unaligned heads (< 16
+// bytes) and tails (< 512 bytes) go through a plain slicing-by-4 loop on lane 0.  Adler-32 rides along on the same
+// registers with dp4a: per word sum(b) and sum(t*b), per row a running sum gives the position weights.
+// Fold kernels: per-tile values -> one value; Horner over equal-length tiles, then crc32_combine's algebra.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace zb {
 
-constexpr int kCkThreads = 256;
-constexpr uint32_t kCkSlice = 256;      // bytes per thread
+constexpr int      kCkWarps  = 32;           // tiles in flight per CTA (one per warp)
+constexpr uint32_t kCkRow    = 512;          // bytes per warp row (32 lanes x 16)
 
-struct CkSmem {
-    uint32_t tile[kChunkMax / 4];
-    uint32_t crctab[4][256];
+struct X2N { uint32_t v[32]; };            // x^(2^k) mod P, k = 0..31 (crc32_braid_tbl.h:9437-9444 holds the same values)
+
+struct CkShared {
+    uint32_t big[4][256][32];                // lane-private copies of the advance-by-512-bytes tables (128 KiB)
+    uint32_t t4[4][256];                     // ordinary slicing-by-4 tables (heads / tails)
+    uint32_t klast[128];                     // x^(8 * (512 - 16*lane - 4*k)): last-row accumulators -> end of the rows
     uint32_t x2n[32];
-    uint32_t red_crc[8];
-    uint32_t red_s1[8];
-    unsigned long long red_s2[8];
 };
 
-__global__ void __launch_bounds__(kCkThreads)
-checksum_tiles_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t tile_bytes, uint32_t ntiles,
-                      uint32_t* __restrict__ crcs, uint32_t* __restrict__ adlers) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CkSmem& s = *reinterpret_cast<CkSmem*>(smem_raw);
-    const unsigned tid = threadIdx.x;
-    for (uint32_t i = tid; i < 1024u; i += kCkThreads) s.crctab[i >> 8][i & 255u] = crc_table_entry(i & 255u, (int)(i >> 8));
-    if (tid == 0) build_x2n(s.x2n);
-    const uint8_t* wb = reinterpret_cast<const uint8_t*>(s.tile);
+// c advanced over one 32-bit word of data (slicing-by-4, crc32_braid_c.c semantics for N = 1, W = 4)
+__device__ __forceinline__ uint32_t crc_word(const CkShared& s, uint32_t c, uint32_t w) {
+    w ^= c;
+    return s.t4[3][w & 0xffu] ^ s.t4[2][(w >> 8) & 0xffu] ^ s.t4[1][(w >> 16) & 0xffu] ^ s.t4[0][w >> 24];
+}
 
-    for (uint32_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+// bytes [p, p+len) through lane-0 style serial code (any alignment)
+__device__ uint32_t crc_serial(const CkShared& s, uint32_t c, const uint8_t* p, uint32_t len) {
+    while (len && (reinterpret_cast<uintptr_t>(p) & 3u)) { c = s.t4[0][(c ^ *p++) & 0xffu] ^ (c >> 8); len--; }
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+    for (; len >= 4u; len -= 4u) c = crc_word(s, c, __ldg(w++));
+    p = reinterpret_cast<const uint8_t*>(w);
+    while (len--) c = s.t4[0][(c ^ *p++) & 0xffu] ^ (c >> 8);
+    return c;
+}
+
+template <bool kCrc, bool kAdler>
+__global__ void __launch_bounds__(kCkWarps * 32, 1)
+checksum_tiles_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t tile_bytes, uint32_t ntiles,
+                      uint32_t* __restrict__ crcs, uint32_t* __restrict__ adlers, const X2N x2n_host) {
+    extern __shared__ __align__(16) unsigned char ck_smem[];
+    CkShared& s = *reinterpret_cast<CkShared*>(ck_smem);
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (kCrc) {
+        if (tid < 32u) s.x2n[tid] = x2n_host.v[tid];
+        s.t4[tid >> 8][tid & 255u] = crc_table_entry(tid & 255u, (int)(tid >> 8));
         __syncthreads();
+        const uint32_t adv = x2nmodp(s.x2n, kCkRow, 3);                         // x^(8*512)
+        const uint32_t v = multmodp(adv, (tid & 255u) << (8u * (tid >> 8)));     // state with one byte set, 512 bytes later
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) s.big[tid >> 8][tid & 255u][r] = v;
+        if (tid < 128u) s.klast[tid] = x2nmodp(s.x2n, kCkRow - 16u * (tid >> 2) - 4u * (tid & 3u), 3);
+        __syncthreads();
+    }
+    // per-lane byte offsets into `big`: table k at k*32768, entry b at b*128, this lane's copy at lane*4
+    const unsigned char* bigb = reinterpret_cast<const unsigned char*>(&s.big[0][0][0]) + lane * 4u;
+
+    for (uint32_t ti = blockIdx.x * kCkWarps + warp; ti < ntiles; ti += gridDim.x * kCkWarps) {
         const size_t off = (size_t)ti * tile_bytes;
         const uint32_t len = (uint32_t)min((size_t)tile_bytes, n - off);
         const uint8_t* src = in + off;
-        {
-            uint8_t* tb = reinterpret_cast<uint8_t*>(s.tile);
-            const uint32_t nvec = len >> 4;
-            if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0u) {
-                const uint4* g = reinterpret_cast<const uint4*>(src);
-                uint4* t4 = reinterpret_cast<uint4*>(s.tile);
-                for (uint32_t i = tid; i < nvec; i += kCkThreads) t4[i] = __ldg(g + i);
-            } else {
-                for (uint32_t i = tid; i < (nvec << 4); i += kCkThreads) tb[i] = src[i];
-            }
-            for (uint32_t i = (nvec << 4) + tid; i < len; i += kCkThreads) tb[i] = src[i];
-        }
-        __syncthreads();
+        const uint32_t head = min((uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u), len);
+        const uint32_t rows = (len - head) / kCkRow;
+        const uint32_t body = rows * kCkRow, tail = len - head - body;
+        const uint4* rowp = reinterpret_cast<const uint4*>(src + head) + lane;
 
-        uint32_t crc = 0, s1 = 0; unsigned long long s2 = 0;
-        const uint32_t beg = tid * kCkSlice;
-        if (beg < len || tid == 0) {
-            const uint32_t end = min(beg + kCkSlice, len);
-            uint32_t c = (tid == 0) ? 0xffffffffu : 0u;          // pre-inversion rides on slice 0
-            uint32_t i = beg;
-            for (; i + 4u <= end; i += 4u) {
-                uint32_t w = s.tile[i >> 2] ^ c;
-                c = s.crctab[3][w & 0xffu] ^ s.crctab[2][(w >> 8) & 0xffu] ^ s.crctab[1][(w >> 16) & 0xffu] ^ s.crctab[0][w >> 24];
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;                                 // CRC accumulators (words 0..3 of the lane's 16 bytes)
+        uint32_t A = 0, U = 0, Q = 0;                                            // Adler: sum b, sum (offset in lane piece)*b, row-weighted sum
+        if (kCrc && lane == 0) c0 = crc_serial(s, 0xffffffffu, src, head);       // pre-inversion + head bytes ride on the first word
+        if (rows) {
+            // three rows in flight per warp (32 warps x 3 x 512 B = 48 KiB per SM) to cover the HBM latency
+#define ZB_LK(k, w, sh) (*reinterpret_cast<const uint32_t*>(bigb + (k) * 32768u + ((sh) >= 7 ? (((w) >> ((sh) - 7)) & 0x7f80u) : (((w) << 7) & 0x7f80u))))
+#define ZB_FOLD_ROW(v)                                                                                              \
+            do {                                                                                                    \
+                if (kCrc) {                                                                                         \
+                    const uint32_t w0 = (v).x ^ c0, w1 = (v).y ^ c1, w2 = (v).z ^ c2, w3 = (v).w ^ c3;              \
+                    c0 = ZB_LK(0, w0, 0) ^ ZB_LK(1, w0, 8) ^ ZB_LK(2, w0, 16) ^ ZB_LK(3, w0, 24);                   \
+                    c1 = ZB_LK(0, w1, 0) ^ ZB_LK(1, w1, 8) ^ ZB_LK(2, w1, 16) ^ ZB_LK(3, w1, 24);                   \
+                    c2 = ZB_LK(0, w2, 0) ^ ZB_LK(1, w2, 8) ^ ZB_LK(2, w2, 16) ^ ZB_LK(3, w2, 24);                   \
+                    c3 = ZB_LK(0, w3, 0) ^ ZB_LK(1, w3, 8) ^ ZB_LK(2, w3, 16) ^ ZB_LK(3, w3, 24);                   \
+                }                                                                                                   \
+                if (kAdler) {                                                                                       \
+                    const uint32_t s0 = __dp4a((v).x, 0x01010101u, 0u), s1 = __dp4a((v).y, 0x01010101u, 0u);        \
+                    const uint32_t s2 = __dp4a((v).z, 0x01010101u, 0u), s3 = __dp4a((v).w, 0x01010101u, 0u);        \
+                    U = __dp4a((v).x, 0x03020100u, __dp4a((v).y, 0x03020100u, __dp4a((v).z, 0x03020100u, __dp4a((v).w, 0x03020100u, U)))); \
+                    U += 4u * (s1 + 2u * s2 + 3u * s3);                                                             \
+                    Q += A;                                                                                         \
+                    A += s0 + s1 + s2 + s3;                                                                         \
+                }                                                                                                   \
+            } while (0)
+            const uint32_t adv = rows - 1u;                                      // rows folded through the tables; the last one is multiplied
+            uint4 q0 = __ldg(rowp), q1 = q0, q2 = q0;
+            if (rows > 1u) q1 = __ldg(rowp + 32u);
+            if (rows > 2u) q2 = __ldg(rowp + 64u);
+            uint32_t r = 0;
+            for (; r + 3u <= adv; r += 3u) {
+                uint4 v = q0; if (r + 3u < rows) q0 = __ldg(rowp + (size_t)(r + 3u) * 32u); ZB_FOLD_ROW(v);
+                v = q1;       if (r + 4u < rows) q1 = __ldg(rowp + (size_t)(r + 4u) * 32u); ZB_FOLD_ROW(v);
+                v = q2;       if (r + 5u < rows) q2 = __ldg(rowp + (size_t)(r + 5u) * 32u); ZB_FOLD_ROW(v);
             }
-            for (; i < end; i++) c = (c >> 8) ^ s.crctab[0][(c ^ wb[i]) & 0xffu];
-            const uint32_t after = len - end;
-            crc = after ? multmodp(x2nmodp(s.x2n, after, 3), c) : c;
-            if (adlers) {
-                uint32_t a = 0, b = 0;                            // 256 bytes * 255 * 256 < 2^32
-                for (uint32_t j = beg; j < end; j++) { uint32_t by = wb[j]; a += by; b += (end - j) * by; }
-                s1 = a;
-                s2 = (unsigned long long)b + (unsigned long long)a * after;
+            const uint32_t rem = adv - r;                                        // 0..2 table rows left; q0, q1, q2 hold rows r, r+1, r+2
+            if (rem >= 1u) ZB_FOLD_ROW(q0);
+            if (rem >= 2u) ZB_FOLD_ROW(q1);
+            const uint4 v = rem == 0u ? q0 : (rem == 1u ? q1 : q2);
+            if (kCrc) {                                                          // last row: to the end of the rows by multiplication
+                c0 = multmodp(s.klast[4u * lane + 0u], c0 ^ v.x);
+                c1 = multmodp(s.klast[4u * lane + 1u], c1 ^ v.y);
+                c2 = multmodp(s.klast[4u * lane + 2u], c2 ^ v.z);
+                c3 = multmodp(s.klast[4u * lane + 3u], c3 ^ v.w);
+            }
+            if (kAdler) {
+                const uint32_t s0 = __dp4a(v.x, 0x01010101u, 0u), s1 = __dp4a(v.y, 0x01010101u, 0u);
+                const uint32_t s2 = __dp4a(v.z, 0x01010101u, 0u), s3 = __dp4a(v.w, 0x01010101u, 0u);
+                U = __dp4a(v.x, 0x03020100u, __dp4a(v.y, 0x03020100u, __dp4a(v.z, 0x03020100u, __dp4a(v.w, 0x03020100u, U))));
+                U += 4u * (s1 + 2u * s2 + 3u * s3);
+                Q += A;
+                A += s0 + s1 + s2 + s3;
             }
         }
+        if (kCrc) {
+            uint32_t c = c0 ^ c1 ^ c2 ^ c3;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            crc ^= __shfl_xor_sync(ZB_FULL, crc, d);
-            s1 += __shfl_xor_sync(ZB_FULL, s1, d);
-            s2 += __shfl_xor_sync(ZB_FULL, s2, d);
+            for (int d = 16; d > 0; d >>= 1) c ^= __shfl_xor_sync(ZB_FULL, c, d);
+            if (lane == 0) {
+                c = crc_serial(s, c, src + head + body, tail);
+                if (crcs) crcs[ti] = ~c;
+            }
         }
-        if ((tid & 31u) == 0) { s.red_crc[tid >> 5] = crc; s.red_s1[tid >> 5] = s1; s.red_s2[tid >> 5] = s2; }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t c = 0; unsigned long long a = 1ull, b = len;
-            for (int w = 0; w < kCkThreads / 32; w++) { c ^= s.red_crc[w]; a += s.red_s1[w]; b += s.red_s2[w]; }
-            if (crcs) crcs[ti] = ~c;
-            if (adlers) adlers[ti] = (uint32_t)(a % kAdlerBase) | ((uint32_t)(b % kAdlerBase) << 16);
+        if (kAdler) {
+            // byte j of the tile weighs (len - j); a byte of the rows sits at j = head + 512 r + 16 lane + (offset in piece)
+            unsigned long long s1 = A, s2 = 0;
+            if (rows) {
+                const unsigned long long rem_last = (unsigned long long)(len - head) - (unsigned long long)kCkRow * (rows - 1u);
+                s2 = (rem_last - 16ull * lane) * A + (unsigned long long)kCkRow * Q - U;
+            }
+            for (uint32_t j = lane; j < head; j += 32u) { const uint32_t b = src[j]; s1 += b; s2 += (unsigned long long)(len - j) * b; }
+            for (uint32_t j = head + body + lane; j < len; j += 32u) { const uint32_t b = src[j]; s1 += b; s2 += (unsigned long long)(len - j) * b; }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { s1 += __shfl_xor_sync(ZB_FULL, s1, d); s2 += __shfl_xor_sync(ZB_FULL, s2, d); }
+            if (lane == 0 && adlers) adlers[ti] = (uint32_t)((1ull + s1) % kAdlerBase) | ((uint32_t)((len + s2) % kAdlerBase) << 16);
         }
     }
 }
 
 // ---------------------------------------------------------------- folds (single CTA; 8 B per tile of input)
-// crc = crc32_combine(...combine(combine(init, c_0, l_0), c_1, l_1)..., c_{k-1}, l_{k-1})
-//     = init * x^(8n)  ^  XOR_i c_i * x^(8 * bytes after tile i)          (crc32_braid_comb.c:16-18)
+// crc = crc32_combine(...combine(combine(init, c_0, l_0), c_1, l_1)..., c_{k-1}, l_{k-1})            (crc32_braid_comb.c:16-18)
+// Every thread folds a run of consecutive tiles by Horner (acc = acc * x^(8*tile_bytes) ^ c_i: one multmodp per tile),
+// moves its partial to the end of the buffer with one x2nmodp, and the partials are XORed.
 __global__ void __launch_bounds__(1024)
 crc32_fold_kernel(const uint32_t* __restrict__ crcs, uint32_t ntiles, uint32_t tile_bytes, size_t n, uint32_t init,
-                  uint32_t* __restrict__ result) {
+                  uint32_t* __restrict__ result, const X2N x2n_host) {
     __shared__ uint32_t x2n[32];
     __shared__ uint32_t red[32];
-    if (threadIdx.x == 0) build_x2n(x2n);
+    if (threadIdx.x < 32u) x2n[threadIdx.x] = x2n_host.v[threadIdx.x];
     __syncthreads();
+    const uint32_t per = (ntiles + blockDim.x - 1u) / blockDim.x;
+    const uint32_t t0 = min(threadIdx.x * per, ntiles), t1 = min(t0 + per, ntiles);
     uint32_t acc = 0;
-    for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) {
-        const size_t end = min((size_t)(i + 1u) * tile_bytes, n);
-        const size_t after = n - end;
-        const uint32_t c = crcs[i];
-        acc ^= (after && c) ? multmodp(x2nmodp(x2n, after, 3), c) : c;
+    if (t0 < t1) {
+        const uint32_t ktile = x2nmodp(x2n, tile_bytes, 3);
+        for (uint32_t i = t0; i < t1; i++) {
+            const size_t beg = (size_t)i * tile_bytes;
+            const size_t li = min((size_t)tile_bytes, n - beg);
+            acc = (acc ? multmodp(li == tile_bytes ? ktile : x2nmodp(x2n, li, 3), acc) : 0u) ^ crcs[i];
+        }
+        const size_t end = min((size_t)t1 * tile_bytes, n);
+        if (n - end && acc) acc = multmodp(x2nmodp(x2n, n - end, 3), acc);
     }
-    if (threadIdx.x == 0 && init && n) acc ^= multmodp(x2nmodp(x2n, n, 3), init);
-    if (threadIdx.x == 0 && init && !n) acc ^= init;
+    if (threadIdx.x == 0 && init) acc ^= n ? multmodp(x2nmodp(x2n, n, 3), init) : init;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc ^= __shfl_xor_sync(ZB_FULL, acc, d);
     if ((threadIdx.x & 31u) == 0) red[threadIdx.x >> 5] = acc;
@@ -156,20 +226,38 @@ adler32_fold_kernel(const uint32_t* __restrict__ adlers, uint32_t ntiles, uint32
     }
 }
 
+static const X2N& host_x2n() {
+    static const X2N t = [] { X2N x; build_x2n(x.v); return x; }();
+    return t;
+}
+
+template <bool kCrc, bool kAdler>
+static cudaError_t launch_tiles(const uint8_t* in, size_t n, uint32_t tile_bytes, uint32_t ntiles, uint32_t* crcs, uint32_t* adlers,
+                                int num_sms, cudaStream_t stream) {
+    const int smem = kCrc ? (int)sizeof(CkShared) : 0;
+    if (smem) {
+        cudaError_t e = cudaFuncSetAttribute(checksum_tiles_kernel<kCrc, kAdler>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    uint32_t grid = (uint32_t)num_sms * (kCrc ? 1u : 2u);
+    const uint32_t need = (ntiles + kCkWarps - 1u) / kCkWarps;
+    if (grid > need) grid = need;
+    checksum_tiles_kernel<kCrc, kAdler><<<grid, kCkWarps * 32, smem, stream>>>(in, n, tile_bytes, ntiles, crcs, adlers, host_x2n());
+    return cudaGetLastError();
+}
+
 cudaError_t launch_checksum_tiles(const uint8_t* in, size_t n, uint32_t tile_bytes, uint32_t ntiles,
                                   uint32_t* crcs, uint32_t* adlers, int num_sms, cudaStream_t stream) {
     if (ntiles == 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(checksum_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CkSmem));
-    if (e != cudaSuccess) return e;
-    uint32_t grid = (uint32_t)num_sms * 3u;
-    if (grid > ntiles) grid = ntiles;
-    checksum_tiles_kernel<<<grid, kCkThreads, sizeof(CkSmem), stream>>>(in, n, tile_bytes, ntiles, crcs, adlers);
-    return cudaGetLastError();
+    if (crcs && adlers) return launch_tiles<true, true>(in, n, tile_bytes, ntiles, crcs, adlers, num_sms, stream);
+    if (crcs) return launch_tiles<true, false>(in, n, tile_bytes, ntiles, crcs, nullptr, num_sms, stream);
+    if (adlers) return launch_tiles<false, true>(in, n, tile_bytes, ntiles, nullptr, adlers, num_sms, stream);
+    return cudaSuccess;
 }
 
 cudaError_t launch_crc32_fold(const uint32_t* crcs, uint32_t ntiles, uint32_t tile_bytes, size_t n, uint32_t init,
                               uint32_t* result, cudaStream_t stream) {
-    crc32_fold_kernel<<<1, 1024, 0, stream>>>(crcs, ntiles, tile_bytes, n, init, result);
+    crc32_fold_kernel<<<1, 1024, 0, stream>>>(crcs, ntiles, tile_bytes, n, init, result, host_x2n());
     return cudaGetLastError();
 }
 
