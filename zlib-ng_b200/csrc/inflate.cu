@@ -29,6 +29,10 @@ namespace zb {
 
 constexpr int      kInfWarps = 8;          // members in flight per CTA
 constexpr uint32_t kInfStage = 4096;       // output capacity up to which a member is assembled in shared memory
+constexpr uint32_t kRootBits = 9;          // literal/length codes up to this length decode with one table lookup
+constexpr uint32_t kDRootBits = 7;         // same for distance codes
+constexpr uint32_t kLitLimit = 256u << 4;  // root entries below this are literals (symbol << 4 | length)
+constexpr uint16_t kSlowEntry = 0xffffu;   // root-table entry of a longer (or unused) codeword: ballot decode decides
 
 // error strings: ids are what d_detail carries in its low byte (inflate.c SET_BAD sites)
 __host__ const char* inflate_msg(uint32_t id) {
@@ -54,6 +58,9 @@ struct InfWarp {
     uint16_t dsym[32];
     uint16_t csym[32];
     uint8_t  lens[320];
+    uint32_t tfirst[16], tcount[16], toff[16];   // the code under table construction, per length
+    uint16_t ltab[1u << kRootBits];              // literal/length root table of the current dynamic block
+    uint16_t dtab[1u << kDRootBits];             // distance root table
     alignas(16) uint8_t stage[kInfStage];
 };
 struct InfShared {
@@ -61,6 +68,8 @@ struct InfShared {
     uint32_t x2n[32];
     uint16_t fix_lsym[288];
     uint16_t fix_dsym[32];
+    uint16_t fix_ltab[1u << kRootBits];
+    uint16_t fix_dtab[1u << kDRootBits];
     InfWarp w[kInfWarps];
 };
 
@@ -123,6 +132,25 @@ __device__ __forceinline__ int decode_sym(uint64_t hold, uint32_t bits, const Co
     return (int)sym[idx];
 }
 
+// Root table of a literal/length code (the shortcut inflate_table's root table gives the reference, inftrees.c:137-291):
+// entry e = the kRootBits next bits of the stream, LSB first; value = symbol << 4 | code length when a codeword of
+// <= kRootBits bits starts there, kSlowEntry otherwise.  Every lane resolves 16 entries with the canonical rule.
+__device__ void build_root_table(const Code& c, const uint16_t* sym, InfWarp& P, uint16_t* tab, uint32_t root, unsigned lane) {
+    if (lane >= 1u && lane < 16u) { P.tfirst[lane] = c.first; P.tcount[lane] = c.count; P.toff[lane] = c.off; }
+    __syncwarp();
+    const uint32_t top = min(c.maxlen, root);
+    for (uint32_t e = lane; e < (1u << root); e += 32u) {
+        const uint32_t rev = __brev(e);
+        uint16_t ent = kSlowEntry;
+        for (uint32_t l = 1; l <= top; l++) {
+            const uint32_t d = (rev >> (32u - l)) - P.tfirst[l];
+            if (d < P.tcount[l]) { ent = (uint16_t)((sym[P.toff[l] + d] << 4) | l); break; }
+        }
+        tab[e] = ent;
+    }
+    __syncwarp();
+}
+
 // Bit reader over 4-byte-aligned words; only bytes below `e` (byte offset from w) count as input.
 struct Reader {
     const uint32_t* w; uint32_t wi, e; uint64_t hold; uint32_t bits;
@@ -137,13 +165,12 @@ struct Reader {
             hold = x >> (8u * sk); bits = 8u * (valid - sk); wi++;
         }
     }
-    __device__ __forceinline__ void refill() {               // after this: bits >= 33, or every input byte is in `hold`
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-            if (bits <= 32u && 4u * wi < e) {
-                uint32_t valid = e - 4u * wi; if (valid > 4u) valid = 4u;
-                uint32_t x = __ldg(w + wi);
-                if (valid < 4u) x &= (1u << (8u * valid)) - 1u;
+    __device__ __forceinline__ void refill() {               // after this: bits >= 32, or every input byte is in `hold`
+        if (bits < 32u) {
+            if (4u * wi + 4u <= e) { hold |= (uint64_t)__ldg(w + wi) << bits; bits += 32u; wi++; }
+            else if (4u * wi < e) {                          // the last, partial word
+                const uint32_t valid = e - 4u * wi;
+                const uint32_t x = __ldg(w + wi) & ((1u << (8u * valid)) - 1u);
                 hold |= (uint64_t)x << bits; bits += 8u * valid; wi++;
             }
         }
@@ -279,8 +306,8 @@ __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, u
             if (in_short) INF_MORE_IN();
             continue;
         }
-        Code cl, cd; const uint16_t* lsym; const uint16_t* dsym;
-        if (type == 1u) { cl = FL; cd = FD; lsym = S.fix_lsym; dsym = S.fix_dsym; }
+        Code cl, cd; const uint16_t* lsym; const uint16_t* dsym; const uint16_t* ltab; const uint16_t* dtab;
+        if (type == 1u) { cl = FL; cd = FD; lsym = S.fix_lsym; dsym = S.fix_dsym; ltab = S.fix_ltab; dtab = S.fix_dtab; }
         else {                                              // TABLE
             b.refill();
             if (b.bits < 14u) INF_MORE_IN();
@@ -337,12 +364,31 @@ __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, u
             if (build_code(P.lens, nlen, 1, P.lsym, P, cl, lane)) INF_BAD(E_LITLENS);
             if (build_code(P.lens + nlen, ndist, 2, P.dsym, P, cd, lane)) INF_BAD(E_DISTS);
             __syncwarp();
-            lsym = P.lsym; dsym = P.dsym;
+            lsym = P.lsym; dsym = P.dsym; ltab = P.ltab; dtab = P.dtab;
+            build_root_table(cl, lsym, P, P.ltab, kRootBits, lane);
+            build_root_table(cd, dsym, P, P.dtab, kDRootBits, lane);
         }
         for (;;) {                                          // LEN .. MATCH
             b.refill();
             uint32_t cb = 0;
-            const int sym = decode_sym(b.hold, b.bits, cl, lsym, lane, cb);
+            int sym;
+            uint32_t ent = ltab[(uint32_t)b.hold & ((1u << kRootBits) - 1u)];
+            if (ent < kLitLimit && b.bits >= 3u * kRootBits && o + 3u <= cap) {
+                // literal run: up to three literals from the 32 buffered bits, stored by lanes 0..2 in one instruction
+                uint32_t h = (uint32_t)b.hold >> (ent & 15u), used = ent & 15u, nlit = 1, lit = ent >> 4;
+                const uint32_t e1 = ltab[h & ((1u << kRootBits) - 1u)];
+                if (e1 < kLitLimit) {
+                    h >>= (e1 & 15u); used += e1 & 15u; nlit = 2; if (lane == 1u) lit = e1 >> 4;
+                    const uint32_t e2 = ltab[h & ((1u << kRootBits) - 1u)];
+                    if (e2 < kLitLimit) { used += e2 & 15u; nlit = 3; if (lane == 2u) lit = e2 >> 4; }
+                }
+                if (lane < nlit) ob[o + lane] = (uint8_t)lit;
+                b.drop(used);
+                o += nlit;
+                continue;
+            }
+            if (ent != kSlowEntry && (ent & 15u) <= b.bits) { sym = (int)(ent >> 4); cb = ent & 15u; }   // one lookup
+            else sym = decode_sym(b.hold, b.bits, cl, lsym, lane, cb);
             if (sym == -1) INF_MORE_IN();
             if (sym == -2 || sym > 285) INF_BAD(E_LITCODE);
             if (sym < 256) {
@@ -358,7 +404,10 @@ __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, u
             len_base((uint32_t)sym - 257u, len, lx);
             if (lx) { if (b.bits < lx) INF_MORE_IN(); len += b.peek(lx); b.drop(lx); }
             b.refill();
-            const int ds = decode_sym(b.hold, b.bits, cd, dsym, lane, cb);
+            int ds;
+            ent = dtab[(uint32_t)b.hold & ((1u << kDRootBits) - 1u)];
+            if (ent != kSlowEntry && (ent & 15u) <= b.bits) { ds = (int)(ent >> 4); cb = ent & 15u; }
+            else ds = decode_sym(b.hold, b.bits, cd, dsym, lane, cb);
             if (ds == -1) INF_MORE_IN();
             if (ds == -2 || ds > 29) INF_BAD(E_DISTCODE);
             b.drop(cb);
@@ -367,11 +416,16 @@ __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, u
             if (dx) { if (b.bits < dx) INF_MORE_IN(); dist += b.peek(dx); b.drop(dx); }
             if (dist > o) INF_BAD(E_FAR);                   // nothing precedes this call's output (no window yet)
             const uint32_t can = min(len, cap - o);
-            __syncwarp();                                   // earlier stores of other lanes -> visible
-            const uint8_t* from = ob + o - dist;
-            if (dist >= can) { for (uint32_t k = lane; k < can; k += 32u) ob[o + k] = from[k]; }
-            else { for (uint32_t k = lane; k < can; k += 32u) ob[o + k] = from[k % dist]; }
-            o += can;
+            // out[i] = out[i - dist] byte-serially (chunkset_tpl.h): waves of min(32, D) bytes from D back, where D is a
+            // multiple of dist that doubles while it is below 32 (every copied wave is one more period of the run)
+            uint32_t D = dist, rem = can;
+            while (rem) {
+                __syncwarp();                               // earlier stores of other lanes -> visible
+                const uint32_t wave = min(min(D, 32u), rem);
+                if (lane < wave) ob[o + lane] = ob[o - D + lane];
+                o += wave; rem -= wave;
+                if (D < 32u) D += D;
+            }
             if (can < len) INF_MORE_OUT();
         }
     }
@@ -428,9 +482,13 @@ inflate_members_kernel(const uint8_t* __restrict__ in, const uint64_t* __restric
     __syncwarp();
     build_code(P.lens, 288u, 1, warp == 0 ? S.fix_lsym : P.lsym, P, FL, lane);
     __syncwarp();
+    if (warp == 0) build_root_table(FL, S.fix_lsym, P, S.fix_ltab, kRootBits, lane);
+    __syncwarp();
     P.lens[lane] = 5;
     __syncwarp();
     build_code(P.lens, 32u, 2, warp == 0 ? S.fix_dsym : P.dsym, P, FD, lane);
+    __syncwarp();
+    if (warp == 0) build_root_table(FD, S.fix_dsym, P, S.fix_dtab, kDRootBits, lane);
     __syncthreads();
 
     for (;;) {
