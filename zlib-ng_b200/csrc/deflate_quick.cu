@@ -97,7 +97,7 @@ __device__ uint32_t quick_parse_warp(const Window W, uint32_t n, uint16_t* head,
         }
         uint32_t sink = 0;                                    // "touch" loads: real loads whose values are never needed
         if (flags & 8u) {                                     // (the fill they trigger is: 16 sectors = 512 B of window ahead)
-            if (lane < 16u) sink = W.word((((p + W.skew + 160u) & ~31u) >> 2) + 8u * lane);
+            if (lane < 16u && p + 160u + 512u <= n) sink = W.word((((p + W.skew + 160u) & ~31u) >> 2) + 8u * lane);
         }
         if (flags & 16u) {
 #pragma unroll
