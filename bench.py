@@ -266,7 +266,7 @@ def run_reference(args):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "compression_ratio": res["ratio"],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ B200 arm
@@ -369,7 +369,7 @@ def run_b200(args):
 
             def call():
                 state["out_len"], _, _ = ctx.deflate_host(h_in, n, CHUNK, level, False, h_out, cap)
-            return call, (lambda: (n, int(state["out_len"]))), "zng_b200_deflate_host (pinned host in/out, 6 x 64 MiB slabs in flight on separate streams)"
+            return call, (lambda: (n, int(state["out_len"]))), "zng_b200_deflate_host (pinned host in/out, 4 x 128 MiB slabs in flight on separate streams)"
         e2e_fn = make_e2e
         alg_bytes = lambda ob: n + ob                                     # in + out per chunk, x chunks per launch
         kernel_name = "quick_parse_kernel + static_emit_kernel (+ checksum_tiles_kernel)" if level == 1 else "fast_parse_kernel + block_emit_kernel (+ checksum_tiles_kernel)"
@@ -550,13 +550,31 @@ def run_b200(args):
         "compression_ratio": (out_bytes / n) if wl != "checksum" else None, "parity": parity,
         "pct_hbm_peak_input_only": 100.0 * (value / ngpu) / peak,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if ngpu > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of this run, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # libraries (NCCL's version banner, torchrun notices) must not share stdout with the JSON line: everything
+    # else this process or its libraries print goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

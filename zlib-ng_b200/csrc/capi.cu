@@ -15,8 +15,8 @@ using namespace zb;
 
 namespace {
 constexpr int kCounters = 64;
-constexpr int kPipe = 6;                       // slabs in flight on the host path
-constexpr uint32_t kSlabChunks = 1024;         // 64 MiB of input per slab at 64 KiB chunks
+constexpr int kPipeMax = 16;                   // most slabs in flight on the host path (ctx->pipe of them are used)
+constexpr uint32_t kSlabChunksDefault = 2048;  // 128 MiB of input per slab at 64 KiB chunks (ctx->slab_chunks, env ZNG_B200_SLAB_CHUNKS)
 constexpr uint32_t kBatchChunks = 16384;       // chunks per K1a/K1b launch pair (token scratch: 4 GiB at 64 KiB chunks)
 
 // K1a -> K1b hand-over: LZ77 token lists (4 B per input byte) + token counts
@@ -86,7 +86,9 @@ struct zng_b200_ctx {
     uint32_t* d_result = nullptr;              // small result area
     uint32_t* h_result = nullptr;              // pinned
     // host path
-    Slab slab[kPipe];
+    Slab slab[kPipeMax];
+    int pipe = 4;                              // slabs in flight (env ZNG_B200_PIPE); measured: 2048 x 4 -> 23.2 GB/s e2e, 1024 x 6 -> 20.6
+    uint32_t slab_chunks = kSlabChunksDefault;
     bool slabs_ready = false;
     size_t slab_stride = 0;
     InfSlab inf[kInfPipe];
@@ -223,17 +225,17 @@ int ensure_slabs(zng_b200_ctx* ctx) {
     if (ctx->slabs_ready) return 0;
     const size_t stride = zng_b200_deflate_bound(ZNG_B200_CHUNK_MAX);
     ctx->slab_stride = stride;
-    for (int i = 0; i < kPipe; i++) {
+    for (int i = 0; i < ctx->pipe; i++) {
         Slab& s = ctx->slab[i];
         CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
         CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreate");
         // 32 KiB in front of the slab hold the stream bytes that precede it (level 2: stale-window image of a short last chunk)
-        CK(cudaMalloc(&s.d_in_alloc, (size_t)kSlabChunks * ZNG_B200_CHUNK_MAX + kWSize), "cudaMalloc(slab in)");
+        CK(cudaMalloc(&s.d_in_alloc, (size_t)ctx->slab_chunks * ZNG_B200_CHUNK_MAX + kWSize), "cudaMalloc(slab in)");
         s.d_in = s.d_in_alloc + kWSize;
-        CK(cudaMalloc(&s.d_slots, (size_t)kSlabChunks * stride), "cudaMalloc(slab slots)");
-        CK(cudaMalloc(&s.d_packed, (size_t)kSlabChunks * stride), "cudaMalloc(slab packed)");
-        CK(cudaMalloc(&s.d_sizes, (size_t)kSlabChunks * 3 * sizeof(uint32_t)), "cudaMalloc(slab sizes)");
-        CK(cudaMalloc(&s.d_offsets, ((size_t)kSlabChunks + 1) * sizeof(uint64_t)), "cudaMalloc(slab offsets)");
+        CK(cudaMalloc(&s.d_slots, (size_t)ctx->slab_chunks * stride), "cudaMalloc(slab slots)");
+        CK(cudaMalloc(&s.d_packed, (size_t)ctx->slab_chunks * stride), "cudaMalloc(slab packed)");
+        CK(cudaMalloc(&s.d_sizes, (size_t)ctx->slab_chunks * 3 * sizeof(uint32_t)), "cudaMalloc(slab sizes)");
+        CK(cudaMalloc(&s.d_offsets, ((size_t)ctx->slab_chunks + 1) * sizeof(uint64_t)), "cudaMalloc(slab offsets)");
         CK(cudaMalloc(&s.d_res, 4 * sizeof(uint32_t)), "cudaMalloc(slab res)");
         CK(cudaHostAlloc(&s.h_meta, 4 * sizeof(uint64_t), cudaHostAllocDefault), "cudaHostAlloc(slab meta)");
     }
@@ -284,6 +286,8 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     ctx->sms = prop.multiProcessorCount;
     if (prop.major < 10) { delete ctx; return ZNG_B200_STREAM_ERROR; }       // sm_100a kernels only
     if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm = v; }
+    if (const char* e = getenv("ZNG_B200_SLAB_CHUNKS")) { int v = atoi(e); if (v >= 64 && v <= 16384) ctx->slab_chunks = (uint32_t)v; }
+    if (const char* e = getenv("ZNG_B200_PIPE")) { int v = atoi(e); if (v >= 2 && v <= kPipeMax) ctx->pipe = v; }
     if (const char* e = getenv("ZNG_B200_CHAINS_L2")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm_l2 = v; }
     if (const char* e = getenv("ZNG_B200_FLAGS")) ctx->k1_flags = (uint32_t)atoi(e);
     if (cudaMalloc(&ctx->counters, kCounters * sizeof(uint32_t)) != cudaSuccess ||
@@ -310,7 +314,7 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < kPipe; i++) {
+    for (int i = 0; i < kPipeMax; i++) {
         Slab& s = ctx->slab[i];
         if (s.d_in_alloc) cudaFree(s.d_in_alloc);
         if (s.d_slots) cudaFree(s.d_slots);
@@ -650,7 +654,7 @@ static int drain_slab(zng_b200_ctx* ctx, Slab& s, uint8_t* h_out, size_t out_cap
 }
 
 static int sync_slabs(zng_b200_ctx* ctx) {
-    for (int i = 0; i < kPipe; i++) {
+    for (int i = 0; i < ctx->pipe; i++) {
         ctx->slab[i].busy = false;
         if (ctx->slab[i].stream) cudaStreamSynchronize(ctx->slab[i].stream);
     }
@@ -667,6 +671,7 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
     int r = ensure_slabs(ctx);
     if (r) return r;
     const size_t stride = ctx->slab_stride;
+    const uint32_t kSlabChunks = ctx->slab_chunks;
     const size_t slab_in = (size_t)kSlabChunks * chunk;
     uint8_t* out = (uint8_t*)h_out;
     size_t out_pos = 0, off = 0;
@@ -727,10 +732,10 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
         s.in_bytes = take;
         s.busy = true;
         off += take;
-        k = (k + 1) % kPipe;
+        k = (k + 1) % ctx->pipe;
         // eager drain, oldest first (output order is slab order): start the D2H of finished slabs now
-        for (int i = 0; i < kPipe; i++) {
-            Slab& o = ctx->slab[(k + i) % kPipe];
+        for (int i = 0; i < ctx->pipe; i++) {
+            Slab& o = ctx->slab[(k + i) % ctx->pipe];
             if (!o.busy) continue;
             if (cudaEventQuery(o.done) != cudaSuccess) break;
             r = drain_slab(ctx, o, out, out_cap, out_pos, crc, adler);
@@ -738,11 +743,11 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
         }
     }
     // drain in issue order
-    for (int i = 0; i < kPipe; i++) {
-        r = drain_slab(ctx, ctx->slab[(k + i) % kPipe], out, out_cap, out_pos, crc, adler);
+    for (int i = 0; i < ctx->pipe; i++) {
+        r = drain_slab(ctx, ctx->slab[(k + i) % ctx->pipe], out, out_cap, out_pos, crc, adler);
         if (r) { sync_slabs(ctx); return r; }
     }
-    for (int i = 0; i < kPipe; i++) CK(cudaStreamSynchronize(ctx->slab[i].stream), "final sync");
+    for (int i = 0; i < ctx->pipe; i++) CK(cudaStreamSynchronize(ctx->slab[i].stream), "final sync");
     *out_len = out_pos;
     if (crc32) *crc32 = crc;
     if (adler32) *adler32 = adler;
