@@ -143,6 +143,38 @@ int zng_b200_inflate_members_host(zng_b200_ctx *ctx, const void *h_in, const uin
 int zng_b200_crc32_host(zng_b200_ctx *ctx, const void *h_buf, size_t n, uint32_t init, uint32_t *result);
 int zng_b200_adler32_host(zng_b200_ctx *ctx, const void *h_buf, size_t n, uint32_t init, uint32_t *result);
 
+/* ---- operator surface: functable.h:26-42 and deflate.h:121-131, one device operator per call --------------
+ * The per-position operators of the reference are __device__ functions inside K1 / K2 / K4 here; these entry points
+ * run exactly that device code on caller-supplied device buffers so each can be checked against its counterpart.
+ * (crc32 / adler32 of the table are zng_b200_crc32 / zng_b200_adler32 above.) */
+/* functable.compare256 (compare256_c.c:12-43) for n_pairs operand pairs: d_out[i] = first differing byte (0..256) of the
+ * 256 bytes at d_a + i*stride and d_b + i*stride.  Both buffers must be readable 16 bytes past the last operand. */
+int zng_b200_op_compare256(zng_b200_ctx *ctx, const void *d_a, const void *d_b, size_t stride, uint32_t n_pairs,
+                           uint32_t *d_out, void *stream);
+/* functable.longest_match (match_tpl.h:26-280, level-2 parameters: chain 4, nice 8) for n_q independent queries on one
+ * window: query i = (strstart d_pos[i], cur_match d_cand[i]); lookahead = n - d_pos[i]; d_prev = the 32768-entry prev[]
+ * table.  d_len[i] = returned length when it is >= 4 else 0, d_start[i] = match_start.  The window must be readable
+ * 280 bytes past n (what the reference's window slack provides). */
+int zng_b200_op_longest_match(zng_b200_ctx *ctx, const void *d_window, uint32_t n, const uint16_t *d_prev,
+                              const uint32_t *d_pos, const uint32_t *d_cand, uint32_t n_q, uint32_t *d_len,
+                              uint32_t *d_start, void *stream);
+/* insert_string(s, str, count) (insert_string_tpl.h:82-104) on d_head[65536] / d_prev[32768]. */
+int zng_b200_op_insert_string(zng_b200_ctx *ctx, const void *d_window, uint16_t *d_head, uint16_t *d_prev, uint32_t str,
+                              uint32_t count, void *stream);
+/* functable.chunkmemset_safe (chunkset_tpl.h:112-283): d_out[pos + i] = d_out[pos + i - dist] for i in 0..len, byte serial. */
+int zng_b200_op_chunkmemset(zng_b200_ctx *ctx, void *d_out, uint32_t pos, uint32_t dist, uint32_t len, void *stream);
+
+/* The host-callable operator table, shaped like struct functable_s for the operators that have a host-buffer form
+ * (functable.h:27,30,31,32,33): each call runs on the GPU through the calling thread's context. */
+struct zng_b200_functable {
+    uint32_t (*adler32)(uint32_t adler, const uint8_t *buf, size_t len);
+    uint8_t *(*chunkmemset_safe)(uint8_t *out, uint8_t *from, unsigned len, unsigned left);
+    uint32_t (*chunksize)(void);
+    uint32_t (*compare256)(const uint8_t *src0, const uint8_t *src1);
+    uint32_t (*crc32)(uint32_t crc, const uint8_t *buf, size_t len);
+};
+const struct zng_b200_functable *zng_b200_functable_get(void);
+
 /* ---- synthetic workload (bench / tests; BASELINE.json "synthetic mixed text/binary") ------- */
 int zng_b200_synth_fill(void *h_buf, size_t n, uint64_t seed, uint64_t offset);
 

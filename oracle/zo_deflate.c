@@ -524,6 +524,32 @@ size_t zo_deflate_tokens(const uint8_t *in, uint32_t len, int level, uint32_t *t
     return tb.n;
 }
 
+/* ---- single operators, for the operator-surface tests (functable.longest_match, insert_string) ---- */
+/* window: `avail` readable bytes of which the first n are data (avail <= 65536); prev: 32768 entries.
+ * Returns what longest_match returns for strstart = pos, cur_match = cand, lookahead = n - pos (match_tpl.h:26-280 with
+ * the level-2 parameters); *start = match_start. */
+uint32_t zo_longest_match_l2(const uint8_t *window, uint32_t avail, uint32_t n, const uint16_t *prev, uint32_t pos, uint32_t cand, uint32_t *start) {
+    lzstate *s = (lzstate *)calloc(1, sizeof(lzstate));
+    if (!s || avail > ZO_CHUNK_MAX) { free(s); return 0; }
+    memcpy(s->W, window, avail); s->len = n;
+    memcpy(s->prev, prev, sizeof(s->prev));
+    uint32_t st = 0, r = longest_match_l2(s, pos, cand, n - pos, &st);
+    if (start) *start = st;
+    free(s);
+    return r;
+}
+
+/* insert_string(s, str, count) (insert_string_tpl.h:82-104) on caller-owned head[65536] / prev[32768]. */
+void zo_insert_string(const uint8_t *window, uint32_t avail, uint16_t *head, uint16_t *prev, uint32_t str, uint32_t count) {
+    lzstate *s = (lzstate *)calloc(1, sizeof(lzstate));
+    if (!s || avail > ZO_CHUNK_MAX) { free(s); return; }
+    memcpy(s->W, window, avail); s->len = avail;
+    memcpy(s->head, head, sizeof(s->head)); memcpy(s->prev, prev, sizeof(s->prev));
+    for (uint32_t k = 0; k < count; k++) quick_insert(s, str + k);
+    memcpy(head, s->head, sizeof(s->head)); memcpy(prev, s->prev, sizeof(s->prev));
+    free(s);
+}
+
 /* ---- chunk batch with a tiny pthread pool (mirrors refdrv_deflate_chunks) ---- */
 typedef struct {
     const uint8_t *in; size_t n; uint32_t chunk; int level, flush;

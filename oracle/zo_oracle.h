@@ -63,6 +63,10 @@ int zo_deflate_chunks(const uint8_t *in, size_t n, uint32_t chunk, int level, in
  * (1u<<31) | (len << 16) | dist.  Returns token count (cap = capacity of tokens). */
 size_t zo_deflate_tokens(const uint8_t *in, uint32_t len, int level, uint32_t *tokens, size_t cap);
 
+/* Single operators (operator-surface tests): functable.longest_match at level 2, insert_string. */
+uint32_t zo_longest_match_l2(const uint8_t *window, uint32_t avail, uint32_t n, const uint16_t *prev, uint32_t pos, uint32_t cand, uint32_t *start);
+void zo_insert_string(const uint8_t *window, uint32_t avail, uint16_t *head, uint16_t *prev, uint32_t str, uint32_t count);
+
 /* ---- inflate (zo_inflate.c) ---- */
 /* Return codes follow zlib-ng.h.in:180-188. */
 #define ZO_OK            0

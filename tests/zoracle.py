@@ -43,6 +43,10 @@ def port():
         L.zo_deflate_chunks.restype = c_int
         L.zo_deflate_chunks.argtypes = [c_void_p, c_size_t, c_uint32, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int]
         L.zo_deflate_tokens.restype = c_size_t; L.zo_deflate_tokens.argtypes = [c_void_p, c_uint32, c_int, c_void_p, c_size_t]
+        L.zo_longest_match_l2.restype = c_uint32
+        L.zo_longest_match_l2.argtypes = [c_void_p, c_uint32, c_uint32, c_void_p, c_uint32, c_uint32, POINTER(c_uint32)]
+        L.zo_insert_string.restype = None
+        L.zo_insert_string.argtypes = [c_void_p, c_uint32, c_void_p, c_void_p, c_uint32, c_uint32]
         if hasattr(L, "zo_inflate"):
             L.zo_inflate.restype = c_int
             L.zo_inflate.argtypes = [c_void_p, c_size_t, c_int, c_void_p, c_size_t, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_uint32), POINTER(c_char_p)]

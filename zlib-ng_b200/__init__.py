@@ -66,6 +66,11 @@ def lib() -> ctypes.CDLL:
         "zng_b200_inflate_members": (c_int, [vp, vp, u64p, c_uint32, c_int, vp, u64p, u32p, u32p, vp, u32p, u32p, vp]),
         "zng_b200_inflate_members_host": (c_int, [vp, vp, u64p, c_uint32, c_int, vp, u64p, u32p, u32p, vp, u32p, u32p]),
         "zng_b200_inflate_msg": (c_char_p, [c_uint32]),
+        "zng_b200_op_compare256": (c_int, [vp, vp, vp, c_size_t, c_uint32, u32p, vp]),
+        "zng_b200_op_longest_match": (c_int, [vp, vp, c_uint32, vp, u32p, u32p, c_uint32, u32p, u32p, vp]),
+        "zng_b200_op_insert_string": (c_int, [vp, vp, vp, vp, c_uint32, c_uint32, vp]),
+        "zng_b200_op_chunkmemset": (c_int, [vp, vp, c_uint32, c_uint32, c_uint32, vp]),
+        "zng_b200_functable_get": (c_void_p, []),
         # the C11 host library: zlib-ng's own API (include/zlib-ng.h)
         "zlibng_version": (c_char_p, []),
         "zng_deflateInit2": (c_int32, [vp, c_int32, c_int32, c_int32, c_int32, c_int32]),
@@ -96,6 +101,19 @@ def lib() -> ctypes.CDLL:
         f.argtypes = args
     _lib = L
     return L
+
+
+class Functable(ctypes.Structure):
+    """struct zng_b200_functable (include/zng_b200.h), the host-callable part of the reference's functable_s."""
+    _fields_ = [("adler32", ctypes.CFUNCTYPE(c_uint32, c_uint32, c_void_p, c_size_t)),
+                ("chunkmemset_safe", ctypes.CFUNCTYPE(c_void_p, c_void_p, c_void_p, ctypes.c_uint, ctypes.c_uint)),
+                ("chunksize", ctypes.CFUNCTYPE(c_uint32)),
+                ("compare256", ctypes.CFUNCTYPE(c_uint32, c_void_p, c_void_p)),
+                ("crc32", ctypes.CFUNCTYPE(c_uint32, c_uint32, c_void_p, c_size_t))]
+
+
+def functable() -> "Functable":
+    return ctypes.cast(lib().zng_b200_functable_get(), POINTER(Functable)).contents
 
 
 class ZngStream(ctypes.Structure):

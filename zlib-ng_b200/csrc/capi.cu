@@ -480,6 +480,38 @@ int zng_b200_adler32(zng_b200_ctx* ctx, const void* d_buf, size_t n, uint32_t in
     return 0;
 }
 
+// ---------------------------------------------------------------- operator surface
+int zng_b200_op_compare256(zng_b200_ctx* ctx, const void* d_a, const void* d_b, size_t stride, uint32_t n_pairs, uint32_t* d_out, void* stream) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (n_pairs && (!d_a || !d_b || !d_out)) return bad(ctx, "NULL argument");
+    DeviceGuard g(ctx->device);
+    CK(launch_op_compare256((const uint8_t*)d_a, (const uint8_t*)d_b, stride, n_pairs, d_out, (cudaStream_t)stream), "compare256 launch");
+    return 0;
+}
+int zng_b200_op_longest_match(zng_b200_ctx* ctx, const void* d_window, uint32_t n, const uint16_t* d_prev, const uint32_t* d_pos,
+                              const uint32_t* d_cand, uint32_t n_q, uint32_t* d_len, uint32_t* d_start, void* stream) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (n_q && (!d_window || !d_prev || !d_pos || !d_cand || !d_len || !d_start)) return bad(ctx, "NULL argument");
+    if (n > ZNG_B200_CHUNK_MAX) return bad(ctx, "window larger than 65536");
+    DeviceGuard g(ctx->device);
+    CK(launch_op_longest_match((const uint8_t*)d_window, n, d_prev, d_pos, d_cand, n_q, d_len, d_start, (cudaStream_t)stream), "longest_match launch");
+    return 0;
+}
+int zng_b200_op_insert_string(zng_b200_ctx* ctx, const void* d_window, uint16_t* d_head, uint16_t* d_prev, uint32_t str, uint32_t count, void* stream) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (count && (!d_window || !d_head || !d_prev)) return bad(ctx, "NULL argument");
+    DeviceGuard g(ctx->device);
+    CK(launch_op_insert_string((const uint8_t*)d_window, d_head, d_prev, str, count, (cudaStream_t)stream), "insert_string launch");
+    return 0;
+}
+int zng_b200_op_chunkmemset(zng_b200_ctx* ctx, void* d_out, uint32_t pos, uint32_t dist, uint32_t len, void* stream) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (len && (!d_out || dist == 0 || dist > pos)) return bad(ctx, "dist must be in 1..pos");
+    DeviceGuard g(ctx->device);
+    CK(launch_op_chunkmemset((uint8_t*)d_out, pos, dist, len, (cudaStream_t)stream), "chunkmemset launch");
+    return 0;
+}
+
 // ---------------------------------------------------------------- K4 inflate
 int zng_b200_inflate_members(zng_b200_ctx* ctx, const void* d_in, const uint64_t* d_in_off, uint32_t n_members, int window_bits,
                              void* d_out, const uint64_t* d_out_off, uint32_t* d_sizes, uint32_t* d_checks, int32_t* d_status,

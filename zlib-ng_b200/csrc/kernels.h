@@ -49,6 +49,13 @@ cudaError_t launch_inflate_members(const uint8_t* in, const uint64_t* in_off, ui
                                    uint32_t* in_used, uint32_t* detail, uint32_t* counter, int num_sms, cudaStream_t stream);
 const char* inflate_msg(uint32_t id);
 
+// operator surface (ops.cu): the device operators of K1/K2/K4 one at a time
+cudaError_t launch_op_compare256(const uint8_t* a, const uint8_t* b, size_t stride, uint32_t n_pairs, uint32_t* out, cudaStream_t s);
+cudaError_t launch_op_longest_match(const uint8_t* window, uint32_t n, const uint16_t* prev, const uint32_t* pos, const uint32_t* cand,
+                                    uint32_t n_q, uint32_t* len, uint32_t* start, cudaStream_t s);
+cudaError_t launch_op_insert_string(const uint8_t* window, uint16_t* head, uint16_t* prev, uint32_t str, uint32_t count, cudaStream_t s);
+cudaError_t launch_op_chunkmemset(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t len, cudaStream_t s);
+
 // stream assembly (assemble.cu)
 cudaError_t launch_offsets(const uint32_t* sizes, uint32_t n, uint64_t base, uint64_t* offsets, cudaStream_t stream);
 cudaError_t launch_gather(const uint8_t* slots, size_t stride, const uint32_t* sizes, const uint64_t* offsets,
