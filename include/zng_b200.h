@@ -140,6 +140,16 @@ int zng_b200_deflate_host(zng_b200_ctx *ctx, const void *h_in, size_t n, uint32_
 int zng_b200_inflate_members_host(zng_b200_ctx *ctx, const void *h_in, const uint64_t *h_in_off, uint32_t n_members,
                                   int window_bits, void *h_out, const uint64_t *h_out_off, uint32_t *h_sizes,
                                   uint32_t *h_checks, int32_t *h_status, uint32_t *h_in_used, uint32_t *h_detail);
+/* Inflate ONE stream (raw -15 / zlib 15 / gzip 31 / auto 47) held in host memory: the call zng_inflate of the host
+ * library makes.  A stream whose pieces end with Z_FULL_FLUSH (what zng_deflate of this library and pigz-style tools
+ * emit) is split at its 00 00 FF FF markers on the device and its segments are decoded in parallel, one warp each
+ * (inflateSync's marker search, inflate.c:1290-1360, applied to every marker at once); any other stream, and every
+ * error, goes through the one-member path above and reports exactly what the reference's zng_inflate(Z_FINISH) reports.
+ *   *status   Z_STREAM_END 1 / Z_NEED_DICT 2 / Z_DATA_ERROR -3 / Z_BUF_ERROR -5
+ *   *detail   as d_detail above; 0x400 with Z_BUF_ERROR: cap was too small and *out_len holds the size needed
+ *             (nothing was written) */
+int zng_b200_inflate_stream_host(zng_b200_ctx *ctx, const void *h_in, size_t n, int window_bits, void *h_out, size_t cap,
+                                 size_t *out_len, size_t *in_used, uint32_t *check, int32_t *status, uint32_t *detail);
 int zng_b200_crc32_host(zng_b200_ctx *ctx, const void *h_buf, size_t n, uint32_t init, uint32_t *result);
 int zng_b200_adler32_host(zng_b200_ctx *ctx, const void *h_buf, size_t n, uint32_t init, uint32_t *result);
 

@@ -175,3 +175,83 @@ def test_argument_validation(pkg, ctx):
             ctx.inflate_members_host(one, off, wb, one, off) if False else ctx._check(
                 pkg.lib().zng_b200_inflate_members(ctx._h, 1, 1, 1, wb, 1, 1, 1, 0, 1, 0, 0, 0))
         assert ei.value.code == pkg.Z_STREAM_ERROR
+
+
+# ---- parallel inflate of one flush-delimited stream ------------------------------------------
+def _stream_cases(pkg, zo):
+    import zlib as z
+    data = pkg.synth(40 * 65536 + 12345, seed=55)
+    raw = data.tobytes()
+    cases = []
+    for level in (1, 2):
+        for wb in (-15, 15, 31):
+            st = zo.ref_deflate_stream(data, 65536, level, wb).tobytes() if zo.have_ref() else None
+            if st is None:                                  # no reference build on this box: python zlib with full flushes
+                co = z.compressobj(level, z.DEFLATED, wb)
+                st = b"".join(co.compress(raw[i:i + 65536]) + co.flush(z.Z_FULL_FLUSH) for i in range(0, len(raw), 65536)) + co.flush()
+            cases.append((f"ref L{level} wb{wb}", st, wb, raw))
+    # pigz-like: 128 KiB blocks, level 6, sync-flush markers only at some block ends, and a stream without any marker
+    co = z.compressobj(6, z.DEFLATED, 31)
+    st = b"".join(co.compress(raw[i:i + 131072]) + co.flush(z.Z_FULL_FLUSH) for i in range(0, len(raw), 131072)) + co.flush()
+    cases.append(("zlib L6 128K full", st, 31, raw))
+    cases.append(("zlib L6 no markers", z.compress(raw, 6), 15, raw))
+    co = z.compressobj(6, z.DEFLATED, -15)                   # Z_SYNC_FLUSH keeps the window: segments are NOT independent
+    st = b"".join(co.compress(raw[i:i + 65536]) + co.flush(z.Z_SYNC_FLUSH) for i in range(0, len(raw), 65536)) + co.flush()
+    cases.append(("zlib L6 sync flush (dependent segments)", st, -15, raw))
+    # a literal 00 00 FF FF inside the data of a stored block: a false marker in the middle of a block
+    noisy = bytearray(np.random.default_rng(5).integers(0, 256, size=3 * 65536, dtype=np.uint8).tobytes())
+    for k in (1000, 70000, 140000):
+        noisy[k:k + 4] = b"\x00\x00\xff\xff"
+    co = z.compressobj(1, z.DEFLATED, 31)
+    nb = bytes(noisy) + raw[: 20 * 65536]
+    st = b"".join(co.compress(nb[i:i + 65536]) + co.flush(z.Z_FULL_FLUSH) for i in range(0, len(nb), 65536)) + co.flush()
+    cases.append(("false markers inside stored blocks", st, 31, nb))
+    return cases
+
+
+def test_stream_inflate_parallel_segments(pkg, ctx, zo):
+    for tag, st, wb, raw in _stream_cases(pkg, zo):
+        src = np.frombuffer(st + b"trailing bytes", dtype=np.uint8).copy()
+        out = np.zeros(len(raw) + 16, dtype=np.uint8)
+        status, out_len, in_used, check, detail = ctx.inflate_stream_host(src, src.size, wb, out, out.size)
+        e = zo.port_inflate(st + b"trailing bytes", wb, out.size)
+        assert status == 1 == e[0], (tag, status, detail)
+        assert out_len == len(raw) and out[:out_len].tobytes() == raw, tag
+        assert in_used == len(st) == e[2] and check == e[3], (tag, in_used, len(st), hex(check), hex(e[3]))
+        # too little room: Z_BUF_ERROR, and for the parallel path the size needed
+        status, need, _, _, detail = ctx.inflate_stream_host(src, src.size, wb, out, len(raw) - 1)
+        assert status == pkg.Z_BUF_ERROR and (detail & 0x100), tag
+        if detail & 0x400:
+            assert need == len(raw), tag
+        # corrupt one byte in the middle / cut the stream: same code and message as the oracle
+        bad = bytearray(st); bad[len(bad) // 2] ^= 0x5a
+        for variant in (bytes(bad), st[: len(st) - 3], st[: len(st) // 3]):
+            v = np.frombuffer(variant + b"\0", dtype=np.uint8).copy()
+            status, out_len, in_used, check, detail = ctx.inflate_stream_host(v, len(variant), wb, out, out.size)
+            e = zo.port_inflate(variant, wb, out.size)
+            assert status == e[0] and pkg.inflate_msg(detail) == e[4], (tag, status, e[0], pkg.inflate_msg(detail), e[4])
+
+
+def test_zng_inflate_large_pigz_stream_roundtrip(pkg, ctx, zo):
+    """zng_deflate -> zng_inflate through the host library on 96 MiB: the stream this library writes is decoded in
+    parallel by its flush markers."""
+    import ctypes
+    import zlib as z
+    L = pkg.lib()
+    n = 96 << 20
+    data = pkg.synth(n, seed=77)
+    s = pkg.ZngStream()
+    assert L.zng_deflateInit2(ctypes.byref(s), 1, 8, 31, 8, 0) == 0
+    comp = np.zeros(int(L.zng_deflateBound(ctypes.byref(s), n)) + 64, dtype=np.uint8)
+    s.next_in = data.ctypes.data; s.avail_in = n; s.next_out = comp.ctypes.data; s.avail_out = comp.size
+    assert L.zng_deflate(ctypes.byref(s), pkg.Z_FINISH) == 1
+    clen = int(s.total_out)
+    assert L.zng_deflateEnd(ctypes.byref(s)) == 0
+    d = pkg.ZngStream()
+    assert L.zng_inflateInit2(ctypes.byref(d), 31) == 0
+    back = np.zeros(n, dtype=np.uint8)
+    d.next_in = comp.ctypes.data; d.avail_in = clen; d.next_out = back.ctypes.data; d.avail_out = n
+    assert L.zng_inflate(ctypes.byref(d), pkg.Z_FINISH) == 1
+    assert d.total_out == n and d.total_in == clen and d.avail_in == 0 and d.adler == z.crc32(data.tobytes())
+    assert np.array_equal(back, data)
+    assert L.zng_inflateEnd(ctypes.byref(d)) == 0

@@ -66,6 +66,7 @@ def lib() -> ctypes.CDLL:
         "zng_b200_inflate_members": (c_int, [vp, vp, u64p, c_uint32, c_int, vp, u64p, u32p, u32p, vp, u32p, u32p, vp]),
         "zng_b200_inflate_members_host": (c_int, [vp, vp, u64p, c_uint32, c_int, vp, u64p, u32p, u32p, vp, u32p, u32p]),
         "zng_b200_inflate_msg": (c_char_p, [c_uint32]),
+        "zng_b200_inflate_stream_host": (c_int, [vp, vp, c_size_t, c_int, vp, c_size_t, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_uint32), POINTER(c_int32), POINTER(c_uint32)]),
         "zng_b200_op_compare256": (c_int, [vp, vp, vp, c_size_t, c_uint32, u32p, vp]),
         "zng_b200_op_longest_match": (c_int, [vp, vp, c_uint32, vp, u32p, u32p, c_uint32, u32p, u32p, vp]),
         "zng_b200_op_insert_string": (c_int, [vp, vp, vp, vp, c_uint32, c_uint32, vp]),
@@ -239,6 +240,12 @@ class Context:
         self._check(lib().zng_b200_inflate_members_host(self._h, _ptr(h_in), _ptr(io), n, window_bits, _ptr(h_out), _ptr(oo),
                                                         _ptr(sizes), _ptr(checks), _ptr(status), _ptr(used), _ptr(detail)))
         return sizes[:n], checks[:n], status[:n], used[:n], detail[:n]
+
+    def inflate_stream_host(self, h_in, n: int, window_bits: int, h_out, cap: int):
+        """One stream (parallel over its flush markers when it has them).  Returns (status, out_len, in_used, check, detail)."""
+        ol, iu, chk, st, det = c_size_t(0), c_size_t(0), c_uint32(0), c_int32(0), c_uint32(0)
+        self._check(lib().zng_b200_inflate_stream_host(self._h, _ptr(h_in), n, window_bits, _ptr(h_out), cap, byref(ol), byref(iu), byref(chk), byref(st), byref(det)))
+        return int(st.value), int(ol.value), int(iu.value), int(chk.value), int(det.value)
 
     # ---- host-buffer entry points (numpy arrays / pinned tensors) ------------------------
     def deflate_host(self, h_in, n: int, chunk: int, level: int, final: bool, h_out, out_cap: int):

@@ -6,10 +6,12 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 using namespace zb;
 
@@ -92,6 +94,11 @@ struct zng_b200_ctx {
     bool slabs_ready = false;
     size_t slab_stride = 0;
     InfSlab inf[kInfPipe];
+    // parallel stream inflate: whole-stream device buffers (grow only)
+    uint8_t* d_sin = nullptr;  size_t sin_cap = 0;
+    uint8_t* d_sout = nullptr; size_t sout_cap = 0;
+    uint64_t* d_soff = nullptr; uint32_t* d_sres = nullptr; uint32_t seg_cap = 0;
+    unsigned long long* d_marks = nullptr; uint32_t marks_cap = 0;
     uint8_t* d_hostbuf = nullptr;              // staging for *_host checksums
     size_t hostbuf_cap = 0;
     uint32_t x2n[32];
@@ -339,6 +346,11 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
+    if (ctx->d_sin) cudaFree(ctx->d_sin);
+    if (ctx->d_sout) cudaFree(ctx->d_sout);
+    if (ctx->d_soff) cudaFree(ctx->d_soff);
+    if (ctx->d_sres) cudaFree(ctx->d_sres);
+    if (ctx->d_marks) cudaFree(ctx->d_marks);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->tails) cudaFree(ctx->tails);
     if (ctx->heads) cudaFree(ctx->heads);
@@ -628,6 +640,215 @@ int zng_b200_inflate_members_host(zng_b200_ctx* ctx, const void* h_in, const uin
     for (int i = 0; i < kInfPipe && !r; i++) r = inf_slab_drain(ctx, ctx->inf[(k + i) % kInfPipe], h_sizes, h_checks, h_status, h_in_used, h_detail);
     for (int i = 0; i < kInfPipe; i++) { ctx->inf[i].busy = false; if (ctx->inf[i].stream) cudaStreamSynchronize(ctx->inf[i].stream); }
     return r;
+}
+
+// ---------------------------------------------------------------- parallel inflate of ONE flush-delimited stream
+// (the inverse of the chunked compressor.)  A pigz-style stream -- what zng_deflate of this
+// library and of the reference produce when every piece ends with Z_FULL_FLUSH -- is a sequence of independent raw
+// deflate segments separated by the empty stored block 00 00 FF FF.  The markers are found on the device
+// (inflateSync's search, inflate.c:1290-1306), every segment is decoded by its own warp in two passes (sizes, then
+// bytes at the scanned offsets), a marker that turns out to lie inside a block is dropped and its segment re-sized,
+// and the checksum of the whole output comes from K3.  Anything unusual falls back to the exact one-member path.
+namespace {
+struct Wrapper { int kind; size_t body; };               // kind 0 raw, 1 zlib, 2 gzip
+
+// 0 = header understood, -1 = leave it to the exact path (errors, FDICT, FHCRC ...)
+int parse_wrapper(const uint8_t* p, size_t n, int window_bits, Wrapper& w) {
+    w.kind = 0; w.body = 0;
+    if (window_bits < 0) return 0;
+    const int wrap = (window_bits >> 4) + 5;
+    if (n < 2) return -1;
+    if ((wrap & 2) && p[0] == 0x1f && p[1] == 0x8b) {
+        if (n < 10 || p[2] != 8 || (p[3] & 0xe0) || (p[3] & 0x02)) return -1;
+        size_t b = 10;
+        if (p[3] & 0x04) { if (n < b + 2) return -1; const size_t xlen = p[b] | (p[b + 1] << 8); b += 2; if (n < b + xlen) return -1; b += xlen; }
+        for (int f = 0x08; f <= 0x10; f <<= 1)
+            if (p[3] & f) { while (b < n && p[b]) b++; if (b >= n) return -1; b++; }
+        w.kind = 2; w.body = b;
+        return 0;
+    }
+    if (!(wrap & 1)) return -1;
+    if (((p[0] << 8) + p[1]) % 31 || (p[0] & 0xf) != 8 || (p[0] >> 4) + 8 > 15 || (p[1] & 0x20)) return -1;
+    const int wb = window_bits < 48 ? (window_bits & 15) : window_bits;
+    if (wb && (p[0] >> 4) + 8 > wb) return -1;
+    w.kind = 1; w.body = 2;
+    return 0;
+}
+
+int grow(zng_b200_ctx* ctx, uint8_t*& p, size_t& cap, size_t want, const char* what) {
+    if (cap >= want) return 0;
+    if (p) { cudaDeviceSynchronize(); cudaFree(p); p = nullptr; cap = 0; }
+    want += want / 8 + 4096;
+    CK(cudaMalloc(&p, want), what);
+    cap = want;
+    return 0;
+}
+}  // namespace
+
+int zng_b200_inflate_stream_host(zng_b200_ctx* ctx, const void* h_in, size_t n, int window_bits, void* h_out, size_t cap,
+                                 size_t* out_len, size_t* in_used, uint32_t* check, int32_t* status, uint32_t* detail) {
+    if (!ctx || !out_len || !status || (n && !h_in) || (cap && !h_out)) return ZNG_B200_STREAM_ERROR;
+    uint32_t dummy_detail = 0; if (!detail) detail = &dummy_detail;
+    size_t dummy_used = 0; if (!in_used) in_used = &dummy_used;
+    uint32_t dummy_check = 0; if (!check) check = &dummy_check;
+    const uint8_t* src = (const uint8_t*)h_in;
+    auto exact = [&]() -> int {                               // one member, one warp: reference-exact codes and messages
+        const size_t nn = n > 0xffffffffull ? 0xffffffffull : n, cc = cap > 0xfffffff0ull ? 0xfffffff0ull : cap;
+        uint64_t ioff[2] = {0, nn}, ooff[2] = {0, cc};
+        uint32_t sz = 0, used = 0; uint8_t d0 = 0, d1 = 0;
+        int r = zng_b200_inflate_members_host(ctx, nn ? h_in : &d0, ioff, 1, window_bits, cc ? h_out : &d1, ooff, &sz, check, status, &used, detail);
+        *out_len = sz; *in_used = used;
+        return r;
+    };
+    Wrapper wr;
+    if (n < ((size_t)1 << 20) || n > 0xffffffffull || parse_wrapper(src, n, window_bits, wr) != 0) return exact();
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = 0;
+    int r = grow(ctx, ctx->d_sin, ctx->sin_cap, n + 64, "cudaMalloc(stream in)");
+    if (r) return r;
+    CK(cudaMemcpyAsync(ctx->d_sin, src, n, cudaMemcpyHostToDevice, st), "H2D stream");
+    CK(cudaMemsetAsync(ctx->d_sin + n, 0, 64, st), "memset");
+    // ---- markers
+    const uint32_t want_marks = (uint32_t)std::min<size_t>(n / 64 + 1024, 1u << 24);
+    if (ctx->marks_cap < want_marks) {
+        if (ctx->d_marks) { cudaDeviceSynchronize(); cudaFree(ctx->d_marks); ctx->d_marks = nullptr; ctx->marks_cap = 0; }
+        CK(cudaMalloc(&ctx->d_marks, (size_t)want_marks * sizeof(unsigned long long)), "cudaMalloc(markers)");
+        ctx->marks_cap = want_marks;
+    }
+    CK(launch_marker_scan(ctx->d_sin, n, wr.body, ctx->d_marks, ctx->marks_cap, ctx->d_result, ctx->sms, st), "marker scan");
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H count");
+    CK(cudaStreamSynchronize(st), "sync");
+    const uint32_t nmarks = ctx->h_result[0];
+    if (nmarks == 0 || nmarks > ctx->marks_cap) return exact();
+    std::vector<unsigned long long> marks(nmarks);
+    CK(cudaMemcpy(marks.data(), ctx->d_marks, (size_t)nmarks * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "D2H markers");
+    std::sort(marks.begin(), marks.end());
+    std::vector<uint64_t> starts;
+    starts.push_back(wr.body);
+    for (unsigned long long m : marks) if (m > wr.body && m < n) starts.push_back(m);
+    // ---- size pass (count mode); segments whose end marker proves false are merged with their successor and re-run
+    struct Seg { uint32_t size = 0, used = 0, det = 0; int32_t ret = -5; bool dirty = true; };
+    std::vector<Seg> segs(starts.size());
+    auto ensure_seg = [&](uint32_t cnt) -> int {
+        if (ctx->seg_cap >= cnt) return 0;
+        if (ctx->d_soff) { cudaDeviceSynchronize(); cudaFree(ctx->d_soff); cudaFree(ctx->d_sres); ctx->d_soff = nullptr; ctx->d_sres = nullptr; ctx->seg_cap = 0; }
+        const uint32_t want = cnt + cnt / 4 + 1024;
+        CK(cudaMalloc(&ctx->d_soff, 4 * ((size_t)want + 1) * sizeof(uint64_t)), "cudaMalloc(segment offsets)");
+        CK(cudaMalloc(&ctx->d_sres, 5 * (size_t)want * sizeof(uint32_t)), "cudaMalloc(segment results)");
+        ctx->seg_cap = want;
+        return 0;
+    };
+    std::vector<uint64_t> hoff; std::vector<uint32_t> hres;
+    size_t stream_end = 0; bool finished = false;
+    for (int round = 0; round < 32 && !finished; round++) {
+        std::vector<uint32_t> idx;
+        for (uint32_t i = 0; i < segs.size(); i++) if (segs[i].dirty) idx.push_back(i);
+        if (!idx.empty()) {
+            const uint32_t cnt = (uint32_t)idx.size();
+            r = ensure_seg(cnt);
+            if (r) return r;
+            hoff.assign(4 * (size_t)cnt, 0);                  // (begin, end) pairs: input ranges, then (unused) output ranges
+            for (uint32_t k = 0; k < cnt; k++) {
+                const uint32_t i = idx[k];
+                hoff[2 * k] = starts[i];
+                hoff[2 * k + 1] = (i + 1 < starts.size()) ? starts[i + 1] : n;
+            }
+            CK(cudaMemcpyAsync(ctx->d_soff, hoff.data(), hoff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st), "H2D segment offsets");
+            const size_t capn = ctx->seg_cap;
+            const int slot = next_slot(ctx);
+            CK(launch_inflate_members(ctx->d_sin, ctx->d_soff, cnt, -15, ctx->d_sin, ctx->d_soff + 2 * (size_t)cnt, ctx->d_sres, nullptr,
+                                      (int32_t*)(ctx->d_sres + 2 * capn), ctx->d_sres + 3 * capn, ctx->d_sres + 4 * capn, ctx->counters + slot,
+                                      ctx->sms, st, 1 | 2 | 4),
+               "inflate size pass");
+            hres.resize(5 * capn);
+            CK(cudaMemcpyAsync(hres.data(), ctx->d_sres, 5 * capn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H segment results");
+            CK(cudaStreamSynchronize(st), "sync");
+            for (uint32_t k = 0; k < cnt; k++) {
+                Seg& sg = segs[idx[k]];
+                sg.size = hres[k]; sg.ret = (int32_t)hres[2 * capn + k]; sg.used = hres[3 * capn + k]; sg.det = hres[4 * capn + k];
+                sg.dirty = false;
+            }
+        }
+        // walk in order: clean ends continue, a final block ends the stream, a block cut by its end marker drops that marker
+        std::vector<uint64_t> nstarts; std::vector<Seg> nsegs;
+        bool merged = false, ended = false;
+        for (uint32_t i = 0; i < segs.size() && !ended; i++) {
+            Seg sg = segs[i];
+            const uint64_t bgn = starts[i], end = (i + 1 < starts.size()) ? starts[i + 1] : n;
+            if (sg.ret == 1) { nstarts.push_back(bgn); nsegs.push_back(sg); stream_end = (size_t)(bgn + sg.used); ended = true; }
+            else if (sg.ret == 0 && sg.used == end - bgn) { nstarts.push_back(bgn); nsegs.push_back(sg); }
+            else if (sg.ret == -5 && (sg.det & 0x200u) && i + 1 < starts.size()) {   // input ran out inside a block: false marker
+                sg.dirty = true; merged = true;
+                nstarts.push_back(bgn); nsegs.push_back(sg);
+                i++;                                          // the next start is dropped
+            } else return exact();                            // data error, no final block, ...: the exact path reports it
+        }
+        if (!ended && !merged) return exact();                // ran off the end of the input without a final block
+        if (merged && !ended) {                               // keep the untouched tail behind the last examined segment
+            // (the loop above consumed every segment, so nothing is left to copy)
+        }
+        starts.swap(nstarts); segs.swap(nsegs);
+        finished = ended && !merged;
+        if (ended && merged) {                                // segments behind the final one were cut off; re-run the merged ones
+            // the final segment itself may be among the dirty ones; loop again
+        }
+    }
+    if (!finished) return exact();
+    // ---- trailer present?
+    const size_t tlen = wr.kind == 2 ? 8 : (wr.kind == 1 ? 4 : 0);
+    if (stream_end + tlen > n) return exact();                // truncated trailer: Z_BUF_ERROR from the exact path
+    // ---- offsets, capacity
+    const uint32_t nseg = (uint32_t)segs.size();
+    std::vector<uint64_t> obeg(nseg + 1, 0);
+    for (uint32_t i = 0; i < nseg; i++) obeg[i + 1] = obeg[i] + segs[i].size;
+    const size_t total = (size_t)obeg[nseg];
+    if (total > cap) {                                        // Z_BUF_ERROR; the size needed is reported so the caller can come back
+        *status = ZNG_B200_BUF_ERROR; *detail = 0x100u | 0x400u; *out_len = total; *in_used = 0;
+        return 0;
+    }
+    r = grow(ctx, ctx->d_sout, ctx->sout_cap, total + 64, "cudaMalloc(stream out)");
+    if (r) return r;
+    r = ensure_seg(nseg + 1);
+    if (r) return r;
+    // ---- byte pass.  Segment i reads [starts[i], starts[i+1]) (the last one up to the end of its final block)
+    hoff.assign(2 * ((size_t)nseg + 1), 0);
+    for (uint32_t i = 0; i < nseg; i++) hoff[i] = starts[i];
+    hoff[nseg] = stream_end;
+    for (uint32_t i = 0; i + 1 < nseg; i++) if (starts[i + 1] < starts[i]) return exact();
+    for (uint32_t i = 0; i <= nseg; i++) hoff[nseg + 1 + i] = obeg[i];
+    CK(cudaMemcpyAsync(ctx->d_soff, hoff.data(), hoff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st), "H2D segment offsets");
+    {
+        const size_t capn = ctx->seg_cap;
+        const int slot = next_slot(ctx);
+        CK(launch_inflate_members(ctx->d_sin, ctx->d_soff, nseg, -15, ctx->d_sout, ctx->d_soff + (nseg + 1), ctx->d_sres, nullptr,
+                                  (int32_t*)(ctx->d_sres + 2 * capn), ctx->d_sres + 3 * capn, ctx->d_sres + 4 * capn, ctx->counters + slot, ctx->sms, st, 1),
+           "inflate byte pass");
+        hres.resize(5 * capn);
+        CK(cudaMemcpyAsync(hres.data(), ctx->d_sres, 5 * capn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H segment results");
+        // checksum of the whole output (K3) while the results travel
+        if (wr.kind == 2) { int rc = zng_b200_crc32(ctx, ctx->d_sout, total, 0, ctx->d_result + 1, st); if (rc) return rc; }
+        if (wr.kind == 1) { int rc = zng_b200_adler32(ctx, ctx->d_sout, total, 1, ctx->d_result + 1, st); if (rc) return rc; }
+        CK(cudaMemcpyAsync(ctx->h_result + 1, ctx->d_result + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H check");
+        if (total) CK(cudaMemcpyAsync(h_out, ctx->d_sout, total, cudaMemcpyDeviceToHost, st), "D2H output");
+        CK(cudaStreamSynchronize(st), "sync");
+        for (uint32_t i = 0; i < nseg; i++) {
+            const int32_t ret = (int32_t)hres[2 * capn + i];
+            if (hres[i] != segs[i].size || ret != (i + 1 == nseg ? 1 : 0)) return exact();
+        }
+    }
+    const uint32_t chk = wr.kind ? ctx->h_result[1] : 0u;
+    *out_len = total; *check = chk; *detail = 0; *status = 1;
+    *in_used = stream_end + tlen;
+    const uint8_t* t = src + stream_end;
+    if (wr.kind == 2) {
+        const uint32_t c = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24), l = t[4] | (t[5] << 8) | (t[6] << 16) | ((uint32_t)t[7] << 24);
+        if (c != chk) { *status = ZNG_B200_DATA_ERROR; *detail = 17; }
+        else if (l != (uint32_t)total) { *status = ZNG_B200_DATA_ERROR; *detail = 18; }
+    } else if (wr.kind == 1) {
+        const uint32_t c = ((uint32_t)t[0] << 24) | (t[1] << 16) | (t[2] << 8) | t[3];
+        if (c != chk) { *status = ZNG_B200_DATA_ERROR; *detail = 17; }
+    }
+    return 0;
 }
 
 // ---------------------------------------------------------------- host-buffer entry points

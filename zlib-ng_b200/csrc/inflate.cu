@@ -220,12 +220,17 @@ __device__ uint32_t warp_check(const uint8_t* ob, uint32_t o, bool gz, const Inf
 #define INF_MORE_IN() do { R.detail |= kDetailInEnd; goto done; } while (0)
 #define INF_MORE_OUT() do { R.detail |= kDetailOutFull; goto done; } while (0)
 
+// mode bit 0 (segment): the input is one flush-delimited piece of a longer raw stream; running out of input exactly at
+// a block boundary is a clean end (ret 0 = Z_OK) instead of Z_BUF_ERROR.  mode bit 1 (count): decode the symbols and add
+// up the lengths only -- nothing is stored, the output capacity is unlimited (the size pass of the parallel stream inflate).
 __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, uint8_t* gout, uint32_t cap,
-                               InfShared& S, InfWarp& P, const Code& FL, const Code& FD, InfResult& R, unsigned lane) {
+                               InfShared& S, InfWarp& P, const Code& FL, const Code& FD, InfResult& R, unsigned lane, int mode) {
+    const bool segment = mode & 1, count = mode & 2;
+    if (count) cap = 0xffffffffu;
     const uint32_t sk0 = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3u);
     const uint32_t* w = reinterpret_cast<const uint32_t*>(in - sk0);
     const uint32_t e = sk0 + n;
-    const bool staged = cap <= kInfStage;
+    const bool staged = cap <= kInfStage && !count;
     uint8_t* ob = staged ? P.stage : gout;
     uint32_t o = 0, bp = sk0;
     bool gz = false;
@@ -282,6 +287,7 @@ __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, u
 
     for (bool last = false; !last;) {                       // TYPEDO
         b.refill();
+        if (segment && b.bits == 0u) { R.ret = 0; goto done; }   // every byte used, at a block boundary
         if (b.bits < 3u) INF_MORE_IN();
         last = b.peek(1) != 0u; b.drop(1);
         const uint32_t type = b.peek(2); b.drop(2);
@@ -299,7 +305,7 @@ __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, u
             const bool out_short = can > cap - o;
             can = min(can, cap - o);
             __syncwarp();
-            for (uint32_t k = lane; k < can; k += 32u) ob[o + k] = (uint8_t)in_byte(w, src + k);
+            if (!count) for (uint32_t k = lane; k < can; k += 32u) ob[o + k] = (uint8_t)in_byte(w, src + k);
             o += can;
             b.init(w, src + can, e);
             if (out_short) INF_MORE_OUT();
@@ -382,7 +388,7 @@ __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, u
                     const uint32_t e2 = ltab[h & ((1u << kRootBits) - 1u)];
                     if (e2 < kLitLimit) { used += e2 & 15u; nlit = 3; if (lane == 2u) lit = e2 >> 4; }
                 }
-                if (lane < nlit) ob[o + lane] = (uint8_t)lit;
+                if (lane < nlit && !count) ob[o + lane] = (uint8_t)lit;
                 b.drop(used);
                 o += nlit;
                 continue;
@@ -394,7 +400,7 @@ __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, u
             if (sym < 256) {
                 if (o >= cap) INF_MORE_OUT();
                 b.drop(cb);
-                if (lane == 0u) ob[o] = (uint8_t)sym;
+                if (lane == 0u && !count) ob[o] = (uint8_t)sym;
                 o++;
                 continue;
             }
@@ -419,6 +425,7 @@ __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, u
             // out[i] = out[i - dist] byte-serially (chunkset_tpl.h): waves of min(32, D) bytes from D back, where D is a
             // multiple of dist that doubles while it is below 32 (every copied wave is one more period of the run)
             uint32_t D = dist, rem = can;
+            if (count) { o += rem; rem = 0; }
             while (rem) {
                 __syncwarp();                               // earlier stores of other lanes -> visible
                 const uint32_t wave = min(min(D, 32u), rem);
@@ -450,7 +457,7 @@ __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, u
     R.ret = 1;
 done:
     __syncwarp();
-    if (staged && o) {                                      // shared-memory image -> the caller's buffer
+    if (staged && o && !count) {                            // shared-memory image -> the caller's buffer
         if ((reinterpret_cast<uintptr_t>(gout) & 3u) == 0u) {
             const uint32_t* s4 = reinterpret_cast<const uint32_t*>(P.stage);
             uint32_t* g4 = reinterpret_cast<uint32_t*>(gout);
@@ -469,7 +476,7 @@ __global__ void __launch_bounds__(kInfWarps * 32)
 inflate_members_kernel(const uint8_t* __restrict__ in, const uint64_t* __restrict__ in_off, uint32_t n_members, int window_bits,
                        uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off, uint32_t* __restrict__ sizes,
                        uint32_t* __restrict__ checks, int32_t* __restrict__ status, uint32_t* __restrict__ in_used,
-                       uint32_t* __restrict__ detail, uint32_t* __restrict__ counter) {
+                       uint32_t* __restrict__ detail, uint32_t* __restrict__ counter, int mode) {
     extern __shared__ __align__(16) unsigned char inf_smem[];
     InfShared& S = *reinterpret_cast<InfShared*>(inf_smem);
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -496,9 +503,11 @@ inflate_members_kernel(const uint8_t* __restrict__ in, const uint64_t* __restric
         if (lane == 0u) m = atomicAdd(counter, 1u);
         m = __shfl_sync(ZB_FULL, m, 0);
         if (m >= n_members) break;
-        const uint64_t i0 = in_off[m], i1 = in_off[m + 1u], o0 = out_off[m], o1 = out_off[m + 1u];
+        // mode bit 2: the offset arrays hold (begin, end) pairs per member instead of n + 1 boundaries
+        const size_t mi = (mode & 4) ? 2u * (size_t)m : (size_t)m;
+        const uint64_t i0 = in_off[mi], i1 = in_off[mi + 1u], o0 = out_off[mi], o1 = out_off[mi + 1u];
         InfResult R;
-        inflate_member(in + i0, (uint32_t)(i1 - i0), window_bits, out + o0, (uint32_t)(o1 - o0), S, P, FL, FD, R, lane);
+        inflate_member(in + i0, (uint32_t)(i1 - i0), window_bits, out + o0, (uint32_t)(o1 - o0), S, P, FL, FD, R, lane, mode);
         if (lane == 0u) {
             status[m] = R.ret; sizes[m] = R.out_len;
             if (checks) checks[m] = R.check;
@@ -510,7 +519,7 @@ inflate_members_kernel(const uint8_t* __restrict__ in, const uint64_t* __restric
 
 cudaError_t launch_inflate_members(const uint8_t* in, const uint64_t* in_off, uint32_t n_members, int window_bits,
                                    uint8_t* out, const uint64_t* out_off, uint32_t* sizes, uint32_t* checks, int32_t* status,
-                                   uint32_t* in_used, uint32_t* detail, uint32_t* counter, int num_sms, cudaStream_t stream) {
+                                   uint32_t* in_used, uint32_t* detail, uint32_t* counter, int num_sms, cudaStream_t stream, int mode) {
     if (n_members == 0) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(inflate_members_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InfShared));
     if (e != cudaSuccess) return e;
@@ -520,7 +529,36 @@ cudaError_t launch_inflate_members(const uint8_t* in, const uint64_t* in_off, ui
     const uint32_t need = (n_members + kInfWarps - 1u) / kInfWarps;
     if (grid > need) grid = need;
     inflate_members_kernel<<<grid, kInfWarps * 32, sizeof(InfShared), stream>>>(in, in_off, n_members, window_bits, out, out_off,
-                                                                                sizes, checks, status, in_used, detail, counter);
+                                                                                sizes, checks, status, in_used, detail, counter, mode);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- flush-marker scan (inflate.c:1290-1306 syncsearch on the GPU)
+// Every byte offset p in [from, n] with in[p-4..p) == 00 00 FF FF (the empty stored block Z_SYNC/FULL_FLUSH leaves,
+// deflate.c:1064) is appended to pos[] (unordered, at most cap entries; *count keeps counting).
+__global__ void marker_scan_kernel(const uint8_t* __restrict__ in, size_t n, size_t from, unsigned long long* __restrict__ pos,
+                                   uint32_t cap, uint32_t* __restrict__ count) {
+    const size_t nwords = (n + 3) / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(in);
+        const uint32_t w0 = __ldg(w + i), w1 = (i + 1 < nwords) ? __ldg(w + i + 1) : 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; k++) {
+            const size_t p = i * 4 + k + 4;                 // offset just past the 4 bytes under test
+            if (__funnelshift_r(w0, w1, 8u * k) == 0xffff0000u && p <= n && p - 4 >= from) {
+                const uint32_t slot = atomicAdd(count, 1u);
+                if (slot < cap) pos[slot] = p;
+            }
+        }
+    }
+}
+
+cudaError_t launch_marker_scan(const uint8_t* in, size_t n, size_t from, unsigned long long* pos, uint32_t cap, uint32_t* count,
+                               int num_sms, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    if (n < 4) return cudaSuccess;
+    marker_scan_kernel<<<num_sms * 8, 256, 0, stream>>>(in, n, from, pos, cap, count);
     return cudaGetLastError();
 }
 

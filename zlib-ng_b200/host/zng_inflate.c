@@ -80,19 +80,19 @@ static size_t deliver(zng_stream *strm) {
     return n;
 }
 
-/* one member through the GPU: returns the zng_inflate code of a Z_FINISH call with `cap` bytes of output room */
+/* one stream through the GPU: returns the zng_inflate code of a Z_FINISH call with `cap` bytes of output room */
 static int gpu_member(zng_stream *strm, const uint8_t *in, size_t n, uint8_t *out, size_t cap, uint32_t *out_len,
                       uint32_t *in_used, uint32_t *check, uint32_t *detail) {
     zng_b200_ctx *ctx = zng_b200_thread_ctx();
     if (!ctx) { strm->msg = "no CUDA device"; return Z_MEM_ERROR; }
     if (n > 0xffffffffu) n = 0xffffffffu;
     if (cap > 0xfffffff0u) cap = 0xfffffff0u;
-    uint64_t ioff[2] = {0, n}, ooff[2] = {0, cap};
     int32_t status = Z_BUF_ERROR;
+    size_t ol = 0, iu = 0;
     uint8_t dummy_in = 0, dummy_out = 0;
-    int r = zng_b200_inflate_members_host(ctx, n ? in : &dummy_in, ioff, 1, strm->state->wrap, cap ? out : &dummy_out, ooff, out_len, check,
-                                          &status, in_used, detail);
+    int r = zng_b200_inflate_stream_host(ctx, n ? in : &dummy_in, n, strm->state->wrap, cap ? out : &dummy_out, cap, &ol, &iu, check, &status, detail);
     if (r != ZNG_B200_OK) { strm->msg = zng_b200_last_error(ctx); return r == ZNG_B200_MEM_ERROR ? Z_MEM_ERROR : Z_STREAM_ERROR; }
+    *out_len = (uint32_t)ol; *in_used = (uint32_t)iu;
     return status;
 }
 
@@ -147,7 +147,11 @@ int32_t zng_inflate(zng_stream *strm, int32_t flush) {
             }
             r = gpu_member(strm, src, n, s->pend, s->pend_cap, &out_len, &in_used, &check, &detail);
             if (r == Z_MEM_ERROR || r == Z_STREAM_ERROR) return r;
-            if (r == Z_BUF_ERROR && (detail & 0x100u) && cap < 0xfffffff0u) { cap = cap * 4 > 0xfffffff0u ? 0xfffffff0u : cap * 4; continue; }
+            if (r == Z_BUF_ERROR && (detail & 0x100u) && cap < 0xfffffff0u) {
+                if (detail & 0x400u) cap = (size_t)out_len + 64;                /* the decoder reported the size it needs */
+                else cap = cap * 4 > 0xfffffff0u ? 0xfffffff0u : cap * 4;
+                continue;
+            }
             break;
         }
         s->pend_pos = 0; s->pend_len = 0;
