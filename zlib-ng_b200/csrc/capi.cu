@@ -99,6 +99,8 @@ struct zng_b200_ctx {
     uint8_t* d_sout = nullptr; size_t sout_cap = 0;
     uint64_t* d_soff = nullptr; uint32_t* d_sres = nullptr; uint32_t seg_cap = 0;
     unsigned long long* d_marks = nullptr; uint32_t marks_cap = 0;
+    cudaStream_t sstream[3] = {nullptr, nullptr, nullptr};   // byte pass + D2H of segment groups
+    cudaEvent_t sready = nullptr;
     uint8_t* d_hostbuf = nullptr;              // staging for *_host checksums
     size_t hostbuf_cap = 0;
     uint32_t x2n[32];
@@ -351,6 +353,8 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
     if (ctx->d_soff) cudaFree(ctx->d_soff);
     if (ctx->d_sres) cudaFree(ctx->d_sres);
     if (ctx->d_marks) cudaFree(ctx->d_marks);
+    for (int i = 0; i < 3; i++) if (ctx->sstream[i]) cudaStreamDestroy(ctx->sstream[i]);
+    if (ctx->sready) cudaEventDestroy(ctx->sready);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->tails) cudaFree(ctx->tails);
     if (ctx->heads) cudaFree(ctx->heads);
@@ -818,18 +822,35 @@ int zng_b200_inflate_stream_host(zng_b200_ctx* ctx, const void* h_in, size_t n, 
     for (uint32_t i = 0; i <= nseg; i++) hoff[nseg + 1 + i] = obeg[i];
     CK(cudaMemcpyAsync(ctx->d_soff, hoff.data(), hoff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st), "H2D segment offsets");
     {
+        // groups of segments (~256 MiB of output each) on three streams: the D2H of one group overlaps the decode of the next
+        if (!ctx->sready) {
+            for (int i = 0; i < 3; i++) CK(cudaStreamCreateWithFlags(&ctx->sstream[i], cudaStreamNonBlocking), "cudaStreamCreate");
+            CK(cudaEventCreateWithFlags(&ctx->sready, cudaEventDisableTiming), "cudaEventCreate");
+        }
+        CK(cudaEventRecord(ctx->sready, st), "event record");
         const size_t capn = ctx->seg_cap;
-        const int slot = next_slot(ctx);
-        CK(launch_inflate_members(ctx->d_sin, ctx->d_soff, nseg, -15, ctx->d_sout, ctx->d_soff + (nseg + 1), ctx->d_sres, nullptr,
-                                  (int32_t*)(ctx->d_sres + 2 * capn), ctx->d_sres + 3 * capn, ctx->d_sres + 4 * capn, ctx->counters + slot, ctx->sms, st, 1),
-           "inflate byte pass");
+        int gi = 0;
+        for (uint32_t g0 = 0; g0 < nseg;) {
+            uint32_t g1 = g0;
+            while (g1 < nseg && (g1 == g0 || obeg[g1 + 1] - obeg[g0] <= ((uint64_t)256 << 20))) g1++;
+            cudaStream_t gs = ctx->sstream[gi % 3]; gi++;
+            CK(cudaStreamWaitEvent(gs, ctx->sready, 0), "cudaStreamWaitEvent");
+            const int slot = next_slot(ctx);
+            CK(launch_inflate_members(ctx->d_sin, ctx->d_soff + g0, g1 - g0, -15, ctx->d_sout, ctx->d_soff + (nseg + 1) + g0, ctx->d_sres + g0, nullptr,
+                                      (int32_t*)(ctx->d_sres + 2 * capn) + g0, ctx->d_sres + 3 * capn + g0, ctx->d_sres + 4 * capn + g0,
+                                      ctx->counters + slot, ctx->sms, gs, 1),
+               "inflate byte pass");
+            const size_t ob = (size_t)obeg[g0], ol = (size_t)(obeg[g1] - obeg[g0]);
+            if (ol) CK(cudaMemcpyAsync((uint8_t*)h_out + ob, ctx->d_sout + ob, ol, cudaMemcpyDeviceToHost, gs), "D2H output");
+            g0 = g1;
+        }
+        for (int i = 0; i < 3; i++) CK(cudaStreamSynchronize(ctx->sstream[i]), "sync");
         hres.resize(5 * capn);
         CK(cudaMemcpyAsync(hres.data(), ctx->d_sres, 5 * capn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H segment results");
-        // checksum of the whole output (K3) while the results travel
+        // checksum of the whole output (K3)
         if (wr.kind == 2) { int rc = zng_b200_crc32(ctx, ctx->d_sout, total, 0, ctx->d_result + 1, st); if (rc) return rc; }
         if (wr.kind == 1) { int rc = zng_b200_adler32(ctx, ctx->d_sout, total, 1, ctx->d_result + 1, st); if (rc) return rc; }
         CK(cudaMemcpyAsync(ctx->h_result + 1, ctx->d_result + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H check");
-        if (total) CK(cudaMemcpyAsync(h_out, ctx->d_sout, total, cudaMemcpyDeviceToHost, st), "D2H output");
         CK(cudaStreamSynchronize(st), "sync");
         for (uint32_t i = 0; i < nseg; i++) {
             const int32_t ret = (int32_t)hres[2 * capn + i];

@@ -142,17 +142,28 @@ static int in_append(struct internal_state *s, const uint8_t *b, size_t n) {
     return 0;
 }
 
-/* compress [src, src+n) into the pending buffer; fin: Z_FINISH on the last piece */
+/* compress [src, src+n) into the pending buffer; fin: Z_FINISH on the last piece.  When nothing is pending and the
+ * caller's buffer can take the worst case, the bytes go straight to next_out (no staging copy; with a pinned next_out the
+ * device writes into it directly). */
 static int compress_into_pending(zng_stream *strm, const uint8_t *src, size_t n, int fin) {
     struct internal_state *s = strm->state;
     zng_b200_ctx *ctx = zng_b200_thread_ctx();
     if (!ctx) { strm->msg = "no CUDA device"; return Z_MEM_ERROR; }
-    size_t cap = n + (n >> 3) + (n / ZNG_CHUNK + 2) * 16 + 64;
-    if (pend_reserve(s, cap)) return Z_MEM_ERROR;
+    size_t cap = n + (n >> 3) + (n / ZNG_CHUNK + 1) * 8 + 16;   /* 9 bits per byte + 8 bytes per piece: what zng_deflateBound promises */
     size_t out_len = 0; uint32_t crc = 0, adler = 1;
-    int r = zng_b200_deflate_host(ctx, src, n, ZNG_CHUNK, s->level, fin, s->pend + s->pend_len, s->pend_cap - s->pend_len, &out_len, &crc, &adler);
+    size_t queued = s->pend_len - s->pend_pos;
+    int direct = (size_t)strm->avail_out >= queued + cap;
+    int r;
+    if (direct) {
+        pend_flush(strm);                                   /* header bytes first */
+        r = zng_b200_deflate_host(ctx, src, n, ZNG_CHUNK, s->level, fin, strm->next_out, strm->avail_out, &out_len, &crc, &adler);
+    } else {
+        if (pend_reserve(s, cap)) return Z_MEM_ERROR;
+        r = zng_b200_deflate_host(ctx, src, n, ZNG_CHUNK, s->level, fin, s->pend + s->pend_len, s->pend_cap - s->pend_len, &out_len, &crc, &adler);
+    }
     if (r != ZNG_B200_OK) { strm->msg = zng_b200_last_error(ctx); return r == ZNG_B200_BUF_ERROR ? Z_BUF_ERROR : (r == ZNG_B200_MEM_ERROR ? Z_MEM_ERROR : Z_STREAM_ERROR); }
-    s->pend_len += out_len;
+    if (direct) { strm->next_out += out_len; strm->avail_out -= (uint32_t)out_len; strm->total_out += out_len; }
+    else s->pend_len += out_len;
     if (s->wrap == 2) s->check = zng_crc32_combine(s->check, crc, (z_off64_t)n);
     else if (s->wrap == 1) s->check = zng_adler32_combine(s->check, adler, (z_off64_t)n);
     s->check_len += n;
