@@ -210,3 +210,31 @@ def test_checksum_api(pkg, L, zo, golden):
     assert L.zng_adler32_combine(aa, ab, b.size) == pyzlib.adler32(data.tobytes())
     assert L.zng_crc32_z(ca, b.ctypes.data, b.size) == pyzlib.crc32(data.tobytes())         # running value continues
     assert L.zng_adler32_z(aa, b.ctypes.data, b.size) == pyzlib.adler32(data.tobytes())
+
+
+def test_minigzip_cli_roundtrip(pkg, zo, tmp_path):
+    """tools/minigzip_b200 (the test/minigzip.c use case on the GPU library): gzip -1 / -2 of a file equals the
+    reference's stream for the same pieces, gunzip accepts it and python's gzip module too; -d restores the input,
+    including two concatenated members."""
+    import gzip
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(pkg.LIB_PATH), "minigzip_b200")
+    if not os.path.exists(exe):
+        pytest.skip("minigzip_b200 not built")
+    data = pkg.synth(7 * 65536 + 4321, seed=19)
+    src = tmp_path / "in.bin"
+    src.write_bytes(data.tobytes())
+    for level in (1, 2):
+        comp = subprocess.run([exe, f"-{level}", str(src)], stdout=subprocess.PIPE, check=True).stdout
+        assert comp == expected_stream(zo, data, level, 31)
+        assert gzip.decompress(comp) == data.tobytes()
+        back = subprocess.run([exe, "-d"], input=comp, stdout=subprocess.PIPE, check=True).stdout
+        assert back == data.tobytes()
+        two = subprocess.run([exe, "-d"], input=comp + comp, stdout=subprocess.PIPE, check=True).stdout
+        assert two == data.tobytes() * 2
+    other = gzip.compress(data.tobytes(), 6)                 # a member some other encoder wrote
+    assert subprocess.run([exe, "-d"], input=other, stdout=subprocess.PIPE, check=True).stdout == data.tobytes()
+    bad = bytearray(other); bad[len(bad) // 2] ^= 1
+    r = subprocess.run([exe, "-d"], input=bytes(bad), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"zng_inflate: -3" in r.stderr
