@@ -176,16 +176,16 @@ fast_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint
 
 // ---------------------------------------------------------------- K2b block writer
 constexpr int      kBlkWarps   = 4;
-constexpr uint32_t kBStageWords = 1024;
-constexpr uint32_t kBStageSeg   = 256;
+constexpr uint32_t kBStageWords = 512;             // 2 KiB staging ring per warp (a block header is <= 141 words)
+constexpr uint32_t kBStageSeg   = 128;
 constexpr int L_CODES = 286, D_CODES = 30, BL_CODES = 19, HEAP_SZ = 2 * L_CODES + 1, MAX_BITS = 15;
 
 struct alignas(16) BlockWs {
     uint32_t stage[kBStageWords];
     uint32_t lfreq[L_CODES + 2], dfreq[D_CODES + 2], bfreq[BL_CODES + 1];
     uint16_t wfreq[HEAP_SZ], wdad[HEAP_SZ], wlen[HEAP_SZ];   // the tree under construction (trees.c ct_data)
-    int16_t  heap[HEAP_SZ];
-    uint8_t  depth[HEAP_SZ];
+    unsigned long long heap64[HEAP_SZ + 1];                  // the priority queue of build_tree (key + node per entry)
+    int16_t  heap[HEAP_SZ];                                   // nodes in the order they left the queue
     uint16_t bl_count[MAX_BITS + 1];
     uint16_t lcode[L_CODES + 2], dcode[D_CODES + 2], bcode[BL_CODES + 1];
     uint16_t llen[L_CODES + 2], dlen[D_CODES + 2], blen[BL_CODES + 1];     // +1: the scan_tree guard entry
@@ -254,51 +254,58 @@ struct Emitter {
 // ---- trees.c restated for one lane --------------------------------------------------------------------
 struct TreeKind { int elems, max_len, kind; };          // kind 0 literal/length, 1 distance, 2 bit-length
 
-__device__ __forceinline__ bool node_less(const BlockWs& T, int a, int b) {   // trees.c:141-143 smaller()
-    return T.wfreq[a] < T.wfreq[b] || (T.wfreq[a] == T.wfreq[b] && T.depth[a] <= T.depth[b]);
+// Heap entries carry their own sort key so that a comparison needs no second lookup: bits 0..15 node, 16..23 depth,
+// 24..47 frequency.  smaller(n, m) of trees.c:141-143 -- freq[n] < freq[m] || (freq equal && depth[n] <= depth[m]) --
+// is then (entry_n >> 16) <= (entry_m >> 16).
+__device__ __forceinline__ unsigned long long heap_entry(uint32_t freq, uint32_t depth, uint32_t node) {
+    return ((unsigned long long)freq << 24) | ((unsigned long long)depth << 16) | node;
 }
-__device__ void sift_down(BlockWs& T, int k, int heap_len) {                 // trees.c:151-173 pqdownheap
-    const int v = T.heap[k];
+__device__ __forceinline__ void sift_down(unsigned long long* heap, int k, int heap_len) {   // trees.c:151-173 pqdownheap
+    const unsigned long long v = heap[k];
     int j = k << 1;
     while (j <= heap_len) {
-        if (j < heap_len && node_less(T, T.heap[j + 1], T.heap[j])) j++;
-        if (node_less(T, v, T.heap[j])) break;
-        T.heap[k] = T.heap[j]; k = j; j <<= 1;
+        unsigned long long hj = heap[j];
+        if (j < heap_len) { const unsigned long long hj1 = heap[j + 1]; if ((hj1 >> 16) <= (hj >> 16)) { hj = hj1; j++; } }
+        if ((v >> 16) <= (hj >> 16)) break;
+        heap[k] = hj; k = j; j <<= 1;
     }
-    T.heap[k] = (int16_t)v;
+    heap[k] = v;
 }
 
 // build_tree + gen_bitlen + gen_codes (trees.c:185-405).  freq_in -> code_out/len_out; returns max_code.
 __device__ int build_huffman(BlockWs& T, const uint32_t* freq_in, TreeKind tk, uint16_t* code_out, uint16_t* len_out,
                              uint32_t& opt_len, uint32_t& static_len) {
+    unsigned long long* heap = T.heap64;
     int heap_len = 0, heap_max = HEAP_SZ, max_code = -1, node;
     for (int n = 0; n < tk.elems; n++) {
         T.wfreq[n] = (uint16_t)freq_in[n];
-        if (freq_in[n]) { T.heap[++heap_len] = (int16_t)(max_code = n); T.depth[n] = 0; }
+        if (freq_in[n]) { heap[++heap_len] = heap_entry(freq_in[n], 0, (uint32_t)(max_code = n)); }
         else T.wlen[n] = 0;
     }
     while (heap_len < 2) {                                  // trees.c:352-360: force at least two codes
-        node = T.heap[++heap_len] = (int16_t)(max_code < 2 ? ++max_code : 0);
-        T.wfreq[node] = 1; T.depth[node] = 0;
+        node = (max_code < 2 ? ++max_code : 0);
+        heap[++heap_len] = heap_entry(1, 0, (uint32_t)node);
+        T.wfreq[node] = 1;
         opt_len--;
         if (tk.kind == 0) static_len -= fx_llen((uint32_t)node); else if (tk.kind == 1) static_len -= 5u;
     }
-    for (int n = heap_len / 2; n >= 1; n--) sift_down(T, n, heap_len);
+    for (int n = heap_len / 2; n >= 1; n--) sift_down(heap, n, heap_len);
     node = tk.elems;
     do {
-        const int n = T.heap[1];
-        T.heap[1] = T.heap[heap_len--];
-        sift_down(T, 1, heap_len);
-        const int m = T.heap[1];
-        T.heap[--heap_max] = (int16_t)n;
+        const unsigned long long en = heap[1];
+        heap[1] = heap[heap_len--];
+        sift_down(heap, 1, heap_len);
+        const unsigned long long em = heap[1];
+        const int n = (int)(en & 0xffffu), m = (int)(em & 0xffffu);
+        T.heap[--heap_max] = (int16_t)n;                    // the sorted node list gen_bitlen walks
         T.heap[--heap_max] = (int16_t)m;
-        T.wfreq[node] = (uint16_t)(T.wfreq[n] + T.wfreq[m]);
-        T.depth[node] = (uint8_t)((T.depth[n] >= T.depth[m] ? T.depth[n] : T.depth[m]) + 1);
+        const uint32_t dn = (uint32_t)(en >> 16) & 0xffu, dm = (uint32_t)(em >> 16) & 0xffu;
         T.wdad[n] = T.wdad[m] = (uint16_t)node;
-        T.heap[1] = (int16_t)node++;
-        sift_down(T, 1, heap_len);
+        heap[1] = heap_entry((uint32_t)(en >> 24) + (uint32_t)(em >> 24), ((dn >= dm ? dn : dm) + 1u) & 0xffu, (uint32_t)node);
+        node++;
+        sift_down(heap, 1, heap_len);
     } while (heap_len >= 2);
-    T.heap[--heap_max] = T.heap[1];
+    T.heap[--heap_max] = (int16_t)(heap[1] & 0xffffu);
     // gen_bitlen (trees.c:185-270)
     int overflow = 0, h;
     for (int i = 0; i <= MAX_BITS; i++) T.bl_count[i] = 0;
@@ -408,10 +415,12 @@ __device__ void emit_tokens(Emitter& E, const BlockWs& T, const uint32_t* __rest
     }
 }
 
-// zng_tr_flush_block (trees.c:625-703) for tokens [t0, t1) that cover chunk bytes [bstart, bstart + blen)
-__device__ void flush_block(Emitter& E, BlockWs& T, const uint32_t* __restrict__ tok, uint32_t t0, uint32_t t1,
-                            const uint8_t* raw, uint32_t stored_len, bool can_store, int last, unsigned lane) {
-    uint32_t opt_lenb = 0, static_lenb = 0;
+// zng_tr_flush_block (trees.c:625-703) for tokens [t0, t1), which cover the chunk bytes from bstart on.  Returns the
+// number of bytes the block covers.  `rest` != 0: this is the flush at the end of the input (the block covers the rest of
+// the chunk, len - bstart bytes, and fill_window has run at lookahead 0); otherwise the block was flushed because it is full.
+__device__ uint32_t flush_block(Emitter& E, BlockWs& T, const uint32_t* __restrict__ tok, uint32_t t0, uint32_t t1,
+                                const uint8_t* src, uint32_t bstart, uint32_t len, bool rest, int last, unsigned lane) {
+    uint32_t opt_lenb = 0, static_lenb = 0, span = 0;
     int max_blindex = 0, lmax = 0, dmax = 0;
     const uint32_t nsym = t1 - t0;
     if (nsym != 0u) {
@@ -419,17 +428,28 @@ __device__ void flush_block(Emitter& E, BlockWs& T, const uint32_t* __restrict__
         if (lane < (uint32_t)D_CODES + 2u) T.dfreq[lane] = 0;
         if (lane < (uint32_t)BL_CODES + 1u) T.bfreq[lane] = 0;
         __syncwarp();
-        for (uint32_t i = t0 + lane; i < t1; i += 32u) {     // zng_tr_tally_lit / _dist (deflate_p.h:61-98)
-            const uint32_t t = __ldcs(tok + i);
-            if (!(t & kTokMatch)) atomicAdd(&T.lfreq[t & 0xffu], 1u);
-            else {
-                uint32_t ls, lx, lxb, ds, dx, dxb;
-                len_symbol(((t >> 16) & 0x1ffu) - 3u, ls, lx, lxb);
-                dist_symbol((t & 0xffffu) - 1u, ds, dx, dxb);
-                atomicAdd(&T.lfreq[257u + ls], 1u);
-                atomicAdd(&T.dfreq[ds], 1u);
+        // zng_tr_tally_lit / _dist (deflate_p.h:61-98), four tokens per lane in flight; the byte span rides along
+        for (uint32_t base = t0; base < t1; base += 128u) {
+            uint32_t tk[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const uint32_t i = base + 32u * u + lane; tk[u] = i < t1 ? __ldcs(tok + i) : kTokEnd; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t t = tk[u];
+                if (t == kTokEnd) continue;
+                if (!(t & kTokMatch)) { atomicAdd(&T.lfreq[t & 0xffu], 1u); span += 1u; }
+                else {
+                    uint32_t ls, lx, lxb, ds, dx, dxb;
+                    len_symbol(((t >> 16) & 0x1ffu) - 3u, ls, lx, lxb);
+                    dist_symbol((t & 0xffffu) - 1u, ds, dx, dxb);
+                    atomicAdd(&T.lfreq[257u + ls], 1u);
+                    atomicAdd(&T.dfreq[ds], 1u);
+                    span += (t >> 16) & 0x1ffu;
+                }
             }
         }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) span += __shfl_xor_sync(ZB_FULL, span, d);
         __syncwarp();
         if (lane == 0) {
             T.lfreq[256] = 1;                               // init_block: END_BLOCK
@@ -451,6 +471,17 @@ __device__ void flush_block(Emitter& E, BlockWs& T, const uint32_t* __restrict__
         static_lenb = __shfl_sync(ZB_FULL, static_lenb, 0);
     }
     __syncwarp();
+    // what the block covers, and whether it may still be stored: after the tail slide (deflate.c:1285-1299) a block that
+    // began below 32768 has block_start < 0, FLUSH_BLOCK passes buf == NULL (deflate_p.h:104-112) and trees.c:673 refuses
+    uint32_t stored_len; bool slid;
+    if (rest) { stored_len = len - bstart; slid = len >= kSlideAt; }
+    else {
+        const uint32_t tl = __ldcs(tok + t1 - 1u);
+        const uint32_t s_last = bstart + span - ((tl & kTokMatch) ? ((tl >> 16) & 0x1ffu) : 1u);   // parser position before the last symbol
+        stored_len = span; slid = s_last >= kSlideAt && len - s_last < 262u;
+    }
+    const bool can_store = !(slid && bstart < kWSize);
+    const uint8_t* raw = src + bstart;
     if (stored_len + 4u <= opt_lenb && can_store) {         // zng_tr_stored_block (trees.c:592-609)
         if (lane == 0) {
             E.put_serial((uint32_t)last, 3);
@@ -489,17 +520,7 @@ __device__ void flush_block(Emitter& E, BlockWs& T, const uint32_t* __restrict__
     }
     if (last) { E.bitpos = (E.bitpos + 7u) & ~7u; }          // bi_windup
     __syncwarp();
-}
-
-// byte length covered by tokens [t0, t1) and the start position of the last one (warp-collective)
-__device__ void span_of(const uint32_t* __restrict__ tok, uint32_t t0, uint32_t t1, unsigned lane, uint32_t& bytes, uint32_t& last_tok_len) {
-    uint32_t s = 0;
-    for (uint32_t i = t0 + lane; i < t1; i += 32u) { const uint32_t t = __ldcs(tok + i); s += (t & kTokMatch) ? ((t >> 16) & 0x1ffu) : 1u; }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(ZB_FULL, s, d);
-    bytes = s;
-    const uint32_t t = t1 > t0 ? __ldcs(tok + t1 - 1u) : 0u;
-    last_tok_len = (t & kTokMatch) ? ((t >> 16) & 0x1ffu) : 1u;
+    return stored_len;
 }
 
 __global__ void __launch_bounds__(kBlkWarps * 32)
@@ -521,18 +542,11 @@ block_emit_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ t
         uint32_t t0 = 0, bstart = 0;
         // deflate_fast.c:93-94: a block is flushed as soon as it holds 16383 symbols
         while (nt - t0 >= kSymEnd) {
-            uint32_t bytes, ltl;
-            span_of(tok, t0, t0 + kSymEnd, lane, bytes, ltl);
-            const uint32_t s_last = bstart + bytes - ltl;   // where the parser stood before the block's last symbol
-            const bool slid = s_last >= kSlideAt && len - s_last < 262u;       // deflate.c:1285-1299 ran by then
-            flush_block(E, T, tok, t0, t0 + kSymEnd, src + bstart, bytes, !(slid && bstart < kWSize), 0, lane);
-            t0 += kSymEnd; bstart += bytes;
+            bstart += flush_block(E, T, tok, t0, t0 + kSymEnd, src, bstart, len, false, 0, lane);
+            t0 += kSymEnd;
         }
         // deflate_fast.c:96-103: the rest (also an empty last block for Z_FINISH)
-        if (last || nt > t0) {
-            const bool slid = len >= kSlideAt;              // fill_window at lookahead 0 slides once strstart >= 65274
-            flush_block(E, T, tok, t0, nt, src + bstart, len - bstart, !(slid && bstart < kWSize), last, lane);
-        }
+        if (last || nt > t0) flush_block(E, T, tok, t0, nt, src, bstart, len, true, last, lane);
         if (!last) {                                        // deflate.c:1064-1065 zng_tr_stored_block(NULL, 0, 0)
             if (lane == 0) {
                 E.bitpos += 3;
@@ -572,7 +586,7 @@ cudaError_t launch_block_emit(const uint8_t* in, const uint32_t* tokens, uint32_
     const int smem = (int)(sizeof(BlockWs) * kBlkWarps);
     cudaError_t e = cudaFuncSetAttribute(block_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    uint32_t grid = (uint32_t)num_sms * 4u;
+    uint32_t grid = (uint32_t)num_sms * (uint32_t)((227 * 1024) / (smem + 1024));     // as many CTAs as the shared memory of an SM holds
     const uint32_t need = (nchunks + kBlkWarps - 1u) / kBlkWarps;
     if (grid > need) grid = need;
     block_emit_kernel<<<grid, kBlkWarps * 32, smem, stream>>>(in, tokens, tok_stride, ntok, n, chunk, nchunks, last, out, out_stride, sizes);
