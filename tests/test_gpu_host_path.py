@@ -49,3 +49,70 @@ def test_deflate_host_output_too_small(pkg, ctx):
     with pytest.raises(pkg.ZngB200Error) as ei:
         ctx.deflate_host(data, data.size, 65536, 1, True, out, 1000)
     assert ei.value.code == pkg.Z_BUF_ERROR
+
+
+def test_more_chunks_than_one_batch(pkg, ctx, zo):
+    """More than 16384 chunks in one call: the chunk compressor runs several launches that share the token scratch
+    (small chunks keep the test cheap); level 2's later batches still see the stream bytes in front of them."""
+    import torch
+    for level, chunk, nch in ((1, 2048, 40000), (2, 2048, 20000), (2, 65536, 16384 + 3)):
+        n = chunk * nch - 777
+        data = pkg.synth(n, seed=level * 7 + 1)
+        d_in = torch.from_numpy(data).to(f"cuda:{ctx.device}")
+        slots, stride, sizes, crcs, adlers = ctx.alloc_chunk_outputs(n, chunk)
+        ctx.deflate_chunks(d_in, n, chunk, level, 3, slots, stride, sizes, crcs, adlers)
+        torch.cuda.synchronize()
+        hs = sizes.cpu().numpy().view(np.uint32)[:nch]
+        hslots = slots.cpu().numpy().reshape(-1, stride)
+        pick = np.concatenate([np.arange(0, 4), np.arange(16380, 16390), np.arange(nch - 3, nch), np.random.default_rng(1).choice(nch, 40, replace=False)])
+        for ci in np.unique(pick[pick < nch]):
+            lo = ci * chunk
+            piece = data[lo: min(lo + chunk, n)]
+            if level == 2 and chunk == 65536 and piece.size < chunk:
+                # a short last chunk sees the previous chunk's window bytes: compress it in stream context with the oracle
+                exp, es, _, _ = zo.port_deflate_chunks(data[lo - chunk:], chunk, level, 3, stride, nthreads=1)
+                e_bytes, e_size = exp[1], es[1]
+            else:
+                exp, es, _, _ = zo.port_deflate_chunks(piece, chunk, level, 3, stride, nthreads=1)
+                e_bytes, e_size = exp[0], es[0]
+            assert hs[ci] == e_size and np.array_equal(hslots[ci, : e_size], e_bytes[: e_size]), (level, chunk, int(ci))
+        assert int(crcs.cpu().numpy().view(np.uint32)[nch - 1]) == pyzlib.crc32(data[(nch - 1) * chunk:].tobytes())
+
+
+def test_two_host_threads_two_contexts(pkg, zo):
+    """One context per host thread (the reference's "one zng_stream per thread"): two threads compress and inflate
+    different buffers at the same time through zlib-ng's API names; results must not interfere
+    (test_deflate_concurrency.cc is the reference's analogue)."""
+    import ctypes
+    import threading
+    L = pkg.lib()
+    results = {}
+
+    def work(tid):
+        data = pkg.synth((6 + tid) * 65536 + 1000 * tid, seed=40 + tid)
+        for rep in range(3):
+            s = pkg.ZngStream()
+            assert L.zng_deflateInit2(ctypes.byref(s), 1 + (tid & 1), 8, 31, 8, 0) == 0
+            comp = np.zeros(int(L.zng_deflateBound(ctypes.byref(s), data.size)) + 64, dtype=np.uint8)
+            s.next_in = data.ctypes.data; s.avail_in = data.size; s.next_out = comp.ctypes.data; s.avail_out = comp.size
+            assert L.zng_deflate(ctypes.byref(s), 4) == 1
+            clen = int(s.total_out)
+            L.zng_deflateEnd(ctypes.byref(s))
+            d = pkg.ZngStream()
+            assert L.zng_inflateInit2(ctypes.byref(d), 31) == 0
+            back = np.zeros(data.size, dtype=np.uint8)
+            d.next_in = comp.ctypes.data; d.avail_in = clen; d.next_out = back.ctypes.data; d.avail_out = back.size
+            assert L.zng_inflate(ctypes.byref(d), 4) == 1
+            L.zng_inflateEnd(ctypes.byref(d))
+            assert np.array_equal(back, data)
+            results[(tid, rep)] = pyzlib.crc32(comp[:clen].tobytes())
+        results[("crc", tid)] = L.zng_crc32_z(0, data.ctypes.data, data.size) == pyzlib.crc32(data.tobytes())
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(3)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for tid in range(3):
+        assert results[("crc", tid)]
+        assert results[(tid, 0)] == results[(tid, 1)] == results[(tid, 2)]

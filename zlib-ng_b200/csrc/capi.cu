@@ -79,7 +79,6 @@ struct zng_b200_ctx {
     uint32_t* vtails = nullptr;
     int chains_per_sm = 24;
     int chains_per_sm_l2 = 32;                 // measured on B200: 16 -> 12.4, 24 -> 14.4, 32 -> 15.4 GB/s
-    uint32_t k1_flags = 8;                     // parser tuning switches (deflate_quick.cu), env ZNG_B200_FLAGS
     Scratch scratch;                           // for the device-resident entry points; users are ordered by k1_done
     cudaEvent_t k1_done = nullptr;
     bool k1_pending = false;
@@ -162,11 +161,11 @@ int ensure_scratch(zng_b200_ctx* ctx, Scratch& sc, uint32_t batch, uint32_t stri
     return 0;
 }
 
-// K1 for level 1: K1a parse -> token lists in `sc`, K1b static emit (+ the K3 tile kernel when per-chunk
+// Chunk compression.  Level 1: K1a parse -> token lists in `sc`, K1b static emit (+ the K3 tile kernel when per-chunk
 // checksums are wanted).  Inputs larger than kBatchChunks chunks run as several batches that reuse
 // the token scratch (4 B per input byte).
 // level 2: K2a parse (hash chains) -> token lists, K2b block writer.  have_prev: see kernels.h.
-int run_deflate_quick(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
+int run_deflate_chunks(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
                       uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers,
                       cudaStream_t stream, uint32_t* d_tokens, uint32_t tok_stride, int level = 1, int have_prev = 0) {
     if (nchunks == 0) return 0;
@@ -195,7 +194,7 @@ int run_deflate_quick(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size_
             continue;
         }
         CK(launch_quick_parse(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->sm_slots,
-                              grid, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), ctx->k1_flags, stream),
+                              grid, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream),
            "quick_parse launch");
         CK(launch_static_emit(toks, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
                               d_sizes + c0, ctx->sms, stream),
@@ -207,12 +206,12 @@ int run_deflate_quick(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size_
 }
 
 // the ctx-level scratch is shared by all device-resident calls: order them
-int run_deflate_quick_shared(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
+int run_deflate_shared(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
                              uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers,
                              cudaStream_t stream, uint32_t* d_tokens, uint32_t tok_stride, int level) {
     if (nchunks == 0) return 0;
     if (ctx->k1_pending) CK(cudaStreamWaitEvent(stream, ctx->k1_done, 0), "cudaStreamWaitEvent");
-    int r = run_deflate_quick(ctx, ctx->scratch, d_in, n, chunk, nchunks, last, d_out, out_stride, d_sizes, d_crcs, d_adlers, stream,
+    int r = run_deflate_chunks(ctx, ctx->scratch, d_in, n, chunk, nchunks, last, d_out, out_stride, d_sizes, d_crcs, d_adlers, stream,
                               d_tokens, tok_stride, level, 0);
     if (r) return r;
     CK(cudaEventRecord(ctx->k1_done, stream), "cudaEventRecord");
@@ -298,7 +297,6 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     if (const char* e = getenv("ZNG_B200_SLAB_CHUNKS")) { int v = atoi(e); if (v >= 64 && v <= 16384) ctx->slab_chunks = (uint32_t)v; }
     if (const char* e = getenv("ZNG_B200_PIPE")) { int v = atoi(e); if (v >= 2 && v <= kPipeMax) ctx->pipe = v; }
     if (const char* e = getenv("ZNG_B200_CHAINS_L2")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm_l2 = v; }
-    if (const char* e = getenv("ZNG_B200_FLAGS")) ctx->k1_flags = (uint32_t)atoi(e);
     if (cudaMalloc(&ctx->counters, kCounters * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->tails, (size_t)kCounters * deflate_quick_tail_bytes()) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->k1_done, cudaEventDisableTiming) != cudaSuccess ||
@@ -404,7 +402,7 @@ int zng_b200_deflate_chunks_trace(zng_b200_ctx* ctx, const void* d_in, size_t n,
     if (!d_tokens || tok_stride < chunk + 1u) return bad(ctx, "d_tokens / tok_stride");
     DeviceGuard g(ctx->device);
     const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
-    return run_deflate_quick_shared(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
+    return run_deflate_shared(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
                                     d_sizes, nullptr, nullptr, (cudaStream_t)stream, d_tokens, tok_stride, level);
 }
 
@@ -415,7 +413,7 @@ int zng_b200_deflate_chunks(zng_b200_ctx* ctx, const void* d_in, size_t n, uint3
     if (r) return r;
     DeviceGuard g(ctx->device);
     const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
-    return run_deflate_quick_shared(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
+    return run_deflate_shared(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
                                     d_sizes, d_crcs, d_adlers, (cudaStream_t)stream, nullptr, 0, level);
 }
 
@@ -970,13 +968,13 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
             const uint32_t body = nch ? nch - 1 : 0;
             const size_t body_bytes = (size_t)body * chunk;
             if (body) {
-                r = run_deflate_quick(ctx, s.scratch, s.d_in, body_bytes, chunk, body, 0, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream, nullptr, 0,
+                r = run_deflate_chunks(ctx, s.scratch, s.d_in, body_bytes, chunk, body, 0, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream, nullptr, 0,
                                       level, have_prev);
                 if (r) { sync_slabs(ctx); return r; }
             }
             const size_t tail = take - body_bytes;
             if (tail) {
-                r = run_deflate_quick(ctx, s.scratch, s.d_in + body_bytes, tail, chunk, 1, 1, s.d_slots + (size_t)body * stride, stride,
+                r = run_deflate_chunks(ctx, s.scratch, s.d_in + body_bytes, tail, chunk, 1, 1, s.d_slots + (size_t)body * stride, stride,
                                       d_sizes + body, d_crcs + body, d_adlers + body, s.stream, nullptr, 0, level, (body || have_prev) ? 1 : 0);
                 if (r) { sync_slabs(ctx); return r; }
             } else {
@@ -991,7 +989,7 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
             }
             emitted_final = true;
         } else {
-            r = run_deflate_quick(ctx, s.scratch, s.d_in, take, chunk, nch, 0, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream, nullptr, 0,
+            r = run_deflate_chunks(ctx, s.scratch, s.d_in, take, chunk, nch, 0, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream, nullptr, 0,
                                   level, have_prev);
             if (r) { sync_slabs(ctx); return r; }
         }

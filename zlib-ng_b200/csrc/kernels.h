@@ -16,8 +16,7 @@ size_t deflate_quick_tail_bytes();
 uint32_t deflate_quick_grid(uint32_t nchunks, int num_sms, int chains_per_sm);
 cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                                uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
-                               uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, uint32_t flags,
-                               cudaStream_t stream);
+                               uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream);
 cudaError_t launch_static_emit(const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n, uint32_t chunk,
                                uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
                                int num_sms, cudaStream_t stream);
