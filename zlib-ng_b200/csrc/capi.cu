@@ -786,14 +786,8 @@ int zng_b200_inflate_stream_host(zng_b200_ctx* ctx, const void* h_in, size_t n, 
             } else return exact();                            // data error, no final block, ...: the exact path reports it
         }
         if (!ended && !merged) return exact();                // ran off the end of the input without a final block
-        if (merged && !ended) {                               // keep the untouched tail behind the last examined segment
-            // (the loop above consumed every segment, so nothing is left to copy)
-        }
-        starts.swap(nstarts); segs.swap(nsegs);
-        finished = ended && !merged;
-        if (ended && merged) {                                // segments behind the final one were cut off; re-run the merged ones
-            // the final segment itself may be among the dirty ones; loop again
-        }
+        starts.swap(nstarts); segs.swap(nsegs);               // (segments behind a final block are cut off)
+        finished = ended && !merged;                          // merged segments are re-sized in the next round
     }
     if (!finished) return exact();
     // ---- trailer present?
