@@ -96,6 +96,7 @@ struct zng_b200_ctx {
     // parallel stream inflate: whole-stream device buffers (grow only)
     uint8_t* d_sin = nullptr;  size_t sin_cap = 0;
     uint8_t* d_sout = nullptr; size_t sout_cap = 0;
+    uint8_t* d_sslots = nullptr; size_t sslots_cap = 0;   // one-pass attempt: a 64 KiB output slot per segment
     uint64_t* d_soff = nullptr; uint32_t* d_sres = nullptr; uint32_t seg_cap = 0;
     unsigned long long* d_marks = nullptr; uint32_t marks_cap = 0;
     cudaStream_t sstream[3] = {nullptr, nullptr, nullptr};   // byte pass + D2H of segment groups
@@ -348,6 +349,7 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
     }
     if (ctx->d_sin) cudaFree(ctx->d_sin);
     if (ctx->d_sout) cudaFree(ctx->d_sout);
+    if (ctx->d_sslots) cudaFree(ctx->d_sslots);
     if (ctx->d_soff) cudaFree(ctx->d_soff);
     if (ctx->d_sres) cudaFree(ctx->d_sres);
     if (ctx->d_marks) cudaFree(ctx->d_marks);
@@ -728,6 +730,79 @@ int zng_b200_inflate_stream_host(zng_b200_ctx* ctx, const void* h_in, size_t n, 
     std::vector<uint64_t> starts;
     starts.push_back(wr.body);
     for (unsigned long long m : marks) if (m > wr.body && m < n) starts.push_back(m);
+    const size_t tlen0 = wr.kind == 2 ? 8 : (wr.kind == 1 ? 4 : 0);
+    // ---- one pass when every segment fits a 64 KiB slot (the streams this library and pigz -b 64 write): decode straight
+    // into slots, scan the sizes, gather.  Any surprise (a segment larger than its slot, a false marker, an error) leaves
+    // it to the two-pass path below.
+    {
+        const uint32_t nseg1 = (uint32_t)starts.size();
+        const size_t S = ZNG_B200_CHUNK_MAX;
+        bool ok = (size_t)nseg1 * S <= ((size_t)24 << 30);
+        std::vector<uint32_t> h1;
+        size_t total1 = 0, end1 = 0;
+        if (ok) {
+            r = grow(ctx, ctx->d_sslots, ctx->sslots_cap, (size_t)nseg1 * S + 64, "cudaMalloc(stream slots)");
+            if (r) return r;
+            if (ctx->seg_cap < nseg1 + 1u) {
+                if (ctx->d_soff) { cudaDeviceSynchronize(); cudaFree(ctx->d_soff); cudaFree(ctx->d_sres); ctx->d_soff = nullptr; ctx->d_sres = nullptr; ctx->seg_cap = 0; }
+                const uint32_t want = nseg1 + nseg1 / 4 + 1024;
+                CK(cudaMalloc(&ctx->d_soff, 4 * ((size_t)want + 1) * sizeof(uint64_t)), "cudaMalloc(segment offsets)");
+                CK(cudaMalloc(&ctx->d_sres, 5 * (size_t)want * sizeof(uint32_t)), "cudaMalloc(segment results)");
+                ctx->seg_cap = want;
+            }
+            std::vector<uint64_t> ho(2 * ((size_t)nseg1 + 1));
+            for (uint32_t i = 0; i < nseg1; i++) { ho[i] = starts[i]; ho[nseg1 + 1 + i] = (uint64_t)i * S; }
+            ho[nseg1] = n; ho[2 * (size_t)nseg1 + 1] = (uint64_t)nseg1 * S;
+            CK(cudaMemcpyAsync(ctx->d_soff, ho.data(), ho.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st), "H2D segment offsets");
+            const size_t capn = ctx->seg_cap;
+            const int slot = next_slot(ctx);
+            CK(launch_inflate_members(ctx->d_sin, ctx->d_soff, nseg1, -15, ctx->d_sslots, ctx->d_soff + (nseg1 + 1), ctx->d_sres, nullptr,
+                                      (int32_t*)(ctx->d_sres + 2 * capn), ctx->d_sres + 3 * capn, ctx->d_sres + 4 * capn, ctx->counters + slot,
+                                      ctx->sms, st, 1),
+               "inflate slot pass");
+            h1.resize(5 * capn);
+            CK(cudaMemcpyAsync(h1.data(), ctx->d_sres, 5 * capn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H segment results");
+            CK(cudaStreamSynchronize(st), "sync");
+            uint32_t used_segs = 0;
+            for (uint32_t i = 0; i < nseg1 && ok; i++) {
+                const int32_t ret = (int32_t)h1[2 * capn + i];
+                const uint64_t len_i = ((i + 1 < nseg1) ? starts[i + 1] : n) - starts[i];
+                total1 += h1[i]; used_segs = i + 1;
+                if (ret == 1) { end1 = (size_t)(starts[i] + h1[3 * capn + i]); break; }
+                if (!(ret == 0 && h1[3 * capn + i] == len_i)) ok = false;
+            }
+            if (ok && end1 == 0) ok = false;                    // no final block
+            if (ok && end1 + tlen0 > n) ok = false;
+            if (ok && total1 <= cap) {
+                r = grow(ctx, ctx->d_sout, ctx->sout_cap, total1 + 64, "cudaMalloc(stream out)");
+                if (r) return r;
+                uint64_t* d_goff = ctx->d_soff + 2 * ((size_t)nseg1 + 1);             // scanned offsets (used_segs + 1 entries)
+                CK(launch_offsets(ctx->d_sres, used_segs, 0, d_goff, st), "offsets launch");
+                CK(launch_gather(ctx->d_sslots, S, ctx->d_sres, d_goff, used_segs, ctx->d_sout, ctx->sms, st), "gather launch");
+                if (wr.kind == 2) { int rc = zng_b200_crc32(ctx, ctx->d_sout, total1, 0, ctx->d_result + 1, st); if (rc) return rc; }
+                if (wr.kind == 1) { int rc = zng_b200_adler32(ctx, ctx->d_sout, total1, 1, ctx->d_result + 1, st); if (rc) return rc; }
+                CK(cudaMemcpyAsync(ctx->h_result + 1, ctx->d_result + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H check");
+                if (total1) CK(cudaMemcpyAsync(h_out, ctx->d_sout, total1, cudaMemcpyDeviceToHost, st), "D2H output");
+                CK(cudaStreamSynchronize(st), "sync");
+                const uint32_t chk1 = wr.kind ? ctx->h_result[1] : 0u;
+                *out_len = total1; *check = chk1; *detail = 0; *status = 1; *in_used = end1 + tlen0;
+                const uint8_t* t = src + end1;
+                if (wr.kind == 2) {
+                    const uint32_t c = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24), l = t[4] | (t[5] << 8) | (t[6] << 16) | ((uint32_t)t[7] << 24);
+                    if (c != chk1) { *status = ZNG_B200_DATA_ERROR; *detail = 17; }
+                    else if (l != (uint32_t)total1) { *status = ZNG_B200_DATA_ERROR; *detail = 18; }
+                } else if (wr.kind == 1) {
+                    const uint32_t c = ((uint32_t)t[0] << 24) | (t[1] << 16) | (t[2] << 8) | t[3];
+                    if (c != chk1) { *status = ZNG_B200_DATA_ERROR; *detail = 17; }
+                }
+                return 0;
+            }
+            if (ok && total1 > cap) {                            // Z_BUF_ERROR; the size needed is reported
+                *status = ZNG_B200_BUF_ERROR; *detail = 0x100u | 0x400u; *out_len = total1; *in_used = 0;
+                return 0;
+            }
+        }
+    }
     // ---- size pass (count mode); segments whose end marker proves false are merged with their successor and re-run
     struct Seg { uint32_t size = 0, used = 0, det = 0; int32_t ret = -5; bool dirty = true; };
     std::vector<Seg> segs(starts.size());
