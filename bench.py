@@ -36,6 +36,7 @@ MEMBER = 4096
 SEED = 0x9E3779B97F4A7C15
 UNIT = "GB/s"
 METRICS = {"deflate1": "level1_deflate_input_throughput", "deflate2": "level2_deflate_input_throughput",
+           "deflate3": "level3_deflate_input_throughput",
            "checksum": "crc32_adler32_input_throughput", "inflate": "inflate_output_throughput"}
 
 
@@ -54,8 +55,9 @@ def parse_args():
 
 def workload_text(w, mib, ngpu):
     n = mib << 20
-    if w in ("deflate1", "deflate2"):
-        lvl, fn, cfg = (1, "deflate_quick", "configs[0]") if w == "deflate1" else (2, "deflate_fast", "configs[2] at 1 GiB per GPU")
+    if w.startswith("deflate"):
+        lvl, fn, cfg = {"deflate1": (1, "deflate_quick", "configs[0]"), "deflate2": (2, "deflate_fast", "configs[2] at 1 GiB per GPU"),
+                        "deflate3": (3, "deflate_medium", "configs[2] at 1 GiB per GPU")}[w]
         return (f"{fn} level {lvl}, {mib} MiB per GPU as {n // CHUNK} x 64 KiB raw-deflate chunks + per-chunk crc32, offset scan + gather + "
                 f"crc32_combine fold (BASELINE {cfg})")
     if w == "checksum":
@@ -190,8 +192,8 @@ def cpu_reference_run(workload: str, n_bytes: int, steps: int, warmup: int):
     if kind == "port":
         cores = min(cores, 256)
     ratio = None
-    if workload in ("deflate1", "deflate2"):
-        level = 1 if workload == "deflate1" else 2
+    if workload.startswith("deflate"):
+        level = int(workload[-1])
         fn = zo.ref().refdrv_deflate_chunks if kind == "reference" else zo.port().zo_deflate_chunks
         data = pkg.synth(n_bytes, SEED)
         nch = (n_bytes + CHUNK - 1) // CHUNK
@@ -228,7 +230,7 @@ def cpu_reference_run(workload: str, n_bytes: int, steps: int, warmup: int):
             raise RuntimeError(f"reference {workload} failed: {r}")
         if it >= warmup:
             times.append(t1 - t0)
-    if workload in ("deflate1", "deflate2"):
+    if workload.startswith("deflate"):
         ratio = float(sizes.sum()) / n_bytes
     if workload == "inflate" and not (status == 1).all():
         raise RuntimeError("reference inflate: a member did not reach Z_STREAM_END")
@@ -245,7 +247,7 @@ def ctypes_u32():
 def cpu_sample_bytes(workload, n, seconds, reps):
     """Bounded sample of the workload for the CPU arm: about `seconds` of wall clock over `reps` passes."""
     cores = host_cores()
-    per_core = {"deflate1": 0.10e9, "deflate2": 0.06e9, "checksum": 5e9, "inflate": 0.5e9}[workload]
+    per_core = {"deflate1": 0.10e9, "deflate2": 0.06e9, "deflate3": 0.05e9, "checksum": 5e9, "inflate": 0.5e9}[workload]
     budget = int(per_core * cores * seconds / max(1, reps))
     return min(n, max(64 << 20, (budget >> 26) << 26))
 
@@ -306,8 +308,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    if wl in ("deflate1", "deflate2"):
-        level = 1 if wl == "deflate1" else 2
+    if wl.startswith("deflate"):
+        level = int(wl[-1])
         nch = n // CHUNK
         stride = pkg.deflate_bound(CHUNK)
         h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)        # this rank's shard of the synthetic stream
@@ -372,7 +374,7 @@ def run_b200(args):
             return call, (lambda: (n, int(state["out_len"]))), "zng_b200_deflate_host (pinned host in/out, 4 x 128 MiB slabs in flight on separate streams)"
         e2e_fn = make_e2e
         alg_bytes = lambda ob: n + ob                                     # in + out per chunk, x chunks per launch
-        kernel_name = "quick_parse_kernel + static_emit_kernel (+ checksum_tiles_kernel)" if level == 1 else "fast_parse_kernel + block_emit_kernel (+ checksum_tiles_kernel)"
+        kernel_name = "quick_parse_kernel + static_emit_kernel (+ checksum_tiles_kernel)" if level == 1 else f"fast_parse_kernel<{level}> + block_emit_kernel (+ checksum_tiles_kernel)"
         note = "serial-per-chunk LZ77 parse: latency/issue bound, not HBM bound (see DESIGN.md)"
 
     elif wl == "checksum":

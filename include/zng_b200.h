@@ -12,7 +12,8 @@
  * every entry point fails when the device or the kernels are unavailable.
  *
  * Frozen parameters: windowBits 15, memLevel 8, Z_DEFAULT_STRATEGY,
- * chunk <= 65536 bytes, levels 1 (deflate_quick) and 2 (deflate_fast).
+ * chunk <= 65536 bytes, levels 1 (deflate_quick), 2 (deflate_fast) and 3 (deflate_medium; below level 5 it runs
+ * without its look-ahead branch, deflate_medium.c:151,234).
  */
 #ifndef ZNG_B200_H
 #define ZNG_B200_H
@@ -71,7 +72,8 @@ size_t      zng_b200_deflate_bound(size_t chunk_len);
  *   d_sizes[i]  compressed size of chunk i
  *   d_crcs[i]   zng_crc32(0, chunk i)    (may be NULL)       crc32.c:27-41
  *   d_adlers[i] zng_adler32(1, chunk i)  (may be NULL)       adler32.c:15-28
- * level 1 = deflate_quick (deflate_quick.c:47-130), level 2 = deflate_fast (deflate_fast.c:19-104). */
+ * level 1 = deflate_quick (deflate_quick.c:47-130), level 2 = deflate_fast (deflate_fast.c:19-104),
+ * level 3 = deflate_medium (deflate_medium.c:146-278). */
 int zng_b200_deflate_chunks(zng_b200_ctx *ctx, const void *d_in, size_t n, uint32_t chunk, int level, int flush,
                             void *d_out, size_t out_stride, uint32_t *d_sizes, uint32_t *d_crcs,
                             uint32_t *d_adlers, void *stream);

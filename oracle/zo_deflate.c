@@ -398,10 +398,13 @@ static void flush_block(blockstate *bs, bitw *b, const uint8_t *raw, uint32_t st
     if (last) bw_align(b);
 }
 
-/* match_tpl.h:26-280 restated for level 2 (best_len starts at 2, nice 8, chain 4, level<5).
- * The pre-filter at best_len 2..7 is exactly "bytes 0..best_len equal" (SURVEY 8(a6)). */
-static uint32_t longest_match_l2(const lzstate *s, uint32_t pos, uint32_t cand, uint32_t lookahead, uint32_t *mstart) {
-    uint32_t best = 2, chain = 4;
+/* match_tpl.h:26-280 restated for levels 2 and 3 (best_len starts at 2; level 2: nice 8, chain 4; level 3: nice 16,
+ * chain 6; level < 5).  With OPTIMAL_CMP 64 the pre-filter compares the 2 / 4 / 8 bytes that END at index best_len plus the
+ * first 2 / 4 / 8 bytes; for best_len 2..15 the two ranges touch or overlap, so the filter is exactly "bytes 0..best_len
+ * equal"  -- it leaves a gap only from best_len 16 on, which nice_match <= 16 never reaches. */
+static uint32_t longest_match_l2(const lzstate *s, uint32_t pos, uint32_t cand, uint32_t lookahead, uint32_t *mstart);
+static uint32_t longest_match_lv(const lzstate *s, uint32_t pos, uint32_t cand, uint32_t lookahead, uint32_t chain, uint32_t nice, uint32_t *mstart) {
+    uint32_t best = 2;
     uint32_t limit = pos > ZO_MAX_DIST ? pos - ZO_MAX_DIST : 0;
     for (;;) {
         if (cand >= pos) break;
@@ -413,7 +416,7 @@ static uint32_t longest_match_l2(const lzstate *s, uint32_t pos, uint32_t cand, 
                 *mstart = cand;
                 if (len > lookahead) return lookahead;
                 best = len;
-                if (best >= 8) return best;
+                if (best >= nice) return best;
             } else break;   /* early_exit (unreachable here, kept for fidelity: match_tpl.h:261-266) */
         }
         if (--chain == 0) break;
@@ -423,9 +426,17 @@ static uint32_t longest_match_l2(const lzstate *s, uint32_t pos, uint32_t cand, 
     return best;
 }
 
+static uint32_t longest_match_l2(const lzstate *s, uint32_t pos, uint32_t cand, uint32_t lookahead, uint32_t *mstart) {
+    return longest_match_lv(s, pos, cand, lookahead, 4, 8, mstart);
+}
+
 typedef struct { lzstate lz; blockstate bs; } deflater;
 
-static void fast_parse(deflater *d, bitw *b, int last, tok_sink sink, void *ctx) {   /* deflate_fast.c:25-103 */
+/* level 2: deflate_fast.c:25-103.  level 3: deflate_medium.c:146-278 with early_exit (level < 5), i.e. without the
+ * look-ahead-one branch: a greedy parse with longest_match {nice 16, chain 6}, a match shorter than 4 becomes one literal
+ * (:214-215, :22-32), and insert_match (:44-82) inserts every position inside the match unless
+ * lookahead <= match_length + WANT_MIN_MATCH. */
+static void fast_parse(deflater *d, bitw *b, int last, tok_sink sink, void *ctx, int level) {
     lzstate *s = &d->lz; blockstate *bs = &d->bs;
     uint32_t pos = 0, n = s->len, block_start = 0; int slid = 0;
     block_init(bs);
@@ -437,7 +448,7 @@ static void fast_parse(deflater *d, bitw *b, int last, tok_sink sink, void *ctx)
             uint32_t cand = quick_insert(s, pos);
             uint32_t dist = pos - cand;
             if (dist > 0 && dist <= ZO_MAX_DIST && cand != 0 && cand < pos)
-                ml = longest_match_l2(s, pos, cand, left, &mstart);
+                ml = level == 3 ? longest_match_lv(s, pos, cand, left, 6, 16, &mstart) : longest_match_l2(s, pos, cand, left, &mstart);
         }
         int full;
         if (ml >= ZO_WANT_MIN) {
@@ -445,6 +456,11 @@ static void fast_parse(deflater *d, bitw *b, int last, tok_sink sink, void *ctx)
             bs->d_buf[bs->sym_next] = (uint16_t)dist; bs->l_buf[bs->sym_next++] = (uint8_t)(ml - 3);
             bs->lt.freq[257 + len_sym[ml - 3]]++; bs->dt.freq[dist_sym(dist - 1)]++;
             if (sink) sink(ctx, 0x80000000u | (ml << 16) | dist);
+            if (level == 3) {                            /* insert_match: lookahead (before the match is emitted) > len + 4 */
+                if (left > ml + ZO_WANT_MIN) for (uint32_t k = 1; k < ml; k++) quick_insert(s, pos + k);
+                pos += ml;
+                goto tallied;
+            }
             left -= ml;
             if (ml <= 4 && left >= ZO_WANT_MIN) {        /* max_insert_length = max_lazy = 4 at level 2 */
                 for (uint32_t k = 1; k < ml; k++) quick_insert(s, pos + k);
@@ -459,6 +475,7 @@ static void fast_parse(deflater *d, bitw *b, int last, tok_sink sink, void *ctx)
             if (sink) sink(ctx, s->W[pos]);
             pos++;
         }
+tallied:
         full = (bs->sym_next == ZO_SYM_END);
         if (full) {
             if (b) flush_block(bs, b, (slid && block_start < ZO_WSIZE) ? NULL : s->W + block_start, pos - block_start, 0);
@@ -478,7 +495,7 @@ size_t zo_deflate_bound(size_t n) { return n + (n >> 3) + 64; }
 static size_t deflate_one(deflater *d, const uint8_t *in, uint32_t len, int level, int flush,
                           const uint8_t *stale, uint8_t *out, size_t cap) {
     pthread_once(&tbl_once, build_static_tables);
-    if (len > ZO_CHUNK_MAX || (level != 1 && level != 2)) return (size_t)-1;
+    if (len > ZO_CHUNK_MAX || level < 1 || level > 3) return (size_t)-1;
     if (flush != ZO_SYNC_FLUSH && flush != ZO_FULL_FLUSH && flush != ZO_FINISH) return (size_t)-1;
     int last = (flush == ZO_FINISH);
     bitw b = {out, cap, 0, 0, 0, 0};
@@ -492,7 +509,7 @@ static size_t deflate_one(deflater *d, const uint8_t *in, uint32_t len, int leve
             if (last) bw_align(&b);
         }
     } else {
-        fast_parse(d, &b, last, NULL, NULL);
+        fast_parse(d, &b, last, NULL, NULL, level);
     }
     if (!last) {                         /* deflate.c:1064-1065: empty stored block for SYNC/FULL flush */
         bw_put(&b, 0, 3); bw_align(&b); bw_put(&b, 0x0000, 16); bw_put(&b, 0xffff, 16);
@@ -513,13 +530,13 @@ static void tok_push(void *ctx, uint32_t tok) { tokbuf *tb = (tokbuf *)ctx; if (
 
 size_t zo_deflate_tokens(const uint8_t *in, uint32_t len, int level, uint32_t *tokens, size_t cap) {
     pthread_once(&tbl_once, build_static_tables);
-    if (len > ZO_CHUNK_MAX || (level != 1 && level != 2)) return (size_t)-1;
+    if (len > ZO_CHUNK_MAX || level < 1 || level > 3) return (size_t)-1;
     deflater *d = (deflater *)malloc(sizeof(deflater));
     if (!d) return (size_t)-1;
     tokbuf tb = {tokens, cap, 0};
     lz_reset(&d->lz, in, len, NULL);
     if (level == 1) quick_parse(&d->lz, NULL, tok_push, &tb);
-    else fast_parse(d, NULL, 0, tok_push, &tb);
+    else fast_parse(d, NULL, 0, tok_push, &tb, level);
     free(d);
     return tb.n;
 }

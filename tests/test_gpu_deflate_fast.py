@@ -1,6 +1,7 @@
-"""K2 parity: the sm_100a level-2 chunk compressor (deflate_fast: hash chains + longest_match, dynamic / static /
-stored blocks from the trees.c block writer), called through the C ABI, against the CPU oracle byte for byte,
-the committed digests of the unmodified reference, and round trips through an independent inflater."""
+"""K2 parity: the sm_100a level-2 and level-3 chunk compressors (deflate_fast / deflate_medium: hash chains +
+longest_match, dynamic / static / stored blocks from the trees.c block writer), called through the C ABI, against the
+CPU oracle byte for byte, the committed digests of the unmodified reference, and round trips through an independent
+inflater.  Every test runs for both levels."""
 import zlib as pyzlib
 
 import numpy as np
@@ -11,9 +12,14 @@ from test_gpu_deflate_quick import assert_parity, gpu_deflate
 pytestmark = pytest.mark.gpu
 
 
-def test_synthetic_mix_bit_exact(pkg, ctx, zo):
+@pytest.fixture(params=[2, 3], ids=["level2", "level3"])
+def level(request):
+    return request.param
+
+
+def test_synthetic_mix_bit_exact(pkg, ctx, zo, level):
     data = pkg.synth(64 * 65536 + 4321, seed=101)
-    got, sizes = assert_parity(pkg, ctx, zo, data, level=2)
+    got, sizes = assert_parity(pkg, ctx, zo, data, level=level)
     # every chunk inflates on its own (Z_FULL_FLUSH boundaries) with an independent inflater
     for i in (0, 1, 2, 3, 17, 63, 64):
         piece = data[i * 65536:(i + 1) * 65536].tobytes()
@@ -21,32 +27,32 @@ def test_synthetic_mix_bit_exact(pkg, ctx, zo):
         assert d.decompress(got[i, : sizes[i]].tobytes()) == piece
 
 
-def test_each_unit_type(pkg, ctx, zo):
+def test_each_unit_type(pkg, ctx, zo, level):
     base = pkg.synth(10 * 65536, seed=202)
     for u in range(10):
-        assert_parity(pkg, ctx, zo, base[u * 65536:(u + 1) * 65536], level=2)
+        assert_parity(pkg, ctx, zo, base[u * 65536:(u + 1) * 65536], level=level)
 
 
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 7, 8, 9, 31, 32, 33, 63, 64, 65, 257, 258, 259, 260, 262, 263, 4095, 4096, 65535])
-def test_short_inputs(pkg, ctx, zo, n):
+def test_short_inputs(pkg, ctx, zo, n, level):
     data = pkg.synth(65536, seed=5)[:n]
     for flush in (3, 4):
-        assert_parity(pkg, ctx, zo, data, 65536, flush, level=2)
+        assert_parity(pkg, ctx, zo, data, 65536, flush, level=level)
 
 
-def test_zeros_runs_and_random(pkg, ctx, zo):
+def test_zeros_runs_and_random(pkg, ctx, zo, level):
     rng = np.random.default_rng(7)
-    assert_parity(pkg, ctx, zo, np.zeros(3 * 65536 + 5, dtype=np.uint8), level=2)
-    assert_parity(pkg, ctx, zo, rng.integers(0, 256, size=2 * 65536 + 100, dtype=np.uint8), level=2)      # stored blocks
-    assert_parity(pkg, ctx, zo, np.full(65536, 0xAB, dtype=np.uint8), level=2)
+    assert_parity(pkg, ctx, zo, np.zeros(3 * 65536 + 5, dtype=np.uint8), level=level)
+    assert_parity(pkg, ctx, zo, rng.integers(0, 256, size=2 * 65536 + 100, dtype=np.uint8), level=level)      # stored blocks
+    assert_parity(pkg, ctx, zo, np.full(65536, 0xAB, dtype=np.uint8), level=level)
     for period in (1, 2, 3, 4, 5, 7, 8, 31, 32, 33, 255, 256, 257, 258, 259, 1000):
         pat = rng.integers(0, 256, size=period, dtype=np.uint8)
-        assert_parity(pkg, ctx, zo, np.tile(pat, 65536 // period + 1)[:65536], level=2)
+        assert_parity(pkg, ctx, zo, np.tile(pat, 65536 // period + 1)[:65536], level=level)
     for alphabet in (2, 3, 4, 16):                     # tiny alphabets: long hash chains, many collisions inside a window
-        assert_parity(pkg, ctx, zo, rng.integers(0, alphabet, size=65536, dtype=np.uint8), level=2)
+        assert_parity(pkg, ctx, zo, rng.integers(0, alphabet, size=65536, dtype=np.uint8), level=level)
 
 
-def test_chain_walk_and_nice_match(pkg, ctx, zo):
+def test_chain_walk_and_nice_match(pkg, ctx, zo, level):
     """Several candidates with growing common prefixes (3..7 bytes, then >= 8): exercises best_len updates, the
     chain limit of 4 and the nice_match stop (match_tpl.h)."""
     rng = np.random.default_rng(11)
@@ -58,13 +64,13 @@ def test_chain_walk_and_nice_match(pkg, ctx, zo):
         d[pos + k] = (int(key[k]) + 1 + k) & 0xff
         pos += 97 + 13 * k
     d[pos:pos + 40] = key
-    assert_parity(pkg, ctx, zo, d, level=2)
+    assert_parity(pkg, ctx, zo, d, level=level)
     words = [rng.integers(97, 123, size=int(rng.integers(3, 9)), dtype=np.uint8) for _ in range(50)]
     text = np.concatenate([np.concatenate([words[int(rng.integers(0, 50))], np.array([32], dtype=np.uint8)]) for _ in range(14000)])[:65536]
-    assert_parity(pkg, ctx, zo, text, level=2)
+    assert_parity(pkg, ctx, zo, text, level=level)
 
 
-def test_virtual_bytes_past_the_end(pkg, ctx, zo):
+def test_virtual_bytes_past_the_end(pkg, ctx, zo, level):
     """longest_match does not clamp nice_match to lookahead, so the last match of a chunk depends
     on what lies past the data: chunk[32768+k] for a full chunk (after the tail slide), the previous chunk's bytes
     for a short chunk on the same stream, zeros for a short first chunk."""
@@ -81,45 +87,45 @@ def test_virtual_bytes_past_the_end(pkg, ctx, zo):
             # make one of the earlier copies continue with the virtual bytes
             if c < 2:
                 d[end - 9000:end - 9000 + 6] = d[base + 32768:base + 32774]
-        assert_parity(pkg, ctx, zo, d, level=2)
-        assert_parity(pkg, ctx, zo, d[:30000], level=2)      # short first chunk: zeros past the data
+        assert_parity(pkg, ctx, zo, d, level=level)
+        assert_parity(pkg, ctx, zo, d[:30000], level=level)      # short first chunk: zeros past the data
 
 
-def test_matches_far_and_at_max_dist(pkg, ctx, zo):
+def test_matches_far_and_at_max_dist(pkg, ctx, zo, level):
     rng = np.random.default_rng(8)
     blk = rng.integers(0, 256, size=300, dtype=np.uint8)
     for gap in (32506 - 300, 32506 - 4, 32506 - 3, 32505, 32506, 32507, 32768, 40000):
         d = rng.integers(0, 256, size=65536, dtype=np.uint8)
         d[100:400] = blk
         d[100 + gap:400 + gap] = blk
-        assert_parity(pkg, ctx, zo, d, level=2)
+        assert_parity(pkg, ctx, zo, d, level=level)
 
 
-def test_block_splits_at_16383_symbols(pkg, ctx, zo):
+def test_block_splits_at_16383_symbols(pkg, ctx, zo, level):
     """A chunk of pure literals fills blocks of exactly 16383 symbols (deflate_fast.c:93-94); 65536 = 4 * 16383 + 4,
     and 3 * 16383 / 4 * 16383 exercise the 'block full exactly at the end of input' paths for both flush modes."""
     rng = np.random.default_rng(13)
     lit = rng.permutation(np.arange(65536, dtype=np.uint32) * 2654435761 % 251).astype(np.uint8)
     for n in (16382, 16383, 16384, 2 * 16383, 3 * 16383 + 1, 4 * 16383, 65536):
         for flush in (3, 4):
-            assert_parity(pkg, ctx, zo, rng.integers(0, 256, size=n, dtype=np.uint8), 65536, flush, level=2)
-            assert_parity(pkg, ctx, zo, lit[:n], 65536, flush, level=2)
+            assert_parity(pkg, ctx, zo, rng.integers(0, 256, size=n, dtype=np.uint8), 65536, flush, level=level)
+            assert_parity(pkg, ctx, zo, lit[:n], 65536, flush, level=level)
 
 
-def test_small_chunks_and_finish_members(pkg, ctx, zo):
+def test_small_chunks_and_finish_members(pkg, ctx, zo, level):
     data = pkg.synth(64 * 4096, seed=7)
-    assert_parity(pkg, ctx, zo, data, 4096, 4, level=2)
-    assert_parity(pkg, ctx, zo, pkg.synth(65536, seed=3)[:257 * 40], 257, 3, level=2)
-    assert_parity(pkg, ctx, zo, pkg.synth(3 * 65536, seed=9), 1000, 3, level=2)
+    assert_parity(pkg, ctx, zo, data, 4096, 4, level=level)
+    assert_parity(pkg, ctx, zo, pkg.synth(65536, seed=3)[:257 * 40], 257, 3, level=level)
+    assert_parity(pkg, ctx, zo, pkg.synth(3 * 65536, seed=9), 1000, 3, level=level)
 
 
-def test_golden_digests_of_the_unmodified_reference(pkg, ctx, golden):
+def test_golden_digests_of_the_unmodified_reference(pkg, ctx, golden, level):
     from test_oracle_deflate import golden_cases
     k = 0
     for c, data in golden_cases(pkg, golden):
-        if c["level"] != 2:
+        if c["level"] != level:
             continue
-        got, sizes, crcs, adlers, _ = gpu_deflate(pkg, ctx, data, c["chunk"], 2, c["flush"])
+        got, sizes, crcs, adlers, _ = gpu_deflate(pkg, ctx, data, c["chunk"], level, c["flush"])
         assert [int(x) for x in sizes] == c["sizes"], c["name"]
         assert [int(pyzlib.crc32(got[i, : sizes[i]].tobytes())) for i in range(len(sizes))] == c["comp_crc32"], c["name"]
         assert [int(x) for x in crcs] == c["crc32"], c["name"]
@@ -127,31 +133,31 @@ def test_golden_digests_of_the_unmodified_reference(pkg, ctx, golden):
     assert k >= 30
 
 
-def test_host_path_level2_stream(pkg, ctx, zo):
+def test_host_path_level2_stream(pkg, ctx, zo, level):
     from test_gpu_host_path import oracle_stream
     for n, final in ((5 * 65536 + 99, True), (5 * 65536 + 99, False), ((70 << 20) + 12345, True)):
         data = pkg.synth(n, seed=n % 1000 + 1)
         cap = pkg.deflate_bound(65536) * ((n + 65535) // 65536 + 1)
         out = np.empty(cap, dtype=np.uint8)
-        out_len, crc, adler = ctx.deflate_host(data, n, 65536, 2, final, out, cap)
+        out_len, crc, adler = ctx.deflate_host(data, n, 65536, level, final, out, cap)
         if zo.have_ref() and final:
-            exp = zo.ref_deflate_stream(data, 65536, 2, -15).tobytes()
+            exp = zo.ref_deflate_stream(data, 65536, level, -15).tobytes()
         else:
-            exp = oracle_stream(zo, data, 65536, 2, final)
+            exp = oracle_stream(zo, data, 65536, level, final)
         assert out_len == len(exp) and out[:out_len].tobytes() == exp
         assert crc == pyzlib.crc32(data.tobytes())
         if final:
             assert pyzlib.decompress(out[:out_len].tobytes(), wbits=-15) == data.tobytes()
 
 
-def test_256MiB_round_trip_and_sampled_parity(pkg, ctx, zo):
+def test_256MiB_round_trip_and_sampled_parity(pkg, ctx, zo, level):
     import torch
     n = 256 << 20
     data = pkg.synth(n, seed=404)
     dev = f"cuda:{ctx.device}"
     d_in = torch.from_numpy(data).to(dev)
     slots, stride, sizes, crcs, adlers = ctx.alloc_chunk_outputs(n)
-    ctx.deflate_chunks(d_in, n, 65536, 2, 3, slots, stride, sizes, crcs, None)
+    ctx.deflate_chunks(d_in, n, 65536, level, 3, slots, stride, sizes, crcs, None)
     nch = n // 65536
     offsets = torch.zeros(nch + 1, dtype=torch.int64, device=dev)
     ctx.chunk_offsets(sizes, nch, 0, offsets)
@@ -167,5 +173,5 @@ def test_256MiB_round_trip_and_sampled_parity(pkg, ctx, zo):
     hslots = slots.cpu().numpy().reshape(-1, stride)
     pick = np.random.default_rng(2).choice(nch, size=96, replace=False)
     for ci in pick:
-        exp, es, _, _ = zo.port_deflate_chunks(data[ci * 65536:(ci + 1) * 65536], 65536, 2, 3, stride, nthreads=1)
+        exp, es, _, _ = zo.port_deflate_chunks(data[ci * 65536:(ci + 1) * 65536], 65536, level, 3, stride, nthreads=1)
         assert es[0] == hs[ci] and np.array_equal(hslots[ci, : es[0]], exp[0, : es[0]]), f"chunk {ci}"

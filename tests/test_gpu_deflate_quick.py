@@ -166,7 +166,7 @@ def test_argument_errors(pkg, ctx):
     import torch
     d = torch.zeros(65536, dtype=torch.uint8, device=f"cuda:{ctx.device}")
     slots, stride, sizes, crcs, adlers = ctx.alloc_chunk_outputs(65536)
-    for kwargs in (dict(level=0), dict(level=3), dict(level=9), dict(flush=0), dict(flush=5), dict(chunk=0), dict(chunk=65537), dict(stride=stride - 16), dict(stride=stride + 8)):
+    for kwargs in (dict(level=0), dict(level=4), dict(level=9), dict(flush=0), dict(flush=5), dict(chunk=0), dict(chunk=65537), dict(stride=stride - 16), dict(stride=stride + 8)):
         a = dict(chunk=65536, level=1, flush=3, stride=stride)
         a.update(kwargs)
         with pytest.raises(pkg.ZngB200Error) as ei:

@@ -99,7 +99,7 @@ def test_zng_deflate_piecewise_and_small_output_windows(pkg, L, zo):
 def test_zng_deflate_argument_errors(pkg, L):
     s = pkg.ZngStream()
     assert L.zng_deflateInit2(None, 1, 8, 15, 8, 0) == pkg.Z_STREAM_ERROR
-    for args in ((1, 7, 15, 8, 0), (10, 8, 15, 8, 0), (1, 8, 16 + 16, 8, 0), (1, 8, 15, 10, 0), (1, 8, 15, 8, 5), (6, 8, 15, 8, 0), (1, 8, 12, 8, 0)):
+    for args in ((1, 7, 15, 8, 0), (10, 8, 15, 8, 0), (1, 8, 16 + 16, 8, 0), (1, 8, 15, 10, 0), (1, 8, 15, 8, 5), (6, 8, 15, 8, 0), (4, 8, 15, 8, 0), (1, 8, 12, 8, 0)):
         assert L.zng_deflateInit2(ctypes.byref(s), *args) == pkg.Z_STREAM_ERROR, args
     assert L.zng_deflateInit2(ctypes.byref(s), 1, 8, 15, 8, 0) == 0
     buf = np.zeros(64, dtype=np.uint8)
@@ -225,7 +225,7 @@ def test_minigzip_cli_roundtrip(pkg, zo, tmp_path):
     data = pkg.synth(7 * 65536 + 4321, seed=19)
     src = tmp_path / "in.bin"
     src.write_bytes(data.tobytes())
-    for level in (1, 2):
+    for level in (1, 2, 3):
         comp = subprocess.run([exe, f"-{level}", str(src)], stdout=subprocess.PIPE, check=True).stdout
         assert comp == expected_stream(zo, data, level, 31)
         assert gzip.decompress(comp) == data.tobytes()

@@ -172,7 +172,7 @@ int run_deflate_chunks(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size
     if (nchunks == 0) return 0;
     int r = ensure_heads(ctx);
     if (r) return r;
-    if (level == 2) { r = ensure_prevs(ctx); if (r) return r; }
+    if (level >= 2) { r = ensure_prevs(ctx); if (r) return r; }
     const uint32_t own_stride = (chunk + 32u) & ~31u;                 // tokens per chunk incl. end marker, 128-byte rows
     const uint32_t batch = nchunks < kBatchChunks ? nchunks : kBatchChunks;
     r = ensure_scratch(ctx, sc, batch, own_stride, nchunks, d_tokens == nullptr);
@@ -185,9 +185,9 @@ int run_deflate_chunks(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size
         const uint32_t stride = d_tokens ? tok_stride : own_stride;
         const uint32_t grid = deflate_quick_grid(nb, ctx->sms, ctx->chains_per_sm);
         const int slot = next_slot(ctx);
-        if (level == 2) {
+        if (level >= 2) {
             CK(launch_fast_parse(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->prevs,
-                                 ctx->vtails, ctx->sm_slots, ctx->sms, ctx->chains_per_sm_l2, (c0 > 0 || have_prev) ? 1 : 0, stream),
+                                 ctx->vtails, ctx->sm_slots, ctx->sms, ctx->chains_per_sm_l2, (c0 > 0 || have_prev) ? 1 : 0, level, stream),
                "fast_parse launch");
             CK(launch_block_emit(d_in + off, toks, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
                                  d_sizes + c0, ctx->sms, stream),
@@ -255,7 +255,7 @@ int ensure_slabs(zng_b200_ctx* ctx) {
 int check_chunk_args(zng_b200_ctx* ctx, const void* d_in, size_t n, uint32_t chunk, int level, int flush,
                      const void* d_out, size_t out_stride, const uint32_t* d_sizes) {
     if (!ctx) return ZNG_B200_STREAM_ERROR;
-    if (level != 1 && level != 2) return bad(ctx, "level must be 1 (deflate_quick) or 2 (deflate_fast)");
+    if (level < 1 || level > 3) return bad(ctx, "level must be 1 (deflate_quick), 2 (deflate_fast) or 3 (deflate_medium)");
     if (flush != ZNG_B200_SYNC_FLUSH && flush != ZNG_B200_FULL_FLUSH && flush != ZNG_B200_FINISH)
         return bad(ctx, "flush must be Z_SYNC_FLUSH, Z_FULL_FLUSH or Z_FINISH");
     if (chunk == 0 || chunk > ZNG_B200_CHUNK_MAX) return bad(ctx, "chunk must be in 1..65536");
@@ -1005,7 +1005,7 @@ static int sync_slabs(zng_b200_ctx* ctx) {
 int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_t chunk, int level, int final,
                           void* h_out, size_t out_cap, size_t* out_len, uint32_t* crc32, uint32_t* adler32) {
     if (!ctx) return ZNG_B200_STREAM_ERROR;
-    if (level != 1 && level != 2) return bad(ctx, "level must be 1 or 2");
+    if (level < 1 || level > 3) return bad(ctx, "level must be 1, 2 or 3");
     if (chunk == 0 || chunk > ZNG_B200_CHUNK_MAX) return bad(ctx, "chunk must be in 1..65536");
     if (!out_len || (n && !h_in) || !h_out) return bad(ctx, "NULL argument");
     DeviceGuard g(ctx->device);
@@ -1027,7 +1027,7 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
         if (r) { sync_slabs(ctx); return r; }
         const size_t take = (n - off) < slab_in ? (n - off) : slab_in;
         const bool is_last = (off + take == n);
-        const size_t pre = (level == 2) ? (off < kWSize ? off : (size_t)kWSize) : 0;
+        const size_t pre = (level >= 2) ? (off < kWSize ? off : (size_t)kWSize) : 0;
         const int have_prev = off > 0 ? 1 : 0;
         if (take) CK(cudaMemcpyAsync(s.d_in - pre, (const uint8_t*)h_in + off - pre, take + pre, cudaMemcpyHostToDevice, s.stream), "H2D");
         uint32_t nch = (uint32_t)((take + chunk - 1) / chunk);

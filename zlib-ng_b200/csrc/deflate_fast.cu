@@ -39,48 +39,65 @@ constexpr uint32_t kSlideAt    = kWSize + kMaxDist;   // deflate.c:1285
 
 // ---------------------------------------------------------------- K2a parser (operators: lz_ops.cuh)
 // Parse one chunk; tokens to tok[0..count) + end marker.  Returns the token count.
+// LEVEL 2 = deflate_fast (deflate_fast.c:19-104); LEVEL 3 = deflate_medium below level 5 (deflate_medium.c:146-278 with
+// early_exit: no look-ahead-one branch, so a greedy parse; a match shorter than 4 becomes one literal; insert_match
+// (:44-82) inserts EVERY position inside the match unless lookahead <= match_length + WANT_MIN_MATCH).
+template <int LEVEL>
 __device__ uint32_t fast_parse_warp(const VWindow W, uint32_t n, uint16_t* head, uint16_t* prev, uint32_t* __restrict__ tok) {
+    using P = LmParams<LEVEL>;
+    constexpr uint32_t kCmp = P::kCmp;
+    enum : unsigned { kNone = 0, kAll = 1, kLast = 2 };       // what is still to be inserted behind a match that leaves the window
     const unsigned lane = lane_id();
     const unsigned lt = (1u << lane) - 1u;
     uint32_t wr = 0, p = 0, skip = 0;                         // lanes below `skip` are insert-only (already covered by a match)
     while (p < n) {
         const uint32_t q = p + lane;
         const bool inb = q < n;
-        const bool act = q + kWantMin <= n;                  // deflate_fast.c:43,72 lookahead >= WANT_MIN_MATCH
-        uint32_t v; uint64_t x;
-        load12(W, q, v, x);
+        const bool act = q + kWantMin <= n;                  // deflate_fast.c:43,72 / deflate_medium.c:181 lookahead >= WANT_MIN_MATCH
+        uint32_t v, z = 0; uint64_t x;
+        {
+            const uint32_t qb = q + W.skew, i = qb >> 2, sh = (qb & 3u) << 3;
+            const uint32_t a0 = W.word(i), a1 = W.word(i + 1), a2 = W.word(i + 2), a3 = W.word(i + 3);
+            v = __funnelshift_r(a0, a1, sh);
+            x = (uint64_t)__funnelshift_r(a1, a2, sh) | ((uint64_t)__funnelshift_r(a2, a3, sh) << 32);
+            if (kCmp > 12u) z = __funnelshift_r(a3, W.word(i + 4), sh);
+        }
         const uint32_t h = hash4(v);
         const uint32_t cand0 = act ? (uint32_t)__ldcg(head + h) : 0u;
-        // ---- longest_match for level 2 (match_tpl.h): best_len starts at 2, nice 8, chain 4; the pre-filter at
-        // best_len 2..7 is "bytes 0..best_len equal", so a candidate improves iff its common prefix exceeds best_len
-        uint32_t mlen = 0, mcand = 0;                        // mlen: 0 none, 4..11 exact (clipped), 12 = "12 or more"
-        if (act && lane >= skip && cand0 != 0u && (q - cand0 - 1u) < kMaxDist)      // deflate_fast.c:48-50
-            mlen = longest_match_l2_lane(W, q, v, x, cand0, n - q, prev, mcand);
+        uint32_t mlen = 0, mcand = 0;                        // mlen: 0 none, 4..kCmp-1 exact (clipped), kCmp = "kCmp or more"
+        if (act && lane >= skip && cand0 != 0u && (q - cand0 - 1u) < kMaxDist)      // deflate_fast.c:48-50, deflate_medium.c:194
+            mlen = longest_match_lane<LEVEL>(W, q, v, x, z, cand0, n - q, prev, mcand);
         const unsigned actm = __ballot_sync(ZB_FULL, act);
         const unsigned peers = __match_any_sync(ZB_FULL, act ? h : (0x10000u + lane));
         const unsigned M = __ballot_sync(ZB_FULL, mlen != 0u);
         const unsigned nl = min(32u, n - p);
         // ---- walk 1: replay the greedy decisions
         unsigned cur = skip, covered = 0, icov = 0;
-        uint32_t pend_from = 0;                              // first position index >= 32 whose insert is still due
+        unsigned pending = skip >= 32u ? kAll : kNone;       // a window of insert-only lanes continues an insert-all match
         while (cur < nl) {
             const unsigned rest = M & ~lane_range(0, cur);
             if (rest == 0u) { cur = nl; break; }
             const unsigned k = (unsigned)(__ffs(rest) - 1);
             uint32_t len = __shfl_sync(ZB_FULL, mlen, k);
             const uint32_t qk = p + k;
-            if (len >= 12u) {
+            if (len >= kCmp) {
                 const uint32_t ck = __shfl_sync(ZB_FULL, mcand, k);
-                len = 12u + vwarp_compare256(W, qk + 12u + W.skew, ck + 12u + W.skew, lane);
+                len = kCmp + vwarp_compare256(W, qk + kCmp + W.skew, ck + kCmp + W.skew, lane);
                 len = min(len, kMaxMatch);                   // compare256 + 2 never exceeds 258
                 len = min(len, n - qk);                      // len > lookahead: return lookahead
                 if (lane == k) mlen = len;
             }
             covered |= lane_range(k + 1u, k + len);
             cur = k + len;
-            // deflate_fast.c:72-85: short matches insert every covered position, longer ones only the last
-            if (len <= 4u && n - (qk + len) >= kWantMin) { icov |= lane_range(k + 1u, cur); pend_from = 32u; }
-            else { if (cur - 1u < 32u) icov |= 1u << (cur - 1u); pend_from = max(cur - 1u, 32u); }
+            if (LEVEL == 2) {
+                // deflate_fast.c:72-85: short matches insert every covered position, longer ones only the last
+                if (len <= 4u && n - (qk + len) >= kWantMin) { icov |= lane_range(k + 1u, cur); pending = kAll; }
+                else { if (cur - 1u < 32u) icov |= 1u << (cur - 1u); pending = kLast; }
+            } else {
+                // deflate_medium.c:44-82 insert_match: all of strstart+1 .. strstart+len-1, or nothing near the end
+                if (n - qk > len + kWantMin) { icov |= lane_range(k + 1u, cur); pending = kAll; }
+                else pending = kNone;
+            }
         }
         unsigned V = lane_range(skip, min(cur, nl)) & ~covered;
         unsigned I = (V | icov | lane_range(0, skip)) & actm;
@@ -92,8 +109,9 @@ __device__ uint32_t fast_parse_warp(const VWindow W, uint32_t n, uint16_t* head,
             V &= lane_range(0, j); I &= lane_range(0, j);
             next_p = p + j; next_skip = 0;
         } else if (cur > 32u) {                              // the last match runs past the window
-            const uint32_t from = min(pend_from, cur);
-            next_p = p + from; next_skip = cur - from;
+            if (pending == kAll) { next_p = p + 32u; next_skip = cur - 32u; }          // its covered positions: insert-only lanes
+            else if (pending == kLast && cur - 1u >= 32u) { next_p = p + cur - 1u; next_skip = 1u; }
+            else { next_p = p + cur; next_skip = 0; }
         } else { next_p = p + cur; next_skip = 0; }
         const bool vis = (V >> lane) & 1u;
         if (vis && inb) {
@@ -114,6 +132,7 @@ __device__ uint32_t fast_parse_warp(const VWindow W, uint32_t n, uint16_t* head,
     return wr;
 }
 
+template <int LEVEL>
 __global__ void __launch_bounds__(kFastWarps * 32, 8)
 fast_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint32_t nchunks,
                   uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
@@ -167,7 +186,7 @@ fast_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint
             __stcg(tail + t, wv);
         }
         __syncwarp();
-        const uint32_t cnt = fast_parse_warp(W, len, head, prev, tokens + (size_t)ci * tok_stride);
+        const uint32_t cnt = fast_parse_warp<LEVEL>(W, len, head, prev, tokens + (size_t)ci * tok_stride);
         if (lane == 0) ntok[ci] = cnt;
     }
     __syncwarp();
@@ -566,7 +585,7 @@ size_t deflate_fast_tail_bytes(uint32_t nsmid) { return (size_t)nsmid * 64u * kT
 
 cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t* tokens, uint32_t tok_stride,
                               uint32_t* ntok, uint32_t* counter, uint16_t* heads, uint16_t* prevs, uint32_t* tails,
-                              unsigned long long* sm_slots, int num_sms, int chains_per_sm, int have_prev, cudaStream_t stream) {
+                              unsigned long long* sm_slots, int num_sms, int chains_per_sm, int have_prev, int level, cudaStream_t stream) {
     if (nchunks == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
@@ -574,8 +593,12 @@ cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint3
     uint32_t grid = (uint32_t)num_sms * ctas_per_sm;
     const uint64_t need = ((uint64_t)nchunks + kFastWarps - 1u) / kFastWarps;
     if (need < grid) grid = (uint32_t)need;
-    fast_parse_kernel<<<grid, kFastWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, prevs, tails,
-                                                            sm_slots, have_prev);
+    if (level == 3)
+        fast_parse_kernel<3><<<grid, kFastWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, prevs, tails,
+                                                                   sm_slots, have_prev);
+    else
+        fast_parse_kernel<2><<<grid, kFastWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, prevs, tails,
+                                                                   sm_slots, have_prev);
     return cudaGetLastError();
 }
 

@@ -29,7 +29,7 @@ size_t deflate_fast_prev_bytes(uint32_t nsmid);
 size_t deflate_fast_tail_bytes(uint32_t nsmid);
 cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t* tokens, uint32_t tok_stride,
                               uint32_t* ntok, uint32_t* counter, uint16_t* heads, uint16_t* prevs, uint32_t* tails,
-                              unsigned long long* sm_slots, int num_sms, int chains_per_sm, int have_prev, cudaStream_t stream);
+                              unsigned long long* sm_slots, int num_sms, int chains_per_sm, int have_prev, int level, cudaStream_t stream);
 cudaError_t launch_block_emit(const uint8_t* in, const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n,
                               uint32_t chunk, uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
                               int num_sms, cudaStream_t stream);

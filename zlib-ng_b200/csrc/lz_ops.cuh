@@ -1,7 +1,7 @@
 // lz_ops.cuh -- the device-side operators of the match finder, shared by K2 (deflate_fast.cu) and the operator test
 // kernels (ops.cu).  Each is the sm_100a form of one entry of the reference's operator surface:
 //   vwarp_compare256        functable.compare256      arch/generic/compare256_c.c:12-43   (32 lanes x 8 bytes, ballot/ffs)
-//   longest_match_l2_lane   functable.longest_match   match_tpl.h:26-280 at level 2 {good 4, lazy 4, nice 8, chain 4}
+//   longest_match_lane<L>   functable.longest_match   match_tpl.h:26-280 with the level-2 / level-3 parameters
 //   insert step (in the parsers)  quick_insert_string / insert_string   insert_string_tpl.h:48-104
 #pragma once
 #include "common.cuh"
@@ -40,32 +40,52 @@ __device__ __forceinline__ uint32_t vwarp_compare256(const VWindow& W, uint32_t 
 }
 
 
-// longest_match for one position q (one lane): v / x = the 12 bytes at q, cand0 = hash head (already range-checked),
-// look = lookahead (bytes left from q).  Walks <= 4 candidates through prev[].  best_len starts at 2 and the
-// pre-filter at best_len 2..7 is "bytes 0..best_len equal", so a candidate improves iff its common prefix exceeds
-// best_len.  Returns 0 (no match >= 4), 4..11 (exact length, clipped to look), or 12 = "12 or more: measure with
-// vwarp_compare256 and clip"; mcand = match_start of the returned match.
-__device__ __forceinline__ uint32_t longest_match_l2_lane(const VWindow& W, uint32_t q, uint32_t v, uint64_t x, uint32_t cand0,
-                                                          uint32_t look, const uint16_t* prev, uint32_t& mcand) {
-    uint32_t best = 2, chain = 4, cand = cand0;
+// Parameters of the two greedy strategies on this path (configuration_table, deflate.c:142-168): level 2 = deflate_fast
+// {nice 8, chain 4}, level 3 = deflate_medium below level 5 {nice 16, chain 6}.  kCmp = bytes a lane compares by itself;
+// a common prefix of kCmp bytes means "kCmp or more", which is >= nice_match and therefore final.
+template <int LEVEL> struct LmParams;
+template <> struct LmParams<2> { static constexpr uint32_t kNice = 8, kChain = 4, kCmp = 12; };
+template <> struct LmParams<3> { static constexpr uint32_t kNice = 16, kChain = 6, kCmp = 16; };
+
+// common prefix (0..kCmp) of the kCmp bytes (v, x, z) at the scan position and at candidate `cand`
+template <uint32_t kCmp>
+__device__ __forceinline__ uint32_t prefix_len(const VWindow& W, uint32_t cand, uint32_t v, uint64_t x, uint32_t z) {
+    const uint32_t cb = cand + W.skew, i = cb >> 2, sh = (cb & 3u) << 3;
+    const uint32_t b0 = W.word(i), b1 = W.word(i + 1), b2 = W.word(i + 2), b3 = W.word(i + 3);
+    const uint32_t d0 = v ^ __funnelshift_r(b0, b1, sh);
+    if (d0) return (uint32_t)(__ffs((int)d0) - 1) >> 3;
+    const uint64_t d = x ^ ((uint64_t)__funnelshift_r(b1, b2, sh) | ((uint64_t)__funnelshift_r(b2, b3, sh) << 32));
+    if (d) return 4u + ((uint32_t)(__ffsll((long long)d) - 1) >> 3);
+    if (kCmp == 12u) return 12u;
+    const uint32_t dz = z ^ __funnelshift_r(b3, W.word(i + 4), sh);
+    return dz ? 12u + ((uint32_t)(__ffs((int)dz) - 1) >> 3) : 16u;
+}
+
+// longest_match for one position q (one lane): v / x / z = the bytes at q, cand0 = hash head (already range-checked),
+// look = lookahead (bytes left from q).  Walks <= kChain candidates through prev[].  best_len starts at 2; with
+// OPTIMAL_CMP 64 the pre-filter (match_tpl.h:141-165) compares the 2 / 4 / 8 bytes that end at index best_len plus the
+// first 2 / 4 / 8 bytes, which for best_len 2..15 is exactly "bytes 0..best_len equal": a candidate improves iff its
+// common prefix exceeds best_len (so the early_exit branch :261-266 is never taken).  Returns 0 (no match >= 4),
+// 4..kCmp-1 (exact length, clipped to look), or kCmp = "kCmp or more: measure with vwarp_compare256 and clip";
+// mcand = match_start of the returned match.
+template <int LEVEL>
+__device__ __forceinline__ uint32_t longest_match_lane(const VWindow& W, uint32_t q, uint32_t v, uint64_t x, uint32_t z, uint32_t cand0,
+                                                       uint32_t look, const uint16_t* prev, uint32_t& mcand) {
+    using P = LmParams<LEVEL>;
+    uint32_t best = 2, chain = P::kChain, cand = cand0;
     const uint32_t limit = q > kMaxDist ? q - kMaxDist : 0u;
     for (;;) {
-        uint32_t cv; uint64_t cx;
-        load12(W, cand, cv, cx);
-        const uint32_t d0 = v ^ cv;
-        uint32_t cl;
-        if (d0) cl = (uint32_t)(__ffs((int)d0) - 1) >> 3;
-        else { const uint64_t d = x ^ cx; cl = d ? 4u + ((uint32_t)(__ffsll((long long)d) - 1) >> 3) : 12u; }
+        const uint32_t cl = prefix_len<P::kCmp>(W, cand, v, x, z);
         if (cl > best) {
             mcand = cand;
-            if (cl == 12u) { best = 12u; break; }     // >= nice_match: final, measured by the warp later
-            if (cl > look) { best = look; break; }     // match_tpl.h:177-183 len > lookahead: return lookahead
+            if (cl == P::kCmp) { best = P::kCmp; break; }   // >= nice_match: final, measured by the warp later
+            if (cl > look) { best = look; break; }         // match_tpl.h:177-183 len > lookahead: return lookahead
             best = cl;
-            if (best >= 8u) break;                    // nice_match
+            if (best >= P::kNice) break;                   // nice_match
         }
         if (--chain == 0u) break;
         cand = (uint32_t)__ldcg(prev + (cand & (kWSize - 1u)));
-        if (cand <= limit) break;                     // match_tpl.h:48-51
+        if (cand <= limit) break;                          // match_tpl.h:48-51
     }
     return best >= kWantMin ? best : 0u;
 }

@@ -47,7 +47,7 @@ __global__ void op_longest_match_kernel(const uint8_t* window, uint32_t n, const
         q = pos[qi]; c0 = cand[qi];
         uint32_t v; uint64_t x;
         load12(W, q, v, x);
-        if (q + kWantMin <= n && c0 != 0u && (q - c0 - 1u) < kMaxDist) ml = longest_match_l2_lane(W, q, v, x, c0, n - q, prev, mc);
+        if (q + kWantMin <= n && c0 != 0u && (q - c0 - 1u) < kMaxDist) ml = longest_match_lane<2>(W, q, v, x, 0u, c0, n - q, prev, mc);
     }
     unsigned L = __ballot_sync(ZB_FULL, ml >= 12u);
     while (L) {                                              // long matches: measured by the whole warp, as in K2

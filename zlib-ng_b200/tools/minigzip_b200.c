@@ -3,7 +3,7 @@
  * zng_inflate), linked against libzng_b200.so.  Written for this repository (the reference's tool goes through its
  * gz file layer, gzwrite.c / gzread.c, which is outside the hot path).
  *
- *   minigzip_b200 [-1|-2] [-d] [file]        compressed / decompressed bytes go to stdout
+ *   minigzip_b200 [-1|-2|-3] [-d] [file]     compressed / decompressed bytes go to stdout
  *
  * Compression feeds the whole input with one zng_deflate(Z_FINISH): the library cuts it into 65536-byte pieces, and the
  * output is byte-identical to the reference fed one piece per zng_deflate(Z_FULL_FLUSH) call (pigz -b 64 -i style).
@@ -33,7 +33,8 @@ int main(int argc, char **argv) {
         if (!strcmp(argv[i], "-d")) decompress = 1;
         else if (!strcmp(argv[i], "-1")) level = 1;
         else if (!strcmp(argv[i], "-2")) level = 2;
-        else if (argv[i][0] == '-' && argv[i][1]) { fprintf(stderr, "usage: %s [-1|-2] [-d] [file]\n", argv[0]); return 2; }
+        else if (!strcmp(argv[i], "-3")) level = 3;
+        else if (argv[i][0] == '-' && argv[i][1]) { fprintf(stderr, "usage: %s [-1|-2|-3] [-d] [file]\n", argv[0]); return 2; }
         else path = argv[i];
     }
     FILE *f = path && strcmp(path, "-") ? fopen(path, "rb") : stdin;
