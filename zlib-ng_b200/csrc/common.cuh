@@ -32,17 +32,6 @@ __device__ __forceinline__ uint32_t lane_range(uint32_t a, uint32_t b) {
     return hi & ~lo;
 }
 
-// unaligned little-endian 32/64-bit reads from a word-addressed shared-memory byte array
-__device__ __forceinline__ uint32_t ld32u(const uint32_t* w, uint32_t byteoff) {
-    uint32_t i = byteoff >> 2, s = (byteoff & 3u) << 3;
-    return __funnelshift_r(w[i], w[i + 1], s);
-}
-__device__ __forceinline__ uint64_t ld64u(const uint32_t* w, uint32_t byteoff) {
-    uint32_t i = byteoff >> 2, s = (byteoff & 3u) << 3;
-    uint32_t a = w[i], b = w[i + 1], c = w[i + 2];
-    return (uint64_t)__funnelshift_r(a, b, s) | ((uint64_t)__funnelshift_r(b, c, s) << 32);
-}
-
 // insert_string.c:13  HASH_CALC: (le32 * 2654435761) >> 16
 __device__ __forceinline__ uint32_t hash4(uint32_t le32) { return (le32 * 2654435761u) >> 16; }
 
