@@ -93,3 +93,41 @@ def test_crc_of_1GiB_property(pkg, ctx):
     r = res.cpu().numpy().view(np.uint32)
     assert int(r[0]) == pyzlib.crc32(data) == int(r[3])
     assert int(r[1]) == pyzlib.adler32(data)
+
+
+def test_flat_checksums_at_4GiB_equal_the_combine_of_their_parts(pkg, ctx):
+    """BASELINE configs[1] at full size: zng_crc32 / zng_adler32 of a 4 GiB device buffer must equal the
+    crc32_combine / adler32_combine fold of its four 1 GiB quarters (a checksum of checksums), and the first quarter
+    must agree with an independent CPU implementation."""
+    import torch
+    L = pkg.lib()
+    gib = 1 << 30
+    n = 4 * gib
+    dev = f"cuda:{ctx.device}"
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    h = np.empty(gib, dtype=np.uint8)
+    for q in range(4):
+        assert L.zng_b200_synth_fill(h.ctypes.data, gib, 0x9E3779B97F4A7C15, q * gib) == 0
+        d[q * gib:(q + 1) * gib] = torch.from_numpy(h).to(dev)
+        if q == 0:
+            first = (pyzlib.crc32(h.tobytes()), pyzlib.adler32(h.tobytes()))
+    res = torch.zeros(10, dtype=torch.int32, device=dev)
+    ctx.crc32(d, n, 0, res[0:1])
+    ctx.adler32(d, n, 1, res[1:2])
+    for q in range(4):
+        ctx.crc32(d[q * gib:(q + 1) * gib], gib, 0, res[2 + 2 * q: 3 + 2 * q])
+        ctx.adler32(d[q * gib:(q + 1) * gib], gib, 1, res[3 + 2 * q: 4 + 2 * q])
+    torch.cuda.synchronize()
+    r = [int(x) for x in res.cpu().numpy().view(np.uint32)]
+    assert (r[2], r[3]) == first
+    crc, adler = r[2], r[3]
+    for q in range(1, 4):
+        crc = L.zng_crc32_combine(crc, r[2 + 2 * q], gib)
+        adler = L.zng_adler32_combine(adler, r[3 + 2 * q], gib)
+    assert (r[0], r[1]) == (crc, adler)
+    # running values continue across calls (what zng_crc32(crc, buf, len) promises)
+    ctx.crc32(d[gib:], n - gib, r[2], res[0:1])
+    ctx.adler32(d[gib:], n - gib, r[3], res[1:2])
+    torch.cuda.synchronize()
+    r2 = [int(x) for x in res.cpu().numpy().view(np.uint32)[:2]]
+    assert r2 == [crc, adler]
