@@ -6,6 +6,7 @@
  *
  *   level 1  deflate_quick            deflate_quick.c:47-130
  *   level 2  deflate_fast             deflate_fast.c:19-104
+ *   levels 3-6  deflate_medium        deflate_medium.c:22-278
  *            longest_match            match_tpl.h:26-280 (non-SLOW; nice 8, chain 4: deflate.c:142-168)
  *   hashing  quick_insert_string      insert_string_tpl.h:58-75, insert_string.c:13
  *   emission zng_emit_lit/_dist       trees_emit.h:102-164
@@ -398,26 +399,29 @@ static void flush_block(blockstate *bs, bitw *b, const uint8_t *raw, uint32_t st
     if (last) bw_align(b);
 }
 
-/* match_tpl.h:26-280 restated for levels 2 and 3 (best_len starts at 2; level 2: nice 8, chain 4; level 3: nice 16,
- * chain 6; level < 5).  With OPTIMAL_CMP 64 the pre-filter compares the 2 / 4 / 8 bytes that END at index best_len plus the
- * first 2 / 4 / 8 bytes; for best_len 2..15 the two ranges touch or overlap, so the filter is exactly "bytes 0..best_len
- * equal"  -- it leaves a gap only from best_len 16 on, which nice_match <= 16 never reaches. */
-static uint32_t longest_match_l2(const lzstate *s, uint32_t pos, uint32_t cand, uint32_t lookahead, uint32_t *mstart);
-static uint32_t longest_match_lv(const lzstate *s, uint32_t pos, uint32_t cand, uint32_t lookahead, uint32_t chain, uint32_t nice, uint32_t *mstart) {
+/* match_tpl.h:26-280 (non-SLOW) restated.  best_len starts at 2 (prev_length is 0 on this path, so good_match never
+ * shortens the chain).  With OPTIMAL_CMP 64 the pre-filter (:141-165) compares the first 2 / 4 / 8 bytes and the 2 / 4 / 8
+ * bytes that END at index best_len; for best_len 2..15 the two ranges touch or overlap, so the filter is "bytes
+ * 0..best_len equal" (SURVEY 8(a6)); from best_len 16 on it leaves the gap [8, best_len-7), and a candidate that passes
+ * the filter without beating best_len ends the search on levels below 5 (early_exit, :127,261-266). */
+static uint32_t longest_match_lv(const lzstate *s, uint32_t pos, uint32_t cand, uint32_t lookahead, uint32_t chain, uint32_t nice,
+                                 int level, uint32_t *mstart) {
     uint32_t best = 2;
     uint32_t limit = pos > ZO_MAX_DIST ? pos - ZO_MAX_DIST : 0;
     for (;;) {
         if (cand >= pos) break;
-        int ok = 1;
-        for (uint32_t k = 0; k <= best; k++) if (vb(s, cand + k) != vb(s, pos + k)) { ok = 0; break; }
-        if (ok) {
+        uint32_t w = best < 4 ? 2 : (best < 8 ? 4 : 8), off = best + 1 - w;
+        int pass = 1;
+        for (uint32_t k = 0; k < w && pass; k++)
+            if (vb(s, cand + k) != vb(s, pos + k) || vb(s, cand + off + k) != vb(s, pos + off + k)) pass = 0;
+        if (pass) {
             uint32_t len = match_run(s, pos, cand);
             if (len > best) {
                 *mstart = cand;
                 if (len > lookahead) return lookahead;
                 best = len;
                 if (best >= nice) return best;
-            } else break;   /* early_exit (unreachable here, kept for fidelity: match_tpl.h:261-266) */
+            } else if (level < 5) break;
         }
         if (--chain == 0) break;
         cand = s->prev[cand & (ZO_WSIZE - 1)];
@@ -427,16 +431,24 @@ static uint32_t longest_match_lv(const lzstate *s, uint32_t pos, uint32_t cand, 
 }
 
 static uint32_t longest_match_l2(const lzstate *s, uint32_t pos, uint32_t cand, uint32_t lookahead, uint32_t *mstart) {
-    return longest_match_lv(s, pos, cand, lookahead, 4, 8, mstart);
+    return longest_match_lv(s, pos, cand, lookahead, 4, 8, 2, mstart);
 }
 
 typedef struct { lzstate lz; blockstate bs; } deflater;
 
-/* level 2: deflate_fast.c:25-103.  level 3: deflate_medium.c:146-278 with early_exit (level < 5), i.e. without the
- * look-ahead-one branch: a greedy parse with longest_match {nice 16, chain 6}, a match shorter than 4 becomes one literal
- * (:214-215, :22-32), and insert_match (:44-82) inserts every position inside the match unless
- * lookahead <= match_length + WANT_MIN_MATCH. */
-static void fast_parse(deflater *d, bitw *b, int last, tok_sink sink, void *ctx, int level) {
+static void tally_lit(blockstate *bs, uint8_t c, tok_sink sink, void *ctx) {
+    bs->d_buf[bs->sym_next] = 0; bs->l_buf[bs->sym_next++] = c;
+    bs->lt.freq[c]++;
+    if (sink) sink(ctx, c);
+}
+static void tally_match(blockstate *bs, uint32_t dist, uint32_t ml, tok_sink sink, void *ctx) {
+    bs->d_buf[bs->sym_next] = (uint16_t)dist; bs->l_buf[bs->sym_next++] = (uint8_t)(ml - 3);
+    bs->lt.freq[257 + len_sym[ml - 3]]++; bs->dt.freq[dist_sym(dist - 1)]++;
+    if (sink) sink(ctx, 0x80000000u | (ml << 16) | dist);
+}
+
+/* level 2: deflate_fast.c:25-103 */
+static void fast_parse(deflater *d, bitw *b, int last, tok_sink sink, void *ctx) {
     lzstate *s = &d->lz; blockstate *bs = &d->bs;
     uint32_t pos = 0, n = s->len, block_start = 0; int slid = 0;
     block_init(bs);
@@ -448,19 +460,10 @@ static void fast_parse(deflater *d, bitw *b, int last, tok_sink sink, void *ctx,
             uint32_t cand = quick_insert(s, pos);
             uint32_t dist = pos - cand;
             if (dist > 0 && dist <= ZO_MAX_DIST && cand != 0 && cand < pos)
-                ml = level == 3 ? longest_match_lv(s, pos, cand, left, 6, 16, &mstart) : longest_match_l2(s, pos, cand, left, &mstart);
+                ml = longest_match_l2(s, pos, cand, left, &mstart);
         }
-        int full;
         if (ml >= ZO_WANT_MIN) {
-            uint32_t dist = pos - mstart;
-            bs->d_buf[bs->sym_next] = (uint16_t)dist; bs->l_buf[bs->sym_next++] = (uint8_t)(ml - 3);
-            bs->lt.freq[257 + len_sym[ml - 3]]++; bs->dt.freq[dist_sym(dist - 1)]++;
-            if (sink) sink(ctx, 0x80000000u | (ml << 16) | dist);
-            if (level == 3) {                            /* insert_match: lookahead (before the match is emitted) > len + 4 */
-                if (left > ml + ZO_WANT_MIN) for (uint32_t k = 1; k < ml; k++) quick_insert(s, pos + k);
-                pos += ml;
-                goto tallied;
-            }
+            tally_match(bs, pos - mstart, ml, sink, ctx);
             left -= ml;
             if (ml <= 4 && left >= ZO_WANT_MIN) {        /* max_insert_length = max_lazy = 4 at level 2 */
                 for (uint32_t k = 1; k < ml; k++) quick_insert(s, pos + k);
@@ -470,14 +473,96 @@ static void fast_parse(deflater *d, bitw *b, int last, tok_sink sink, void *ctx,
                 quick_insert(s, pos - 1);               /* deflate_fast.c:80 (may hash virtual bytes) */
             }
         } else {
-            bs->d_buf[bs->sym_next] = 0; bs->l_buf[bs->sym_next++] = s->W[pos];
-            bs->lt.freq[s->W[pos]]++;
-            if (sink) sink(ctx, s->W[pos]);
+            tally_lit(bs, s->W[pos], sink, ctx);
             pos++;
         }
-tallied:
-        full = (bs->sym_next == ZO_SYM_END);
-        if (full) {
+        if (bs->sym_next == ZO_SYM_END) {
+            if (b) flush_block(bs, b, (slid && block_start < ZO_WSIZE) ? NULL : s->W + block_start, pos - block_start, 0);
+            else block_reset(bs);
+            block_start = pos;
+        }
+    }
+    if (!b) return;
+    const uint8_t *raw = (slid && block_start < ZO_WSIZE) ? NULL : s->W + block_start;
+    if (last) flush_block(bs, b, raw, pos - block_start, 1);
+    else if (bs->sym_next) flush_block(bs, b, raw, pos - block_start, 0);
+}
+
+/* levels 3-6: deflate_medium.c.  {nice, chain} = {16,6} {32,24} {32,32} {128,128} (deflate.c:160-163); levels 3-4 run
+ * without the look-ahead-one branch (early_exit, deflate_medium.c:151,234), i.e. as a greedy parse. */
+typedef struct { uint32_t from, len, at, org; } mmatch;      /* match_start, match_length, strstart, orgstart (:15-20) */
+static const uint16_t medium_nice[7]  = {0, 0, 0, 16, 32, 32, 128};
+static const uint16_t medium_chain[7] = {0, 0, 0, 6, 24, 32, 128};
+
+static void medium_insert(lzstate *s, mmatch m, uint32_t lookahead) {       /* insert_match, :44-82 */
+    if (lookahead <= m.len + ZO_WANT_MIN) return;
+    m.at++; m.len--;                                     /* the string at strstart is in the table already */
+    if (m.len < ZO_WANT_MIN - 1) {
+        if (m.len > 0 && m.at >= m.org) {
+            uint32_t cnt = (m.at + m.len - 1 >= m.org) ? m.len : m.org - m.at + 1;
+            for (uint32_t k = 0; k < cnt; k++) quick_insert(s, m.at + k);
+        }
+        return;
+    }
+    if (m.at >= m.org) {
+        uint32_t cnt = (m.at + m.len - 1 >= m.org) ? m.len : m.org - m.at + 1;
+        for (uint32_t k = 0; k < cnt; k++) quick_insert(s, m.at + k);
+    } else if (m.org < m.at + m.len) {
+        for (uint32_t q = m.org; q < m.at + m.len; q++) quick_insert(s, q);
+    }
+}
+
+static void medium_fizzle(const lzstate *s, mmatch *cur, mmatch *nxt) {     /* fizzle_matches, :84-144 */
+    if (cur->len <= 1) return;
+    if (cur->len > 1 + nxt->from || cur->len > 1 + nxt->at) return;
+    if (s->W[nxt->from + 1 - cur->len] != s->W[nxt->at + 1 - cur->len]) return;   /* the quick exit check */
+    mmatch c = *cur, n = *nxt;
+    uint32_t limit = nxt->at > ZO_MAX_DIST ? nxt->at - ZO_MAX_DIST : 0;
+    int moved = 0;
+    while (s->W[n.from - 1] == s->W[n.at - 1]) {         /* pull the next match to the left, shortening the current one */
+        if (c.len < 1 || n.at <= limit || n.len >= 256 || n.from <= 1) break;
+        n.at--; n.from--; n.len++; c.len--; moved++;
+    }
+    if (!moved) return;
+    if (c.len <= 1 && n.len != 2) { n.org++; *cur = c; *nxt = n; }
+}
+
+static void medium_find(lzstate *s, uint32_t pos, uint32_t cand, uint32_t lookahead, int level, mmatch *m) {   /* :191-215 */
+    uint32_t dist = pos - cand;
+    m->at = m->org = pos;
+    if (dist <= ZO_MAX_DIST && dist > 0 && cand != 0 && cand < pos) {
+        uint32_t from = 0;
+        m->len = longest_match_lv(s, pos, cand, lookahead, medium_chain[level], medium_nice[level], level, &from);
+        m->from = from;
+        if (m->len < ZO_WANT_MIN || m->from >= pos) m->len = 1;
+    } else { m->from = 0; m->len = 1; }
+}
+
+static void medium_parse(deflater *d, bitw *b, int last, tok_sink sink, void *ctx, int level) {
+    lzstate *s = &d->lz; blockstate *bs = &d->bs;
+    uint32_t pos = 0, n = s->len, block_start = 0; int slid = 0;
+    const int greedy = level < 5;
+    mmatch cur = {0, 0, 0, 0}, nxt = {0, 0, 0, 0};
+    block_init(bs);
+    for (;;) {
+        uint32_t left = n - pos;
+        if (left < 262) {                                /* :164-172 fill_window; it slides at strstart >= 65274 */
+            if (!slid && pos >= ZO_SLIDE_AT) slid = 1;
+            if (left == 0) break;
+            nxt.len = 0;
+        }
+        if (!greedy && nxt.len > 0) { cur = nxt; nxt.len = 0; }
+        else medium_find(s, pos, left >= ZO_WANT_MIN ? quick_insert(s, pos) : 0, left, level, &cur);
+        medium_insert(s, cur, left);
+        if (!greedy && left > 262 && cur.at + cur.len < ZO_CHUNK_MAX - 262) {   /* :234 look ahead one */
+            uint32_t np = cur.at + cur.len;
+            medium_find(s, np, quick_insert(s, np), left /* s->lookahead is not advanced yet */, level, &nxt);
+            if (nxt.len >= ZO_WANT_MIN) medium_fizzle(s, &cur, &nxt);
+        } else nxt.len = 0;
+        if (cur.len < ZO_WANT_MIN) { for (uint32_t k = 0; k < cur.len; k++) tally_lit(bs, s->W[cur.at + k], sink, ctx); }   /* emit_match, :22-42 */
+        else tally_match(bs, cur.at - cur.from, cur.len, sink, ctx);
+        pos += cur.len;
+        if (bs->sym_next == ZO_SYM_END) {
             if (b) flush_block(bs, b, (slid && block_start < ZO_WSIZE) ? NULL : s->W + block_start, pos - block_start, 0);
             else block_reset(bs);
             block_start = pos;
@@ -495,7 +580,7 @@ size_t zo_deflate_bound(size_t n) { return n + (n >> 3) + 64; }
 static size_t deflate_one(deflater *d, const uint8_t *in, uint32_t len, int level, int flush,
                           const uint8_t *stale, uint8_t *out, size_t cap) {
     pthread_once(&tbl_once, build_static_tables);
-    if (len > ZO_CHUNK_MAX || level < 1 || level > 3) return (size_t)-1;
+    if (len > ZO_CHUNK_MAX || level < 1 || level > 6) return (size_t)-1;
     if (flush != ZO_SYNC_FLUSH && flush != ZO_FULL_FLUSH && flush != ZO_FINISH) return (size_t)-1;
     int last = (flush == ZO_FINISH);
     bitw b = {out, cap, 0, 0, 0, 0};
@@ -509,7 +594,7 @@ static size_t deflate_one(deflater *d, const uint8_t *in, uint32_t len, int leve
             if (last) bw_align(&b);
         }
     } else {
-        fast_parse(d, &b, last, NULL, NULL, level);
+        if (level == 2) fast_parse(d, &b, last, NULL, NULL); else medium_parse(d, &b, last, NULL, NULL, level);
     }
     if (!last) {                         /* deflate.c:1064-1065: empty stored block for SYNC/FULL flush */
         bw_put(&b, 0, 3); bw_align(&b); bw_put(&b, 0x0000, 16); bw_put(&b, 0xffff, 16);
@@ -530,13 +615,14 @@ static void tok_push(void *ctx, uint32_t tok) { tokbuf *tb = (tokbuf *)ctx; if (
 
 size_t zo_deflate_tokens(const uint8_t *in, uint32_t len, int level, uint32_t *tokens, size_t cap) {
     pthread_once(&tbl_once, build_static_tables);
-    if (len > ZO_CHUNK_MAX || level < 1 || level > 3) return (size_t)-1;
+    if (len > ZO_CHUNK_MAX || level < 1 || level > 6) return (size_t)-1;
     deflater *d = (deflater *)malloc(sizeof(deflater));
     if (!d) return (size_t)-1;
     tokbuf tb = {tokens, cap, 0};
     lz_reset(&d->lz, in, len, NULL);
     if (level == 1) quick_parse(&d->lz, NULL, tok_push, &tb);
-    else fast_parse(d, NULL, 0, tok_push, &tb, level);
+    else if (level == 2) fast_parse(d, NULL, 0, tok_push, &tb);
+    else medium_parse(d, NULL, 0, tok_push, &tb, level);
     free(d);
     return tb.n;
 }

@@ -118,7 +118,7 @@ def deflate_digests():
                       "crc32": [int(x) for x in crcs], "adler32": [int(x) for x in adlers]})
 
     rng = np.random.default_rng(20261018)
-    for level in (1, 2, 3):
+    for level in (1, 2, 3, 4, 5, 6):
         add(f"synth_2MiB_l{level}", pkg.synth(32 * 65536), 65536, level, 3)
         add(f"synth_ragged_l{level}", pkg.synth(10 * 65536 + 777, seed=12345), 65536, level, 3)
         add(f"synth_finish_l{level}", pkg.synth(4 * 65536 + 4097, seed=99), 65536, level, 4)
