@@ -3,7 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (BASELINE metric: level 1)
     python bench.py --impl reference --gpus N --steps K ...  # zlib-ng's own CPU path, all host cores
-    python bench.py --workload deflate2|checksum|inflate     # the other BASELINE configs (same JSON contract)
+    python bench.py --workload deflate2..deflate6|checksum|inflate     # the other BASELINE configs (same JSON contract)
 
 Default workload (BASELINE.json configs[0], the configuration the metric is quoted on): per GPU a 1 GiB synthetic
 mixed text/binary buffer = 16,384 independent 64 KiB chunks, deflate_quick (level 1) raw deflate with Z_FULL_FLUSH
@@ -36,7 +36,8 @@ MEMBER = 4096
 SEED = 0x9E3779B97F4A7C15
 UNIT = "GB/s"
 METRICS = {"deflate1": "level1_deflate_input_throughput", "deflate2": "level2_deflate_input_throughput",
-           "deflate3": "level3_deflate_input_throughput",
+           "deflate3": "level3_deflate_input_throughput", "deflate4": "level4_deflate_input_throughput",
+           "deflate5": "level5_deflate_input_throughput", "deflate6": "level6_deflate_input_throughput",
            "checksum": "crc32_adler32_input_throughput", "inflate": "inflate_output_throughput"}
 
 
@@ -57,7 +58,10 @@ def workload_text(w, mib, ngpu):
     n = mib << 20
     if w.startswith("deflate"):
         lvl, fn, cfg = {"deflate1": (1, "deflate_quick", "configs[0]"), "deflate2": (2, "deflate_fast", "configs[2] at 1 GiB per GPU"),
-                        "deflate3": (3, "deflate_medium", "configs[2] at 1 GiB per GPU")}[w]
+                        "deflate3": (3, "deflate_medium", "configs[2] at 1 GiB per GPU"),
+                        "deflate4": (4, "deflate_medium", "configs[2] at 1 GiB per GPU, higher level"),
+                        "deflate5": (5, "deflate_medium", "configs[2] at 1 GiB per GPU, higher level"),
+                        "deflate6": (6, "deflate_medium", "configs[2] at 1 GiB per GPU, zlib-ng's default level")}[w]
         return (f"{fn} level {lvl}, {mib} MiB per GPU as {n // CHUNK} x 64 KiB raw-deflate chunks + per-chunk crc32, offset scan + gather + "
                 f"crc32_combine fold (BASELINE {cfg})")
     if w == "checksum":
@@ -247,7 +251,7 @@ def ctypes_u32():
 def cpu_sample_bytes(workload, n, seconds, reps):
     """Bounded sample of the workload for the CPU arm: about `seconds` of wall clock over `reps` passes."""
     cores = host_cores()
-    per_core = {"deflate1": 0.10e9, "deflate2": 0.06e9, "deflate3": 0.05e9, "checksum": 5e9, "inflate": 0.5e9}[workload]
+    per_core = {"deflate1": 0.10e9, "deflate2": 0.06e9, "deflate3": 0.05e9, "deflate4": 0.04e9, "deflate5": 0.035e9, "deflate6": 0.02e9, "checksum": 5e9, "inflate": 0.5e9}[workload]
     budget = int(per_core * cores * seconds / max(1, reps))
     return min(n, max(64 << 20, (budget >> 26) << 26))
 

@@ -1,7 +1,7 @@
-"""K2 parity: the sm_100a level-2 and level-3 chunk compressors (deflate_fast / deflate_medium: hash chains +
+"""K2 parity: the sm_100a level-2 .. level-6 chunk compressors (deflate_fast / deflate_medium: hash chains +
 longest_match, dynamic / static / stored blocks from the trees.c block writer), called through the C ABI, against the
 CPU oracle byte for byte, the committed digests of the unmodified reference, and round trips through an independent
-inflater.  Every test runs for both levels."""
+inflater.  Every test runs for every level."""
 import zlib as pyzlib
 
 import numpy as np
@@ -12,7 +12,7 @@ from test_gpu_deflate_quick import assert_parity, gpu_deflate
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[2, 3], ids=["level2", "level3"])
+@pytest.fixture(params=[2, 3, 4, 5, 6], ids=["level2", "level3", "level4", "level5", "level6"])
 def level(request):
     return request.param
 
@@ -110,6 +110,25 @@ def test_block_splits_at_16383_symbols(pkg, ctx, zo, level):
         for flush in (3, 4):
             assert_parity(pkg, ctx, zo, rng.integers(0, 256, size=n, dtype=np.uint8), 65536, flush, level=level)
             assert_parity(pkg, ctx, zo, lit[:n], 65536, flush, level=level)
+
+
+def test_lookahead_hand_over_and_fizzle(pkg, ctx, zo, level):
+    """Many short chunks: every chunk ends in the zone where deflate_medium stops looking ahead (deflate_medium.c:164-172,
+    234); low-entropy and periodic data make adjacent matches that fizzle_matches (:84-144) shifts."""
+    rng = np.random.default_rng(77)
+    data = pkg.synth(6 * 65536, seed=31)
+    for chunk in (553, 554, 555, 600, 777, 1024, 2500, 8191):
+        assert_parity(pkg, ctx, zo, data[:200 * chunk if 200 * chunk < data.size else data.size], chunk, 3, level=level)
+    low = rng.integers(0, 3, size=4 * 65536, dtype=np.uint8)
+    assert_parity(pkg, ctx, zo, low, level=level)
+    assert_parity(pkg, ctx, zo, low[:150000], 3000, 4, level=level)
+    words = rng.integers(97, 101, size=(16, 5), dtype=np.uint8)
+    text = words[rng.integers(0, 16, size=60000)].reshape(-1)
+    assert_parity(pkg, ctx, zo, text[:4 * 65536], level=level)
+    assert_parity(pkg, ctx, zo, text[:100 * 1234], 1234, 3, level=level)
+    for n in (65536 - 262, 65536 - 263, 65536 - 261, 65274, 65275, 65273, 65535, 65534):
+        assert_parity(pkg, ctx, zo, np.concatenate([text[:65536], text[1000:1000 + n]]), level=level)
+        assert_parity(pkg, ctx, zo, low[:n], 65536, 4, level=level)
 
 
 def test_small_chunks_and_finish_members(pkg, ctx, zo, level):

@@ -255,7 +255,7 @@ int ensure_slabs(zng_b200_ctx* ctx) {
 int check_chunk_args(zng_b200_ctx* ctx, const void* d_in, size_t n, uint32_t chunk, int level, int flush,
                      const void* d_out, size_t out_stride, const uint32_t* d_sizes) {
     if (!ctx) return ZNG_B200_STREAM_ERROR;
-    if (level < 1 || level > 3) return bad(ctx, "level must be 1 (deflate_quick), 2 (deflate_fast) or 3 (deflate_medium)");
+    if (level < 1 || level > 6) return bad(ctx, "level must be 1 (deflate_quick), 2 (deflate_fast) or 3..6 (deflate_medium)");
     if (flush != ZNG_B200_SYNC_FLUSH && flush != ZNG_B200_FULL_FLUSH && flush != ZNG_B200_FINISH)
         return bad(ctx, "flush must be Z_SYNC_FLUSH, Z_FULL_FLUSH or Z_FINISH");
     if (chunk == 0 || chunk > ZNG_B200_CHUNK_MAX) return bad(ctx, "chunk must be in 1..65536");
@@ -1005,7 +1005,7 @@ static int sync_slabs(zng_b200_ctx* ctx) {
 int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_t chunk, int level, int final,
                           void* h_out, size_t out_cap, size_t* out_len, uint32_t* crc32, uint32_t* adler32) {
     if (!ctx) return ZNG_B200_STREAM_ERROR;
-    if (level < 1 || level > 3) return bad(ctx, "level must be 1, 2 or 3");
+    if (level < 1 || level > 6) return bad(ctx, "level must be 1..6");
     if (chunk == 0 || chunk > ZNG_B200_CHUNK_MAX) return bad(ctx, "chunk must be in 1..65536");
     if (!out_len || (n && !h_in) || !h_out) return bad(ctx, "NULL argument");
     DeviceGuard g(ctx->device);

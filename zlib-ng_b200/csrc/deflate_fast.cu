@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "lz_ops.cuh"
+#include "lazy_parse.cuh"
 
 namespace zb {
 
@@ -133,7 +134,7 @@ __device__ uint32_t fast_parse_warp(const VWindow W, uint32_t n, uint16_t* head,
 }
 
 template <int LEVEL>
-__global__ void __launch_bounds__(kFastWarps * 32, 8)
+__global__ void __launch_bounds__(kFastWarps * 32, LEVEL >= 5 ? 6 : 8)
 fast_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint32_t nchunks,
                   uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
                   uint32_t* __restrict__ counter, uint16_t* __restrict__ heads, uint16_t* __restrict__ prevs,
@@ -186,7 +187,9 @@ fast_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint
             __stcg(tail + t, wv);
         }
         __syncwarp();
-        const uint32_t cnt = fast_parse_warp<LEVEL>(W, len, head, prev, tokens + (size_t)ci * tok_stride);
+        uint32_t cnt;
+        if constexpr (LEVEL >= 5) cnt = lazy_parse_warp<LEVEL>(W, len, head, prev, tokens + (size_t)ci * tok_stride);
+        else cnt = fast_parse_warp<LEVEL>(W, len, head, prev, tokens + (size_t)ci * tok_stride);
         if (lane == 0) ntok[ci] = cnt;
     }
     __syncwarp();
@@ -593,12 +596,17 @@ cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint3
     uint32_t grid = (uint32_t)num_sms * ctas_per_sm;
     const uint64_t need = ((uint64_t)nchunks + kFastWarps - 1u) / kFastWarps;
     if (need < grid) grid = (uint32_t)need;
-    if (level == 3)
-        fast_parse_kernel<3><<<grid, kFastWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, prevs, tails,
-                                                                   sm_slots, have_prev);
-    else
-        fast_parse_kernel<2><<<grid, kFastWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, prevs, tails,
-                                                                   sm_slots, have_prev);
+#define ZB_LAUNCH_PARSE(L) fast_parse_kernel<L><<<grid, kFastWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, \
+                                                                                     counter, heads, prevs, tails, sm_slots, have_prev)
+    switch (level) {
+        case 2: ZB_LAUNCH_PARSE(2); break;
+        case 3: ZB_LAUNCH_PARSE(3); break;
+        case 4: ZB_LAUNCH_PARSE(4); break;
+        case 5: ZB_LAUNCH_PARSE(5); break;
+        case 6: ZB_LAUNCH_PARSE(6); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef ZB_LAUNCH_PARSE
     return cudaGetLastError();
 }
 

@@ -40,16 +40,29 @@ __device__ __forceinline__ uint32_t vwarp_compare256(const VWindow& W, uint32_t 
 }
 
 
-// Parameters of the two greedy strategies on this path (configuration_table, deflate.c:142-168): level 2 = deflate_fast
-// {nice 8, chain 4}, level 3 = deflate_medium below level 5 {nice 16, chain 6}.  kCmp = bytes a lane compares by itself;
+// Parameters of the hash-chain strategies on this path (configuration_table, deflate.c:142-168): level 2 = deflate_fast
+// {nice 8, chain 4}; levels 3-6 = deflate_medium {16,6} {32,24} {32,32} {128,128}.  kCmp = bytes a lane compares by itself;
 // a common prefix of kCmp bytes means "kCmp or more", which is >= nice_match and therefore final.
 template <int LEVEL> struct LmParams;
 template <> struct LmParams<2> { static constexpr uint32_t kNice = 8, kChain = 4, kCmp = 12; };
 template <> struct LmParams<3> { static constexpr uint32_t kNice = 16, kChain = 6, kCmp = 16; };
+template <> struct LmParams<4> { static constexpr uint32_t kNice = 32, kChain = 24, kCmp = 32; };
+template <> struct LmParams<5> { static constexpr uint32_t kNice = 32, kChain = 32, kCmp = 32; };
+template <> struct LmParams<6> { static constexpr uint32_t kNice = 128, kChain = 128, kCmp = 128; };
 
-// common prefix (0..kCmp) of the kCmp bytes (v, x, z) at the scan position and at candidate `cand`
+// the 4 bytes at chunk position `pos` (any alignment)
+__device__ __forceinline__ uint32_t load32(const VWindow& W, uint32_t pos) {
+    const uint32_t b = pos + W.skew, i = b >> 2;
+    return __funnelshift_r(W.word(i), W.word(i + 1), (b & 3u) << 3);
+}
+__device__ __forceinline__ uint32_t load8(const VWindow& W, uint32_t pos) {
+    const uint32_t b = pos + W.skew;
+    return (W.word(b >> 2) >> ((b & 3u) << 3)) & 0xffu;
+}
+
+// common prefix (0..kCmp) of the bytes at the scan position q (the first 16 of them in v, x, z) and at candidate `cand`
 template <uint32_t kCmp>
-__device__ __forceinline__ uint32_t prefix_len(const VWindow& W, uint32_t cand, uint32_t v, uint64_t x, uint32_t z) {
+__device__ __forceinline__ uint32_t prefix_len(const VWindow& W, uint32_t q, uint32_t cand, uint32_t v, uint64_t x, uint32_t z) {
     const uint32_t cb = cand + W.skew, i = cb >> 2, sh = (cb & 3u) << 3;
     const uint32_t b0 = W.word(i), b1 = W.word(i + 1), b2 = W.word(i + 2), b3 = W.word(i + 3);
     const uint32_t d0 = v ^ __funnelshift_r(b0, b1, sh);
@@ -57,31 +70,49 @@ __device__ __forceinline__ uint32_t prefix_len(const VWindow& W, uint32_t cand, 
     const uint64_t d = x ^ ((uint64_t)__funnelshift_r(b1, b2, sh) | ((uint64_t)__funnelshift_r(b2, b3, sh) << 32));
     if (d) return 4u + ((uint32_t)(__ffsll((long long)d) - 1) >> 3);
     if (kCmp == 12u) return 12u;
-    const uint32_t dz = z ^ __funnelshift_r(b3, W.word(i + 4), sh);
-    return dz ? 12u + ((uint32_t)(__ffs((int)dz) - 1) >> 3) : 16u;
+    uint32_t bl = W.word(i + 4);
+    const uint32_t dz = z ^ __funnelshift_r(b3, bl, sh);
+    if (dz) return 12u + ((uint32_t)(__ffs((int)dz) - 1) >> 3);
+    if (kCmp == 16u) return 16u;
+    const uint32_t qb = q + W.skew, qi = qb >> 2, qsh = (qb & 3u) << 3;
+    uint32_t al = W.word(qi + 4);
+    for (uint32_t k = 4; k < kCmp / 4u; k++) {               // words 4.. of both strings, one aligned word of each per step
+        const uint32_t an = W.word(qi + k + 1), bn = W.word(i + k + 1);
+        const uint32_t dd = __funnelshift_r(al, an, qsh) ^ __funnelshift_r(bl, bn, sh);
+        if (dd) return 4u * k + ((uint32_t)(__ffs((int)dd) - 1) >> 3);
+        al = an; bl = bn;
+    }
+    return kCmp;
 }
 
 // longest_match for one position q (one lane): v / x / z = the bytes at q, cand0 = hash head (already range-checked),
 // look = lookahead (bytes left from q).  Walks <= kChain candidates through prev[].  best_len starts at 2; with
-// OPTIMAL_CMP 64 the pre-filter (match_tpl.h:141-165) compares the 2 / 4 / 8 bytes that end at index best_len plus the
-// first 2 / 4 / 8 bytes, which for best_len 2..15 is exactly "bytes 0..best_len equal": a candidate improves iff its
-// common prefix exceeds best_len (so the early_exit branch :261-266 is never taken).  Returns 0 (no match >= 4),
-// 4..kCmp-1 (exact length, clipped to look), or kCmp = "kCmp or more: measure with vwarp_compare256 and clip";
-// mcand = match_start of the returned match.
+// OPTIMAL_CMP 64 the pre-filter (match_tpl.h:141-165) compares the first 2 / 4 / 8 bytes and the 2 / 4 / 8 bytes that end
+// at index best_len, which for best_len 2..15 is exactly "bytes 0..best_len equal": a candidate improves iff its common
+// prefix exceeds best_len.  From best_len 16 on (levels 4+) the filter leaves the gap [8, best_len-7): a candidate that
+// passes it without improving ends the search below level 5 (early_exit, :127,261-266) and is skipped from level 5 on.
+// Returns 0 (no match >= 4), 4..kCmp-1 (exact length, clipped to look), or kCmp = "kCmp or more: measure with
+// vwarp_compare256 and clip"; mcand = match_start of the returned match.
 template <int LEVEL>
 __device__ __forceinline__ uint32_t longest_match_lane(const VWindow& W, uint32_t q, uint32_t v, uint64_t x, uint32_t z, uint32_t cand0,
                                                        uint32_t look, const uint16_t* prev, uint32_t& mcand) {
     using P = LmParams<LEVEL>;
-    uint32_t best = 2, chain = P::kChain, cand = cand0;
+    constexpr bool kDeep = P::kChain > 6u;                  // worth a 4-byte pre-check at the end of the current best
+    uint32_t best = 2, chain = P::kChain, cand = cand0, endw = 0;
     const uint32_t limit = q > kMaxDist ? q - kMaxDist : 0u;
     for (;;) {
-        const uint32_t cl = prefix_len<P::kCmp>(W, cand, v, x, z);
-        if (cl > best) {
-            mcand = cand;
-            if (cl == P::kCmp) { best = P::kCmp; break; }   // >= nice_match: final, measured by the warp later
-            if (cl > look) { best = look; break; }         // match_tpl.h:177-183 len > lookahead: return lookahead
-            best = cl;
-            if (best >= P::kNice) break;                   // nice_match
+        if (kDeep && cand >= q) break;                     // match_tpl.h:131-132 (a re-inserted string can link forward)
+        if (!kDeep || best < 3u || load32(W, cand + best - 3u) == endw) {      // bytes best-3..best must match to improve
+            const uint32_t cl = prefix_len<P::kCmp>(W, q, cand, v, x, z);
+            if (cl > best) {
+                mcand = cand;
+                if (cl == P::kCmp) { best = P::kCmp; break; }   // >= nice_match: final, measured by the warp later
+                if (cl > look) { best = look; break; }         // match_tpl.h:177-183 len > lookahead: return lookahead
+                best = cl;
+                if (best >= P::kNice) break;                   // nice_match
+                if (kDeep) endw = load32(W, q + best - 3u);
+            } else if (LEVEL == 4 && best >= 16u && cl >= 8u &&
+                       load32(W, cand + best - 7u) == load32(W, q + best - 7u)) break;   // filter passed, no gain: early_exit
         }
         if (--chain == 0u) break;
         cand = (uint32_t)__ldcg(prev + (cand & (kWSize - 1u)));

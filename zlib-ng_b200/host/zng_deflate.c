@@ -54,8 +54,8 @@ int32_t zng_deflateInit2(zng_stream *strm, int32_t level, int32_t method, int32_
         level < 0 || level > 9 || strategy < 0 || strategy > Z_FIXED || (windowBits == 8 && wrap != 1))
         return Z_STREAM_ERROR;
     /* ... then the frozen parameter set of the GPU path (no CPU fallback) */
-    if (level < 1 || level > 3 || windowBits != 15 || memLevel != DEF_MEM_LEVEL || strategy != Z_DEFAULT_STRATEGY) {
-        strm->msg = "unsupported parameters: levels 1-3, windowBits 15, memLevel 8, default strategy only";
+    if (level < 1 || level > 6 || windowBits != 15 || memLevel != DEF_MEM_LEVEL || strategy != Z_DEFAULT_STRATEGY) {
+        strm->msg = "unsupported parameters: levels 1-6, windowBits 15, memLevel 8, default strategy only";
         return Z_STREAM_ERROR;
     }
     if (zng_b200_thread_ctx() == NULL) { strm->msg = "no CUDA device"; return Z_MEM_ERROR; }
@@ -197,7 +197,7 @@ int32_t zng_deflate(zng_stream *strm, int32_t flush) {
     if (!s->header_done) {
         if (s->wrap == 1) {
             unsigned header = (Z_DEFLATED + ((15 - 8) << 4)) << 8;
-            unsigned level_flags = s->level < 2 ? 0 : 1;
+            unsigned level_flags = s->level < 2 ? 0 : (s->level < 6 ? 1 : 2);   /* deflate.c:873-880 */
             header |= level_flags << 6;
             header += 31 - (header % 31);
             uint8_t h[2] = {(uint8_t)(header >> 8), (uint8_t)header};
@@ -260,7 +260,7 @@ size_t zng_compressBound(size_t sourceLen) { return (size_t)zng_deflateBound(NUL
 int32_t zng_compress2(uint8_t *dest, size_t *destLen, const uint8_t *source, size_t sourceLen, int32_t level) {
     zng_stream strm;
     memset(&strm, 0, sizeof(strm));
-    if (level == Z_DEFAULT_COMPRESSION) level = 1;          /* the GPU path has levels 1-3 only */
+    if (level == Z_DEFAULT_COMPRESSION) level = 6;
     int err = zng_deflateInit(&strm, level);
     if (err != Z_OK) return err;
     size_t left = *destLen; *destLen = 0;
