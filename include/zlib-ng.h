@@ -13,7 +13,8 @@
  * produces exactly the bytes the reference produces for k (+1) calls zng_deflate(Z_FULL_FLUSH) that
  * feed one 65536-byte piece each, and zng_deflate(strm, Z_FINISH) finishes the stream the way the
  * reference does when the remaining input is fed the same way with Z_FINISH on the last piece.
- * Z_NO_FLUSH only buffers input.  Supported parameters: level 1 (deflate_quick), 2 (deflate_fast) and 3 (deflate_medium),
+ * Z_NO_FLUSH only buffers input.  Supported parameters: levels 1 (deflate_quick), 2 (deflate_fast), 3..6 (deflate_medium) and
+ * Z_DEFAULT_COMPRESSION (= 6),
  * method Z_DEFLATED, windowBits -15 / 15 / 31, memLevel 8, Z_DEFAULT_STRATEGY; anything else is
  * Z_STREAM_ERROR.
  */

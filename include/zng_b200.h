@@ -12,8 +12,9 @@
  * every entry point fails when the device or the kernels are unavailable.
  *
  * Frozen parameters: windowBits 15, memLevel 8, Z_DEFAULT_STRATEGY,
- * chunk <= 65536 bytes, levels 1 (deflate_quick), 2 (deflate_fast) and 3 (deflate_medium; below level 5 it runs
- * without its look-ahead branch, deflate_medium.c:151,234).
+ * chunk <= 65536 bytes, levels 1 (deflate_quick), 2 (deflate_fast) and 3..6 (deflate_medium; below level 5 it runs
+ * without its look-ahead branch, deflate_medium.c:151,234; levels 5-6 look ahead and run fizzle_matches).  Level 6 is
+ * zlib-ng's Z_DEFAULT_COMPRESSION.
  */
 #ifndef ZNG_B200_H
 #define ZNG_B200_H
@@ -73,7 +74,7 @@ size_t      zng_b200_deflate_bound(size_t chunk_len);
  *   d_crcs[i]   zng_crc32(0, chunk i)    (may be NULL)       crc32.c:27-41
  *   d_adlers[i] zng_adler32(1, chunk i)  (may be NULL)       adler32.c:15-28
  * level 1 = deflate_quick (deflate_quick.c:47-130), level 2 = deflate_fast (deflate_fast.c:19-104),
- * level 3 = deflate_medium (deflate_medium.c:146-278). */
+ * levels 3..6 = deflate_medium (deflate_medium.c:22-278) with configuration_table's {nice, chain} (deflate.c:160-163). */
 int zng_b200_deflate_chunks(zng_b200_ctx *ctx, const void *d_in, size_t n, uint32_t chunk, int level, int flush,
                             void *d_out, size_t out_stride, uint32_t *d_sizes, uint32_t *d_crcs,
                             uint32_t *d_adlers, void *stream);

@@ -37,7 +37,7 @@ def expected_stream(zo, data, level, wb):
     if wb < 0:
         return raw
     if wb == 15:
-        return bytes([0x78, 0x01 if level < 2 else 0x5e]) + raw + struct.pack(">I", pyzlib.adler32(data.tobytes()))
+        return bytes([0x78, 0x01 if level < 2 else (0x5e if level < 6 else 0x9c)]) + raw + struct.pack(">I", pyzlib.adler32(data.tobytes()))
     return bytes([31, 139, 8, 0, 0, 0, 0, 0, 4 if level < 2 else 0, 3]) + raw + struct.pack("<II", pyzlib.crc32(data.tobytes()), n & 0xffffffff)
 
 
@@ -82,6 +82,18 @@ def test_zng_deflate_one_call_equals_reference_piecewise(pkg, L, zo, n, wb):
         assert adler == pyzlib.crc32(data.tobytes())
 
 
+@pytest.mark.parametrize("level", [2, 3, 4, 5, 6, -1])
+def test_zng_deflate_every_level(pkg, L, zo, level):
+    """Levels 2-6 and Z_DEFAULT_COMPRESSION (= 6, deflate.c:43) through zng_deflateInit2 / zng_deflate, zlib and gzip wrappers
+    (the FLEVEL bits of the zlib header follow deflate.c:873-880)."""
+    n = 3 * 65536 + 777
+    data = pkg.synth(n, seed=level + 40)
+    for wb in (15, 31):
+        got, _ = deflate_via_api(pkg, L, data, level, wb, [(n, pkg.Z_FINISH)])
+        assert got == expected_stream(zo, data, 6 if level < 0 else level, wb)
+        assert pyzlib.decompress(got, wbits=wb) == data.tobytes()
+
+
 def test_zng_deflate_piecewise_and_small_output_windows(pkg, L, zo):
     n = 5 * 65536 + 1234
     data = pkg.synth(n, seed=11)
@@ -99,7 +111,7 @@ def test_zng_deflate_piecewise_and_small_output_windows(pkg, L, zo):
 def test_zng_deflate_argument_errors(pkg, L):
     s = pkg.ZngStream()
     assert L.zng_deflateInit2(None, 1, 8, 15, 8, 0) == pkg.Z_STREAM_ERROR
-    for args in ((1, 7, 15, 8, 0), (10, 8, 15, 8, 0), (1, 8, 16 + 16, 8, 0), (1, 8, 15, 10, 0), (1, 8, 15, 8, 5), (6, 8, 15, 8, 0), (4, 8, 15, 8, 0), (1, 8, 12, 8, 0)):
+    for args in ((1, 7, 15, 8, 0), (10, 8, 15, 8, 0), (1, 8, 16 + 16, 8, 0), (1, 8, 15, 10, 0), (1, 8, 15, 8, 5), (7, 8, 15, 8, 0), (9, 8, 15, 8, 0), (0, 8, 15, 8, 0), (1, 8, 12, 8, 0)):
         assert L.zng_deflateInit2(ctypes.byref(s), *args) == pkg.Z_STREAM_ERROR, args
     assert L.zng_deflateInit2(ctypes.byref(s), 1, 8, 15, 8, 0) == 0
     buf = np.zeros(64, dtype=np.uint8)
@@ -225,7 +237,7 @@ def test_minigzip_cli_roundtrip(pkg, zo, tmp_path):
     data = pkg.synth(7 * 65536 + 4321, seed=19)
     src = tmp_path / "in.bin"
     src.write_bytes(data.tobytes())
-    for level in (1, 2, 3):
+    for level in (1, 2, 3, 4, 5, 6):
         comp = subprocess.run([exe, f"-{level}", str(src)], stdout=subprocess.PIPE, check=True).stdout
         assert comp == expected_stream(zo, data, level, 31)
         assert gzip.decompress(comp) == data.tobytes()

@@ -27,14 +27,12 @@ static uint8_t *slurp(FILE *f, size_t *n) {
 }
 
 int main(int argc, char **argv) {
-    int level = 1, decompress = 0;
+    int level = 6, decompress = 0;                          /* test/minigzip.c: Z_DEFAULT_COMPRESSION */
     const char *path = NULL;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "-d")) decompress = 1;
-        else if (!strcmp(argv[i], "-1")) level = 1;
-        else if (!strcmp(argv[i], "-2")) level = 2;
-        else if (!strcmp(argv[i], "-3")) level = 3;
-        else if (argv[i][0] == '-' && argv[i][1]) { fprintf(stderr, "usage: %s [-1|-2|-3] [-d] [file]\n", argv[0]); return 2; }
+        else if (argv[i][0] == '-' && argv[i][1] >= '1' && argv[i][1] <= '6' && !argv[i][2]) level = argv[i][1] - '0';
+        else if (argv[i][0] == '-' && argv[i][1]) { fprintf(stderr, "usage: %s [-1 .. -6] [-d] [file]\n", argv[0]); return 2; }
         else path = argv[i];
     }
     FILE *f = path && strcmp(path, "-") ? fopen(path, "rb") : stdin;
