@@ -134,7 +134,7 @@ __device__ uint32_t fast_parse_warp(const VWindow W, uint32_t n, uint16_t* head,
 }
 
 template <int LEVEL>
-__global__ void __launch_bounds__(kFastWarps * 32, LEVEL >= 5 ? 6 : 8)
+__global__ void __launch_bounds__(kFastWarps * 32, 8)
 fast_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint32_t nchunks,
                   uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
                   uint32_t* __restrict__ counter, uint16_t* __restrict__ heads, uint16_t* __restrict__ prevs,

@@ -102,6 +102,7 @@ __device__ __forceinline__ uint32_t longest_match_lane(const VWindow& W, uint32_
     const uint32_t limit = q > kMaxDist ? q - kMaxDist : 0u;
     for (;;) {
         if (kDeep && cand >= q) break;                     // match_tpl.h:131-132 (a re-inserted string can link forward)
+        const uint32_t link = (uint32_t)__ldcg(prev + (cand & (kWSize - 1u)));   // issued before the compare: the two latencies overlap
         if (!kDeep || best < 3u || load32(W, cand + best - 3u) == endw) {      // bytes best-3..best must match to improve
             const uint32_t cl = prefix_len<P::kCmp>(W, q, cand, v, x, z);
             if (cl > best) {
@@ -115,7 +116,7 @@ __device__ __forceinline__ uint32_t longest_match_lane(const VWindow& W, uint32_
                        load32(W, cand + best - 7u) == load32(W, q + best - 7u)) break;   // filter passed, no gain: early_exit
         }
         if (--chain == 0u) break;
-        cand = (uint32_t)__ldcg(prev + (cand & (kWSize - 1u)));
+        cand = link;
         if (cand <= limit) break;                          // match_tpl.h:48-51
     }
     return best >= kWantMin ? best : 0u;
