@@ -79,6 +79,15 @@ int zng_b200_deflate_chunks(zng_b200_ctx *ctx, const void *d_in, size_t n, uint3
                             void *d_out, size_t out_stride, uint32_t *d_sizes, uint32_t *d_crcs,
                             uint32_t *d_adlers, void *stream);
 
+/* Replaces: per chunk, a fresh zng_deflateInit2(level, Z_DEFLATED, -15, 8, 0) + zng_deflateSetDictionary(the 32768
+ * stream bytes in front of the chunk) (deflate.c:456-512) + one zng_deflate(flush) -- pigz's default, dependent-chunk
+ * mode: chunks stay independent units of work, but chunk i may reference the last 32 KiB of chunk
+ * i-1, so the concatenation (Z_SYNC_FLUSH joins) is one raw-deflate stream that must be inflated in order.  The first
+ * chunk of the buffer has no dictionary.  Level 1 and chunk 65536 only; other arguments as zng_b200_deflate_chunks. */
+int zng_b200_deflate_chunks_primed(zng_b200_ctx *ctx, const void *d_in, size_t n, uint32_t chunk, int level, int flush,
+                                   void *d_out, size_t out_stride, uint32_t *d_sizes, uint32_t *d_crcs,
+                                   uint32_t *d_adlers, void *stream);
+
 /* Debug aid (ZLIB_DEBUG's Tracevv token trace analogue, deflate_p.h:39-44,72): as above for level 1,
  * additionally writing the LZ77 token stream of chunk i to d_tokens[i*tok_stride ...]: a literal is
  * its byte value, a match is 0x80000000 | len << 16 | dist, the list ends with 0x40000000. */

@@ -11,6 +11,8 @@
  *                   worker; per chunk zng_deflateReset + one zng_deflate(Z_FULL_FLUSH)
  *   gzip member   : zng_deflateInit2(level, Z_DEFLATED, 31, 8, 0) + one zng_deflate(Z_FINISH)
  *   inflate member: zng_inflateInit2(31) once per worker; zng_inflateReset + zng_inflate(Z_FINISH)
+ *   primed chunk  : (pigz's default mode) a FRESH zng_deflateInit2(level, Z_DEFLATED, -15, 8, 0) per chunk,
+ *                   zng_deflateSetDictionary(the 32768 stream bytes in front of the chunk), one zng_deflate(flush)
  */
 #include <pthread.h>
 #include <stdatomic.h>
@@ -24,7 +26,7 @@
 
 typedef struct {
     /* common */
-    int kind;               /* 0 deflate chunks, 1 checksum chunks, 2 inflate members, 3 gzip members */
+    int kind;               /* 0 deflate chunks, 1 checksum chunks, 2 inflate members, 3 gzip members, 4 primed chunks */
     atomic_size_t next;     /* next unit to claim */
     size_t n_units;
     atomic_int err;
@@ -69,6 +71,21 @@ static void *worker(void *arg) {
             j->sizes[u] = (uint32_t)s.total_out;
             if (j->crcs) j->crcs[u] = zng_crc32(0, j->in + off, len);
             if (j->adlers) j->adlers[u] = zng_adler32(1, j->in + off, len);
+        } else if (j->kind == 4) {
+            size_t off = u * (size_t)j->chunk;
+            uint32_t len = (uint32_t)((j->n - off < j->chunk) ? (j->n - off) : j->chunk);
+            zng_stream d;
+            memset(&d, 0, sizeof(d));
+            if (zng_deflateInit2(&d, j->level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { atomic_store(&j->err, 1); break; }
+            if (off >= 32768 && zng_deflateSetDictionary(&d, j->in + off - 32768, 32768) != Z_OK) atomic_store(&j->err, 3);
+            d.next_in = j->in + off; d.avail_in = len;
+            d.next_out = j->out + u * j->out_stride; d.avail_out = (uint32_t)j->out_stride;
+            int r = zng_deflate(&d, j->flush);
+            if ((j->flush == Z_FINISH ? r != Z_STREAM_END : r != Z_OK) || d.avail_in != 0) atomic_store(&j->err, 2);
+            j->sizes[u] = (uint32_t)d.total_out;
+            if (j->crcs) j->crcs[u] = zng_crc32(0, j->in + off, len);
+            if (j->adlers) j->adlers[u] = zng_adler32(1, j->in + off, len);
+            zng_deflateEnd(&d);
         } else if (j->kind == 1) {
             size_t off = u * (size_t)j->chunk;
             uint32_t len = (uint32_t)((j->n - off < j->chunk) ? (j->n - off) : j->chunk);
@@ -128,6 +145,19 @@ REFDRV_EXPORT int refdrv_deflate_chunks(const uint8_t *in, size_t n, uint32_t ch
     j.kind = 0; j.in = in; j.n = n; j.chunk = chunk; j.level = level; j.flush = flush;
     j.out = out; j.out_stride = out_stride; j.sizes = sizes; j.crcs = crcs; j.adlers = adlers;
     j.n_units = chunk ? (n + chunk - 1) / chunk : 0;
+    return run_job(&j, nthreads);
+}
+
+/* As refdrv_deflate_chunks, but every chunk after the first is primed with the 32768 stream bytes in front of it
+ * (deflateSetDictionary on a fresh raw stream): pigz's default, dependent-chunk mode.  chunk must be >= 32768. */
+REFDRV_EXPORT int refdrv_deflate_chunks_primed(const uint8_t *in, size_t n, uint32_t chunk, int level, int flush,
+                                               uint8_t *out, size_t out_stride, uint32_t *sizes,
+                                               uint32_t *crcs, uint32_t *adlers, int nthreads) {
+    job_t j; memset(&j, 0, sizeof(j));
+    if (chunk < 32768) return 4;
+    j.kind = 4; j.in = in; j.n = n; j.chunk = chunk; j.level = level; j.flush = flush;
+    j.out = out; j.out_stride = out_stride; j.sizes = sizes; j.crcs = crcs; j.adlers = adlers;
+    j.n_units = (n + chunk - 1) / chunk;
     return run_job(&j, nthreads);
 }
 

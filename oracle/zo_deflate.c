@@ -166,11 +166,15 @@ static void lz_reset(lzstate *s, const uint8_t *in, uint32_t len, const uint8_t 
 typedef void (*tok_sink)(void *ctx, uint32_t tok);
 
 static void quick_parse(lzstate *s, bitw *b, tok_sink sink, void *ctx) {   /* deflate_quick.c:65-120 */
-    uint32_t pos = 0, n = s->len;
+    uint32_t pos = 0, n = s->len; int slid = 0;
     while (pos < n) {
         uint32_t left = n - pos;
+        if (left < 262 && pos >= ZO_SLIDE_AT) slid = 1;       /* fill_window slides (deflate.c:1285-1299) */
         if (left >= ZO_WANT_MIN) {
             uint32_t cand = quick_insert(s, pos);
+            /* slide_hash turned every entry below 32768 into 0, and deflate_quick has no hash_head != 0 test: such a
+             * slot now names window position 0 = original position 32768 (in reach only for strstart 65274) */
+            if (slid && cand < ZO_WSIZE) cand = ZO_WSIZE;
             uint32_t dist = pos - cand;
             if (dist > 0 && dist <= ZO_MAX_DIST && cand < pos &&
                 s->W[pos] == s->W[cand] && s->W[pos + 1] == s->W[cand + 1]) {
@@ -574,6 +578,92 @@ static void medium_parse(deflater *d, bitw *b, int last, tok_sink sink, void *ct
     else if (bs->sym_next) flush_block(bs, b, raw, pos - block_start, 0);
 }
 
+/* ------------------------------------------------------------------ primed chunks (pigz's dependent mode), level 1
+ * Call sequence restated: fresh zng_deflateInit2(1, -15) ; zng_deflateSetDictionary(the 32768 bytes in front of the chunk,
+ * deflate.c:456-512) ; one zng_deflate(flush) (deflate_quick.c:47-130 with fill_window, deflate.c:1272-1376).
+ * Positions are ABSOLUTE from the start of the dictionary (0 .. 32768 + len), the head table holds 32-bit absolute
+ * positions and is never slid: an entry the reference's slide_hash would have zeroed lies more than MAX_DIST behind
+ * strstart, and so does the window position 0 an empty slot stands for, so the distance test (:90-92) rejects the same
+ * candidates.  What the slides and refills DO change is restated: (i) deflateSetDictionary hashes position 32765 with the
+ * still-zero byte behind the dictionary, (ii) the first fill_window of zng_deflate re-inserts 32765 and inserts the two
+ * pending strings 32766, 32767 (s->insert), (iii) every later refill that reads input inserts strstart - 1
+ * (deflate.c:1321-1336). */
+typedef struct { const uint8_t *B; uint32_t N, R; uint32_t *head; } pstate;   /* B[0..N): dictionary + chunk; R: bytes loaded */
+
+static inline uint32_t p_hash(const pstate *s, uint32_t pos) {
+    uint32_t v = 0;
+    for (int k = 0; k < 4; k++) v |= (uint32_t)(pos + k < s->R ? s->B[pos + k] : 0) << (8 * k);   /* not yet loaded: zeroed (high_water) */
+    return (v * 2654435761u) >> 16;
+}
+static inline uint32_t p_insert(pstate *s, uint32_t pos) {
+    uint32_t h = p_hash(s, pos), old = s->head[h];
+    if (old != pos) s->head[h] = pos;
+    return old;
+}
+
+static void quick_parse_primed(pstate *s, uint32_t D, bitw *b, tok_sink sink, void *ctx) {
+    uint32_t pos = D, base = 0, pend = 2;
+    s->R = D;
+    for (uint32_t q = 0; q + 2 < D; q++) p_insert(s, q);          /* insert_string(s, 0, D - 2) */
+    for (;;) {
+        if (s->R - pos < 262) {                                   /* fill_window */
+            do {
+                if (pos - base >= ZO_SLIDE_AT) base += ZO_WSIZE;
+                if (s->R == s->N) break;
+                uint32_t room = base + ZO_CHUNK_MAX - s->R;
+                s->R = s->N - s->R < room ? s->N : s->R + room;
+                if (s->R - pos + pend >= 3) {
+                    uint32_t str = pos - pend;
+                    if (str - base >= 1) p_insert(s, str - 1);
+                    uint32_t cnt = pend;
+                    if (s->R - pos == 1) cnt--;
+                    for (uint32_t k = 0; k < cnt; k++) p_insert(s, str + k);
+                    pend -= cnt;
+                }
+            } while (s->R - pos < 262 && s->R != s->N);
+            if (s->R == pos) break;
+        }
+        uint32_t left = s->R - pos;
+        if (left >= ZO_WANT_MIN) {
+            uint32_t cand = p_insert(s, pos);
+            if (cand < base) cand = base;                       /* empty or slid-out slot: window index 0 (no hash_head != 0 test) */
+            uint32_t dist = pos - cand;
+            if (cand < pos && dist <= ZO_MAX_DIST && s->B[pos] == s->B[cand] && s->B[pos + 1] == s->B[cand + 1]) {
+                uint32_t ml = 2;
+                while (ml < 258 && pos + ml < s->N && s->B[pos + ml] == s->B[cand + ml]) ml++;
+                if (ml >= ZO_WANT_MIN) {
+                    if (ml > left) ml = left;
+                    if (b) emit_match(b, fx_lcode, fx_llen, fx_dcode, fx_dlen, ml, dist);
+                    if (sink) sink(ctx, 0x80000000u | (ml << 16) | dist);
+                    pos += ml;
+                    continue;
+                }
+            }
+        }
+        if (b) emit_lit(b, fx_lcode, fx_llen, s->B[pos]);
+        if (sink) sink(ctx, s->B[pos]);
+        pos++;
+    }
+}
+
+/* one primed chunk: in[-dict .. 0) is the dictionary (dict = 32768), in[0 .. len) the chunk */
+static size_t deflate_one_primed(const uint8_t *in, uint32_t len, int flush, uint8_t *out, size_t cap) {
+    pthread_once(&tbl_once, build_static_tables);
+    int last = (flush == ZO_FINISH);
+    bitw b = {out, cap, 0, 0, 0, 0};
+    pstate s = {in - ZO_WSIZE, ZO_WSIZE + len, 0, (uint32_t *)calloc(65536, sizeof(uint32_t))};
+    if (!s.head) return (size_t)-1;
+    if (len > 0 || last) {
+        bw_put(&b, (uint64_t)(1 << 1) + (unsigned)last, 3);
+        quick_parse_primed(&s, ZO_WSIZE, &b, NULL, NULL);
+        bw_put(&b, fx_lcode[256], fx_llen[256]);
+        if (last) bw_align(&b);
+    }
+    free(s.head);
+    if (!last) { bw_put(&b, 0, 3); bw_align(&b); bw_put(&b, 0x0000, 16); bw_put(&b, 0xffff, 16); }
+    return b.ovf ? (size_t)-1 : b.n;
+}
+
 /* ------------------------------------------------------------------ public */
 size_t zo_deflate_bound(size_t n) { return n + (n >> 3) + 64; }
 
@@ -657,7 +747,7 @@ void zo_insert_string(const uint8_t *window, uint32_t avail, uint16_t *head, uin
 typedef struct {
     const uint8_t *in; size_t n; uint32_t chunk; int level, flush;
     uint8_t *out; size_t out_stride; uint32_t *sizes, *crcs, *adlers;
-    size_t units; atomic_size_t next; atomic_int err;
+    size_t units; atomic_size_t next; atomic_int err; int primed;
 } zjob;
 
 static void *zworker(void *arg) {
@@ -671,7 +761,8 @@ static void *zworker(void *arg) {
         uint32_t len = (uint32_t)((j->n - off < j->chunk) ? (j->n - off) : j->chunk);
         /* a short chunk that follows a full one sees the previous chunk's stale upper half */
         const uint8_t *stale = (len < ZO_CHUNK_MAX && u > 0 && j->chunk == ZO_CHUNK_MAX) ? j->in + off - ZO_WSIZE : NULL;
-        size_t r = deflate_one(d, j->in + off, len, j->level, j->flush, stale, j->out + u * j->out_stride, j->out_stride);
+        size_t r = (j->primed && u > 0) ? deflate_one_primed(j->in + off, len, j->flush, j->out + u * j->out_stride, j->out_stride)
+                                        : deflate_one(d, j->in + off, len, j->level, j->flush, j->primed ? NULL : stale, j->out + u * j->out_stride, j->out_stride);
         if (r == (size_t)-1) { atomic_store(&j->err, 2); r = 0; }
         j->sizes[u] = (uint32_t)r;
         if (j->crcs) j->crcs[u] = zo_crc32(0, j->in + off, len);
@@ -681,18 +772,35 @@ static void *zworker(void *arg) {
     return NULL;
 }
 
+static int run_zjob_impl(zjob *j, int nthreads);
+static int run_zjob(zjob *j, int nthreads) { return run_zjob_impl(j, nthreads); }
+
 int zo_deflate_chunks(const uint8_t *in, size_t n, uint32_t chunk, int level, int flush,
                       uint8_t *out, size_t out_stride, uint32_t *sizes,
                       uint32_t *crcs, uint32_t *adlers, int nthreads) {
     if (chunk == 0 || chunk > ZO_CHUNK_MAX) return -2;
-    zjob j = {in, n, chunk, level, flush, out, out_stride, sizes, crcs, adlers, (n + chunk - 1) / chunk, 0, 0};
-    atomic_store(&j.next, 0); atomic_store(&j.err, 0);
+    zjob j = {in, n, chunk, level, flush, out, out_stride, sizes, crcs, adlers, (n + chunk - 1) / chunk, 0, 0, 0};
+    return run_zjob(&j, nthreads);
+}
+
+/* pigz's dependent mode: chunk u > 0 is compressed by a fresh stream primed (deflateSetDictionary) with the 32768 stream
+ * bytes in front of it.  Level 1, chunk = 65536 (every dictionary is then a full window). */
+int zo_deflate_chunks_primed(const uint8_t *in, size_t n, uint32_t chunk, int level, int flush,
+                             uint8_t *out, size_t out_stride, uint32_t *sizes,
+                             uint32_t *crcs, uint32_t *adlers, int nthreads) {
+    if (chunk != ZO_CHUNK_MAX || level != 1) return -2;
+    zjob j = {in, n, chunk, level, flush, out, out_stride, sizes, crcs, adlers, (n + chunk - 1) / chunk, 0, 0, 1};
+    return run_zjob(&j, nthreads);
+}
+
+static int run_zjob_impl(zjob *j, int nthreads) {
+    atomic_store(&j->next, 0); atomic_store(&j->err, 0);
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
-    if (nthreads == 1) { zworker(&j); return atomic_load(&j.err); }
+    if (nthreads == 1) { zworker(j); return atomic_load(&j->err); }
     pthread_t t[256]; int started = 0;
-    for (int i = 0; i < nthreads; i++) { if (pthread_create(&t[i], NULL, zworker, &j) == 0) started++; else break; }
-    if (!started) zworker(&j);
+    for (int i = 0; i < nthreads; i++) { if (pthread_create(&t[i], NULL, zworker, j) == 0) started++; else break; }
+    if (!started) zworker(j);
     for (int i = 0; i < started; i++) pthread_join(t[i], NULL);
-    return atomic_load(&j.err);
+    return atomic_load(&j->err);
 }

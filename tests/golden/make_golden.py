@@ -7,6 +7,7 @@ can still check parity.
       The known-answer vectors of the reference's own unit tests, extracted from the C
       initialisers in test/test_crc32.cc:29-183 and test/test_adler32.cc:26-345.
   deflate_digests.json
+  primed_digests.json
       Per-chunk (compressed size, crc32 of the compressed bytes, crc32 and adler32 of the input)
       produced by the UNMODIFIED reference (oracle/_ref, zlib-ng 2.2.2, gcc -O3, default build
       flags, x86-64 => OPTIMAL_CMP 64) for seeded inputs of the synthetic generator
@@ -132,6 +133,22 @@ def deflate_digests():
     return cases
 
 
+def primed_digests():
+    """pigz's dependent-chunk mode: per chunk a fresh stream + zng_deflateSetDictionary(32768 bytes in front) + zng_deflate(flush)."""
+    from __graft_entry__ import load_oracle, load_package
+    pkg = load_package()
+    zo = load_oracle()
+    cases = []
+    for seed, n, flush in ((61, 16 * 65536 + 4321, 2), (62, 8 * 65536, 3), (63, 3 * 65536 + 1, 4), (64, 2 * 65536 + 261, 2), (65, 2 * 65536 + 262, 2),
+                           (66, 2 * 65536 + 263, 4), (67, 65536 + 32768, 2), (68, 65536 + 32769, 2), (69, 65536 + 65274, 4), (70, 65536 + 65275, 2),
+                           (71, 65536 + 65535, 2), (72, 65536 + 3, 2), (73, 4097, 4)):
+        data = pkg.synth(n, seed=seed)
+        out, sizes, _, _ = zo.ref_deflate_chunks_primed(data, 65536, 1, flush)
+        cases.append({"seed": seed, "n": n, "flush": flush, "sizes": [int(x) for x in sizes],
+                      "comp_crc32": [int(_pyzlib.crc32(out[i, : sizes[i]].tobytes())) for i in range(len(sizes))]})
+    return cases
+
+
 def main():
     long_string = parse_long_string(f"{REF}/test/test_adler32.cc")
     crc = parse_vectors(f"{REF}/test/test_crc32.cc", "static const crc32_test tests[]", None)
@@ -144,6 +161,10 @@ def main():
     dd = deflate_digests()
     json.dump({"source": "oracle/_ref (unmodified zlib-ng 2.2.2) via refdrv_deflate_chunks; inputs from zlib-ng_b200/host/synth.c",
                "cases": dd}, open(f"{HERE}/deflate_digests.json", "w"))
+    pd = primed_digests()
+    json.dump({"source": "oracle/_ref (unmodified zlib-ng 2.2.2) via refdrv_deflate_chunks_primed, level 1; inputs pkg.synth(n, seed)",
+               "cases": pd}, open(f"{HERE}/primed_digests.json", "w"))
+    print(f"primed digest cases {len(pd)}")
     print(f"crc32 KATs {len(crc)}, adler32 KATs {len(adl)}, infcover vectors {len(inf)}, deflate digest cases {len(dd)}")
 
 

@@ -166,9 +166,21 @@ def test_argument_errors(pkg, ctx):
     import torch
     d = torch.zeros(65536, dtype=torch.uint8, device=f"cuda:{ctx.device}")
     slots, stride, sizes, crcs, adlers = ctx.alloc_chunk_outputs(65536)
-    for kwargs in (dict(level=0), dict(level=4), dict(level=9), dict(flush=0), dict(flush=5), dict(chunk=0), dict(chunk=65537), dict(stride=stride - 16), dict(stride=stride + 8)):
+    for kwargs in (dict(level=0), dict(level=7), dict(level=9), dict(flush=0), dict(flush=5), dict(chunk=0), dict(chunk=65537), dict(stride=stride - 16), dict(stride=stride + 8)):
         a = dict(chunk=65536, level=1, flush=3, stride=stride)
         a.update(kwargs)
         with pytest.raises(pkg.ZngB200Error) as ei:
             ctx.deflate_chunks(d, 65536, a["chunk"], a["level"], a["flush"], slots, a["stride"], sizes, crcs, adlers)
         assert ei.value.code in (pkg.Z_STREAM_ERROR, pkg.Z_BUF_ERROR)
+
+
+def test_slid_window_position_zero_alias(pkg, ctx, zo):
+    """A chunk of 65275..65535 bytes is slid with the parser at 65274; slide_hash zeroes the entries below 32768 and
+    deflate_quick, which has no hash_head != 0 test, then tries window position 0 (= byte 32768) at distance MAX_DIST."""
+    rng = np.random.default_rng(1)
+    for n in (65535, 65400, 65290, 65279, 65536):
+        d = rng.integers(0, 256, size=n, dtype=np.uint8)
+        d[32760:32780] = d[1000:1020]          # a match covers 32768, so that position is not inserted
+        d[65274:65282] = d[32768:32776] if n >= 65282 else d[32768:32768 + n - 65274]
+        for flush in (3, 4):
+            assert_parity(pkg, ctx, zo, d, 65536, flush)

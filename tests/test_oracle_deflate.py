@@ -69,6 +69,22 @@ def test_port_matches_reference_live(pkg, zo):
             assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
 
 
+def test_port_slid_window_position_zero_alias(pkg, zo):
+    """Level 1 after the tail slide of a 65275..65535-byte chunk: a zeroed hash slot names window position 0 (deflate.c:1285-1299,
+    deflate_quick.c:88-92 has no hash_head != 0 test)."""
+    if not zo.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(1)
+    for n in (65535, 65400, 65290, 65536):
+        d = rng.integers(0, 256, size=n, dtype=np.uint8)
+        d[32760:32780] = d[1000:1020]
+        d[65274:65282] = d[32768:32776]
+        for level in (1, 2, 3, 6):
+            a = zo.port_deflate_chunks(d, 65536, level, 4, nthreads=1)
+            b = zo.ref_deflate_chunks(d, 65536, level, 4, nthreads=1)
+            assert a[1][0] == b[1][0] and np.array_equal(a[0][0, : a[1][0]], b[0][0, : b[1][0]]), (n, level)
+
+
 def test_port_output_inflates(pkg, zo):
     # independent check of validity: CPython's zlib inflates the concatenated chunk stream
     data = pkg.synth(6 * 65536 + 999, seed=21)

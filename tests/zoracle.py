@@ -42,6 +42,8 @@ def port():
         L.zo_deflate_chunk.restype = c_size_t; L.zo_deflate_chunk.argtypes = [c_void_p, c_uint32, c_int, c_int, c_void_p, c_size_t]
         L.zo_deflate_chunks.restype = c_int
         L.zo_deflate_chunks.argtypes = [c_void_p, c_size_t, c_uint32, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int]
+        L.zo_deflate_chunks_primed.restype = c_int
+        L.zo_deflate_chunks_primed.argtypes = L.zo_deflate_chunks.argtypes
         L.zo_deflate_tokens.restype = c_size_t; L.zo_deflate_tokens.argtypes = [c_void_p, c_uint32, c_int, c_void_p, c_size_t]
         L.zo_longest_match_l2.restype = c_uint32
         L.zo_longest_match_l2.argtypes = [c_void_p, c_uint32, c_uint32, c_void_p, c_uint32, c_uint32, POINTER(c_uint32)]
@@ -68,6 +70,9 @@ def ref():
         L = ctypes.CDLL(REF_PATH)
         L.refdrv_deflate_chunks.restype = c_int
         L.refdrv_deflate_chunks.argtypes = [c_void_p, c_size_t, c_uint32, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int]
+        if hasattr(L, "refdrv_deflate_chunks_primed"):
+            L.refdrv_deflate_chunks_primed.restype = c_int
+            L.refdrv_deflate_chunks_primed.argtypes = L.refdrv_deflate_chunks.argtypes
         L.refdrv_checksum_chunks.restype = c_int
         L.refdrv_checksum_chunks.argtypes = [c_void_p, c_size_t, c_uint32, c_void_p, c_void_p, c_int]
         L.refdrv_checksum_flat.restype = c_int
@@ -134,6 +139,17 @@ def port_deflate_chunks(data, chunk=65536, level=1, flush=3, stride=None, nthrea
 def ref_deflate_chunks(data, chunk=65536, level=1, flush=3, stride=None, nthreads=None):
     stride = stride or int(port().zo_deflate_bound(chunk))
     return _deflate_chunks(ref().refdrv_deflate_chunks, data, chunk, level, flush, stride, nthreads or min(os.cpu_count() or 1, 32))
+
+
+def port_deflate_chunks_primed(data, chunk=65536, level=1, flush=2, stride=None, nthreads=None):
+    """pigz's dependent mode: chunk u > 0 primed with the 32768 stream bytes in front of it (fresh stream + deflateSetDictionary)."""
+    stride = stride or int(port().zo_deflate_bound(chunk))
+    return _deflate_chunks(port().zo_deflate_chunks_primed, data, chunk, level, flush, stride, nthreads or min(os.cpu_count() or 1, 32))
+
+
+def ref_deflate_chunks_primed(data, chunk=65536, level=1, flush=2, stride=None, nthreads=None):
+    stride = stride or int(port().zo_deflate_bound(chunk))
+    return _deflate_chunks(ref().refdrv_deflate_chunks_primed, data, chunk, level, flush, stride, nthreads or min(os.cpu_count() or 1, 32))
 
 
 def port_tokens(chunk_bytes, level=1) -> np.ndarray:

@@ -51,6 +51,7 @@ def lib() -> ctypes.CDLL:
         "zng_b200_host_free": (None, [vp]),
         "zng_b200_deflate_bound": (c_size_t, [c_size_t]),
         "zng_b200_deflate_chunks": (c_int, [vp, vp, c_size_t, c_uint32, c_int, c_int, vp, c_size_t, u32p, u32p, u32p, vp]),
+        "zng_b200_deflate_chunks_primed": (c_int, [vp, vp, c_size_t, c_uint32, c_int, c_int, vp, c_size_t, u32p, u32p, u32p, vp]),
         "zng_b200_deflate_chunks_trace": (c_int, [vp, vp, c_size_t, c_uint32, c_int, c_int, vp, c_size_t, u32p, u32p, c_uint32, vp]),
         "zng_b200_chunk_offsets": (c_int, [vp, u32p, c_uint32, c_uint64, u64p, vp]),
         "zng_b200_gather_chunks": (c_int, [vp, vp, c_size_t, u32p, u64p, c_uint32, vp, vp]),
@@ -199,6 +200,11 @@ class Context:
     def deflate_chunks(self, d_in, n: int, chunk: int, level: int, flush: int, slots, stride: int, sizes, crcs=None, adlers=None):
         self._check(lib().zng_b200_deflate_chunks(self._h, _ptr(d_in), n, chunk, level, flush, _ptr(slots), stride,
                                                   _ptr(sizes), _ptr(crcs), _ptr(adlers), self._stream()))
+
+    def deflate_chunks_primed(self, d_in, n: int, chunk: int, level: int, flush: int, slots, stride: int, sizes, crcs=None, adlers=None):
+        """pigz's dependent-chunk mode: every chunk after the first is primed with the 32768 bytes in front of it."""
+        self._check(lib().zng_b200_deflate_chunks_primed(self._h, _ptr(d_in), n, chunk, level, flush, _ptr(slots), stride,
+                                                         _ptr(sizes), _ptr(crcs), _ptr(adlers), self._stream()))
 
     def deflate_chunks_trace(self, d_in, n: int, chunk: int, level: int, flush: int, slots, stride: int, sizes, tokens, tok_stride: int):
         self._check(lib().zng_b200_deflate_chunks_trace(self._h, _ptr(d_in), n, chunk, level, flush, _ptr(slots), stride,

@@ -75,6 +75,8 @@ struct zng_b200_ctx {
     uint16_t* heads = nullptr;
     unsigned long long* sm_slots = nullptr;
     uint32_t nsmid = 0;
+    uint32_t* heads32 = nullptr;               // primed K1: 256 KiB slabs of absolute positions, same (sm, slot) indexing
+    uint8_t* ptails = nullptr;                 // primed K1: kCounters padded copies of the last chunks + their dictionary
     uint16_t* prevs = nullptr;                 // K2: prev[] slab pool and stale-window images, same (sm, slot) indexing
     uint32_t* vtails = nullptr;
     int chains_per_sm = 24;
@@ -137,6 +139,13 @@ int ensure_heads(zng_b200_ctx* ctx) {
     CK(cudaMalloc(&ctx->sm_slots, (size_t)ctx->nsmid * sizeof(unsigned long long)), "cudaMalloc(sm slots)");
     CK(cudaMemset(ctx->sm_slots, 0, (size_t)ctx->nsmid * sizeof(unsigned long long)), "cudaMemset(sm slots)");
     CK(cudaMalloc(&ctx->heads, deflate_quick_head_bytes(ctx->nsmid)), "cudaMalloc(hash-head slab pool)");
+    return 0;
+}
+
+int ensure_primed(zng_b200_ctx* ctx) {
+    if (ctx->heads32) return 0;
+    CK(cudaMalloc(&ctx->heads32, deflate_primed_head_bytes(ctx->nsmid)), "cudaMalloc(primed hash-head slab pool)");
+    CK(cudaMalloc(&ctx->ptails, (size_t)kCounters * deflate_primed_tail_bytes()), "cudaMalloc(primed tails)");
     return 0;
 }
 
@@ -215,6 +224,41 @@ int run_deflate_shared(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_
     int r = run_deflate_chunks(ctx, ctx->scratch, d_in, n, chunk, nchunks, last, d_out, out_stride, d_sizes, d_crcs, d_adlers, stream,
                               d_tokens, tok_stride, level, 0);
     if (r) return r;
+    CK(cudaEventRecord(ctx->k1_done, stream), "cudaEventRecord");
+    ctx->k1_pending = true;
+    return 0;
+}
+
+// pigz's dependent-chunk mode at level 1: as run_deflate_shared, every chunk after the stream's first primed with the 32768
+// bytes in front of it (deflate.c:456-512 deflateSetDictionary on a fresh stream).
+int run_deflate_primed(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
+                       uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers, cudaStream_t stream) {
+    if (nchunks == 0) return 0;
+    if (ctx->k1_pending) CK(cudaStreamWaitEvent(stream, ctx->k1_done, 0), "cudaStreamWaitEvent");
+    int r = ensure_heads(ctx);
+    if (r) return r;
+    r = ensure_primed(ctx);
+    if (r) return r;
+    Scratch& sc = ctx->scratch;
+    const uint32_t stride = (chunk + 32u) & ~31u;
+    const uint32_t batch = nchunks < kBatchChunks ? nchunks : kBatchChunks;
+    r = ensure_scratch(ctx, sc, batch, stride, nchunks, true);
+    if (r) return r;
+    for (uint32_t c0 = 0; c0 < nchunks; c0 += batch) {
+        const uint32_t nb = (nchunks - c0) < batch ? (nchunks - c0) : batch;
+        const size_t off = (size_t)c0 * chunk;
+        const size_t nbytes = (c0 + nb == nchunks) ? n - off : (size_t)nb * chunk;
+        const uint32_t grid = deflate_quick_grid(nb, ctx->sms, ctx->chains_per_sm);
+        const int slot = next_slot(ctx);
+        CK(launch_primed_parse(d_in + off, nbytes, chunk, nb, c0, sc.tokens, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads32,
+                               ctx->sm_slots, grid, ctx->ptails + (size_t)slot * deflate_primed_tail_bytes(), stream),
+           "primed_parse launch");
+        CK(launch_static_emit(sc.tokens, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
+                              d_sizes + c0, ctx->sms, stream),
+           "static_emit launch");
+    }
+    if (d_crcs || d_adlers)
+        CK(launch_checksum_tiles(d_in, n, chunk, nchunks, d_crcs, d_adlers, ctx->sms, stream), "checksum launch");
     CK(cudaEventRecord(ctx->k1_done, stream), "cudaEventRecord");
     ctx->k1_pending = true;
     return 0;
@@ -359,6 +403,8 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
     if (ctx->tails) cudaFree(ctx->tails);
     if (ctx->heads) cudaFree(ctx->heads);
     if (ctx->prevs) cudaFree(ctx->prevs);
+    if (ctx->heads32) cudaFree(ctx->heads32);
+    if (ctx->ptails) cudaFree(ctx->ptails);
     if (ctx->vtails) cudaFree(ctx->vtails);
     if (ctx->sm_slots) cudaFree(ctx->sm_slots);
     if (ctx->scratch.tokens) cudaFree(ctx->scratch.tokens);
@@ -417,6 +463,18 @@ int zng_b200_deflate_chunks(zng_b200_ctx* ctx, const void* d_in, size_t n, uint3
     const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
     return run_deflate_shared(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
                                     d_sizes, d_crcs, d_adlers, (cudaStream_t)stream, nullptr, 0, level);
+}
+
+int zng_b200_deflate_chunks_primed(zng_b200_ctx* ctx, const void* d_in, size_t n, uint32_t chunk, int level, int flush,
+                                   void* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs,
+                                   uint32_t* d_adlers, void* stream) {
+    int r = check_chunk_args(ctx, d_in, n, chunk, level, flush, d_out, out_stride, d_sizes);
+    if (r) return r;
+    if (level != 1 || chunk != 65536u) return bad(ctx, "primed chunks: level 1 and chunk 65536 only");
+    DeviceGuard g(ctx->device);
+    const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
+    return run_deflate_primed(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
+                              d_sizes, d_crcs, d_adlers, (cudaStream_t)stream);
 }
 
 int zng_b200_chunk_offsets(zng_b200_ctx* ctx, const uint32_t* d_sizes, uint32_t nchunks, uint64_t base,

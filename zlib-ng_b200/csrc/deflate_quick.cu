@@ -87,6 +87,10 @@ __device__ uint32_t quick_parse_warp(const Window W, uint32_t n, uint16_t* head,
         const uint32_t h = hash4(v);
         uint32_t cand = 0u;
         if (act) cand = (uint32_t)__ldcg(head + h);
+        // A chunk of 65275..65535 bytes is slid when the parser stands at 65274 (deflate.c:1285-1299): slide_hash zeroes every
+        // entry below 32768, and as deflate_quick has no hash_head != 0 test such a slot then names window position 0 =
+        // original position 32768, at distance MAX_DIST exactly.  (Later positions are out of its reach.)
+        if (q == kWSize + kMaxDist && n < kChunkMax && cand < kWSize) cand = kWSize;
         // "touch" loads: real loads whose values are never needed; the fill they trigger is the 512 bytes of window the
         // next steps will read (measured +5 %; prefetch instructions and head-entry prefetches gained nothing)
         uint32_t sink = 0;
@@ -146,6 +150,127 @@ __device__ uint32_t quick_parse_warp(const Window W, uint32_t n, uint16_t* head,
         asm volatile("{ .reg .pred pp; setp.eq.u32 pp, %0, %1; @pp nanosleep.u32 1; }" :: "r"(sink), "r"(0x5a5a5a5au));   // keeps the touch loads alive
         p += cur;
         __syncwarp();                                        // orders this window's head stores before the next lookups
+    }
+    if (lane == 0) __stcs(tok + wr, kTokEnd);
+    return wr;
+}
+
+// ---------------------------------------------------------------- primed parser (pigz's dependent-chunk mode)
+// Reference call sequence per chunk: a fresh zng_deflateInit2(1, -15), zng_deflateSetDictionary(the 32768 stream bytes in
+// front of the chunk, deflate.c:456-512), one zng_deflate(flush).  Positions are ABSOLUTE from the start of the dictionary
+// (0 .. D + len, D = 32768 or 0 for the first chunk) and the head table holds 32-bit absolute positions, so the two window
+// slides of such a chunk (deflate.c:1285-1299) need no pass over the table: an entry slide_hash would have zeroed lies
+// more than MAX_DIST behind strstart.  What the slides and refills do change is restated:
+//   * `base` = absolute position of window index 0; a slot that is empty or below `base` names window index 0
+//     (deflate_quick.c:88-92 has no hash_head != 0 test) -- in reach only right after a slide at strstart 65274;
+//   * deflateSetDictionary hashes position D-3 with the still-zero byte behind the dictionary; the first fill_window of
+//     zng_deflate re-inserts D-3 and inserts the pending strings D-2, D-1 (s->insert); every later refill that reads
+//     input inserts strstart-1 (deflate.c:1321-1336);
+//   * R = bytes loaded so far: a position is only parsed once 262 bytes of lookahead are loaded (or the input has ended).
+__device__ __forceinline__ uint32_t load4_upto(const Window& W, uint32_t pos, uint32_t limit) {    // bytes at pos.., zero from `limit` on
+    const uint32_t qb = pos + W.skew, i = qb >> 2, sh = (qb & 3u) << 3;
+    uint32_t v = __funnelshift_r(W.word(i), W.word(i + 1), sh);
+    if (pos + 4u > limit) v &= pos >= limit ? 0u : (0xffffffffu >> (8u * (pos + 4u - limit)));
+    return v;
+}
+__device__ __forceinline__ void primed_insert(const Window& W, uint32_t* head, uint32_t pos, uint32_t limit, unsigned lane) {
+    const uint32_t h = hash4(load4_upto(W, pos, limit));
+    if (lane == 0) __stcg(head + h, pos);
+    __syncwarp();
+}
+
+__device__ uint32_t primed_parse_warp(const Window W, uint32_t D, uint32_t N, uint32_t* head, uint32_t* __restrict__ tok) {
+    const unsigned lane = lane_id();
+    const unsigned lt = (1u << lane) - 1u;
+    for (uint32_t p0 = 0; p0 + 2u < D; p0 += 32u) {           // insert_string(s, 0, D - 2): the highest position of a hash wins
+        const uint32_t q = p0 + lane;
+        const bool ins = q + 2u < D;
+        const uint32_t h = hash4(load4_upto(W, q, D));
+        const unsigned peers = __match_any_sync(ZB_FULL, ins ? h : (0x10000u + lane));
+        if (ins && (peers & ~lt & ~(1u << lane)) == 0u) __stcg(head + h, q);
+    }
+    __syncwarp();
+    uint32_t wr = 0, p = D, base = 0, R = D, pend = D ? 2u : 0u;
+    for (;;) {
+        if (R - p < 262u) {                                   // fill_window at an iteration boundary (deflate.c:1272-1340)
+            do {
+                if (p - base >= kWSize + kMaxDist) base += kWSize;
+                if (R == N) break;
+                const uint32_t room = base + kChunkMax - R;
+                R = (N - R < room) ? N : R + room;
+                if (R - p + pend >= 3u) {
+                    const uint32_t str = p - pend;
+                    if (str - base >= 1u) primed_insert(W, head, str - 1u, R, lane);
+                    uint32_t cnt = pend;
+                    if (R - p == 1u) cnt--;
+                    for (uint32_t k = 0; k < cnt; k++) primed_insert(W, head, str + k, R, lane);
+                    pend -= cnt;
+                }
+            } while (R - p < 262u && R != N);
+            if (R == p) break;
+        }
+        const unsigned nl = min(32u, R == N ? N - p : R - 261u - p);      // lanes whose own iteration needs no refill first
+        const uint32_t q = p + lane;
+        const bool inb = lane < nl;
+        const bool act = inb && q + kWantMin <= R;             // deflate_quick.c:88 lookahead >= WANT_MIN_MATCH
+        uint32_t v; uint64_t x;
+        {
+            const uint32_t qb = q + W.skew, i = qb >> 2, sh = (qb & 3u) << 3;
+            const uint32_t a0 = W.word(i), a1 = W.word(i + 1), a2 = W.word(i + 2), a3 = W.word(i + 3);
+            v = __funnelshift_r(a0, a1, sh);
+            x = (uint64_t)__funnelshift_r(a1, a2, sh) | ((uint64_t)__funnelshift_r(a2, a3, sh) << 32);
+        }
+        const uint32_t h = hash4(v);
+        uint32_t cand = 0u;
+        if (act) {
+            cand = __ldcg(head + h);
+            const uint32_t bq = (R == N && q + 262u > N && q - base >= kWSize + kMaxDist) ? base + kWSize : base;   // slid at or before q
+            if (cand < bq) cand = bq;
+        }
+        uint32_t slen = 0;                                    // 0 none, 4..11 exact, 12 = "12 or more"
+        if (act && (q - cand - 1u) < kMaxDist) {
+            const uint32_t cb = cand + W.skew, i = cb >> 2, sh = (cb & 3u) << 3;
+            const uint32_t b0 = W.word(i), b1 = W.word(i + 1), b2 = W.word(i + 2), b3 = W.word(i + 3);
+            if (__funnelshift_r(b0, b1, sh) == v) {
+                const uint64_t d = x ^ ((uint64_t)__funnelshift_r(b1, b2, sh) | ((uint64_t)__funnelshift_r(b2, b3, sh) << 32));
+                slen = d ? 4u + ((unsigned)(__ffsll((long long)d) - 1) >> 3) : 12u;
+                if (slen < 12u) slen = min(slen, R - q);
+            }
+        }
+        const unsigned peers = __match_any_sync(ZB_FULL, act ? h : (0x10000u + lane));
+        const unsigned low = peers & lt;
+        const unsigned M = __ballot_sync(ZB_FULL, slen != 0u);
+        uint32_t mytok = v & 0xffu;
+        unsigned cur = 0, covered = 0;
+        while (cur < nl) {
+            const unsigned rest = M & ~lane_range(0, cur);
+            if (rest == 0u) { cur = nl; break; }
+            const unsigned k = (unsigned)(__ffs(rest) - 1);
+            uint32_t len = __shfl_sync(ZB_FULL, slen, k);
+            if (len >= 12u) {
+                const uint32_t ck = __shfl_sync(ZB_FULL, cand, k);
+                const uint32_t qk = p + k;
+                len = 12u + warp_compare256(W, qk + 12u + W.skew, ck + 12u + W.skew, lane);
+                len = min(min(len, R - qk), kMaxMatch);
+                if (lane == k) slen = len;
+            }
+            covered |= lane_range(k + 1u, k + len);
+            cur = k + len;
+        }
+        unsigned V = lane_range(0, min(cur, nl)) & ~covered;
+        const unsigned S = __ballot_sync(ZB_FULL, ((V >> lane) & 1u) && (low & V) != 0u);
+        if (S) {
+            const unsigned j = __ffs(S) - 1u;
+            V &= lane_range(0, j);
+            cur = j;
+        }
+        const bool vis = (V >> lane) & 1u;
+        if (vis && slen) mytok = kTokMatch | (slen << 16) | (q - cand);
+        if (vis && act) __stcg(head + h, q);
+        if (vis) __stcs(tok + wr + __popc(V & lt), mytok);
+        wr += __popc(V);
+        p += cur;
+        __syncwarp();
     }
     if (lane == 0) __stcs(tok + wr, kTokEnd);
     return wr;
@@ -265,6 +390,46 @@ quick_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uin
     if (lane == 0) atomicAnd(sm_slots + sm, ~(1ull << slot));
 }
 
+// Primed chunks: chunk g (global index first + ci) reads its dictionary from the 32768 bytes in front of it; g == 0 has none.
+// heads: 65536 x u32 per chain.  tail: a zero-padded private copy of [tail_first * chunk - 32768, n) for the chunks whose
+// read-ahead could leave the caller's allocation (tail_dict = dictionary bytes present in front of that copy).
+__global__ void __launch_bounds__(kParseWarps * 32, 12)
+primed_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t first,
+                    uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
+                    uint32_t* __restrict__ counter, uint32_t* __restrict__ heads, unsigned long long* __restrict__ sm_slots,
+                    const uint8_t* __restrict__ tail, uint32_t tail_first, uint32_t tail_dict) {
+    const unsigned lane = lane_id();
+    const uint32_t sm = smid();
+    uint32_t slot = 0;
+    if (lane == 0) slot = slot_acquire(sm_slots + sm);
+    slot = __shfl_sync(ZB_FULL, slot, 0);
+    uint32_t* head = heads + ((size_t)sm * 64u + slot) * 65536u;
+    for (;;) {
+        uint32_t ci = 0;
+        if (lane == 0) ci = atomicAdd(counter, 1u);
+        ci = __shfl_sync(ZB_FULL, ci, 0);
+        if (ci >= nchunks) break;
+        {
+            uint4* h4 = reinterpret_cast<uint4*>(head);
+#pragma unroll 8
+            for (uint32_t i = lane; i < 65536u * 4u / 16u; i += 32u) h4[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+        const size_t off = (size_t)ci * chunk;
+        const uint32_t len = (uint32_t)min((size_t)chunk, n - off);
+        const uint32_t D = (first + ci) > 0u ? kWSize : 0u;
+        const uint8_t* src = (ci >= tail_first) ? tail + tail_dict + (size_t)(ci - tail_first) * chunk : in + off;
+        src -= D;
+        Window W;
+        W.skew = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+        W.w = reinterpret_cast<const uint32_t*>(src - W.skew);
+        const uint32_t cnt = primed_parse_warp(W, D, D + len, head, tokens + (size_t)ci * tok_stride);
+        if (lane == 0) ntok[ci] = cnt;
+    }
+    __syncwarp();
+    if (lane == 0) atomicAnd(sm_slots + sm, ~(1ull << slot));
+}
+
 __global__ void __launch_bounds__(kEmitWarps * 32)
 static_emit_kernel(const uint32_t* __restrict__ tokens, uint32_t tok_stride, const uint32_t* __restrict__ ntok,
                    size_t n, uint32_t chunk, uint32_t nchunks, int last,
@@ -315,6 +480,28 @@ cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint
     e = cudaMemsetAsync(tail + tail_bytes, 0, 2u * kWinPad, stream);
     if (e != cudaSuccess) return e;
     quick_parse_kernel<<<grid, kParseWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, tail, tail_first);
+    return cudaGetLastError();
+}
+
+size_t deflate_primed_head_bytes(uint32_t nsmid) { return (size_t)nsmid * 64u * 65536u * sizeof(uint32_t); }
+size_t deflate_primed_tail_bytes() { return kWSize + 2u * kChunkMax + 4u * kWinPad; }
+
+// `in` points at chunk `first` of the stream (first > 0: the 32768 bytes in front of it are readable: its dictionary)
+cudaError_t launch_primed_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t first,
+                                uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
+                                uint32_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream) {
+    if (grid == 0 || nchunks == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    const uint32_t tail_first = n >= kWinPad ? (uint32_t)((n - kWinPad) / chunk) : 0u;
+    const size_t tail_off = (size_t)tail_first * chunk, tail_bytes = n - tail_off;
+    const uint32_t tail_dict = (first + tail_first) > 0u ? kWSize : 0u;
+    e = cudaMemcpyAsync(tail, in + tail_off - tail_dict, tail_dict + tail_bytes, cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(tail + tail_dict + tail_bytes, 0, 2u * kWinPad, stream);
+    if (e != cudaSuccess) return e;
+    primed_parse_kernel<<<grid, kParseWarps * 32, 0, stream>>>(in, n, chunk, nchunks, first, tokens, tok_stride, ntok, counter, heads, sm_slots,
+                                                              tail, tail_first, tail_dict);
     return cudaGetLastError();
 }
 

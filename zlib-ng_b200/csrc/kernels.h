@@ -17,6 +17,13 @@ uint32_t deflate_quick_grid(uint32_t nchunks, int num_sms, int chains_per_sm);
 cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                                uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
                                uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream);
+// K1 primed (pigz's dependent-chunk mode): every chunk but the stream's first has the 32768 bytes in front of it as its
+// preset dictionary.  heads = deflate_primed_head_bytes() pool of 256 KiB slabs (32-bit absolute positions).
+size_t deflate_primed_head_bytes(uint32_t nsmid);
+size_t deflate_primed_tail_bytes();
+cudaError_t launch_primed_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t first,
+                                uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
+                                uint32_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream);
 cudaError_t launch_static_emit(const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n, uint32_t chunk,
                                uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
                                int num_sms, cudaStream_t stream);
