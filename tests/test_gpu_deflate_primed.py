@@ -109,3 +109,20 @@ def test_primed_256MiB_round_trip(pkg, ctx, zo):
         piece = data[(ci - 1) * 65536:(ci + 1) * 65536]
         exp, es, _, _ = zo.port_deflate_chunks_primed(piece, 65536, 1, 2, stride, nthreads=1)
         assert sz[ci] == es[1] and np.array_equal(host[ci, : es[1]], exp[1, : es[1]]), ci
+
+
+def test_primed_stream_inflates_through_the_stream_path(pkg, ctx, zo):
+    """A dependent stream has sync-flush markers but its segments reference their predecessors: the parallel marker split
+    of zng_b200_inflate_stream_host must notice and give the exact in-order result."""
+    rng = np.random.default_rng(8)
+    words = rng.integers(97, 123, size=(64, 6), dtype=np.uint8)
+    text = words[rng.integers(0, 64, size=90000)].reshape(-1)[:7 * 65536 + 999]
+    for data in (text, pkg.synth(6 * 65536 + 5, seed=91)):
+        got, sizes, _, _, _ = gpu_primed(pkg, ctx, data, 2)
+        raw = b"".join(got[i, : sizes[i]].tobytes() for i in range(len(sizes))) + b"\x03\x00"
+        assert pyzlib.decompress(raw, wbits=-15) == data.tobytes()
+        src = np.frombuffer(raw + b"\0" * 8, dtype=np.uint8).copy()
+        out = np.zeros(data.size + 16, dtype=np.uint8)
+        status, out_len, in_used, check, detail = ctx.inflate_stream_host(src, len(raw), -15, out, out.size)
+        assert status == 1, (status, detail)
+        assert out_len == data.size and in_used == len(raw) and np.array_equal(out[:out_len], data)

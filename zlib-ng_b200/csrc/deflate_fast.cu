@@ -584,7 +584,8 @@ block_emit_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ t
 }
 
 size_t deflate_fast_prev_bytes(uint32_t nsmid) { return (size_t)nsmid * 64u * kWSize * sizeof(uint16_t); }
-size_t deflate_fast_tail_bytes(uint32_t nsmid) { return (size_t)nsmid * 64u * kTailWords * sizeof(uint32_t); }
+// + 64 bytes: the warp-wide compare behind a 128-byte prefix (level 6) may read a few words past the last image
+size_t deflate_fast_tail_bytes(uint32_t nsmid) { return (size_t)nsmid * 64u * kTailWords * sizeof(uint32_t) + 64u; }
 
 cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t* tokens, uint32_t tok_stride,
                               uint32_t* ntok, uint32_t* counter, uint16_t* heads, uint16_t* prevs, uint32_t* tails,
