@@ -105,6 +105,8 @@ int32_t zng_deflateInit(zng_stream *strm, int32_t level);
 int32_t zng_deflateInit2(zng_stream *strm, int32_t level, int32_t method, int32_t windowBits, int32_t memLevel, int32_t strategy);
 int32_t zng_deflate(zng_stream *strm, int32_t flush);
 int32_t zng_deflateReset(zng_stream *strm);
+/* deflate.c:456-512; raw level-1 streams, >= 32768-byte dictionaries: switches the stream to pigz's dependent-chunk mode */
+int32_t zng_deflateSetDictionary(zng_stream *strm, const uint8_t *dictionary, uint32_t dictLength);
 int32_t zng_deflateEnd(zng_stream *strm);
 unsigned long zng_deflateBound(zng_stream *strm, unsigned long sourceLen);
 

@@ -147,6 +147,13 @@ const char *zng_b200_inflate_msg(uint32_t detail);
  * copies are pipelined with the kernels; pinned buffers (zng_b200_host_alloc) avoid staging. */
 int zng_b200_deflate_host(zng_b200_ctx *ctx, const void *h_in, size_t n, uint32_t chunk, int level, int final,
                           void *h_out, size_t out_cap, size_t *out_len, uint32_t *crc32, uint32_t *adler32);
+
+/* Replaces: what zng_deflate does on a raw level-1 stream after zng_deflateSetDictionary (deflate.c:456-512), pigz's
+ * dependent mode -- every 65536-byte piece of h_in is compressed by a fresh stream primed with the 32768 bytes in front of it
+ * (h_dict, 32768 bytes, for the first piece; NULL = the first piece has no dictionary).  Pieces end with the sync-flush
+ * marker, final != 0: Z_FINISH on the last one.  Synchronous (not pipelined). */
+int zng_b200_deflate_host_primed(zng_b200_ctx *ctx, const void *h_dict, const void *h_in, size_t n, int final,
+                                 void *h_out, size_t out_cap, size_t *out_len, uint32_t *crc32, uint32_t *adler32);
 /* Host-buffer form of zng_b200_inflate_members (same arrays, all in host memory; offsets are copied to the
  * device with the data, results come back in the h_ arrays). */
 int zng_b200_inflate_members_host(zng_b200_ctx *ctx, const void *h_in, const uint64_t *h_in_off, uint32_t n_members,

@@ -94,6 +94,53 @@ def test_zng_deflate_every_level(pkg, L, zo, level):
         assert pyzlib.decompress(got, wbits=wb) == data.tobytes()
 
 
+def test_zng_deflateSetDictionary_dependent_chunks(pkg, L, zo):
+    """pigz's loop on the library: per chunk zng_deflateReset + zng_deflateSetDictionary(last 32 KiB of the previous chunk) +
+    zng_deflate(Z_SYNC_FLUSH / Z_FINISH) -- every chunk equals what the unmodified reference emits for the same calls on a
+    fresh stream, and one call over several pieces equals the same pieces joined."""
+    data = pkg.synth(5 * 65536 + 4321, seed=73)
+    n = data.size
+    exp, esz, _, _ = (zo.ref_deflate_chunks_primed if zo.have_ref() else zo.port_deflate_chunks_primed)(data, 65536, 1, 2)
+    expf, efsz, _, _ = (zo.ref_deflate_chunks_primed if zo.have_ref() else zo.port_deflate_chunks_primed)(data, 65536, 1, 4)
+    nch = len(esz)
+    s = pkg.ZngStream()
+    assert L.zng_deflateInit2(ctypes.byref(s), 1, 8, -15, 8, 0) == 0
+    parts = []
+    for i in range(nch):
+        piece = np.ascontiguousarray(data[i * 65536:(i + 1) * 65536])
+        assert L.zng_deflateReset(ctypes.byref(s)) == 0
+        if i:
+            assert L.zng_deflateSetDictionary(ctypes.byref(s), data[i * 65536 - 40000:].ctypes.data, 40000) == 0    # only the last 32768 count
+        out = np.zeros(int(L.zng_deflateBound(ctypes.byref(s), piece.size)) + 64, dtype=np.uint8)
+        s.next_in = piece.ctypes.data; s.avail_in = piece.size; s.next_out = out.ctypes.data; s.avail_out = out.size
+        last = i == nch - 1
+        assert L.zng_deflate(ctypes.byref(s), pkg.Z_FINISH if last else 2) == (1 if last else 0)
+        got = out[: s.total_out].tobytes()
+        assert got == (expf[i, : efsz[i]] if last else exp[i, : esz[i]]).tobytes(), i
+        parts.append(got)
+    assert pyzlib.decompress(b"".join(parts), wbits=-15) == data.tobytes()
+    # one call for everything behind the first chunk: the same pieces, joined
+    assert L.zng_deflateReset(ctypes.byref(s)) == 0
+    assert L.zng_deflateSetDictionary(ctypes.byref(s), data[65536 - 32768:].ctypes.data, 32768) == 0
+    rest = np.ascontiguousarray(data[65536:])
+    out = np.zeros(int(L.zng_deflateBound(ctypes.byref(s), rest.size)) + 64, dtype=np.uint8)
+    s.next_in = rest.ctypes.data; s.avail_in = rest.size; s.next_out = out.ctypes.data; s.avail_out = out.size
+    assert L.zng_deflate(ctypes.byref(s), pkg.Z_FINISH) == 1
+    assert out[: s.total_out].tobytes() == b"".join(parts[1:])
+    # what the GPU path cannot reproduce is refused, not approximated
+    assert L.zng_deflateSetDictionary(ctypes.byref(s), data.ctypes.data, 32768) in (0, pkg.Z_STREAM_ERROR)
+    assert L.zng_deflateEnd(ctypes.byref(s)) in (0, pkg.Z_DATA_ERROR)
+    for level, wb in ((2, -15), (1, 31), (1, 15)):
+        t = pkg.ZngStream()
+        assert L.zng_deflateInit2(ctypes.byref(t), level, 8, wb, 8, 0) == 0
+        assert L.zng_deflateSetDictionary(ctypes.byref(t), data.ctypes.data, 32768) == pkg.Z_STREAM_ERROR
+        assert L.zng_deflateEnd(ctypes.byref(t)) == 0
+    t = pkg.ZngStream()
+    assert L.zng_deflateInit2(ctypes.byref(t), 1, 8, -15, 8, 0) == 0
+    assert L.zng_deflateSetDictionary(ctypes.byref(t), data.ctypes.data, 1000) == pkg.Z_STREAM_ERROR        # shorter than a window
+    assert L.zng_deflateEnd(ctypes.byref(t)) == 0
+
+
 def test_zng_deflate_piecewise_and_small_output_windows(pkg, L, zo):
     n = 5 * 65536 + 1234
     data = pkg.synth(n, seed=11)

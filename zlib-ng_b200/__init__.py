@@ -61,6 +61,7 @@ def lib() -> ctypes.CDLL:
         "zng_b200_crc32": (c_int, [vp, vp, c_size_t, c_uint32, u32p, vp]),
         "zng_b200_adler32": (c_int, [vp, vp, c_size_t, c_uint32, u32p, vp]),
         "zng_b200_deflate_host": (c_int, [vp, vp, c_size_t, c_uint32, c_int, c_int, vp, c_size_t, POINTER(c_size_t), POINTER(c_uint32), POINTER(c_uint32)]),
+        "zng_b200_deflate_host_primed": (c_int, [vp, vp, vp, c_size_t, c_int, vp, c_size_t, POINTER(c_size_t), POINTER(c_uint32), POINTER(c_uint32)]),
         "zng_b200_crc32_host": (c_int, [vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
         "zng_b200_adler32_host": (c_int, [vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
         "zng_b200_synth_fill": (c_int, [vp, c_size_t, c_uint64, c_uint64]),
@@ -78,6 +79,7 @@ def lib() -> ctypes.CDLL:
         "zng_deflateInit2": (c_int32, [vp, c_int32, c_int32, c_int32, c_int32, c_int32]),
         "zng_deflate": (c_int32, [vp, c_int32]),
         "zng_deflateReset": (c_int32, [vp]),
+        "zng_deflateSetDictionary": (c_int32, [vp, vp, c_uint32]),
         "zng_deflateEnd": (c_int32, [vp]),
         "zng_deflateBound": (ctypes.c_ulong, [vp, ctypes.c_ulong]),
         "zng_inflateInit2": (c_int32, [vp, c_int32]),

@@ -103,6 +103,9 @@ struct zng_b200_ctx {
     unsigned long long* d_marks = nullptr; uint32_t marks_cap = 0;
     cudaStream_t sstream[3] = {nullptr, nullptr, nullptr};   // byte pass + D2H of segment groups
     cudaEvent_t sready = nullptr;
+    uint8_t* d_pbuf = nullptr; size_t pbuf_cap = 0;   // zng_b200_deflate_host_primed: [dictionary | input], slots | packed, sizes | crcs | adlers | offsets
+    uint8_t* d_pout = nullptr; size_t pout_cap = 0;
+    uint32_t* d_pmeta = nullptr; size_t pmeta_cap = 0;
     uint8_t* d_hostbuf = nullptr;              // staging for *_host checksums
     size_t hostbuf_cap = 0;
     uint32_t x2n[32];
@@ -231,8 +234,10 @@ int run_deflate_shared(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_
 
 // pigz's dependent-chunk mode at level 1: as run_deflate_shared, every chunk after the stream's first primed with the 32768
 // bytes in front of it (deflate.c:456-512 deflateSetDictionary on a fresh stream).
+// first0: index of d_in's first chunk in the stream (> 0: the 32768 bytes in front of d_in are its dictionary)
 int run_deflate_primed(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
-                       uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers, cudaStream_t stream) {
+                       uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers, cudaStream_t stream,
+                       uint32_t first0 = 0) {
     if (nchunks == 0) return 0;
     if (ctx->k1_pending) CK(cudaStreamWaitEvent(stream, ctx->k1_done, 0), "cudaStreamWaitEvent");
     int r = ensure_heads(ctx);
@@ -250,7 +255,7 @@ int run_deflate_primed(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_
         const size_t nbytes = (c0 + nb == nchunks) ? n - off : (size_t)nb * chunk;
         const uint32_t grid = deflate_quick_grid(nb, ctx->sms, ctx->chains_per_sm);
         const int slot = next_slot(ctx);
-        CK(launch_primed_parse(d_in + off, nbytes, chunk, nb, c0, sc.tokens, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads32,
+        CK(launch_primed_parse(d_in + off, nbytes, chunk, nb, c0 + first0, sc.tokens, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads32,
                                ctx->sm_slots, grid, ctx->ptails + (size_t)slot * deflate_primed_tail_bytes(), stream),
            "primed_parse launch");
         CK(launch_static_emit(sc.tokens, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
@@ -414,6 +419,9 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
     if (ctx->d_result) cudaFree(ctx->d_result);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->d_hostbuf) cudaFree(ctx->d_hostbuf);
+    if (ctx->d_pbuf) cudaFree(ctx->d_pbuf);
+    if (ctx->d_pout) cudaFree(ctx->d_pout);
+    if (ctx->d_pmeta) cudaFree(ctx->d_pmeta);
     delete ctx;
 }
 
@@ -1057,6 +1065,73 @@ static int sync_slabs(zng_b200_ctx* ctx) {
         ctx->slab[i].busy = false;
         if (ctx->slab[i].stream) cudaStreamSynchronize(ctx->slab[i].stream);
     }
+    return 0;
+}
+
+extern "C++" {
+template <typename T>
+static int grow(zng_b200_ctx* ctx, T*& p, size_t& cap, size_t want, const char* what) {
+    if (cap >= want) return 0;
+    if (p) { cudaDeviceSynchronize(); cudaFree(p); p = nullptr; cap = 0; }
+    want += want / 4;
+    CK(cudaMalloc(&p, want * sizeof(T)), what);
+    cap = want;
+    return 0;
+}
+}
+
+// pigz's dependent mode from host buffers (what zng_deflate does after zng_deflateSetDictionary): every 65536-byte piece is
+// compressed by a fresh level-1 stream primed with the 32768 bytes in front of it -- h_dict for the first piece (NULL: the
+// first piece has no dictionary).  Pieces end with the sync-flush marker; final: Z_FINISH on the last one.
+int zng_b200_deflate_host_primed(zng_b200_ctx* ctx, const void* h_dict, const void* h_in, size_t n, int final,
+                                 void* h_out, size_t out_cap, size_t* out_len, uint32_t* crc32, uint32_t* adler32) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (!out_len || (n && !h_in) || !h_out) return bad(ctx, "NULL argument");
+    if (n > ((size_t)1 << 32)) return bad(ctx, "primed host call: at most 4 GiB per call");
+    DeviceGuard g(ctx->device);
+    const uint32_t chunk = ZNG_B200_CHUNK_MAX;
+    const uint32_t nin = (uint32_t)((n + chunk - 1) / chunk);
+    const uint32_t nch = nin ? nin : (final ? 1u : 0u);                  // no input + final: one empty Z_FINISH piece ("03 00")
+    if (nch == 0) { *out_len = 0; if (crc32) *crc32 = 0; if (adler32) *adler32 = 1; return 0; }
+    const size_t stride = zng_b200_deflate_bound(chunk);
+    int r = grow(ctx, ctx->d_pbuf, ctx->pbuf_cap, (size_t)kWSize + n + 4096, "cudaMalloc(primed input)");
+    if (r) return r;
+    r = grow(ctx, ctx->d_pout, ctx->pout_cap, 2 * (size_t)nch * stride + 4096, "cudaMalloc(primed output)");
+    if (r) return r;
+    r = grow(ctx, ctx->d_pmeta, ctx->pmeta_cap, 3 * (size_t)nch + 2 * ((size_t)nch + 1) + 16, "cudaMalloc(primed meta)");
+    if (r) return r;
+    cudaStream_t st = nullptr;
+    uint8_t* d_in = ctx->d_pbuf + kWSize;
+    uint8_t* d_slots = ctx->d_pout; uint8_t* d_packed = ctx->d_pout + (size_t)nch * stride;
+    uint32_t* d_sizes = ctx->d_pmeta; uint32_t* d_crcs = d_sizes + nch; uint32_t* d_adlers = d_crcs + nch;
+    uint64_t* d_off = reinterpret_cast<uint64_t*>(ctx->d_pmeta + ((3 * (size_t)nch + 1) & ~(size_t)1));
+    if (h_dict) CK(cudaMemcpyAsync(ctx->d_pbuf, h_dict, kWSize, cudaMemcpyHostToDevice, st), "H2D dictionary");
+    if (n) CK(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, st), "H2D");
+    const uint32_t first0 = h_dict ? 1u : 0u;
+    const uint32_t body = final ? nch - 1 : nch;
+    const size_t body_bytes = final ? (size_t)body * chunk : n;
+    if (body) {
+        r = run_deflate_primed(ctx, d_in, body_bytes, chunk, body, 0, d_slots, stride, d_sizes, d_crcs, d_adlers, st, first0);
+        if (r) return r;
+    }
+    if (final) {                                             // the Z_FINISH piece (possibly empty: "03 00")
+        r = run_deflate_primed(ctx, d_in + body_bytes, n - body_bytes, chunk, 1, 1, d_slots + (size_t)body * stride, stride, d_sizes + body,
+                               d_crcs + body, d_adlers + body, st, first0 + body);
+        if (r) return r;
+    }
+    CK(launch_offsets(d_sizes, nch, 0, d_off, st), "offsets launch");
+    CK(launch_gather(d_slots, stride, d_sizes, d_off, nch, d_packed, ctx->sms, st), "gather launch");
+    CK(launch_crc32_fold(d_crcs, nin, chunk, n, 0, ctx->d_result, st), "crc fold");
+    CK(launch_adler32_fold(d_adlers, nin, chunk, n, 1, ctx->d_result + 1, st), "adler fold");
+    uint64_t total = 0; uint32_t res[2] = {0, 1};
+    CK(cudaMemcpyAsync(&total, d_off + nch, sizeof(uint64_t), cudaMemcpyDeviceToHost, st), "D2H total");
+    CK(cudaMemcpyAsync(res, ctx->d_result, sizeof(res), cudaMemcpyDeviceToHost, st), "D2H checks");
+    CK(cudaStreamSynchronize(st), "sync");
+    if (total > out_cap) return ZNG_B200_BUF_ERROR;
+    CK(cudaMemcpy(h_out, d_packed, (size_t)total, cudaMemcpyDeviceToHost), "D2H packed");
+    *out_len = (size_t)total;
+    if (crc32) *crc32 = n ? res[0] : 0;
+    if (adler32) *adler32 = n ? res[1] : 1;
     return 0;
 }
 

@@ -83,6 +83,7 @@ int32_t zng_deflateReset(zng_stream *strm) {
     s->check = strm->adler; s->check_len = 0;
     s->last_flush = -2;
     s->header_done = s->trailer_done = s->finished = 0;
+    s->have_dict = 0; s->after_sync = 0;
     return Z_OK;
 }
 
@@ -90,10 +91,27 @@ int32_t zng_deflateEnd(zng_stream *strm) {
     if (state_check(strm, 'D')) return Z_STREAM_ERROR;
     struct internal_state *s = strm->state;
     int busy = (s->status == ST_BUSY && (s->in_len || s->pend_len > s->pend_pos));
-    free(s->in_buf); free(s->pend);
+    free(s->in_buf); free(s->pend); free(s->dict);
     strm->zfree(strm->opaque, s);
     strm->state = NULL;
     return busy ? Z_DATA_ERROR : Z_OK;                     /* deflate.c:1125 */
+}
+
+/* deflate.c:456-512.  Supported where the GPU path reproduces the reference bit for bit: a raw (windowBits -15) level-1
+ * stream with no input pending and a dictionary of at least one window (the last 32768 bytes are used, :479-488).  The
+ * stream then works in pigz's dependent mode: each 65536-byte piece is compressed exactly as a FRESH stream primed with
+ * the 32768 bytes in front of it does (zng_deflateSetDictionary + one zng_deflate per piece), Z_SYNC_FLUSH allowed. */
+int32_t zng_deflateSetDictionary(zng_stream *strm, const uint8_t *dictionary, uint32_t dictLength) {
+    if (state_check(strm, 'D') || dictionary == NULL) return Z_STREAM_ERROR;
+    struct internal_state *s = strm->state;
+    if (s->wrap == 2 || (s->wrap == 1 && s->status != ST_INIT) || s->in_len) return Z_STREAM_ERROR;     /* deflate.c:468-469 */
+    if (s->wrap != 0 || s->level != 1 || dictLength < 32768u) {
+        strm->msg = "unsupported: preset dictionaries on raw level-1 streams, 32768 bytes or more"; return Z_STREAM_ERROR;
+    }
+    if (!s->dict && !(s->dict = (uint8_t *)malloc(32768))) return Z_MEM_ERROR;
+    memcpy(s->dict, dictionary + (dictLength - 32768u), 32768);
+    s->have_dict = 1;
+    return Z_OK;
 }
 
 unsigned long zng_deflateBound(zng_stream *strm, unsigned long sourceLen) {
@@ -154,12 +172,20 @@ static int compress_into_pending(zng_stream *strm, const uint8_t *src, size_t n,
     size_t queued = s->pend_len - s->pend_pos;
     int direct = (size_t)strm->avail_out >= queued + cap;
     int r;
+    uint8_t *dst; size_t room;
     if (direct) {
         pend_flush(strm);                                   /* header bytes first */
-        r = zng_b200_deflate_host(ctx, src, n, ZNG_CHUNK, s->level, fin, strm->next_out, strm->avail_out, &out_len, &crc, &adler);
+        dst = strm->next_out; room = strm->avail_out;
     } else {
         if (pend_reserve(s, cap)) return Z_MEM_ERROR;
-        r = zng_b200_deflate_host(ctx, src, n, ZNG_CHUNK, s->level, fin, s->pend + s->pend_len, s->pend_cap - s->pend_len, &out_len, &crc, &adler);
+        dst = s->pend + s->pend_len; room = s->pend_cap - s->pend_len;
+    }
+    if (s->have_dict) {
+        r = zng_b200_deflate_host_primed(ctx, s->dict, src, n, fin, dst, room, &out_len, &crc, &adler);
+        if (n >= 32768) memcpy(s->dict, src + n - 32768, 32768);            /* the window in front of the next piece */
+        else if (n) { memmove(s->dict, s->dict + n, 32768 - n); memcpy(s->dict + 32768 - n, src, n); }
+    } else {
+        r = zng_b200_deflate_host(ctx, src, n, ZNG_CHUNK, s->level, fin, dst, room, &out_len, &crc, &adler);
     }
     if (r != ZNG_B200_OK) { strm->msg = zng_b200_last_error(ctx); return r == ZNG_B200_BUF_ERROR ? Z_BUF_ERROR : (r == ZNG_B200_MEM_ERROR ? Z_MEM_ERROR : Z_STREAM_ERROR); }
     if (direct) { strm->next_out += out_len; strm->avail_out -= (uint32_t)out_len; strm->total_out += out_len; }
@@ -178,6 +204,16 @@ int32_t zng_deflate(zng_stream *strm, int32_t flush) {
         strm->msg = "stream error"; return Z_STREAM_ERROR;
     }
     if (strm->avail_out == 0) { strm->msg = "buffer error"; return Z_BUF_ERROR; }
+    if (s->after_sync && strm->avail_in) {
+        strm->msg = "unsupported: input after Z_SYNC_FLUSH continues the reference's window; call zng_deflateReset (+ zng_deflateSetDictionary)";
+        return Z_STREAM_ERROR;
+    }
+    if (flush == Z_SYNC_FLUSH && s->have_dict) flush = Z_FULL_FLUSH;   /* dependent mode: the pieces are joined by sync-flush markers */
+    else if (flush == Z_SYNC_FLUSH && strm->total_in == 0 && s->in_len == 0 && strm->avail_in <= ZNG_CHUNK) {
+        /* pigz's first chunk: one piece on a fresh stream; the bytes of a sync flush and of a full flush are the same
+         * (deflate.c:1061-1083), only what may follow differs */
+        flush = Z_FULL_FLUSH; s->after_sync = 1;
+    }
     if (flush != Z_NO_FLUSH && flush != Z_FULL_FLUSH && flush != Z_FINISH) {
         /* Z_SYNC/PARTIAL_FLUSH/Z_BLOCK keep the window across the flush in the reference: not a chunk boundary */
         strm->msg = "unsupported flush mode: Z_NO_FLUSH, Z_FULL_FLUSH, Z_FINISH only"; return Z_STREAM_ERROR;

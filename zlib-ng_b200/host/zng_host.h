@@ -25,6 +25,9 @@ struct internal_state {
     uint32_t check;            /* running adler32 (zlib) / crc32 (gzip) of all consumed input */
     uint64_t check_len;
     int header_done, trailer_done, finished;
+    /* dependent-chunk mode (zng_deflateSetDictionary on a raw level-1 stream): the 32768 bytes in front of the next piece */
+    uint8_t *dict; int have_dict;
+    int after_sync;            /* a Z_SYNC_FLUSH closed the (only) piece of a stream without dictionary: nothing may follow but Reset */
 };
 
 void *zng_host_default_alloc(void *opaque, unsigned items, unsigned size);
