@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <chrono>
 
 using namespace zb;
 
@@ -27,6 +28,26 @@ struct Scratch {
     size_t tok_words = 0;
     uint32_t* ntok = nullptr;
     uint32_t ntok_cap = 0;
+};
+
+// Streamed level-1 host path: ONE persistent parse kernel per call takes the chunks in order as the copy engine delivers
+// them; emit / checksum / gather / D2H run per output slab on high-priority streams as soon as the slab is parsed.
+constexpr uint32_t kStreamSlab = 1024;            // chunks per output slab (64 MiB of input)
+constexpr uint32_t kStreamSlabShift = 10;
+constexpr uint32_t kStreamPiece = 256;            // chunks per H2D piece (16 MiB)
+constexpr uint32_t kStreamMaxChunks = 16384;      // chunks per call of the streamed path (1 GiB); longer inputs run as several
+constexpr int kStreamOut = 4;
+struct Streamed {
+    bool ready = false;
+    cudaStream_t copy = nullptr, parse = nullptr, d2h = nullptr, out[kStreamOut] = {};
+    cudaEvent_t reset_done = nullptr, slab_done[kStreamMaxChunks / kStreamSlab] = {};
+    uint8_t* d_in = nullptr; uint8_t* d_slots = nullptr; uint8_t* d_packed = nullptr;
+    uint32_t* tokens = nullptr; uint32_t* ntok = nullptr; uint32_t* d_meta = nullptr; uint64_t* d_offsets = nullptr;
+    uint32_t* d_sync = nullptr;                   // [0] chunks delivered, [1] failed, [2] chunk counter, [4..] parsed chunks per slab
+    uint32_t* d_res = nullptr;
+    uint32_t* h_ready = nullptr; uint64_t* h_meta = nullptr; uint32_t* h_failed = nullptr;
+    uint32_t* h_done = nullptr; uint32_t* d_h_done = nullptr;   // mapped: chunks parsed per slab, written by the parse kernel when a slab is complete
+    uint32_t cap_chunks = 0;
 };
 
 struct Slab {
@@ -80,6 +101,7 @@ struct zng_b200_ctx {
     uint16_t* prevs = nullptr;                 // K2: prev[] slab pool and stale-window images, same (sm, slot) indexing
     uint32_t* vtails = nullptr;
     int chains_per_sm = 24;
+    uint32_t slot_limit = 64;                  // chains per SM over ALL concurrent K1 launches (env ZNG_B200_SLOT_LIMIT)
     int chains_per_sm_l2 = 32;                 // measured on B200: 16 -> 12.4, 24 -> 14.4, 32 -> 15.4 GB/s
     Scratch scratch;                           // for the device-resident entry points; users are ordered by k1_done
     cudaEvent_t k1_done = nullptr;
@@ -90,6 +112,8 @@ struct zng_b200_ctx {
     uint32_t* h_result = nullptr;              // pinned
     // host path
     Slab slab[kPipeMax];
+    Streamed st;
+    int streamed = 1;                          // env ZNG_B200_STREAMED=0: level 1 goes through the slab pipeline as well
     int pipe = 4;                              // slabs in flight (env ZNG_B200_PIPE); measured: 2048 x 4 -> 23.2 GB/s e2e, 1024 x 6 -> 20.6
     uint32_t slab_chunks = kSlabChunksDefault;
     bool slabs_ready = false;
@@ -180,7 +204,7 @@ int ensure_scratch(zng_b200_ctx* ctx, Scratch& sc, uint32_t batch, uint32_t stri
 // level 2: K2a parse (hash chains) -> token lists, K2b block writer.  have_prev: see kernels.h.
 int run_deflate_chunks(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
                       uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers,
-                      cudaStream_t stream, uint32_t* d_tokens, uint32_t tok_stride, int level = 1, int have_prev = 0) {
+                      cudaStream_t stream, uint32_t* d_tokens, uint32_t tok_stride, int level = 1, int have_prev = 0, int ck_warps = 32) {
     if (nchunks == 0) return 0;
     int r = ensure_heads(ctx);
     if (r) return r;
@@ -207,14 +231,14 @@ int run_deflate_chunks(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size
             continue;
         }
         CK(launch_quick_parse(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->sm_slots,
-                              grid, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream),
+                              grid, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream, ctx->slot_limit),
            "quick_parse launch");
         CK(launch_static_emit(toks, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
                               d_sizes + c0, ctx->sms, stream),
            "static_emit launch");
     }
     if (d_crcs || d_adlers)
-        CK(launch_checksum_tiles(d_in, n, chunk, nchunks, d_crcs, d_adlers, ctx->sms, stream), "checksum launch");
+        CK(launch_checksum_tiles(d_in, n, chunk, nchunks, d_crcs, d_adlers, ctx->sms, stream, ck_warps), "checksum launch");
     return 0;
 }
 
@@ -345,6 +369,8 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     if (prop.major < 10) { delete ctx; return ZNG_B200_STREAM_ERROR; }       // sm_100a kernels only
     if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm = v; }
     if (const char* e = getenv("ZNG_B200_SLAB_CHUNKS")) { int v = atoi(e); if (v >= 64 && v <= 16384) ctx->slab_chunks = (uint32_t)v; }
+    if (const char* e = getenv("ZNG_B200_SLOT_LIMIT")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->slot_limit = (uint32_t)v; }
+    if (const char* e = getenv("ZNG_B200_STREAMED")) ctx->streamed = atoi(e);
     if (const char* e = getenv("ZNG_B200_PIPE")) { int v = atoi(e); if (v >= 2 && v <= kPipeMax) ctx->pipe = v; }
     if (const char* e = getenv("ZNG_B200_CHAINS_L2")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm_l2 = v; }
     if (cudaMalloc(&ctx->counters, kCounters * sizeof(uint32_t)) != cudaSuccess ||
@@ -418,6 +444,18 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
     if (ctx->ck_scratch) cudaFree(ctx->ck_scratch);
     if (ctx->d_result) cudaFree(ctx->d_result);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    {
+        Streamed& S = ctx->st;
+        for (void* p : {(void*)S.d_in, (void*)S.d_slots, (void*)S.d_packed, (void*)S.tokens, (void*)S.ntok, (void*)S.d_meta, (void*)S.d_offsets,
+                        (void*)S.d_sync, (void*)S.d_res}) if (p) cudaFree(p);
+        for (void* p : {(void*)S.h_ready, (void*)S.h_meta, (void*)S.h_failed, (void*)S.h_done}) if (p) cudaFreeHost(p);
+        if (S.copy) cudaStreamDestroy(S.copy);
+        if (S.parse) cudaStreamDestroy(S.parse);
+        if (S.d2h) cudaStreamDestroy(S.d2h);
+        for (auto st : S.out) if (st) cudaStreamDestroy(st);
+        if (S.reset_done) cudaEventDestroy(S.reset_done);
+        for (auto e : S.slab_done) if (e) cudaEventDestroy(e);
+    }
     if (ctx->d_hostbuf) cudaFree(ctx->d_hostbuf);
     if (ctx->d_pbuf) cudaFree(ctx->d_pbuf);
     if (ctx->d_pout) cudaFree(ctx->d_pout);
@@ -1135,6 +1173,180 @@ int zng_b200_deflate_host_primed(zng_b200_ctx* ctx, const void* h_dict, const vo
     return 0;
 }
 
+extern "C++" {
+static int ensure_streamed(zng_b200_ctx* ctx, uint32_t nch) {
+    Streamed& S = ctx->st;
+    if (!S.ready) {
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest), "stream priorities");
+        if (getenv("ZNG_B200_NOPRIO")) least = greatest = 0;
+        CK(cudaStreamCreateWithPriority(&S.copy, cudaStreamNonBlocking, greatest), "stream");
+        CK(cudaStreamCreateWithPriority(&S.parse, cudaStreamNonBlocking, least), "stream");
+        CK(cudaStreamCreateWithPriority(&S.d2h, cudaStreamNonBlocking, greatest), "stream");
+        for (int i = 0; i < kStreamOut; i++) CK(cudaStreamCreateWithPriority(&S.out[i], cudaStreamNonBlocking, greatest), "stream");
+        CK(cudaEventCreateWithFlags(&S.reset_done, cudaEventDisableTiming), "event");
+        for (auto& e : S.slab_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
+        CK(cudaMalloc(&S.d_sync, 64 * sizeof(uint32_t)), "cudaMalloc(stream sync)");
+        CK(cudaMalloc(&S.d_res, 2 * (kStreamMaxChunks / kStreamSlab) * sizeof(uint32_t)), "cudaMalloc(stream res)");
+        CK(cudaHostAlloc(&S.h_ready, (kStreamMaxChunks / kStreamPiece + 1) * sizeof(uint32_t), cudaHostAllocDefault), "cudaHostAlloc");
+        CK(cudaHostAlloc(&S.h_meta, 2 * (kStreamMaxChunks / kStreamSlab) * sizeof(uint64_t), cudaHostAllocDefault), "cudaHostAlloc");
+        CK(cudaHostAlloc(&S.h_failed, sizeof(uint32_t), cudaHostAllocDefault), "cudaHostAlloc");
+        CK(cudaHostAlloc(&S.h_done, (kStreamMaxChunks / kStreamSlab) * sizeof(uint32_t), cudaHostAllocMapped), "cudaHostAlloc(mapped)");
+        CK(cudaHostGetDevicePointer(&S.d_h_done, S.h_done, 0), "cudaHostGetDevicePointer");
+        S.ready = true;
+    }
+    if (S.cap_chunks >= nch) return 0;
+    cudaDeviceSynchronize();
+    for (void* p : {(void*)S.d_in, (void*)S.d_slots, (void*)S.d_packed, (void*)S.tokens, (void*)S.ntok, (void*)S.d_meta, (void*)S.d_offsets}) if (p) cudaFree(p);
+    S.d_in = S.d_slots = S.d_packed = nullptr; S.tokens = S.ntok = S.d_meta = nullptr; S.d_offsets = nullptr; S.cap_chunks = 0;
+    const size_t stride = zng_b200_deflate_bound(ZNG_B200_CHUNK_MAX), tstride = (ZNG_B200_CHUNK_MAX + 32u) & ~31u;
+    const size_t nslabs = (nch + kStreamSlab - 1) / kStreamSlab;
+    CK(cudaMalloc(&S.d_in, (size_t)nch * ZNG_B200_CHUNK_MAX + 4096), "cudaMalloc(stream in)");
+    CK(cudaMemset(S.d_in + (size_t)nch * ZNG_B200_CHUNK_MAX, 0, 4096), "cudaMemset(stream pad)");
+    CK(cudaMalloc(&S.d_slots, (size_t)nch * stride), "cudaMalloc(stream slots)");
+    CK(cudaMalloc(&S.d_packed, (size_t)nch * stride), "cudaMalloc(stream packed)");
+    CK(cudaMalloc(&S.tokens, (size_t)nch * tstride * sizeof(uint32_t)), "cudaMalloc(stream tokens)");
+    CK(cudaMalloc(&S.ntok, (size_t)nch * sizeof(uint32_t)), "cudaMalloc(stream ntok)");
+    CK(cudaMalloc(&S.d_meta, (size_t)nch * 3 * sizeof(uint32_t)), "cudaMalloc(stream meta)");
+    CK(cudaMalloc(&S.d_offsets, nslabs * (kStreamSlab + 1) * sizeof(uint64_t)), "cudaMalloc(stream offsets)");
+    S.cap_chunks = nch;
+    return 0;
+}
+
+// one call of the streamed path: n <= kStreamMaxChunks * 65536 bytes, n > 0
+static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t n, int final, uint8_t* h_out, size_t out_cap,
+                                 size_t& out_pos, uint32_t& crc, uint32_t& adler) {
+    const uint32_t chunk = ZNG_B200_CHUNK_MAX;
+    const uint32_t nch = (uint32_t)((n + chunk - 1) / chunk);
+    const uint32_t nslabs = (nch + kStreamSlab - 1) / kStreamSlab, npieces = (nch + kStreamPiece - 1) / kStreamPiece;
+    int r = ensure_heads(ctx);
+    if (r) return r;
+    r = ensure_streamed(ctx, nch < 4096u ? 4096u : nch);
+    if (r) return r;
+    Streamed& S = ctx->st;
+    const size_t stride = ctx->slab_stride, tstride = (chunk + 32u) & ~31u;
+    uint32_t* d_sizes = S.d_meta; uint32_t* d_crcs = S.d_meta + nch; uint32_t* d_adlers = S.d_meta + 2 * (size_t)nch;
+    const long long patience = 20000000000ll;                 // ~10 s of SM clocks: a wait that long means something is broken
+    static const bool trace = getenv("ZNG_B200_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+    CK(cudaMemsetAsync(S.d_sync, 0, 64 * sizeof(uint32_t), S.parse), "memset sync");
+    mark(S.parse);                                                       // [0] start
+    CK(cudaEventRecord(S.reset_done, S.parse), "event");
+    CK(cudaStreamWaitEvent(S.copy, S.reset_done, 0), "wait");
+    std::vector<cudaEvent_t> d2h_ev;
+    for (uint32_t j = 0; j < nslabs; j++) S.h_done[j] = 0;
+    StreamSync sy; sy.ready = S.d_sync; sy.failed = S.d_sync + 1; sy.done = S.d_sync + 4; sy.done_shift = kStreamSlabShift; sy.patience = patience;
+    sy.host_done = S.d_h_done;
+    CK(launch_quick_parse(S.d_in, n, chunk, nch, S.tokens, (uint32_t)tstride, S.ntok, S.d_sync + 2, ctx->heads, ctx->sm_slots,
+                          deflate_quick_grid(nch, ctx->sms, ctx->chains_per_sm), nullptr, S.parse, 64u, &sy),
+       "quick_parse launch");
+    mark(S.parse);                                                       // [1] parse kernel done
+    // the copy engine delivers the input piece by piece; chunk ci may start once chunk ci + 1 is there as well (its
+    // read-ahead reaches a few hundred bytes into the next chunk, and nothing may be cached before it has arrived)
+    for (uint32_t i = 0; i < npieces; i++) {
+        const size_t off = (size_t)i * kStreamPiece * chunk;
+        const size_t len = (n - off) < (size_t)kStreamPiece * chunk ? (n - off) : (size_t)kStreamPiece * chunk;
+        CK(cudaMemcpyAsync(S.d_in + off, h_in + off, len, cudaMemcpyHostToDevice, S.copy), "H2D piece");
+        const uint32_t delivered = (i + 1 == npieces) ? nch : (i + 1) * kStreamPiece;
+        S.h_ready[i] = (i + 1 == npieces) ? nch : delivered - 1u;
+        CK(cudaMemcpyAsync(S.d_sync, &S.h_ready[i], sizeof(uint32_t), cudaMemcpyHostToDevice, S.copy), "H2D ready");
+    }
+    mark(S.copy);                                                        // [2] last piece delivered
+    // The host drives the rest: it launches a slab's emit / checksum / gather work when the parse kernel reports the slab
+    // complete, and copies a slab's packed bytes out when that work is done.  Nothing is ever queued behind a wait, so
+    // streams that happen to share a hardware queue (CUDA_DEVICE_MAX_CONNECTIONS) cannot hold each other up.
+    constexpr int kCoCarve = 44;                                         // the split the streamed parse kernel runs with
+    int rc = 0;
+    uint32_t next_launch = 0, next_drain = 0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    while (next_drain < nslabs) {
+        bool progressed = false;
+        if (next_launch < nslabs) {
+            const uint32_t j = next_launch;
+            const uint32_t c0 = j * kStreamSlab, nb = (nch - c0) < kStreamSlab ? (nch - c0) : kStreamSlab;
+            if (*(volatile uint32_t*)&S.h_done[j] == nb) {
+                cudaStream_t st = S.out[j % kStreamOut];
+                const size_t off = (size_t)c0 * chunk, bytes = (c0 + nb == nch) ? n - off : (size_t)nb * chunk;
+                mark(st);                                                // [3+2j] slab j parsed
+                const uint32_t* toks = S.tokens + (size_t)c0 * tstride;
+                if (final && c0 + nb == nch) {                           // the stream's last chunk is the Z_FINISH chunk
+                    const uint32_t body = nb - 1;
+                    if (body) CK(launch_static_emit(toks, (uint32_t)tstride, S.ntok + c0, (size_t)body * chunk, chunk, body, 0, S.d_slots + (size_t)c0 * stride,
+                                                    stride, d_sizes + c0, ctx->sms, st, kCoCarve), "static_emit launch");
+                    CK(launch_static_emit(toks + (size_t)body * tstride, (uint32_t)tstride, S.ntok + c0 + body, bytes - (size_t)body * chunk, chunk, 1, 1,
+                                          S.d_slots + (size_t)(c0 + body) * stride, stride, d_sizes + c0 + body, ctx->sms, st, kCoCarve), "static_emit launch");
+                } else {
+                    CK(launch_static_emit(toks, (uint32_t)tstride, S.ntok + c0, bytes, chunk, nb, 0, S.d_slots + (size_t)c0 * stride, stride, d_sizes + c0,
+                                          ctx->sms, st, kCoCarve), "static_emit launch");
+                }
+                CK(launch_checksum_tiles(S.d_in + off, bytes, chunk, nb, d_crcs + c0, d_adlers + c0, ctx->sms, st, 8), "checksum launch");
+                uint64_t* offs = S.d_offsets + (size_t)j * (kStreamSlab + 1);
+                CK(launch_offsets(d_sizes + c0, nb, 0, offs, st), "offsets launch");
+                CK(launch_gather(S.d_slots + (size_t)c0 * stride, stride, d_sizes + c0, offs, nb, S.d_packed + (size_t)c0 * stride, ctx->sms, st), "gather launch");
+                CK(launch_crc32_fold(d_crcs + c0, nb, chunk, bytes, 0, S.d_res + 2 * j, st), "crc fold");
+                CK(launch_adler32_fold(d_adlers + c0, nb, chunk, bytes, 1, S.d_res + 2 * j + 1, st), "adler fold");
+                CK(cudaMemcpyAsync(&S.h_meta[2 * j], offs + nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, st), "D2H total");
+                CK(cudaMemcpyAsync(&S.h_meta[2 * j + 1], S.d_res + 2 * j, sizeof(uint64_t), cudaMemcpyDeviceToHost, st), "D2H checks");
+                CK(cudaEventRecord(S.slab_done[j], st), "event record");
+                mark(st);                                                // [4+2j] slab j packed
+                next_launch++; progressed = true;
+            }
+        }
+        if (next_drain < next_launch && cudaEventQuery(S.slab_done[next_drain]) == cudaSuccess) {
+            const uint32_t j = next_drain;
+            const uint32_t c0 = j * kStreamSlab, nb = (nch - c0) < kStreamSlab ? (nch - c0) : kStreamSlab;
+            const size_t bytes = (c0 + nb == nch) ? n - (size_t)c0 * chunk : (size_t)nb * chunk;
+            const size_t total = (size_t)S.h_meta[2 * j];
+            if (!rc && out_pos + total > out_cap) { snprintf(ctx->err, sizeof(ctx->err), "output buffer too small"); rc = ZNG_B200_BUF_ERROR; }
+            if (!rc) {
+                CK(cudaMemcpyAsync(h_out + out_pos, S.d_packed + (size_t)c0 * stride, total, cudaMemcpyDeviceToHost, S.d2h), "D2H packed");
+                if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, S.d2h); d2h_ev.push_back(e); }
+                out_pos += total;
+                crc = crc32_combine_dev(ctx->x2n, crc, (uint32_t)S.h_meta[2 * j + 1], bytes);
+                adler = adler32_combine_dev(adler, (uint32_t)(S.h_meta[2 * j + 1] >> 32), bytes);
+            }
+            next_drain++; progressed = true;
+        }
+        if (!progressed) {
+            if (std::chrono::steady_clock::now() - t_begin > std::chrono::seconds(30)) {
+                snprintf(ctx->err, sizeof(ctx->err), "streamed pipeline: no progress for 30 s");
+                cudaDeviceSynchronize();
+                return ZNG_B200_CUDA_ERROR;
+            }
+            if (cudaStreamQuery(S.parse) == cudaSuccess && next_launch < nslabs &&
+                *(volatile uint32_t*)&S.h_done[next_launch] == 0u && cudaStreamQuery(S.parse) == cudaSuccess) {
+                // the parse kernel is gone and never reported this slab: a device-side wait gave up
+                cudaDeviceSynchronize();
+                if (*(volatile uint32_t*)&S.h_done[next_launch] == 0u) {
+                    snprintf(ctx->err, sizeof(ctx->err), "streamed pipeline: the parse kernel ended early");
+                    return ZNG_B200_CUDA_ERROR;
+                }
+            }
+        }
+    }
+    CK(cudaMemcpyAsync(S.h_failed, S.d_sync + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, S.d2h), "D2H failed flag");
+    CK(cudaStreamSynchronize(S.parse), "sync");
+    CK(cudaStreamSynchronize(S.d2h), "sync");
+    CK(cudaStreamSynchronize(S.copy), "sync");
+    for (int i = 0; i < kStreamOut; i++) CK(cudaStreamSynchronize(S.out[i]), "sync");
+    if (trace && !tev.empty()) {
+        cudaEvent_t end; cudaEventCreate(&end); cudaEventRecord(end, S.d2h); cudaEventSynchronize(end);
+        auto ms = [&](cudaEvent_t e) { float t = 0; cudaEventElapsedTime(&t, tev[0], e); return t; };
+        fprintf(stderr, "streamed: parse kernel done %.2f, input delivered %.2f, all drained %.2f ms\n", ms(tev[1]), ms(tev[2]), ms(end));
+        for (size_t j = 0; 4 + 2 * j < tev.size(); j++) fprintf(stderr, "  slab %2zu: parsed %7.2f  packed %7.2f\n", j, ms(tev[3 + 2 * j]), ms(tev[4 + 2 * j]));
+        fprintf(stderr, "  packed bytes on the host at:");
+        for (cudaEvent_t e : d2h_ev) { fprintf(stderr, " %.2f", ms(e)); cudaEventDestroy(e); }
+        fprintf(stderr, " ms\n");
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        cudaEventDestroy(end);
+    }
+    if (rc) return rc;
+    if (*S.h_failed) { snprintf(ctx->err, sizeof(ctx->err), "streamed pipeline: a device-side wait ran out of patience"); return ZNG_B200_CUDA_ERROR; }
+    return 0;
+}
+}
+
 int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_t chunk, int level, int final,
                           void* h_out, size_t out_cap, size_t* out_len, uint32_t* crc32, uint32_t* adler32) {
     if (!ctx) return ZNG_B200_STREAM_ERROR;
@@ -1144,6 +1356,21 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
     DeviceGuard g(ctx->device);
     int r = ensure_slabs(ctx);
     if (r) return r;
+    if (level == 1 && chunk == ZNG_B200_CHUNK_MAX && ctx->streamed && n >= ((size_t)32 << 20)) {
+        // large level-1 inputs: one persistent parse kernel fed by the copy engine (see Streamed)
+        size_t pos = 0, done = 0; uint32_t c = 0, a = 1;
+        const size_t super = (size_t)kStreamMaxChunks * chunk;
+        while (done < n) {
+            const size_t take = (n - done) < super ? (n - done) : super;
+            r = deflate_host_streamed(ctx, (const uint8_t*)h_in + done, take, (final && done + take == n) ? 1 : 0, (uint8_t*)h_out, out_cap, pos, c, a);
+            if (r) return r;
+            done += take;
+        }
+        *out_len = pos;
+        if (crc32) *crc32 = c;
+        if (adler32) *adler32 = a;
+        return 0;
+    }
     const size_t stride = ctx->slab_stride;
     const uint32_t kSlabChunks = ctx->slab_chunks;
     const size_t slab_in = (size_t)kSlabChunks * chunk;
@@ -1154,15 +1381,21 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
     // n == 0 with final: one empty Z_FINISH chunk ("03 00"); n == 0 without final: nothing to emit.
     // Slabs run on their own streams: H2D, K1a/K1b, K3, gather and D2H of different slabs overlap.
     bool emitted_final = false;
+    // ZNG_B200_TRACE=1: per-slab stage times (ms since the first H2D was issued) on stderr -- a debugging aid for the pipeline
+    static const bool trace = getenv("ZNG_B200_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
     while (off < n || (final && !emitted_final)) {
         Slab& s = ctx->slab[k];
         r = drain_slab(ctx, s, out, out_cap, out_pos, crc, adler);     // the previous occupant's bytes leave first
         if (r) { sync_slabs(ctx); return r; }
+        mark(s.stream);                                                 // [4i+0] slab stream free again (behind the old occupant's D2H)
         const size_t take = (n - off) < slab_in ? (n - off) : slab_in;
         const bool is_last = (off + take == n);
         const size_t pre = (level >= 2) ? (off < kWSize ? off : (size_t)kWSize) : 0;
         const int have_prev = off > 0 ? 1 : 0;
         if (take) CK(cudaMemcpyAsync(s.d_in - pre, (const uint8_t*)h_in + off - pre, take + pre, cudaMemcpyHostToDevice, s.stream), "H2D");
+        mark(s.stream);                                                 // [4i+1] H2D done
         uint32_t nch = (uint32_t)((take + chunk - 1) / chunk);
         uint32_t* d_sizes = s.d_sizes; uint32_t* d_crcs = s.d_sizes + kSlabChunks; uint32_t* d_adlers = s.d_sizes + 2 * kSlabChunks;
         if (final && is_last) {
@@ -1171,13 +1404,13 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
             const size_t body_bytes = (size_t)body * chunk;
             if (body) {
                 r = run_deflate_chunks(ctx, s.scratch, s.d_in, body_bytes, chunk, body, 0, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream, nullptr, 0,
-                                      level, have_prev);
+                                      level, have_prev, 8);
                 if (r) { sync_slabs(ctx); return r; }
             }
             const size_t tail = take - body_bytes;
             if (tail) {
                 r = run_deflate_chunks(ctx, s.scratch, s.d_in + body_bytes, tail, chunk, 1, 1, s.d_slots + (size_t)body * stride, stride,
-                                      d_sizes + body, d_crcs + body, d_adlers + body, s.stream, nullptr, 0, level, (body || have_prev) ? 1 : 0);
+                                      d_sizes + body, d_crcs + body, d_adlers + body, s.stream, nullptr, 0, level, (body || have_prev) ? 1 : 0, 8);
                 if (r) { sync_slabs(ctx); return r; }
             } else {
                 // zng_deflate(Z_FINISH) with no input: "03 00" (empty static block, BFINAL) -- deflate_quick.c:53-58
@@ -1192,9 +1425,10 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
             emitted_final = true;
         } else {
             r = run_deflate_chunks(ctx, s.scratch, s.d_in, take, chunk, nch, 0, s.d_slots, stride, d_sizes, d_crcs, d_adlers, s.stream, nullptr, 0,
-                                  level, have_prev);
+                                  level, have_prev, 8);
             if (r) { sync_slabs(ctx); return r; }
         }
+        mark(s.stream);                                                 // [4i+2] parse + emit + checksums done
         CK(launch_offsets(d_sizes, nch, 0, s.d_offsets, s.stream), "offsets launch");
         CK(launch_gather(s.d_slots, stride, d_sizes, s.d_offsets, nch, s.d_packed, ctx->sms, s.stream), "gather launch");
         const uint32_t ntiles = (uint32_t)((take + chunk - 1) / chunk);
@@ -1203,6 +1437,7 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
         CK(cudaMemcpyAsync(&s.h_meta[0], s.d_offsets + nch, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream), "D2H total");
         CK(cudaMemcpyAsync(&s.h_meta[1], s.d_res, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream), "D2H checks");
         CK(cudaEventRecord(s.done, s.stream), "event record");
+        mark(s.stream);                                                 // [4i+3] gather + folds done (the slab is drainable)
         s.in_bytes = take;
         s.busy = true;
         off += take;
@@ -1222,6 +1457,19 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
         if (r) { sync_slabs(ctx); return r; }
     }
     for (int i = 0; i < ctx->pipe; i++) CK(cudaStreamSynchronize(ctx->slab[i].stream), "final sync");
+    if (trace && !tev.empty()) {
+        cudaEvent_t end; cudaEventCreate(&end); cudaEventRecord(end, ctx->slab[0].stream); cudaEventSynchronize(end);
+        for (size_t i = 0; i + 3 < tev.size(); i += 4) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a, tev[1], tev[i]); cudaEventElapsedTime(&b, tev[1], tev[i + 1]);
+            cudaEventElapsedTime(&c, tev[1], tev[i + 2]); cudaEventElapsedTime(&d, tev[1], tev[i + 3]);
+            fprintf(stderr, "slab %2zu: stream free %7.2f  h2d done %7.2f  kernels done %7.2f  packed %7.2f ms\n", i / 4, a, b, c, d);
+        }
+        float e = 0; cudaEventElapsedTime(&e, tev[1], end);
+        fprintf(stderr, "all drained %7.2f ms (relative to the end of the first H2D)\n", e);
+        for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+        cudaEventDestroy(end);
+    }
     *out_len = out_pos;
     if (crc32) *crc32 = crc;
     if (adler32) *adler32 = adler;

@@ -28,21 +28,24 @@ constexpr uint32_t kCkRow    = 512;          // bytes per warp row (32 lanes x 1
 
 struct X2N { uint32_t v[32]; };            // x^(2^k) mod P, k = 0..31 (crc32_braid_tbl.h:9437-9444 holds the same values)
 
+template <int R>                             // R = 32: one copy of the tables per lane (conflict free, 128 KiB); R = 1: one shared copy (4 KiB)
 struct CkShared {
-    uint32_t big[4][256][32];                // lane-private copies of the advance-by-512-bytes tables (128 KiB)
+    uint32_t big[4][256][R];                 // the advance-by-512-bytes tables
     uint32_t t4[4][256];                     // ordinary slicing-by-4 tables (heads / tails)
     uint32_t klast[128];                     // x^(8 * (512 - 16*lane - 4*k)): last-row accumulators -> end of the rows
     uint32_t x2n[32];
 };
 
 // c advanced over one 32-bit word of data (slicing-by-4, crc32_braid_c.c semantics for N = 1, W = 4)
-__device__ __forceinline__ uint32_t crc_word(const CkShared& s, uint32_t c, uint32_t w) {
+template <int R>
+__device__ __forceinline__ uint32_t crc_word(const CkShared<R>& s, uint32_t c, uint32_t w) {
     w ^= c;
     return s.t4[3][w & 0xffu] ^ s.t4[2][(w >> 8) & 0xffu] ^ s.t4[1][(w >> 16) & 0xffu] ^ s.t4[0][w >> 24];
 }
 
 // bytes [p, p+len) through lane-0 style serial code (any alignment)
-__device__ uint32_t crc_serial(const CkShared& s, uint32_t c, const uint8_t* p, uint32_t len) {
+template <int R>
+__device__ uint32_t crc_serial(const CkShared<R>& s, uint32_t c, const uint8_t* p, uint32_t len) {
     while (len && (reinterpret_cast<uintptr_t>(p) & 3u)) { c = s.t4[0][(c ^ *p++) & 0xffu] ^ (c >> 8); len--; }
     const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
     for (; len >= 4u; len -= 4u) c = crc_word(s, c, __ldg(w++));
@@ -51,28 +54,31 @@ __device__ uint32_t crc_serial(const CkShared& s, uint32_t c, const uint8_t* p, 
     return c;
 }
 
-template <bool kCrc, bool kAdler>
+template <bool kCrc, bool kAdler, int R = 32>
 __global__ void __launch_bounds__(kCkWarps * 32, 1)
 checksum_tiles_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t tile_bytes, uint32_t ntiles,
                       uint32_t* __restrict__ crcs, uint32_t* __restrict__ adlers, const X2N x2n_host) {
     extern __shared__ __align__(16) unsigned char ck_smem[];
-    CkShared& s = *reinterpret_cast<CkShared*>(ck_smem);
+    CkShared<R>& s = *reinterpret_cast<CkShared<R>*>(ck_smem);
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned cta_warps = blockDim.x >> 5;              // 32 when the kernel has the SM to itself, fewer next to a parse kernel
     if (kCrc) {
         if (tid < 32u) s.x2n[tid] = x2n_host.v[tid];
-        s.t4[tid >> 8][tid & 255u] = crc_table_entry(tid & 255u, (int)(tid >> 8));
+        for (unsigned e = tid; e < 1024u; e += blockDim.x) s.t4[e >> 8][e & 255u] = crc_table_entry(e & 255u, (int)(e >> 8));
         __syncthreads();
         const uint32_t adv = x2nmodp(s.x2n, kCkRow, 3);                         // x^(8*512)
-        const uint32_t v = multmodp(adv, (tid & 255u) << (8u * (tid >> 8)));     // state with one byte set, 512 bytes later
+        for (unsigned e = tid; e < 1024u; e += blockDim.x) {
+            const uint32_t v = multmodp(adv, (e & 255u) << (8u * (e >> 8)));      // state with one byte set, 512 bytes later
 #pragma unroll 8
-        for (int r = 0; r < 32; r++) s.big[tid >> 8][tid & 255u][r] = v;
+            for (int r = 0; r < R; r++) s.big[e >> 8][e & 255u][r] = v;
+        }
         if (tid < 128u) s.klast[tid] = x2nmodp(s.x2n, kCkRow - 16u * (tid >> 2) - 4u * (tid & 3u), 3);
         __syncthreads();
     }
-    // per-lane byte offsets into `big`: table k at k*32768, entry b at b*128, this lane's copy at lane*4
-    const unsigned char* bigb = reinterpret_cast<const unsigned char*>(&s.big[0][0][0]) + lane * 4u;
+    // byte offsets into `big`: table k at k*1024*R, entry b at b*4*R, (R = 32) this lane's copy at lane*4
+    const unsigned char* bigb = reinterpret_cast<const unsigned char*>(&s.big[0][0][0]) + (R == 32 ? lane * 4u : 0u);
 
-    for (uint32_t ti = blockIdx.x * kCkWarps + warp; ti < ntiles; ti += gridDim.x * kCkWarps) {
+    for (uint32_t ti = blockIdx.x * cta_warps + warp; ti < ntiles; ti += gridDim.x * cta_warps) {
         const size_t off = (size_t)ti * tile_bytes;
         const uint32_t len = (uint32_t)min((size_t)tile_bytes, n - off);
         const uint8_t* src = in + off;
@@ -86,7 +92,8 @@ checksum_tiles_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t tile_by
         if (kCrc && lane == 0) c0 = crc_serial(s, 0xffffffffu, src, head);       // pre-inversion + head bytes ride on the first word
         if (rows) {
             // three rows in flight per warp (32 warps x 3 x 512 B = 48 KiB per SM) to cover the HBM latency
-#define ZB_LK(k, w, sh) (*reinterpret_cast<const uint32_t*>(bigb + (k) * 32768u + ((sh) >= 7 ? (((w) >> ((sh) - 7)) & 0x7f80u) : (((w) << 7) & 0x7f80u))))
+#define ZB_LK(k, w, sh) (*reinterpret_cast<const uint32_t*>(bigb + (k) * (1024u * R) + (R == 32 ? ((sh) >= 7 ? (((w) >> ((sh) - 7)) & 0x7f80u) : (((w) << 7) & 0x7f80u)) \
+                                                                                                  : ((sh) >= 2 ? (((w) >> ((sh) - 2)) & 0x3fcu) : (((w) << 2) & 0x3fcu)))))
 #define ZB_FOLD_ROW(v)                                                                                              \
             do {                                                                                                    \
                 if (kCrc) {                                                                                         \
@@ -231,27 +238,35 @@ static const X2N& host_x2n() {
     return t;
 }
 
-template <bool kCrc, bool kAdler>
+template <bool kCrc, bool kAdler, int R>
 static cudaError_t launch_tiles(const uint8_t* in, size_t n, uint32_t tile_bytes, uint32_t ntiles, uint32_t* crcs, uint32_t* adlers,
-                                int num_sms, cudaStream_t stream) {
-    const int smem = kCrc ? (int)sizeof(CkShared) : 0;
-    if (smem) {
-        cudaError_t e = cudaFuncSetAttribute(checksum_tiles_kernel<kCrc, kAdler>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                                int num_sms, cudaStream_t stream, int cta_warps) {
+    const int smem = kCrc ? (int)sizeof(CkShared<R>) : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(checksum_tiles_kernel<kCrc, kAdler, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
     uint32_t grid = (uint32_t)num_sms * (kCrc ? 1u : 2u);
-    const uint32_t need = (ntiles + kCkWarps - 1u) / kCkWarps;
+    const uint32_t need = (ntiles + (uint32_t)cta_warps - 1u) / (uint32_t)cta_warps;
     if (grid > need) grid = need;
-    checksum_tiles_kernel<kCrc, kAdler><<<grid, kCkWarps * 32, smem, stream>>>(in, n, tile_bytes, ntiles, crcs, adlers, host_x2n());
+    checksum_tiles_kernel<kCrc, kAdler, R><<<grid, cta_warps * 32, smem, stream>>>(in, n, tile_bytes, ntiles, crcs, adlers, host_x2n());
     return cudaGetLastError();
 }
 
+// cta_warps: 32 = the whole SM (device-resident calls); the host pipelines pass 8 so that the CTAs fit NEXT TO a running
+// parse kernel: 1024 threads x 56 registers and 133 KiB of lane-private tables do not, and the checksums of a finished slab
+// would wait for the parse to end
 cudaError_t launch_checksum_tiles(const uint8_t* in, size_t n, uint32_t tile_bytes, uint32_t ntiles,
-                                  uint32_t* crcs, uint32_t* adlers, int num_sms, cudaStream_t stream) {
+                                  uint32_t* crcs, uint32_t* adlers, int num_sms, cudaStream_t stream, int cta_warps) {
     if (ntiles == 0) return cudaSuccess;
-    if (crcs && adlers) return launch_tiles<true, true>(in, n, tile_bytes, ntiles, crcs, adlers, num_sms, stream);
-    if (crcs) return launch_tiles<true, false>(in, n, tile_bytes, ntiles, crcs, nullptr, num_sms, stream);
-    if (adlers) return launch_tiles<false, true>(in, n, tile_bytes, ntiles, nullptr, adlers, num_sms, stream);
+    if (cta_warps < 1 || cta_warps > kCkWarps) cta_warps = kCkWarps;
+    if (cta_warps < kCkWarps) {     // next to a parse kernel: 8 KiB of tables (bank conflicts cost ~3x on the lookups, the slab is small)
+        if (crcs && adlers) return launch_tiles<true, true, 1>(in, n, tile_bytes, ntiles, crcs, adlers, num_sms, stream, cta_warps);
+        if (crcs) return launch_tiles<true, false, 1>(in, n, tile_bytes, ntiles, crcs, nullptr, num_sms, stream, cta_warps);
+    }
+    if (crcs && adlers) return launch_tiles<true, true, 32>(in, n, tile_bytes, ntiles, crcs, adlers, num_sms, stream, cta_warps);
+    if (crcs) return launch_tiles<true, false, 32>(in, n, tile_bytes, ntiles, crcs, nullptr, num_sms, stream, cta_warps);
+    if (adlers) return launch_tiles<false, true, 32>(in, n, tile_bytes, ntiles, nullptr, adlers, num_sms, stream, cta_warps);
     return cudaSuccess;
 }
 

@@ -30,6 +30,7 @@
 // Per-chunk CRC-32 / Adler-32 come from the K3 tile kernel (checksum.cu) launched on the same stream.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace zb {
 
@@ -358,11 +359,12 @@ __global__ void __launch_bounds__(kParseWarps * 32, 12)
 quick_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint32_t nchunks,
                    uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
                    uint32_t* __restrict__ counter, uint16_t* __restrict__ heads, unsigned long long* __restrict__ sm_slots,
-                   const uint8_t* __restrict__ tail, uint32_t tail_first) {
+                   const uint8_t* __restrict__ tail, uint32_t tail_first, uint32_t slot_limit, StreamSync sy) {
+    extern __shared__ uint32_t carve_out_only[];              // never touched: see launch_quick_parse (streamed launches)
     const unsigned lane = lane_id();
     const uint32_t sm = smid();
     uint32_t slot = 0;
-    if (lane == 0) slot = slot_acquire(sm_slots + sm);
+    if (lane == 0) slot = slot_acquire(sm_slots + sm, slot_limit);
     slot = __shfl_sync(ZB_FULL, slot, 0);
     uint16_t* head = heads + ((size_t)sm * 64u + slot) * 65536u;
     for (;;) {
@@ -370,6 +372,16 @@ quick_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uin
         if (lane == 0) ci = atomicAdd(counter, 1u);
         ci = __shfl_sync(ZB_FULL, ci, 0);
         if (ci >= nchunks) break;
+        if (sy.ready) {                                        // streamed input: chunk ci is parsed once the copy engine has delivered it
+            if (lane == 0) {
+                const long long t0 = clock64();
+                while (*(volatile const uint32_t*)sy.ready <= ci) {
+                    __nanosleep(1000);
+                    if (clock64() - t0 > sy.patience) { atomicExch(sy.failed, 1u); break; }
+                }
+            }
+            __syncwarp();
+        }
         // CLEAR_HASH (deflate.c:182-184): 128 KiB of zeros into this chain's slab
         {
             uint4* h4 = reinterpret_cast<uint4*>(head);
@@ -385,9 +397,34 @@ quick_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uin
         W.w = reinterpret_cast<const uint32_t*>(src - W.skew);
         const uint32_t cnt = quick_parse_warp(W, len, head, tokens + (size_t)ci * tok_stride);
         if (lane == 0) ntok[ci] = cnt;
+        if (sy.done) {                                         // per output slab: how many of its chunks are parsed
+            __syncwarp();
+            __threadfence();
+            if (lane == 0) {
+                const uint32_t k = atomicAdd(sy.done + (ci >> sy.done_shift), 1u) + 1u;
+                if (sy.host_done) {                            // tell the host (mapped pinned memory) when a slab is complete
+                    const uint32_t slab = ci >> sy.done_shift, first = slab << sy.done_shift;
+                    const uint32_t want = min(nchunks - first, 1u << sy.done_shift);
+                    if (k == want) { __threadfence_system(); *(volatile uint32_t*)(sy.host_done + slab) = want; }
+                }
+            }
+        }
     }
     __syncwarp();
     if (lane == 0) atomicAnd(sm_slots + sm, ~(1ull << slot));
+}
+
+// stream-ordered wait on a device counter (the parse kernel's per-slab `done` count): one thread, high-priority stream
+__global__ void wait_geq_kernel(const uint32_t* p, uint32_t v, long long patience, uint32_t* failed) {
+    const long long t0 = clock64();
+    while (*(volatile const uint32_t*)p < v) {
+        __nanosleep(2000);
+        if (clock64() - t0 > patience || *(volatile uint32_t*)failed) { atomicExch(failed, 1u); break; }
+    }
+}
+cudaError_t launch_wait_geq(const uint32_t* p, uint32_t v, long long patience, uint32_t* failed, cudaStream_t stream) {
+    wait_geq_kernel<<<1, 1, 0, stream>>>(p, v, patience, failed);
+    return cudaGetLastError();
 }
 
 // Primed chunks: chunk g (global index first + ci) reads its dictionary from the 32768 bytes in front of it; g == 0 has none.
@@ -468,10 +505,23 @@ uint32_t deflate_quick_grid(uint32_t nchunks, int num_sms, int chains_per_sm) {
 
 cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                                uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
-                               uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream) {
+                               uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream, uint32_t slot_limit,
+                               const StreamSync* sync) {
     if (grid == 0 || nchunks == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
+    if (sync) {            // streamed input: the caller's buffer is padded by kWinPad readable bytes, no private copy of the last chunks
+        // This launch owns the SMs for the whole call and needs no shared memory itself.  The L1 / shared-memory split of an SM
+        // can only change while the SM is idle, and for a kernel without shared memory it is all-L1: the emit / checksum /
+        // gather kernels of the finished slabs (17 KiB of shared memory per CTA) could then not start before this kernel ends.
+        // A few KiB per CTA that are never touched make the driver pick a middle split at no cost to the parser (a carve-out
+        // preference alone is ignored below 50 %, and from 50 % on the parser loses its L1: 31 -> 23 GB/s); the kernels that
+        // must run next to it ask for the same split (launch_static_emit's co_carve).  Measured: profiles/r1_e2e_pipeline.md.
+        static int dyn = [] { const char* e = getenv("ZNG_B200_STREAM_DYNSMEM"); return e ? atoi(e) : 4096; }();
+        quick_parse_kernel<<<grid, kParseWarps * 32, dyn, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, in, nchunks,
+                                                                   slot_limit, *sync);
+        return cudaGetLastError();
+    }
     // chunk i may read kWinPad bytes past its end: safe iff (i+1)*chunk + kWinPad <= n
     const uint32_t tail_first = n >= kWinPad ? (uint32_t)((n - kWinPad) / chunk) : 0u;
     const size_t tail_off = (size_t)tail_first * chunk, tail_bytes = n - tail_off;       // <= 2*chunk + kWinPad
@@ -479,7 +529,14 @@ cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(tail + tail_bytes, 0, 2u * kWinPad, stream);
     if (e != cudaSuccess) return e;
-    quick_parse_kernel<<<grid, kParseWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, tail, tail_first);
+    static int carve_all = [] { const char* e = getenv("ZNG_B200_CARVEOUT_ALL"); return e ? atoi(e) : -1; }();   // experiment knob
+    static int dyn_all = [] { const char* e = getenv("ZNG_B200_DYNSMEM_ALL"); return e ? atoi(e) : 1024; }();
+    if (carve_all >= 0 || dyn_all != 1024) {
+        cudaFuncSetAttribute(quick_parse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve_all);
+        quick_parse_kernel<<<grid, kParseWarps * 32, dyn_all, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, tail, tail_first, slot_limit, StreamSync{});
+        return cudaGetLastError();
+    }
+    quick_parse_kernel<<<grid, kParseWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, tail, tail_first, slot_limit, StreamSync{});
     return cudaGetLastError();
 }
 
@@ -507,11 +564,14 @@ cudaError_t launch_primed_parse(const uint8_t* in, size_t n, uint32_t chunk, uin
 
 cudaError_t launch_static_emit(const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n, uint32_t chunk,
                                uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
-                               int num_sms, cudaStream_t stream) {
+                               int num_sms, cudaStream_t stream, int co_carve) {
     if (nchunks == 0) return cudaSuccess;
     uint32_t grid = (uint32_t)num_sms * 12u;
     uint32_t need = (nchunks + kEmitWarps - 1u) / kEmitWarps;
     if (grid > need) grid = need;
+    // co_carve >= 0: this launch has to start NEXT TO a running (streamed) parse kernel.  Two kernels only share an SM when
+    // they ask for the same L1 / shared-memory split; left alone the driver would give this kernel the all-shared split.
+    cudaFuncSetAttribute(static_emit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co_carve);
     static_emit_kernel<<<grid, kEmitWarps * 32, 0, stream>>>(tokens, tok_stride, ntok, n, chunk, nchunks, last, out, out_stride, sizes);
     return cudaGetLastError();
 }

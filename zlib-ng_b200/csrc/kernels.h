@@ -14,9 +14,22 @@ size_t deflate_quick_head_bytes(uint32_t nsmid);       // pool of nsmid x 64 sla
 cudaError_t query_nsmid(uint32_t* d_scratch, uint32_t* nsmid);
 size_t deflate_quick_tail_bytes();
 uint32_t deflate_quick_grid(uint32_t nchunks, int num_sms, int chains_per_sm);
+// Streamed input (host pipeline): `ready` = chunks delivered so far (written by the copy stream), `done[ci >> done_shift]`
+// counts parsed chunks per output slab; `patience` clocks bound every wait, `failed` is raised when one runs out.
+struct StreamSync {
+    const uint32_t* ready = nullptr;
+    uint32_t* done = nullptr;
+    uint32_t done_shift = 0;
+    uint32_t* host_done = nullptr;      // mapped pinned memory: host_done[slab] = chunks of the slab once all are parsed
+    long long patience = 0;
+    uint32_t* failed = nullptr;
+};
+cudaError_t launch_wait_geq(const uint32_t* p, uint32_t v, long long patience, uint32_t* failed, cudaStream_t stream);
 cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                                uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
-                               uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream);
+                               uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream,
+                               uint32_t slot_limit = 64u,    // < 64: concurrent launches share `slot_limit` chains per SM
+                               const StreamSync* sync = nullptr);
 // K1 primed (pigz's dependent-chunk mode): every chunk but the stream's first has the 32768 bytes in front of it as its
 // preset dictionary.  heads = deflate_primed_head_bytes() pool of 256 KiB slabs (32-bit absolute positions).
 size_t deflate_primed_head_bytes(uint32_t nsmid);
@@ -26,7 +39,7 @@ cudaError_t launch_primed_parse(const uint8_t* in, size_t n, uint32_t chunk, uin
                                 uint32_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream);
 cudaError_t launch_static_emit(const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n, uint32_t chunk,
                                uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
-                               int num_sms, cudaStream_t stream);
+                               int num_sms, cudaStream_t stream, int co_carve = -1);
 
 // K2: level-2 chunk deflate (deflate_fast.cu): K2a parse with hash chains -> token lists, K2b block writer
 // (dynamic / static / stored blocks).  Shares the head slab pool and sm_slots with K1; prevs / tails are the
@@ -43,7 +56,7 @@ cudaError_t launch_block_emit(const uint8_t* in, const uint32_t* tokens, uint32_
 
 // K3: checksums (checksum.cu)
 cudaError_t launch_checksum_tiles(const uint8_t* in, size_t n, uint32_t tile_bytes, uint32_t ntiles,
-                                  uint32_t* crcs, uint32_t* adlers, int num_sms, cudaStream_t stream);
+                                  uint32_t* crcs, uint32_t* adlers, int num_sms, cudaStream_t stream, int cta_warps = 32);
 cudaError_t launch_crc32_fold(const uint32_t* crcs, uint32_t ntiles, uint32_t tile_bytes, size_t n, uint32_t init,
                               uint32_t* result, cudaStream_t stream);
 cudaError_t launch_adler32_fold(const uint32_t* adlers, uint32_t ntiles, uint32_t tile_bytes, size_t n, uint32_t init,
