@@ -41,7 +41,7 @@ struct Streamed {
     bool ready = false;
     cudaStream_t copy = nullptr, parse = nullptr, d2h = nullptr, out[kStreamOut] = {};
     cudaEvent_t reset_done = nullptr, slab_done[kStreamMaxChunks / kStreamSlab] = {};
-    uint8_t* d_in = nullptr; uint8_t* d_slots = nullptr; uint8_t* d_packed = nullptr;
+    uint8_t* d_in_alloc = nullptr; uint8_t* d_in = nullptr; uint8_t* d_slots = nullptr; uint8_t* d_packed = nullptr;
     uint32_t* tokens = nullptr; uint32_t* ntok = nullptr; uint32_t* d_meta = nullptr; uint64_t* d_offsets = nullptr;
     uint32_t* d_sync = nullptr;                   // [0] chunks delivered, [1] failed, [2] chunk counter, [4..] parsed chunks per slab
     uint32_t* d_res = nullptr;
@@ -446,7 +446,7 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     {
         Streamed& S = ctx->st;
-        for (void* p : {(void*)S.d_in, (void*)S.d_slots, (void*)S.d_packed, (void*)S.tokens, (void*)S.ntok, (void*)S.d_meta, (void*)S.d_offsets,
+        for (void* p : {(void*)S.d_in_alloc, (void*)S.d_slots, (void*)S.d_packed, (void*)S.tokens, (void*)S.ntok, (void*)S.d_meta, (void*)S.d_offsets,
                         (void*)S.d_sync, (void*)S.d_res}) if (p) cudaFree(p);
         for (void* p : {(void*)S.h_ready, (void*)S.h_meta, (void*)S.h_failed, (void*)S.h_done}) if (p) cudaFreeHost(p);
         if (S.copy) cudaStreamDestroy(S.copy);
@@ -1197,11 +1197,12 @@ static int ensure_streamed(zng_b200_ctx* ctx, uint32_t nch) {
     }
     if (S.cap_chunks >= nch) return 0;
     cudaDeviceSynchronize();
-    for (void* p : {(void*)S.d_in, (void*)S.d_slots, (void*)S.d_packed, (void*)S.tokens, (void*)S.ntok, (void*)S.d_meta, (void*)S.d_offsets}) if (p) cudaFree(p);
-    S.d_in = S.d_slots = S.d_packed = nullptr; S.tokens = S.ntok = S.d_meta = nullptr; S.d_offsets = nullptr; S.cap_chunks = 0;
+    for (void* p : {(void*)S.d_in_alloc, (void*)S.d_slots, (void*)S.d_packed, (void*)S.tokens, (void*)S.ntok, (void*)S.d_meta, (void*)S.d_offsets}) if (p) cudaFree(p);
+    S.d_in_alloc = S.d_in = S.d_slots = S.d_packed = nullptr; S.tokens = S.ntok = S.d_meta = nullptr; S.d_offsets = nullptr; S.cap_chunks = 0;
     const size_t stride = zng_b200_deflate_bound(ZNG_B200_CHUNK_MAX), tstride = (ZNG_B200_CHUNK_MAX + 32u) & ~31u;
     const size_t nslabs = (nch + kStreamSlab - 1) / kStreamSlab;
-    CK(cudaMalloc(&S.d_in, (size_t)nch * ZNG_B200_CHUNK_MAX + 4096), "cudaMalloc(stream in)");
+    CK(cudaMalloc(&S.d_in_alloc, (size_t)nch * ZNG_B200_CHUNK_MAX + kWSize + 4096), "cudaMalloc(stream in)");
+    S.d_in = S.d_in_alloc + kWSize;                           // 32 KiB in front: the stream bytes that precede this call's first chunk (levels 2+)
     CK(cudaMemset(S.d_in + (size_t)nch * ZNG_B200_CHUNK_MAX, 0, 4096), "cudaMemset(stream pad)");
     CK(cudaMalloc(&S.d_slots, (size_t)nch * stride), "cudaMalloc(stream slots)");
     CK(cudaMalloc(&S.d_packed, (size_t)nch * stride), "cudaMalloc(stream packed)");
@@ -1215,15 +1216,18 @@ static int ensure_streamed(zng_b200_ctx* ctx, uint32_t nch) {
 
 // one call of the streamed path: n <= kStreamMaxChunks * 65536 bytes, n > 0
 static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t n, int final, uint8_t* h_out, size_t out_cap,
-                                 size_t& out_pos, uint32_t& crc, uint32_t& adler) {
+                                 size_t& out_pos, uint32_t& crc, uint32_t& adler, int level, int have_prev) {
     const uint32_t chunk = ZNG_B200_CHUNK_MAX;
     const uint32_t nch = (uint32_t)((n + chunk - 1) / chunk);
     const uint32_t nslabs = (nch + kStreamSlab - 1) / kStreamSlab, npieces = (nch + kStreamPiece - 1) / kStreamPiece;
     int r = ensure_heads(ctx);
     if (r) return r;
+    if (level >= 2) { r = ensure_prevs(ctx); if (r) return r; }
     r = ensure_streamed(ctx, nch < 4096u ? 4096u : nch);
     if (r) return r;
     Streamed& S = ctx->st;
+    static const int k2_dyn = [] { const char* e = getenv("ZNG_B200_STREAM_DYNSMEM_L2"); return e ? atoi(e) : 4096; }();
+    static const int k2_carve = [] { const char* e = getenv("ZNG_B200_CO_CARVE_L2"); return e ? atoi(e) : 44; }();
     const size_t stride = ctx->slab_stride, tstride = (chunk + 32u) & ~31u;
     uint32_t* d_sizes = S.d_meta; uint32_t* d_crcs = S.d_meta + nch; uint32_t* d_adlers = S.d_meta + 2 * (size_t)nch;
     const long long patience = 20000000000ll;                 // ~10 s of SM clocks: a wait that long means something is broken
@@ -1238,10 +1242,16 @@ static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t 
     for (uint32_t j = 0; j < nslabs; j++) S.h_done[j] = 0;
     StreamSync sy; sy.ready = S.d_sync; sy.failed = S.d_sync + 1; sy.done = S.d_sync + 4; sy.done_shift = kStreamSlabShift; sy.patience = patience;
     sy.host_done = S.d_h_done;
-    CK(launch_quick_parse(S.d_in, n, chunk, nch, S.tokens, (uint32_t)tstride, S.ntok, S.d_sync + 2, ctx->heads, ctx->sm_slots,
-                          deflate_quick_grid(nch, ctx->sms, ctx->chains_per_sm), nullptr, S.parse, 64u, &sy),
-       "quick_parse launch");
+    if (level == 1)
+        CK(launch_quick_parse(S.d_in, n, chunk, nch, S.tokens, (uint32_t)tstride, S.ntok, S.d_sync + 2, ctx->heads, ctx->sm_slots,
+                              deflate_quick_grid(nch, ctx->sms, ctx->chains_per_sm), nullptr, S.parse, 64u, &sy),
+           "quick_parse launch");
+    else                                                                 // 28 chains per SM: 8 CTAs would hold every register of the SM
+        CK(launch_fast_parse(S.d_in, n, chunk, nch, S.tokens, (uint32_t)tstride, S.ntok, S.d_sync + 2, ctx->heads, ctx->prevs, ctx->vtails,
+                             ctx->sm_slots, ctx->sms, ctx->chains_per_sm_l2 < 28 ? ctx->chains_per_sm_l2 : 28, have_prev, level, S.parse, &sy, k2_dyn),
+           "fast_parse launch");
     mark(S.parse);                                                       // [1] parse kernel done
+    if (have_prev) CK(cudaMemcpyAsync(S.d_in - kWSize, h_in - kWSize, kWSize, cudaMemcpyHostToDevice, S.copy), "H2D window in front");
     // the copy engine delivers the input piece by piece; chunk ci may start once chunk ci + 1 is there as well (its
     // read-ahead reaches a few hundred bytes into the next chunk, and nothing may be cached before it has arrived)
     for (uint32_t i = 0; i < npieces; i++) {
@@ -1269,16 +1279,24 @@ static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t 
                 cudaStream_t st = S.out[j % kStreamOut];
                 const size_t off = (size_t)c0 * chunk, bytes = (c0 + nb == nch) ? n - off : (size_t)nb * chunk;
                 mark(st);                                                // [3+2j] slab j parsed
-                const uint32_t* toks = S.tokens + (size_t)c0 * tstride;
+                auto emit = [&](uint32_t first, uint32_t count, size_t nbytes, int last) -> int {     // chunks [c0 + first, c0 + first + count) of the slab
+                    const uint32_t* tk = S.tokens + (size_t)(c0 + first) * tstride;
+                    if (level == 1)
+                        CK(launch_static_emit(tk, (uint32_t)tstride, S.ntok + c0 + first, nbytes, chunk, count, last, S.d_slots + (size_t)(c0 + first) * stride,
+                                              stride, d_sizes + c0 + first, ctx->sms, st, kCoCarve), "static_emit launch");
+                    else
+                        CK(launch_block_emit(S.d_in + off + (size_t)first * chunk, tk, (uint32_t)tstride, S.ntok + c0 + first, nbytes, chunk, count, last,
+                                             S.d_slots + (size_t)(c0 + first) * stride, stride, d_sizes + c0 + first, ctx->sms, st, k2_carve), "block_emit launch");
+                    return 0;
+                };
                 if (final && c0 + nb == nch) {                           // the stream's last chunk is the Z_FINISH chunk
                     const uint32_t body = nb - 1;
-                    if (body) CK(launch_static_emit(toks, (uint32_t)tstride, S.ntok + c0, (size_t)body * chunk, chunk, body, 0, S.d_slots + (size_t)c0 * stride,
-                                                    stride, d_sizes + c0, ctx->sms, st, kCoCarve), "static_emit launch");
-                    CK(launch_static_emit(toks + (size_t)body * tstride, (uint32_t)tstride, S.ntok + c0 + body, bytes - (size_t)body * chunk, chunk, 1, 1,
-                                          S.d_slots + (size_t)(c0 + body) * stride, stride, d_sizes + c0 + body, ctx->sms, st, kCoCarve), "static_emit launch");
+                    if (body) { r = emit(0, body, (size_t)body * chunk, 0); if (r) return r; }
+                    r = emit(body, 1, bytes - (size_t)body * chunk, 1);
+                    if (r) return r;
                 } else {
-                    CK(launch_static_emit(toks, (uint32_t)tstride, S.ntok + c0, bytes, chunk, nb, 0, S.d_slots + (size_t)c0 * stride, stride, d_sizes + c0,
-                                          ctx->sms, st, kCoCarve), "static_emit launch");
+                    r = emit(0, nb, bytes, 0);
+                    if (r) return r;
                 }
                 CK(launch_checksum_tiles(S.d_in + off, bytes, chunk, nb, d_crcs + c0, d_adlers + c0, ctx->sms, st, 8), "checksum launch");
                 uint64_t* offs = S.d_offsets + (size_t)j * (kStreamSlab + 1);
@@ -1356,13 +1374,14 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
     DeviceGuard g(ctx->device);
     int r = ensure_slabs(ctx);
     if (r) return r;
-    if (level == 1 && chunk == ZNG_B200_CHUNK_MAX && ctx->streamed && n >= ((size_t)32 << 20)) {
-        // large level-1 inputs: one persistent parse kernel fed by the copy engine (see Streamed)
+    if ((level == 1 || ctx->streamed >= 2) && chunk == ZNG_B200_CHUNK_MAX && ctx->streamed && n >= ((size_t)32 << 20)) {
+        // large inputs: one persistent parse kernel fed by the copy engine (see Streamed)
         size_t pos = 0, done = 0; uint32_t c = 0, a = 1;
         const size_t super = (size_t)kStreamMaxChunks * chunk;
         while (done < n) {
             const size_t take = (n - done) < super ? (n - done) : super;
-            r = deflate_host_streamed(ctx, (const uint8_t*)h_in + done, take, (final && done + take == n) ? 1 : 0, (uint8_t*)h_out, out_cap, pos, c, a);
+            r = deflate_host_streamed(ctx, (const uint8_t*)h_in + done, take, (final && done + take == n) ? 1 : 0, (uint8_t*)h_out, out_cap, pos, c, a,
+                                      level, (level >= 2 && done > 0) ? 1 : 0);
             if (r) return r;
             done += take;
         }

@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8)
 fast_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint32_t nchunks,
                   uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
                   uint32_t* __restrict__ counter, uint16_t* __restrict__ heads, uint16_t* __restrict__ prevs,
-                  uint32_t* __restrict__ tails, unsigned long long* __restrict__ sm_slots, int have_prev) {
+                  uint32_t* __restrict__ tails, unsigned long long* __restrict__ sm_slots, int have_prev, StreamSync sy) {
+    extern __shared__ uint32_t carve_out_only[];              // never touched: see launch_fast_parse (streamed launches)
     const unsigned lane = lane_id();
     const uint32_t sm = smid();
     uint32_t slot = 0;
@@ -153,6 +154,16 @@ fast_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint
         if (lane == 0) ci = atomicAdd(counter, 1u);
         ci = __shfl_sync(ZB_FULL, ci, 0);
         if (ci >= nchunks) break;
+        if (sy.ready) {                                        // streamed input (see quick_parse_kernel)
+            if (lane == 0) {
+                const long long t0 = clock64();
+                while (*(volatile const uint32_t*)sy.ready <= ci) {
+                    __nanosleep(1000);
+                    if (clock64() - t0 > sy.patience) { atomicExch(sy.failed, 1u); break; }
+                }
+            }
+            __syncwarp();
+        }
         {   // CLEAR_HASH (deflate.c:182-184); prev[] needs no clearing: only links of inserted positions are ever followed
             uint4* h4 = reinterpret_cast<uint4*>(head);
 #pragma unroll 8
@@ -191,6 +202,18 @@ fast_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint
         if constexpr (LEVEL >= 5) cnt = lazy_parse_warp<LEVEL>(W, len, head, prev, tokens + (size_t)ci * tok_stride);
         else cnt = fast_parse_warp<LEVEL>(W, len, head, prev, tokens + (size_t)ci * tok_stride);
         if (lane == 0) ntok[ci] = cnt;
+        if (sy.done) {
+            __syncwarp();
+            __threadfence();
+            if (lane == 0) {
+                const uint32_t k = atomicAdd(sy.done + (ci >> sy.done_shift), 1u) + 1u;
+                if (sy.host_done) {
+                    const uint32_t slab = ci >> sy.done_shift, first = slab << sy.done_shift;
+                    const uint32_t want = min(nchunks - first, 1u << sy.done_shift);
+                    if (k == want) { __threadfence_system(); *(volatile uint32_t*)(sy.host_done + slab) = want; }
+                }
+            }
+        }
     }
     __syncwarp();
     if (lane == 0) atomicAnd(sm_slots + sm, ~(1ull << slot));
@@ -589,7 +612,8 @@ size_t deflate_fast_tail_bytes(uint32_t nsmid) { return (size_t)nsmid * 64u * kT
 
 cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t* tokens, uint32_t tok_stride,
                               uint32_t* ntok, uint32_t* counter, uint16_t* heads, uint16_t* prevs, uint32_t* tails,
-                              unsigned long long* sm_slots, int num_sms, int chains_per_sm, int have_prev, int level, cudaStream_t stream) {
+                              unsigned long long* sm_slots, int num_sms, int chains_per_sm, int have_prev, int level, cudaStream_t stream,
+                              const StreamSync* sync, int dyn_smem) {
     if (nchunks == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
@@ -597,8 +621,9 @@ cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint3
     uint32_t grid = (uint32_t)num_sms * ctas_per_sm;
     const uint64_t need = ((uint64_t)nchunks + kFastWarps - 1u) / kFastWarps;
     if (need < grid) grid = (uint32_t)need;
-#define ZB_LAUNCH_PARSE(L) fast_parse_kernel<L><<<grid, kFastWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, \
-                                                                                     counter, heads, prevs, tails, sm_slots, have_prev)
+    const StreamSync sy = sync ? *sync : StreamSync{};
+#define ZB_LAUNCH_PARSE(L) fast_parse_kernel<L><<<grid, kFastWarps * 32, dyn_smem, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, \
+                                                                                            counter, heads, prevs, tails, sm_slots, have_prev, sy)
     switch (level) {
         case 2: ZB_LAUNCH_PARSE(2); break;
         case 3: ZB_LAUNCH_PARSE(3); break;
@@ -613,11 +638,12 @@ cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint3
 
 cudaError_t launch_block_emit(const uint8_t* in, const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n,
                               uint32_t chunk, uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
-                              int num_sms, cudaStream_t stream) {
+                              int num_sms, cudaStream_t stream, int co_carve) {
     if (nchunks == 0) return cudaSuccess;
     const int smem = (int)(sizeof(BlockWs) * kBlkWarps);
     cudaError_t e = cudaFuncSetAttribute(block_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(block_emit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co_carve);   // see launch_static_emit
     uint32_t grid = (uint32_t)num_sms * (uint32_t)((227 * 1024) / (smem + 1024));     // as many CTAs as the shared memory of an SM holds
     const uint32_t need = (nchunks + kBlkWarps - 1u) / kBlkWarps;
     if (grid > need) grid = need;

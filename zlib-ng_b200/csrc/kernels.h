@@ -7,13 +7,6 @@
 
 namespace zb {
 
-// K1: level-1 chunk deflate (deflate_quick.cu): K1a parse (one warp per chain) -> token lists, K1b
-// static-Huffman emit.  `heads` = 128 KiB hash-head slab per warp of the parse grid, `tail` =
-// deflate_quick_tail_bytes() of scratch for the padded copy of the last chunks.
-size_t deflate_quick_head_bytes(uint32_t nsmid);       // pool of nsmid x 64 slabs, handed out per SM via sm_slots[nsmid]
-cudaError_t query_nsmid(uint32_t* d_scratch, uint32_t* nsmid);
-size_t deflate_quick_tail_bytes();
-uint32_t deflate_quick_grid(uint32_t nchunks, int num_sms, int chains_per_sm);
 // Streamed input (host pipeline): `ready` = chunks delivered so far (written by the copy stream), `done[ci >> done_shift]`
 // counts parsed chunks per output slab; `patience` clocks bound every wait, `failed` is raised when one runs out.
 struct StreamSync {
@@ -24,6 +17,14 @@ struct StreamSync {
     long long patience = 0;
     uint32_t* failed = nullptr;
 };
+
+// K1: level-1 chunk deflate (deflate_quick.cu): K1a parse (one warp per chain) -> token lists, K1b
+// static-Huffman emit.  `heads` = 128 KiB hash-head slab per warp of the parse grid, `tail` =
+// deflate_quick_tail_bytes() of scratch for the padded copy of the last chunks.
+size_t deflate_quick_head_bytes(uint32_t nsmid);       // pool of nsmid x 64 slabs, handed out per SM via sm_slots[nsmid]
+cudaError_t query_nsmid(uint32_t* d_scratch, uint32_t* nsmid);
+size_t deflate_quick_tail_bytes();
+uint32_t deflate_quick_grid(uint32_t nchunks, int num_sms, int chains_per_sm);
 cudaError_t launch_wait_geq(const uint32_t* p, uint32_t v, long long patience, uint32_t* failed, cudaStream_t stream);
 cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                                uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
@@ -49,10 +50,11 @@ size_t deflate_fast_prev_bytes(uint32_t nsmid);
 size_t deflate_fast_tail_bytes(uint32_t nsmid);
 cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t* tokens, uint32_t tok_stride,
                               uint32_t* ntok, uint32_t* counter, uint16_t* heads, uint16_t* prevs, uint32_t* tails,
-                              unsigned long long* sm_slots, int num_sms, int chains_per_sm, int have_prev, int level, cudaStream_t stream);
+                              unsigned long long* sm_slots, int num_sms, int chains_per_sm, int have_prev, int level, cudaStream_t stream,
+                              const StreamSync* sync = nullptr, int dyn_smem = 0);
 cudaError_t launch_block_emit(const uint8_t* in, const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n,
                               uint32_t chunk, uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
-                              int num_sms, cudaStream_t stream);
+                              int num_sms, cudaStream_t stream, int co_carve = -1);
 
 // K3: checksums (checksum.cu)
 cudaError_t launch_checksum_tiles(const uint8_t* in, size_t n, uint32_t tile_bytes, uint32_t ntiles,
