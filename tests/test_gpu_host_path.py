@@ -116,3 +116,29 @@ def test_two_host_threads_two_contexts(pkg, zo):
     for tid in range(3):
         assert results[("crc", tid)]
         assert results[(tid, 0)] == results[(tid, 1)] == results[(tid, 2)]
+
+
+def test_streamed_and_slab_pipelines_agree(pkg, monkeypatch):
+    """The streamed path (one persistent parse kernel fed by the copy engine; default for level 1, opt-in for levels 2-6
+    with ZNG_B200_STREAMED=2) and the slab pipeline (ZNG_B200_STREAMED=0) must write the same bytes, checksums included:
+    ragged tail, Z_FINISH and flush-only endings, more than one output slab."""
+    n = (72 << 20) + 4321
+    data = pkg.synth(n, seed=55)
+    cap = n + n // 8 + (n // 65536 + 1) * 8 + 64
+    got = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("ZNG_B200_STREAMED", mode)
+        c = pkg.Context(0)                                   # the knob is read when the context is created
+        for level in (1, 2, 6):
+            for final in (True, False):
+                out = np.zeros(cap, dtype=np.uint8)
+                ol, crc, ad = c.deflate_host(data, n, 65536, level, final, out, cap)
+                got[(mode, level, final)] = (ol, crc, ad, out[:ol].copy())
+        c.close()
+    for level in (1, 2, 6):
+        for final in (True, False):
+            a, b = got[("0", level, final)], got[("2", level, final)]
+            assert a[:3] == b[:3] and np.array_equal(a[3], b[3]), (level, final)
+    stream = got[("2", 1, True)][3].tobytes()
+    assert pyzlib.decompress(stream, wbits=-15) == data.tobytes()
+    assert got[("2", 1, True)][1] == pyzlib.crc32(data.tobytes()) and got[("2", 1, True)][2] == pyzlib.adler32(data.tobytes())

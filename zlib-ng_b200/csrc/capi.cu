@@ -101,7 +101,6 @@ struct zng_b200_ctx {
     uint16_t* prevs = nullptr;                 // K2: prev[] slab pool and stale-window images, same (sm, slot) indexing
     uint32_t* vtails = nullptr;
     int chains_per_sm = 24;
-    uint32_t slot_limit = 64;                  // chains per SM over ALL concurrent K1 launches (env ZNG_B200_SLOT_LIMIT)
     int chains_per_sm_l2 = 32;                 // measured on B200: 16 -> 12.4, 24 -> 14.4, 32 -> 15.4 GB/s
     Scratch scratch;                           // for the device-resident entry points; users are ordered by k1_done
     cudaEvent_t k1_done = nullptr;
@@ -231,7 +230,7 @@ int run_deflate_chunks(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size
             continue;
         }
         CK(launch_quick_parse(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->sm_slots,
-                              grid, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream, ctx->slot_limit),
+                              grid, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream),
            "quick_parse launch");
         CK(launch_static_emit(toks, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
                               d_sizes + c0, ctx->sms, stream),
@@ -369,7 +368,6 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     if (prop.major < 10) { delete ctx; return ZNG_B200_STREAM_ERROR; }       // sm_100a kernels only
     if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm = v; }
     if (const char* e = getenv("ZNG_B200_SLAB_CHUNKS")) { int v = atoi(e); if (v >= 64 && v <= 16384) ctx->slab_chunks = (uint32_t)v; }
-    if (const char* e = getenv("ZNG_B200_SLOT_LIMIT")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->slot_limit = (uint32_t)v; }
     if (const char* e = getenv("ZNG_B200_STREAMED")) ctx->streamed = atoi(e);
     if (const char* e = getenv("ZNG_B200_PIPE")) { int v = atoi(e); if (v >= 2 && v <= kPipeMax) ctx->pipe = v; }
     if (const char* e = getenv("ZNG_B200_CHAINS_L2")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm_l2 = v; }
@@ -1179,7 +1177,6 @@ static int ensure_streamed(zng_b200_ctx* ctx, uint32_t nch) {
     if (!S.ready) {
         int least = 0, greatest = 0;
         CK(cudaDeviceGetStreamPriorityRange(&least, &greatest), "stream priorities");
-        if (getenv("ZNG_B200_NOPRIO")) least = greatest = 0;
         CK(cudaStreamCreateWithPriority(&S.copy, cudaStreamNonBlocking, greatest), "stream");
         CK(cudaStreamCreateWithPriority(&S.parse, cudaStreamNonBlocking, least), "stream");
         CK(cudaStreamCreateWithPriority(&S.d2h, cudaStreamNonBlocking, greatest), "stream");
@@ -1244,7 +1241,7 @@ static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t 
     sy.host_done = S.d_h_done;
     if (level == 1)
         CK(launch_quick_parse(S.d_in, n, chunk, nch, S.tokens, (uint32_t)tstride, S.ntok, S.d_sync + 2, ctx->heads, ctx->sm_slots,
-                              deflate_quick_grid(nch, ctx->sms, ctx->chains_per_sm), nullptr, S.parse, 64u, &sy),
+                              deflate_quick_grid(nch, ctx->sms, ctx->chains_per_sm), nullptr, S.parse, &sy),
            "quick_parse launch");
     else                                                                 // 28 chains per SM: 8 CTAs would hold every register of the SM
         CK(launch_fast_parse(S.d_in, n, chunk, nch, S.tokens, (uint32_t)tstride, S.ntok, S.d_sync + 2, ctx->heads, ctx->prevs, ctx->vtails,

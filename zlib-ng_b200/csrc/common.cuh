@@ -101,17 +101,14 @@ __device__ __forceinline__ uint32_t crc_table_entry(uint32_t i, int slice) {
 // concurrently on one pool, sized nsmid x 64 (a resident warp always finds a free bit).
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 
-// limit < 64: only the first `limit` slabs of the SM are handed out -- chains of SEVERAL kernels running at once (the host
-// pipeline's slabs) then share the per-SM budget instead of adding up; a warp that finds none free waits for one.
-__device__ __forceinline__ uint32_t slot_acquire(unsigned long long* word, uint32_t limit = 64u) {
-    const unsigned long long closed = limit >= 64u ? 0ull : ~((1ull << limit) - 1ull);
+__device__ __forceinline__ uint32_t slot_acquire(unsigned long long* word) {
     for (;;) {
-        const unsigned long long m = *(volatile unsigned long long*)word | closed;
+        const unsigned long long m = *(volatile unsigned long long*)word;
         const int b = __ffsll((long long)~m) - 1;
         if (b >= 0) {
             const unsigned long long bit = 1ull << b;
             if (!(atomicOr(word, bit) & bit)) return (uint32_t)b;
-        } else __nanosleep(500);
+        }
     }
 }
 

@@ -359,12 +359,12 @@ __global__ void __launch_bounds__(kParseWarps * 32, 12)
 quick_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint32_t nchunks,
                    uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
                    uint32_t* __restrict__ counter, uint16_t* __restrict__ heads, unsigned long long* __restrict__ sm_slots,
-                   const uint8_t* __restrict__ tail, uint32_t tail_first, uint32_t slot_limit, StreamSync sy) {
+                   const uint8_t* __restrict__ tail, uint32_t tail_first, StreamSync sy) {
     extern __shared__ uint32_t carve_out_only[];              // never touched: see launch_quick_parse (streamed launches)
     const unsigned lane = lane_id();
     const uint32_t sm = smid();
     uint32_t slot = 0;
-    if (lane == 0) slot = slot_acquire(sm_slots + sm, slot_limit);
+    if (lane == 0) slot = slot_acquire(sm_slots + sm);
     slot = __shfl_sync(ZB_FULL, slot, 0);
     uint16_t* head = heads + ((size_t)sm * 64u + slot) * 65536u;
     for (;;) {
@@ -414,18 +414,6 @@ quick_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uin
     if (lane == 0) atomicAnd(sm_slots + sm, ~(1ull << slot));
 }
 
-// stream-ordered wait on a device counter (the parse kernel's per-slab `done` count): one thread, high-priority stream
-__global__ void wait_geq_kernel(const uint32_t* p, uint32_t v, long long patience, uint32_t* failed) {
-    const long long t0 = clock64();
-    while (*(volatile const uint32_t*)p < v) {
-        __nanosleep(2000);
-        if (clock64() - t0 > patience || *(volatile uint32_t*)failed) { atomicExch(failed, 1u); break; }
-    }
-}
-cudaError_t launch_wait_geq(const uint32_t* p, uint32_t v, long long patience, uint32_t* failed, cudaStream_t stream) {
-    wait_geq_kernel<<<1, 1, 0, stream>>>(p, v, patience, failed);
-    return cudaGetLastError();
-}
 
 // Primed chunks: chunk g (global index first + ci) reads its dictionary from the 32768 bytes in front of it; g == 0 has none.
 // heads: 65536 x u32 per chain.  tail: a zero-padded private copy of [tail_first * chunk - 32768, n) for the chunks whose
@@ -505,8 +493,7 @@ uint32_t deflate_quick_grid(uint32_t nchunks, int num_sms, int chains_per_sm) {
 
 cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                                uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
-                               uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream, uint32_t slot_limit,
-                               const StreamSync* sync) {
+                               uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream, const StreamSync* sync) {
     if (grid == 0 || nchunks == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
@@ -518,8 +505,7 @@ cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint
         // preference alone is ignored below 50 %, and from 50 % on the parser loses its L1: 31 -> 23 GB/s); the kernels that
         // must run next to it ask for the same split (launch_static_emit's co_carve).  Measured: profiles/r1_e2e_pipeline.md.
         static int dyn = [] { const char* e = getenv("ZNG_B200_STREAM_DYNSMEM"); return e ? atoi(e) : 4096; }();
-        quick_parse_kernel<<<grid, kParseWarps * 32, dyn, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, in, nchunks,
-                                                                   slot_limit, *sync);
+        quick_parse_kernel<<<grid, kParseWarps * 32, dyn, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, in, nchunks, *sync);
         return cudaGetLastError();
     }
     // chunk i may read kWinPad bytes past its end: safe iff (i+1)*chunk + kWinPad <= n
@@ -529,14 +515,7 @@ cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(tail + tail_bytes, 0, 2u * kWinPad, stream);
     if (e != cudaSuccess) return e;
-    static int carve_all = [] { const char* e = getenv("ZNG_B200_CARVEOUT_ALL"); return e ? atoi(e) : -1; }();   // experiment knob
-    static int dyn_all = [] { const char* e = getenv("ZNG_B200_DYNSMEM_ALL"); return e ? atoi(e) : 1024; }();
-    if (carve_all >= 0 || dyn_all != 1024) {
-        cudaFuncSetAttribute(quick_parse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve_all);
-        quick_parse_kernel<<<grid, kParseWarps * 32, dyn_all, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, tail, tail_first, slot_limit, StreamSync{});
-        return cudaGetLastError();
-    }
-    quick_parse_kernel<<<grid, kParseWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, tail, tail_first, slot_limit, StreamSync{});
+    quick_parse_kernel<<<grid, kParseWarps * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, tail, tail_first, StreamSync{});
     return cudaGetLastError();
 }
 

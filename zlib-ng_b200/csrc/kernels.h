@@ -25,11 +25,9 @@ size_t deflate_quick_head_bytes(uint32_t nsmid);       // pool of nsmid x 64 sla
 cudaError_t query_nsmid(uint32_t* d_scratch, uint32_t* nsmid);
 size_t deflate_quick_tail_bytes();
 uint32_t deflate_quick_grid(uint32_t nchunks, int num_sms, int chains_per_sm);
-cudaError_t launch_wait_geq(const uint32_t* p, uint32_t v, long long patience, uint32_t* failed, cudaStream_t stream);
 cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                                uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
                                uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream,
-                               uint32_t slot_limit = 64u,    // < 64: concurrent launches share `slot_limit` chains per SM
                                const StreamSync* sync = nullptr);
 // K1 primed (pigz's dependent-chunk mode): every chunk but the stream's first has the 32768 bytes in front of it as its
 // preset dictionary.  heads = deflate_primed_head_bytes() pool of 256 KiB slabs (32-bit absolute positions).
