@@ -375,7 +375,7 @@ def run_b200(args):
 
             def call():
                 state["out_len"], _, _ = ctx.deflate_host(h_in, n, CHUNK, level, False, h_out, cap)
-            return call, (lambda: (n, int(state["out_len"]))), ("zng_b200_deflate_host (pinned host in/out; streamed: one persistent parse kernel fed by the copy engine in 16 MiB pieces, emit / gather / D2H per 64 MiB slab)"
+            return call, (lambda: (n, int(state["out_len"]))), ("zng_b200_deflate_host (pinned host in/out; streamed: one persistent parse kernel fed by the copy engine in 16 MiB pieces, emit / gather / D2H per 32 MiB slab)"
                                                                      if level == 1 else "zng_b200_deflate_host (pinned host in/out, 4 x 128 MiB slabs in flight on separate streams)")
         e2e_fn = make_e2e
         alg_bytes = lambda ob: n + ob                                     # in + out per chunk, x chunks per launch

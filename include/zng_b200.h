@@ -145,7 +145,7 @@ const char *zng_b200_inflate_msg(uint32_t detail);
  * stored block); otherwise every chunk ends with the Z_FULL_FLUSH marker.  *crc32 / *adler32
  * (optional) receive zng_crc32_z(0,...) / zng_adler32_z(1,...) of the whole input.  Host<->device
  * copies are pipelined with the kernels; pinned buffers (zng_b200_host_alloc) avoid staging.  Level 1 from 32 MiB on
- * is streamed: one persistent parse kernel takes the chunks as the copy engine delivers them and every finished 64 MiB
+ * is streamed: one persistent parse kernel takes the chunks as the copy engine delivers them and every finished 32 MiB
  * slab is emitted, packed and copied out next to it (environment: ZNG_B200_STREAMED=0 selects the slab pipeline that
  * levels 2-6 use, ZNG_B200_TRACE=1 prints the timeline). */
 int zng_b200_deflate_host(zng_b200_ctx *ctx, const void *h_in, size_t n, uint32_t chunk, int level, int final,

@@ -32,15 +32,14 @@ struct Scratch {
 
 // Streamed level-1 host path: ONE persistent parse kernel per call takes the chunks in order as the copy engine delivers
 // them; emit / checksum / gather / D2H run per output slab on high-priority streams as soon as the slab is parsed.
-constexpr uint32_t kStreamSlab = 1024;            // chunks per output slab (64 MiB of input)
-constexpr uint32_t kStreamSlabShift = 10;
+constexpr uint32_t kStreamMinSlab = 256;           // smallest output slab (chunks); the default is 512 = 32 MiB of input (ctx->stream_shift; measured 2^8: 27.8, 2^9: 31.95, 2^10: 31.66, 2^11: 30.96 GB/s)
 constexpr uint32_t kStreamPiece = 256;            // chunks per H2D piece (16 MiB)
 constexpr uint32_t kStreamMaxChunks = 16384;      // chunks per call of the streamed path (1 GiB); longer inputs run as several
 constexpr int kStreamOut = 4;
 struct Streamed {
     bool ready = false;
     cudaStream_t copy = nullptr, parse = nullptr, d2h = nullptr, out[kStreamOut] = {};
-    cudaEvent_t reset_done = nullptr, slab_done[kStreamMaxChunks / kStreamSlab] = {};
+    cudaEvent_t reset_done = nullptr, slab_done[kStreamMaxChunks / kStreamMinSlab] = {};
     uint8_t* d_in_alloc = nullptr; uint8_t* d_in = nullptr; uint8_t* d_slots = nullptr; uint8_t* d_packed = nullptr;
     uint32_t* tokens = nullptr; uint32_t* ntok = nullptr; uint32_t* d_meta = nullptr; uint64_t* d_offsets = nullptr;
     uint32_t* d_sync = nullptr;                   // [0] chunks delivered, [1] failed, [2] chunk counter, [4..] parsed chunks per slab
@@ -113,6 +112,7 @@ struct zng_b200_ctx {
     Slab slab[kPipeMax];
     Streamed st;
     int streamed = 1;                          // env ZNG_B200_STREAMED=0: level 1 goes through the slab pipeline as well
+    uint32_t stream_shift = 9;                 // log2(chunks per output slab) of the streamed path (env ZNG_B200_STREAM_SHIFT, 8..11)
     int pipe = 4;                              // slabs in flight (env ZNG_B200_PIPE); measured: 2048 x 4 -> 23.2 GB/s e2e, 1024 x 6 -> 20.6
     uint32_t slab_chunks = kSlabChunksDefault;
     bool slabs_ready = false;
@@ -369,6 +369,7 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm = v; }
     if (const char* e = getenv("ZNG_B200_SLAB_CHUNKS")) { int v = atoi(e); if (v >= 64 && v <= 16384) ctx->slab_chunks = (uint32_t)v; }
     if (const char* e = getenv("ZNG_B200_STREAMED")) ctx->streamed = atoi(e);
+    if (const char* e = getenv("ZNG_B200_STREAM_SHIFT")) { int v = atoi(e); if (v >= 8 && v <= 11) ctx->stream_shift = (uint32_t)v; }
     if (const char* e = getenv("ZNG_B200_PIPE")) { int v = atoi(e); if (v >= 2 && v <= kPipeMax) ctx->pipe = v; }
     if (const char* e = getenv("ZNG_B200_CHAINS_L2")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm_l2 = v; }
     if (cudaMalloc(&ctx->counters, kCounters * sizeof(uint32_t)) != cudaSuccess ||
@@ -1183,12 +1184,12 @@ static int ensure_streamed(zng_b200_ctx* ctx, uint32_t nch) {
         for (int i = 0; i < kStreamOut; i++) CK(cudaStreamCreateWithPriority(&S.out[i], cudaStreamNonBlocking, greatest), "stream");
         CK(cudaEventCreateWithFlags(&S.reset_done, cudaEventDisableTiming), "event");
         for (auto& e : S.slab_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
-        CK(cudaMalloc(&S.d_sync, 64 * sizeof(uint32_t)), "cudaMalloc(stream sync)");
-        CK(cudaMalloc(&S.d_res, 2 * (kStreamMaxChunks / kStreamSlab) * sizeof(uint32_t)), "cudaMalloc(stream res)");
+        CK(cudaMalloc(&S.d_sync, 128 * sizeof(uint32_t)), "cudaMalloc(stream sync)");
+        CK(cudaMalloc(&S.d_res, 2 * (kStreamMaxChunks / kStreamMinSlab) * sizeof(uint32_t)), "cudaMalloc(stream res)");
         CK(cudaHostAlloc(&S.h_ready, (kStreamMaxChunks / kStreamPiece + 1) * sizeof(uint32_t), cudaHostAllocDefault), "cudaHostAlloc");
-        CK(cudaHostAlloc(&S.h_meta, 2 * (kStreamMaxChunks / kStreamSlab) * sizeof(uint64_t), cudaHostAllocDefault), "cudaHostAlloc");
+        CK(cudaHostAlloc(&S.h_meta, 2 * (kStreamMaxChunks / kStreamMinSlab) * sizeof(uint64_t), cudaHostAllocDefault), "cudaHostAlloc");
         CK(cudaHostAlloc(&S.h_failed, sizeof(uint32_t), cudaHostAllocDefault), "cudaHostAlloc");
-        CK(cudaHostAlloc(&S.h_done, (kStreamMaxChunks / kStreamSlab) * sizeof(uint32_t), cudaHostAllocMapped), "cudaHostAlloc(mapped)");
+        CK(cudaHostAlloc(&S.h_done, (kStreamMaxChunks / kStreamMinSlab) * sizeof(uint32_t), cudaHostAllocMapped), "cudaHostAlloc(mapped)");
         CK(cudaHostGetDevicePointer(&S.d_h_done, S.h_done, 0), "cudaHostGetDevicePointer");
         S.ready = true;
     }
@@ -1197,7 +1198,7 @@ static int ensure_streamed(zng_b200_ctx* ctx, uint32_t nch) {
     for (void* p : {(void*)S.d_in_alloc, (void*)S.d_slots, (void*)S.d_packed, (void*)S.tokens, (void*)S.ntok, (void*)S.d_meta, (void*)S.d_offsets}) if (p) cudaFree(p);
     S.d_in_alloc = S.d_in = S.d_slots = S.d_packed = nullptr; S.tokens = S.ntok = S.d_meta = nullptr; S.d_offsets = nullptr; S.cap_chunks = 0;
     const size_t stride = zng_b200_deflate_bound(ZNG_B200_CHUNK_MAX), tstride = (ZNG_B200_CHUNK_MAX + 32u) & ~31u;
-    const size_t nslabs = (nch + kStreamSlab - 1) / kStreamSlab;
+    const size_t nslabs = (nch + kStreamMinSlab - 1) / kStreamMinSlab;
     CK(cudaMalloc(&S.d_in_alloc, (size_t)nch * ZNG_B200_CHUNK_MAX + kWSize + 4096), "cudaMalloc(stream in)");
     S.d_in = S.d_in_alloc + kWSize;                           // 32 KiB in front: the stream bytes that precede this call's first chunk (levels 2+)
     CK(cudaMemset(S.d_in + (size_t)nch * ZNG_B200_CHUNK_MAX, 0, 4096), "cudaMemset(stream pad)");
@@ -1206,7 +1207,7 @@ static int ensure_streamed(zng_b200_ctx* ctx, uint32_t nch) {
     CK(cudaMalloc(&S.tokens, (size_t)nch * tstride * sizeof(uint32_t)), "cudaMalloc(stream tokens)");
     CK(cudaMalloc(&S.ntok, (size_t)nch * sizeof(uint32_t)), "cudaMalloc(stream ntok)");
     CK(cudaMalloc(&S.d_meta, (size_t)nch * 3 * sizeof(uint32_t)), "cudaMalloc(stream meta)");
-    CK(cudaMalloc(&S.d_offsets, nslabs * (kStreamSlab + 1) * sizeof(uint64_t)), "cudaMalloc(stream offsets)");
+    CK(cudaMalloc(&S.d_offsets, ((size_t)nch + nslabs + 1) * sizeof(uint64_t)), "cudaMalloc(stream offsets)");
     S.cap_chunks = nch;
     return 0;
 }
@@ -1216,6 +1217,7 @@ static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t 
                                  size_t& out_pos, uint32_t& crc, uint32_t& adler, int level, int have_prev) {
     const uint32_t chunk = ZNG_B200_CHUNK_MAX;
     const uint32_t nch = (uint32_t)((n + chunk - 1) / chunk);
+    const uint32_t kStreamSlabShift = ctx->stream_shift, kStreamSlab = 1u << kStreamSlabShift;
     const uint32_t nslabs = (nch + kStreamSlab - 1) / kStreamSlab, npieces = (nch + kStreamPiece - 1) / kStreamPiece;
     int r = ensure_heads(ctx);
     if (r) return r;
@@ -1231,7 +1233,7 @@ static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t 
     static const bool trace = getenv("ZNG_B200_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;
     auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
-    CK(cudaMemsetAsync(S.d_sync, 0, 64 * sizeof(uint32_t), S.parse), "memset sync");
+    CK(cudaMemsetAsync(S.d_sync, 0, 128 * sizeof(uint32_t), S.parse), "memset sync");
     mark(S.parse);                                                       // [0] start
     CK(cudaEventRecord(S.reset_done, S.parse), "event");
     CK(cudaStreamWaitEvent(S.copy, S.reset_done, 0), "wait");
