@@ -276,6 +276,45 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ B200 arm
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Multi-rank runs: keep this rank's threads (and so its pinned host buffers, by first touch) on the NUMA node its GPU
+    hangs off -- what a pigz-style tool would do with numactl.  Best effort: any missing piece of /sys leaves things as
+    they are.  Returns the node or None."""
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        if hasattr(props, "pci_bus_id"):
+            path = f"/sys/bus/pci/devices/{getattr(props, 'pci_domain_id', 0):04x}:{props.pci_bus_id:02x}:{getattr(props, 'pci_device_id', 0):02x}.0/numa_node"
+        else:
+            import pynvml
+            pynvml.nvmlInit()
+            want = str(getattr(props, "uuid", ""))
+            path = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                u = pynvml.nvmlDeviceGetUUID(h)
+                u = u.decode() if isinstance(u, bytes) else u
+                if want and want in u:
+                    b = pynvml.nvmlDeviceGetPciInfo(h).busId
+                    b = b.decode() if isinstance(b, bytes) else b
+                    path = f"/sys/bus/pci/devices/{b[-12:].lower()}/numa_node"
+            if path is None:
+                return None
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -290,6 +329,7 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -553,7 +593,7 @@ def run_b200(args):
                    "sharding": f"contiguous chunk ranges x{ngpu}",
                    "collective": ("nccl allgather of (size, crc32) per chunk" if wl.startswith("deflate") else ("nccl allgather of (crc32, adler32) per rank" if wl == "checksum" else "none")) if ngpu > 1 else "none",
                    "l2": f"input {args.mib_per_gpu} MiB per step >> 126 MB L2, no flush needed"},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["n"], "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["n"], "clocks": clocks, "numa_node": numa,
         "compression_ratio": (out_bytes / n) if wl != "checksum" else None, "parity": parity,
         "pct_hbm_peak_input_only": 100.0 * (value / ngpu) / peak,
     }
