@@ -142,3 +142,17 @@ def test_streamed_and_slab_pipelines_agree(pkg, monkeypatch):
     stream = got[("2", 1, True)][3].tobytes()
     assert pyzlib.decompress(stream, wbits=-15) == data.tobytes()
     assert got[("2", 1, True)][1] == pyzlib.crc32(data.tobytes()) and got[("2", 1, True)][2] == pyzlib.adler32(data.tobytes())
+
+
+def test_streamed_path_output_too_small_then_recovers(pkg, ctx, zo):
+    """Z_BUF_ERROR from the streamed path (the output runs out in the middle of the drain) must leave the context usable."""
+    n = (40 << 20) + 777
+    data = pkg.synth(n, seed=8)
+    small = np.zeros(n // 4, dtype=np.uint8)
+    with pytest.raises(pkg.ZngB200Error) as ei:
+        ctx.deflate_host(data, n, 65536, 1, True, small, small.size)
+    assert ei.value.code == pkg.Z_BUF_ERROR
+    cap = pkg.deflate_bound(65536) * ((n + 65535) // 65536 + 1)
+    out = np.zeros(cap, dtype=np.uint8)
+    ol, crc, ad = ctx.deflate_host(data, n, 65536, 1, True, out, cap)
+    assert pyzlib.decompress(out[:ol].tobytes(), wbits=-15) == data.tobytes() and crc == pyzlib.crc32(data.tobytes())
