@@ -112,7 +112,7 @@ def deflate_digests():
 
     def add(name, data, chunk, level, flush):
         data = np.ascontiguousarray(data, dtype=np.uint8)
-        out, sizes, crcs, adlers = zo.ref_deflate_chunks(data, chunk, level, flush)
+        out, sizes, crcs, adlers = zo.ref_deflate_chunks(data, chunk, level, flush, nthreads=1)   # stream order: see SURVEY 0.6
         comp_crc = [int(_pyzlib.crc32(out[i, : sizes[i]].tobytes())) for i in range(len(sizes))]
         cases.append({"name": name, "chunk": chunk, "level": level, "flush": flush, "n": int(data.size),
                       "sizes": [int(x) for x in sizes], "comp_crc32": comp_crc,
