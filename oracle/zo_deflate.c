@@ -664,6 +664,216 @@ static size_t deflate_one_primed(const uint8_t *in, uint32_t len, int flush, uin
     return b.ovf ? (size_t)-1 : b.n;
 }
 
+/* ------------------------------------------------------------------ window engine: levels 2-6 with a REAL window
+ * The restatements above keep positions in chunk coordinates and model the one tail slide of a <= 64 KiB chunk.  A primed
+ * chunk (32 KiB dictionary + up to 64 KiB) slides twice and refills in between, and at levels 2-6 the slides are visible
+ * (prev[] is indexed modulo 32768, head/prev values are cut to 0, deflate_medium drops its next_match at every refill).  So
+ * this engine keeps the reference's own state -- window[], head[], prev[], strstart, lookahead, block_start, insert,
+ * high_water -- and restates fill_window (deflate.c:1272-1376), slide_hash (arch/generic/slide_hash_c.c:15-52),
+ * deflateSetDictionary (deflate.c:456-512), deflate_fast (deflate_fast.c:19-104) and deflate_medium
+ * (deflate_medium.c:22-278) on it.  It is also a second, independent restatement of the un-primed levels 2-6
+ * (tests/test_oracle_primed.py compares the two). */
+typedef struct {
+    uint8_t  win[ZO_CHUNK_MAX + 512];
+    uint16_t head[65536], prev[ZO_WSIZE];
+    uint32_t strstart, lookahead, insert, high_water, match_start;
+    int32_t  block_start;
+    const uint8_t *next_in; uint32_t avail_in;
+    int level;
+} wstate;
+
+static inline uint32_t w_hash(const wstate *s, uint32_t pos) {
+    uint32_t v = (uint32_t)s->win[pos] | ((uint32_t)s->win[pos + 1] << 8) | ((uint32_t)s->win[pos + 2] << 16) | ((uint32_t)s->win[pos + 3] << 24);
+    return (v * 2654435761u) >> 16;
+}
+static inline uint32_t w_insert(wstate *s, uint32_t pos) {                 /* insert_string_tpl.h:58-75 */
+    uint32_t h = w_hash(s, pos), old = s->head[h];
+    if (old != (uint16_t)pos) { s->prev[pos & (ZO_WSIZE - 1)] = (uint16_t)old; s->head[h] = (uint16_t)pos; }
+    return old;
+}
+static void w_fill(wstate *s) {                                             /* fill_window */
+    do {
+        uint32_t more = ZO_CHUNK_MAX - s->lookahead - s->strstart;
+        if (s->strstart >= ZO_SLIDE_AT) {
+            memcpy(s->win, s->win + ZO_WSIZE, ZO_WSIZE);
+            if (s->match_start >= ZO_WSIZE) s->match_start -= ZO_WSIZE; else s->match_start = 0;
+            s->strstart -= ZO_WSIZE;
+            s->block_start -= (int32_t)ZO_WSIZE;
+            if (s->insert > s->strstart) s->insert = s->strstart;
+            for (uint32_t i = 0; i < 65536; i++) s->head[i] = (uint16_t)(s->head[i] >= ZO_WSIZE ? s->head[i] - ZO_WSIZE : 0);
+            for (uint32_t i = 0; i < ZO_WSIZE; i++) s->prev[i] = (uint16_t)(s->prev[i] >= ZO_WSIZE ? s->prev[i] - ZO_WSIZE : 0);
+            more += ZO_WSIZE;
+        }
+        if (s->avail_in == 0) break;
+        uint32_t n = s->avail_in < more ? s->avail_in : more;
+        memcpy(s->win + s->strstart + s->lookahead, s->next_in, n);
+        s->next_in += n; s->avail_in -= n; s->lookahead += n;
+        if (s->lookahead + s->insert >= 3) {                                /* deflate.c:1321-1336 */
+            uint32_t str = s->strstart - s->insert;
+            if (str >= 1) w_insert(s, str - 1);
+            uint32_t count = s->insert;
+            if (s->lookahead == 1) count--;
+            for (uint32_t k = 0; k < count; k++) w_insert(s, str + k);
+            s->insert -= count;
+        }
+    } while (s->lookahead < 262 && s->avail_in != 0);
+    if (s->high_water < ZO_CHUNK_MAX) {                                     /* deflate.c:1345-1372 */
+        uint32_t curr = s->strstart + s->lookahead, init;
+        if (s->high_water < curr) {
+            init = ZO_CHUNK_MAX - curr; if (init > 258) init = 258;
+            memset(s->win + curr, 0, init); s->high_water = curr + init;
+        } else if (s->high_water < curr + 258) {
+            init = curr + 258 - s->high_water;
+            if (init > ZO_CHUNK_MAX - s->high_water) init = ZO_CHUNK_MAX - s->high_water;
+            memset(s->win + s->high_water, 0, init); s->high_water += init;
+        }
+    }
+}
+static uint32_t w_longest_match(wstate *s, uint32_t cand) {                 /* match_tpl.h:26-280, non-SLOW, prev_length 0 */
+    static const uint16_t nice_[7] = {0, 0, 8, 16, 32, 32, 128}, chain_[7] = {0, 0, 4, 6, 24, 32, 128};
+    const uint32_t pos = s->strstart, nice = nice_[s->level];
+    uint32_t best = 2, chain = chain_[s->level];
+    const uint32_t limit = pos > ZO_MAX_DIST ? pos - ZO_MAX_DIST : 0;
+    for (;;) {
+        if (cand >= pos) break;
+        uint32_t w = best < 4 ? 2 : (best < 8 ? 4 : 8), off = best + 1 - w;
+        if (memcmp(s->win + cand, s->win + pos, w) == 0 && memcmp(s->win + cand + off, s->win + pos + off, w) == 0) {
+            uint32_t len = 2;
+            while (len < 258 && s->win[pos + len] == s->win[cand + len]) len++;
+            if (len > best) {
+                s->match_start = cand;
+                if (len > s->lookahead) return s->lookahead;
+                best = len;
+                if (best >= nice) return best;
+            } else if (s->level < 5) break;
+        }
+        if (--chain == 0) break;
+        cand = s->prev[cand & (ZO_WSIZE - 1)];
+        if (cand <= limit) break;
+    }
+    return best;
+}
+typedef struct { wstate *s; blockstate *bs; bitw *b; tok_sink sink; void *ctx; } wenv;
+static void w_flush(wenv *e, int last) {                                   /* FLUSH_BLOCK_ONLY, deflate_p.h:104-112 */
+    wstate *s = e->s;
+    flush_block(e->bs, e->b, s->block_start >= 0 ? s->win + s->block_start : NULL, (uint32_t)((int32_t)s->strstart - s->block_start), last);
+    s->block_start = (int32_t)s->strstart;
+}
+static void w_deflate_fast(wenv *e, int last) {
+    wstate *s = e->s; blockstate *bs = e->bs;
+    uint32_t match_len = 0;
+    for (;;) {
+        if (s->lookahead < 262) { w_fill(s); if (s->lookahead == 0) break; }
+        if (s->lookahead >= ZO_WANT_MIN) {
+            uint32_t hh = w_insert(s, s->strstart);
+            int64_t dist = (int64_t)s->strstart - hh;
+            if (dist <= (int64_t)ZO_MAX_DIST && dist > 0 && hh != 0) match_len = w_longest_match(s, hh);
+        }
+        if (match_len >= ZO_WANT_MIN) {
+            tally_match(bs, s->strstart - s->match_start, match_len, e->sink, e->ctx);
+            s->lookahead -= match_len;
+            if (match_len <= 4 && s->lookahead >= ZO_WANT_MIN) {
+                match_len--; s->strstart++;
+                for (uint32_t k = 0; k < match_len; k++) w_insert(s, s->strstart + k);
+                s->strstart += match_len;
+            } else { s->strstart += match_len; w_insert(s, s->strstart - 1); }
+            match_len = 0;
+        } else { tally_lit(bs, s->win[s->strstart], e->sink, e->ctx); s->lookahead--; s->strstart++; }
+        if (bs->sym_next == ZO_SYM_END) w_flush(e, 0);
+    }
+    if (last) w_flush(e, 1); else if (bs->sym_next) w_flush(e, 0);
+}
+static void w_find(wstate *s, uint32_t cand, mmatch *m) {                   /* deflate_medium.c:191-215 / :243-262 */
+    int64_t dist = (int64_t)s->strstart - cand;
+    m->at = m->org = s->strstart;
+    if (dist <= (int64_t)ZO_MAX_DIST && dist > 0 && cand != 0) {
+        m->len = w_longest_match(s, cand); m->from = s->match_start;
+        if (m->len < ZO_WANT_MIN || m->from >= m->at) m->len = 1;
+    } else { m->from = 0; m->len = 1; }
+}
+static void w_insert_match(wstate *s, mmatch m) {                           /* :44-82 */
+    if (s->lookahead <= m.len + ZO_WANT_MIN) return;
+    m.at++; m.len--;
+    if (m.len < ZO_WANT_MIN - 1) {
+        if (m.len > 0 && m.at >= m.org) {
+            uint32_t cnt = (m.at + m.len - 1 >= m.org) ? m.len : m.org - m.at + 1;
+            for (uint32_t k = 0; k < cnt; k++) w_insert(s, m.at + k);
+        }
+        return;
+    }
+    if (m.at >= m.org) {
+        uint32_t cnt = (m.at + m.len - 1 >= m.org) ? m.len : m.org - m.at + 1;
+        for (uint32_t k = 0; k < cnt; k++) w_insert(s, m.at + k);
+    } else if (m.org < m.at + m.len) {
+        for (uint32_t q = m.org; q < m.at + m.len; q++) w_insert(s, q);
+    }
+}
+static void w_fizzle(const wstate *s, mmatch *cur, mmatch *nxt) {           /* :84-144 */
+    if (cur->len <= 1) return;
+    if (cur->len > 1 + nxt->from || cur->len > 1 + nxt->at) return;
+    if (s->win[nxt->from + 1 - cur->len] != s->win[nxt->at + 1 - cur->len]) return;
+    mmatch c = *cur, n = *nxt;
+    uint32_t limit = nxt->at > ZO_MAX_DIST ? nxt->at - ZO_MAX_DIST : 0;
+    int moved = 0;
+    while (s->win[n.from - 1] == s->win[n.at - 1]) {
+        if (c.len < 1 || n.at <= limit || n.len >= 256 || n.from <= 1) break;
+        n.at--; n.from--; n.len++; c.len--; moved++;
+    }
+    if (!moved) return;
+    if (c.len <= 1 && n.len != 2) { n.org++; *cur = c; *nxt = n; }
+}
+static void w_deflate_medium(wenv *e, int last) {
+    wstate *s = e->s; blockstate *bs = e->bs;
+    const int greedy = s->level < 5;
+    mmatch cur = {0, 0, 0, 0}, nxt = {0, 0, 0, 0};
+    for (;;) {
+        if (s->lookahead < 262) { w_fill(s); if (s->lookahead == 0) break; nxt.len = 0; }
+        if (!greedy && nxt.len > 0) { cur = nxt; nxt.len = 0; }
+        else w_find(s, s->lookahead >= ZO_WANT_MIN ? w_insert(s, s->strstart) : 0, &cur);
+        w_insert_match(s, cur);
+        if (!greedy && s->lookahead > 262 && cur.at + cur.len < ZO_CHUNK_MAX - 262) {
+            s->strstart = cur.at + cur.len;
+            w_find(s, w_insert(s, s->strstart), &nxt);
+            if (nxt.len >= ZO_WANT_MIN) w_fizzle(s, &cur, &nxt);
+            s->strstart = cur.at;
+        } else nxt.len = 0;
+        if (cur.len < ZO_WANT_MIN) { for (uint32_t k = 0; k < cur.len; k++) { tally_lit(bs, s->win[cur.at + k], e->sink, e->ctx); s->lookahead--; } }
+        else { tally_match(bs, cur.at - cur.from, cur.len, e->sink, e->ctx); s->lookahead -= cur.len; }
+        s->strstart += cur.len;
+        if (bs->sym_next == ZO_SYM_END) w_flush(e, 0);
+    }
+    if (last) w_flush(e, 1); else if (bs->sym_next) w_flush(e, 0);
+}
+/* one chunk on a fresh stream, optionally primed with `dict` (32768 bytes); levels 2-6 */
+static size_t window_deflate_one(const uint8_t *dict, const uint8_t *in, uint32_t len, int level, int flush, uint8_t *out, size_t cap) {
+    pthread_once(&tbl_once, build_static_tables);
+    if (level < 2 || level > 6 || len > ZO_CHUNK_MAX) return (size_t)-1;
+    wstate *s = (wstate *)calloc(1, sizeof(wstate));
+    blockstate *bs = (blockstate *)malloc(sizeof(blockstate));
+    if (!s || !bs) { free(s); free(bs); return (size_t)-1; }
+    s->level = level;
+    if (dict) {                                                             /* deflateSetDictionary, dictLength == w_size */
+        s->next_in = dict; s->avail_in = ZO_WSIZE;
+        w_fill(s);
+        while (s->lookahead >= 3) {
+            uint32_t str = s->strstart, n = s->lookahead - 2;
+            for (uint32_t k = 0; k < n; k++) w_insert(s, str + k);
+            s->strstart = str + n; s->lookahead = 2;
+            w_fill(s);
+        }
+        s->strstart += s->lookahead; s->block_start = (int32_t)s->strstart; s->insert = s->lookahead; s->lookahead = 0;
+    }
+    s->next_in = in; s->avail_in = len;
+    int last = (flush == ZO_FINISH);
+    bitw b = {out, cap, 0, 0, 0, 0};
+    block_init(bs);
+    wenv e = {s, bs, &b, NULL, NULL};
+    if (level == 2) w_deflate_fast(&e, last); else w_deflate_medium(&e, last);
+    if (!last) { bw_put(&b, 0, 3); bw_align(&b); bw_put(&b, 0x0000, 16); bw_put(&b, 0xffff, 16); }
+    free(s); free(bs);
+    return b.ovf ? (size_t)-1 : b.n;
+}
+
 /* ------------------------------------------------------------------ public */
 size_t zo_deflate_bound(size_t n) { return n + (n >> 3) + 64; }
 
@@ -761,7 +971,9 @@ static void *zworker(void *arg) {
         uint32_t len = (uint32_t)((j->n - off < j->chunk) ? (j->n - off) : j->chunk);
         /* a short chunk that follows a full one sees the previous chunk's stale upper half */
         const uint8_t *stale = (len < ZO_CHUNK_MAX && u > 0 && j->chunk == ZO_CHUNK_MAX) ? j->in + off - ZO_WSIZE : NULL;
-        size_t r = (j->primed && u > 0) ? deflate_one_primed(j->in + off, len, j->flush, j->out + u * j->out_stride, j->out_stride)
+        size_t r = (j->primed == 2) ? window_deflate_one(NULL, j->in + off, len, j->level, j->flush, j->out + u * j->out_stride, j->out_stride)
+                 : (j->primed && j->level >= 2) ? window_deflate_one(u > 0 ? j->in + off - ZO_WSIZE : NULL, j->in + off, len, j->level, j->flush, j->out + u * j->out_stride, j->out_stride)
+                 : (j->primed && u > 0) ? deflate_one_primed(j->in + off, len, j->flush, j->out + u * j->out_stride, j->out_stride)
                                         : deflate_one(d, j->in + off, len, j->level, j->flush, j->primed ? NULL : stale, j->out + u * j->out_stride, j->out_stride);
         if (r == (size_t)-1) { atomic_store(&j->err, 2); r = 0; }
         j->sizes[u] = (uint32_t)r;
@@ -784,12 +996,21 @@ int zo_deflate_chunks(const uint8_t *in, size_t n, uint32_t chunk, int level, in
 }
 
 /* pigz's dependent mode: chunk u > 0 is compressed by a fresh stream primed (deflateSetDictionary) with the 32768 stream
- * bytes in front of it.  Level 1, chunk = 65536 (every dictionary is then a full window). */
+ * bytes in front of it.  Levels 1-6 (2-6 through the window engine), chunk = 65536 (every dictionary is then a full window). */
 int zo_deflate_chunks_primed(const uint8_t *in, size_t n, uint32_t chunk, int level, int flush,
                              uint8_t *out, size_t out_stride, uint32_t *sizes,
                              uint32_t *crcs, uint32_t *adlers, int nthreads) {
-    if (chunk != ZO_CHUNK_MAX || level != 1) return -2;
+    if (chunk != ZO_CHUNK_MAX || level < 1 || level > 6) return -2;
     zjob j = {in, n, chunk, level, flush, out, out_stride, sizes, crcs, adlers, (n + chunk - 1) / chunk, 0, 0, 1};
+    return run_zjob(&j, nthreads);
+}
+
+/* levels 2-6, every chunk on a FRESH stream, through the window engine (the second restatement; cross-check only) */
+int zo_deflate_chunks_fresh_window(const uint8_t *in, size_t n, uint32_t chunk, int level, int flush,
+                                   uint8_t *out, size_t out_stride, uint32_t *sizes,
+                                   uint32_t *crcs, uint32_t *adlers, int nthreads) {
+    if (chunk == 0 || chunk > ZO_CHUNK_MAX || level < 2 || level > 6) return -2;
+    zjob j = {in, n, chunk, level, flush, out, out_stride, sizes, crcs, adlers, (n + chunk - 1) / chunk, 0, 0, 2};
     return run_zjob(&j, nthreads);
 }
 

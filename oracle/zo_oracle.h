@@ -62,10 +62,16 @@ int zo_deflate_chunks(const uint8_t *in, size_t n, uint32_t chunk, int level, in
 /* Token trace of the LZ77 parse for debugging mismatches: tokens[i] = literal byte, or
  * (1u<<31) | (len << 16) | dist.  Returns token count (cap = capacity of tokens). */
 /* pigz's dependent mode: every chunk after the first is compressed by a FRESH stream primed with
- * zng_deflateSetDictionary(the 32768 stream bytes in front of it) (deflate.c:456-512).  Level 1, chunk 65536. */
+ * zng_deflateSetDictionary(the 32768 stream bytes in front of it) (deflate.c:456-512).  Levels 1-6, chunk 65536. */
 int zo_deflate_chunks_primed(const uint8_t *in, size_t n, uint32_t chunk, int level, int flush,
                              uint8_t *out, size_t out_stride, uint32_t *sizes,
                              uint32_t *crcs, uint32_t *adlers, int nthreads);
+
+/* levels 2-6, every chunk on a fresh stream, through the window engine of zo_deflate.c (a second restatement that keeps the
+ * reference's own window / head / prev state; used to cross-check the chunk-coordinate restatement) */
+int zo_deflate_chunks_fresh_window(const uint8_t *in, size_t n, uint32_t chunk, int level, int flush,
+                                   uint8_t *out, size_t out_stride, uint32_t *sizes,
+                                   uint32_t *crcs, uint32_t *adlers, int nthreads);
 
 size_t zo_deflate_tokens(const uint8_t *in, uint32_t len, int level, uint32_t *tokens, size_t cap);
 

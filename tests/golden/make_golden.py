@@ -143,9 +143,12 @@ def primed_digests():
                            (66, 2 * 65536 + 263, 4), (67, 65536 + 32768, 2), (68, 65536 + 32769, 2), (69, 65536 + 65274, 4), (70, 65536 + 65275, 2),
                            (71, 65536 + 65535, 2), (72, 65536 + 3, 2), (73, 4097, 4)):
         data = pkg.synth(n, seed=seed)
-        out, sizes, _, _ = zo.ref_deflate_chunks_primed(data, 65536, 1, flush)
-        cases.append({"seed": seed, "n": n, "flush": flush, "sizes": [int(x) for x in sizes],
-                      "comp_crc32": [int(_pyzlib.crc32(out[i, : sizes[i]].tobytes())) for i in range(len(sizes))]})
+        for level in (1, 2, 3, 4, 5, 6):
+            if level > 1 and n > 9 * 65536:
+                continue
+            out, sizes, _, _ = zo.ref_deflate_chunks_primed(data, 65536, level, flush)
+            cases.append({"seed": seed, "n": n, "flush": flush, "level": level, "sizes": [int(x) for x in sizes],
+                          "comp_crc32": [int(_pyzlib.crc32(out[i, : sizes[i]].tobytes())) for i in range(len(sizes))]})
     return cases
 
 
@@ -162,7 +165,7 @@ def main():
     json.dump({"source": "oracle/_ref (unmodified zlib-ng 2.2.2) via refdrv_deflate_chunks; inputs from zlib-ng_b200/host/synth.c",
                "cases": dd}, open(f"{HERE}/deflate_digests.json", "w"))
     pd = primed_digests()
-    json.dump({"source": "oracle/_ref (unmodified zlib-ng 2.2.2) via refdrv_deflate_chunks_primed, level 1; inputs pkg.synth(n, seed)",
+    json.dump({"source": "oracle/_ref (unmodified zlib-ng 2.2.2) via refdrv_deflate_chunks_primed, levels 1-6; inputs pkg.synth(n, seed)",
                "cases": pd}, open(f"{HERE}/primed_digests.json", "w"))
     print(f"primed digest cases {len(pd)}")
     print(f"crc32 KATs {len(crc)}, adler32 KATs {len(adl)}, infcover vectors {len(inf)}, deflate digest cases {len(dd)}")

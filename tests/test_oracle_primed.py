@@ -1,4 +1,4 @@
-"""The oracle's primed level-1 restatement (pigz's dependent-chunk mode) against the committed digests of the
+"""The oracle's primed restatements (level 1: quick_parse_primed; levels 2-6: the window engine) (pigz's dependent-chunk mode) against the committed digests of the
 unmodified reference (tests/golden/primed_digests.json, written by tests/golden/make_golden.py) and, live, against
 oracle/_ref: fresh zng_deflateInit2 + zng_deflateSetDictionary(32768 bytes in front of the chunk) + one zng_deflate(flush)."""
 import zlib as pyzlib
@@ -12,7 +12,7 @@ def test_port_primed_matches_golden_digests(pkg, zo, golden):
     assert len(cases) >= 10
     for c in cases:
         data = pkg.synth(c["n"], seed=c["seed"])
-        out, sizes, _, _ = zo.port_deflate_chunks_primed(data, 65536, 1, c["flush"])
+        out, sizes, _, _ = zo.port_deflate_chunks_primed(data, 65536, c.get("level", 1), c["flush"])
         assert [int(x) for x in sizes] == c["sizes"], c
         assert [int(pyzlib.crc32(out[i, : sizes[i]].tobytes())) for i in range(len(sizes))] == c["comp_crc32"], c
 
@@ -25,12 +25,29 @@ def test_port_primed_matches_reference_live(pkg, zo):
               np.tile(np.arange(251, dtype=np.uint8), 1100)[:4 * 65536]]
     inputs += [pkg.synth(2 * 65536 + t, seed=t) for t in (1, 2, 3, 4, 261, 262, 263, 32768, 32769, 65274, 65275, 65535)]
     for d in inputs:
-        for flush in (2, 3, 4):
-            a = zo.port_deflate_chunks_primed(d, 65536, 1, flush)
-            b = zo.ref_deflate_chunks_primed(d, 65536, 1, flush)
-            assert np.array_equal(a[1], b[1])
-            assert all(np.array_equal(a[0][i, : a[1][i]], b[0][i, : b[1][i]]) for i in range(len(a[1])))
+        for level in (1, 2, 3, 4, 5, 6):
+            for flush in ((2, 3, 4) if level == 1 else (2, 4)):
+                a = zo.port_deflate_chunks_primed(d, 65536, level, flush)
+                b = zo.ref_deflate_chunks_primed(d, 65536, level, flush)
+                assert np.array_equal(a[1], b[1]), (level, flush)
+                assert all(np.array_equal(a[0][i, : a[1][i]], b[0][i, : b[1][i]]) for i in range(len(a[1]))), (level, flush)
         st = b"".join(a[0][i, : a[1][i]].tobytes() for i in range(len(a[1])))     # flush 4: every chunk ends its own stream
     out, sizes, _, _ = zo.port_deflate_chunks_primed(inputs[0], 65536, 1, 2)
     stream = b"".join(out[i, : sizes[i]].tobytes() for i in range(len(sizes))) + b"\x03\x00"
     assert pyzlib.decompress(stream, wbits=-15) == inputs[0].tobytes()
+
+
+def test_window_engine_agrees_with_the_chunk_coordinate_restatement(pkg, zo):
+    """Levels 2-6 have two independent restatements in the oracle: chunk coordinates with a modelled tail slide
+    (fast_parse / medium_parse) and the window engine that keeps the reference's own window / head / prev state.
+    On fresh streams they must agree byte for byte (and both are pinned to the reference elsewhere)."""
+    rng = np.random.default_rng(9)
+    words = rng.integers(97, 123, size=(64, 6), dtype=np.uint8)
+    inputs = [pkg.synth(6 * 65536, seed=14), rng.integers(0, 4, size=2 * 65536, dtype=np.uint8), words[rng.integers(0, 64, size=30000)].reshape(-1)[:2 * 65536],
+              pkg.synth(65536, seed=2)[:65300], pkg.synth(65536, seed=3)[:65275], pkg.synth(65536, seed=4)[:300], np.zeros(65536, dtype=np.uint8)]
+    for d in inputs:
+        for level in (2, 3, 4, 5, 6):
+            a = zo.port_deflate_chunks_fresh_window(d, 65536, level, 4)
+            for i in range(len(a[1])):
+                b = zo.port_deflate_chunks(d[i * 65536:(i + 1) * 65536], 65536, level, 4, nthreads=1)
+                assert a[1][i] == b[1][0] and np.array_equal(a[0][i, : a[1][i]], b[0][0, : b[1][0]]), (level, i)

@@ -44,6 +44,8 @@ def port():
         L.zo_deflate_chunks.argtypes = [c_void_p, c_size_t, c_uint32, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int]
         L.zo_deflate_chunks_primed.restype = c_int
         L.zo_deflate_chunks_primed.argtypes = L.zo_deflate_chunks.argtypes
+        L.zo_deflate_chunks_fresh_window.restype = c_int
+        L.zo_deflate_chunks_fresh_window.argtypes = L.zo_deflate_chunks.argtypes
         L.zo_deflate_tokens.restype = c_size_t; L.zo_deflate_tokens.argtypes = [c_void_p, c_uint32, c_int, c_void_p, c_size_t]
         L.zo_longest_match_l2.restype = c_uint32
         L.zo_longest_match_l2.argtypes = [c_void_p, c_uint32, c_uint32, c_void_p, c_uint32, c_uint32, POINTER(c_uint32)]
@@ -145,6 +147,12 @@ def port_deflate_chunks_primed(data, chunk=65536, level=1, flush=2, stride=None,
     """pigz's dependent mode: chunk u > 0 primed with the 32768 stream bytes in front of it (fresh stream + deflateSetDictionary)."""
     stride = stride or int(port().zo_deflate_bound(chunk))
     return _deflate_chunks(port().zo_deflate_chunks_primed, data, chunk, level, flush, stride, nthreads or min(os.cpu_count() or 1, 32))
+
+
+def port_deflate_chunks_fresh_window(data, chunk=65536, level=2, flush=4, stride=None, nthreads=None):
+    """Levels 2-6, every chunk on a fresh stream, through the oracle's window engine (second restatement)."""
+    stride = stride or int(port().zo_deflate_bound(chunk))
+    return _deflate_chunks(port().zo_deflate_chunks_fresh_window, data, chunk, level, flush, stride, nthreads or min(os.cpu_count() or 1, 32))
 
 
 def ref_deflate_chunks_primed(data, chunk=65536, level=1, flush=2, stride=None, nthreads=None):
