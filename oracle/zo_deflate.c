@@ -844,8 +844,9 @@ static void w_deflate_medium(wenv *e, int last) {
     }
     if (last) w_flush(e, 1); else if (bs->sym_next) w_flush(e, 0);
 }
-/* one chunk on a fresh stream, optionally primed with `dict` (32768 bytes); levels 2-6 */
-static size_t window_deflate_one(const uint8_t *dict, const uint8_t *in, uint32_t len, int level, int flush, uint8_t *out, size_t cap) {
+/* one chunk on a fresh stream, optionally primed with `dict` (32768 bytes); levels 2-6.  sink: the LZ77 tokens as they are tallied */
+static size_t window_deflate_one_sink(const uint8_t *dict, const uint8_t *in, uint32_t len, int level, int flush, uint8_t *out, size_t cap,
+                                      tok_sink sink, void *ctx) {
     pthread_once(&tbl_once, build_static_tables);
     if (level < 2 || level > 6 || len > ZO_CHUNK_MAX) return (size_t)-1;
     wstate *s = (wstate *)calloc(1, sizeof(wstate));
@@ -867,11 +868,15 @@ static size_t window_deflate_one(const uint8_t *dict, const uint8_t *in, uint32_
     int last = (flush == ZO_FINISH);
     bitw b = {out, cap, 0, 0, 0, 0};
     block_init(bs);
-    wenv e = {s, bs, &b, NULL, NULL};
+    wenv e = {s, bs, &b, sink, ctx};
     if (level == 2) w_deflate_fast(&e, last); else w_deflate_medium(&e, last);
     if (!last) { bw_put(&b, 0, 3); bw_align(&b); bw_put(&b, 0x0000, 16); bw_put(&b, 0xffff, 16); }
     free(s); free(bs);
     return b.ovf ? (size_t)-1 : b.n;
+}
+
+static size_t window_deflate_one(const uint8_t *dict, const uint8_t *in, uint32_t len, int level, int flush, uint8_t *out, size_t cap) {
+    return window_deflate_one_sink(dict, in, len, level, flush, out, cap, NULL, NULL);
 }
 
 /* ------------------------------------------------------------------ public */
@@ -924,6 +929,28 @@ size_t zo_deflate_tokens(const uint8_t *in, uint32_t len, int level, uint32_t *t
     else if (level == 2) fast_parse(d, NULL, 0, tok_push, &tb);
     else medium_parse(d, NULL, 0, tok_push, &tb, level);
     free(d);
+    return tb.n;
+}
+
+/* the LZ77 tokens of a PRIMED chunk (in[-32768 .. 0) is its dictionary): level 1 through quick_parse_primed, levels 2-6
+ * through the window engine -- the trace a kernel under construction is diffed against */
+size_t zo_deflate_tokens_primed(const uint8_t *in, uint32_t len, int level, uint32_t *tokens, size_t cap) {
+    pthread_once(&tbl_once, build_static_tables);
+    if (len > ZO_CHUNK_MAX || level < 1 || level > 6) return (size_t)-1;
+    tokbuf tb = {tokens, cap, 0};
+    if (level == 1) {
+        pstate s = {in - ZO_WSIZE, ZO_WSIZE + len, 0, (uint32_t *)calloc(65536, sizeof(uint32_t))};
+        if (!s.head) return (size_t)-1;
+        quick_parse_primed(&s, ZO_WSIZE, NULL, tok_push, &tb);
+        free(s.head);
+    } else {
+        size_t bound = zo_deflate_bound(len) + 64;
+        uint8_t *scratch = (uint8_t *)malloc(bound);
+        if (!scratch) return (size_t)-1;
+        size_t r = window_deflate_one_sink(in - ZO_WSIZE, in, len, level, ZO_SYNC_FLUSH, scratch, bound, tok_push, &tb);
+        free(scratch);
+        if (r == (size_t)-1) return (size_t)-1;
+    }
     return tb.n;
 }
 

@@ -74,6 +74,8 @@ int zo_deflate_chunks_fresh_window(const uint8_t *in, size_t n, uint32_t chunk, 
                                    uint32_t *crcs, uint32_t *adlers, int nthreads);
 
 size_t zo_deflate_tokens(const uint8_t *in, uint32_t len, int level, uint32_t *tokens, size_t cap);
+/* the same for a primed chunk: in[-32768 .. 0) must be readable (the dictionary) */
+size_t zo_deflate_tokens_primed(const uint8_t *in, uint32_t len, int level, uint32_t *tokens, size_t cap);
 
 /* Single operators (operator-surface tests): functable.longest_match at level 2, insert_string. */
 uint32_t zo_longest_match_l2(const uint8_t *window, uint32_t avail, uint32_t n, const uint16_t *prev, uint32_t pos, uint32_t cand, uint32_t *start);

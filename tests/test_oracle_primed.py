@@ -51,3 +51,31 @@ def test_window_engine_agrees_with_the_chunk_coordinate_restatement(pkg, zo):
             for i in range(len(a[1])):
                 b = zo.port_deflate_chunks(d[i * 65536:(i + 1) * 65536], 65536, level, 4, nthreads=1)
                 assert a[1][i] == b[1][0] and np.array_equal(a[0][i, : a[1][i]], b[0][0, : b[1][0]]), (level, i)
+
+
+def test_primed_token_trace_is_consistent(pkg, zo):
+    """zo_deflate_tokens_primed (what a kernel under construction is diffed against): the tokens cover the chunk exactly, every
+    match copies bytes that are really there -- reaching into the dictionary where the data repeats across the join."""
+    rng = np.random.default_rng(4)
+    words = rng.integers(97, 123, size=(64, 6), dtype=np.uint8)
+    text = words[rng.integers(0, 64, size=40000)].reshape(-1)[:32768 + 65536]
+    for data in (text, pkg.synth(32768 + 65536, seed=6), pkg.synth(32768 + 1000, seed=7)):
+        chunk = data[32768:]
+        for level in (1, 2, 6):
+            toks = zo.port_tokens_primed(data, level)
+            pos, into_dict = 32768, 0
+            for t in toks:
+                t = int(t)
+                if t & 0x80000000:
+                    ln, dist = (t >> 16) & 0x1ff, t & 0xffff
+                    assert 3 <= ln <= 258 and 1 <= dist <= 32768 - 262 and pos - dist >= 0
+                    assert np.array_equal(data[pos:pos + ln], np.array([data[pos - dist + (k % dist)] for k in range(ln)], dtype=np.uint8)) or \
+                        bytes(data[pos - dist:pos - dist + ln]) == bytes(data[pos:pos + ln])
+                    into_dict += pos - dist < 32768
+                    pos += ln
+                else:
+                    assert t == int(data[pos])
+                    pos += 1
+            assert pos == data.size, (level, pos, data.size)
+            if data is text:
+                assert into_dict > 0

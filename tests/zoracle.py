@@ -47,6 +47,7 @@ def port():
         L.zo_deflate_chunks_fresh_window.restype = c_int
         L.zo_deflate_chunks_fresh_window.argtypes = L.zo_deflate_chunks.argtypes
         L.zo_deflate_tokens.restype = c_size_t; L.zo_deflate_tokens.argtypes = [c_void_p, c_uint32, c_int, c_void_p, c_size_t]
+        L.zo_deflate_tokens_primed.restype = c_size_t; L.zo_deflate_tokens_primed.argtypes = [c_void_p, c_uint32, c_int, c_void_p, c_size_t]
         L.zo_longest_match_l2.restype = c_uint32
         L.zo_longest_match_l2.argtypes = [c_void_p, c_uint32, c_uint32, c_void_p, c_uint32, c_uint32, POINTER(c_uint32)]
         L.zo_insert_string.restype = None
@@ -158,6 +159,16 @@ def port_deflate_chunks_fresh_window(data, chunk=65536, level=2, flush=4, stride
 def ref_deflate_chunks_primed(data, chunk=65536, level=1, flush=2, stride=None, nthreads=None):
     stride = stride or int(port().zo_deflate_bound(chunk))
     return _deflate_chunks(ref().refdrv_deflate_chunks_primed, data, chunk, level, flush, stride, nthreads or min(os.cpu_count() or 1, 32))
+
+
+def port_tokens_primed(dict_and_chunk, level=1) -> np.ndarray:
+    """LZ77 tokens of a primed chunk; the first 32768 bytes of the argument are its dictionary."""
+    d = _u8(dict_and_chunk)
+    assert d.size >= 32768
+    n = d.size - 32768
+    tok = np.zeros(n + 8, dtype=np.uint32)
+    k = port().zo_deflate_tokens_primed(d.ctypes.data + 32768, n, level, tok.ctypes.data, tok.size)
+    return tok[:k]
 
 
 def port_tokens(chunk_bytes, level=1) -> np.ndarray:
