@@ -7,8 +7,8 @@ Rank r of N owns the contiguous chunk range [r, r+1) * n/N of a synthetic stream
 independent 64 KiB level-1 chunks with Z_FULL_FLUSH ends, and the only collective is an NCCL allgather of the per-chunk
 (compressed size, crc32) pairs (8 bytes per chunk).  Every rank then scans the sizes (its bytes' offset in the file) and
 folds the CRCs (crc32_combine), packs its chunks and writes them at its offset; rank 0 adds the gzip header, the "03 00"
-terminator and the trailer.  --verify runs the unmodified reference's zng_inflate (oracle/_ref, test infrastructure) or,
-if that is absent, CPython's zlib over the finished file.
+terminator and the trailer.  --verify reads the finished file back with CPython's zlib (an independent inflater); the check
+against the unmodified reference's zng_inflate lives with the tests: tests/verify_gzip_with_reference.py FILE.
 """
 import argparse
 import importlib.util
@@ -28,7 +28,6 @@ def main():
     ap.add_argument("--verify", action="store_true")
     args = ap.parse_args()
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     from __graft_entry__ import load_package
@@ -113,26 +112,16 @@ def main():
               f"file written in {t2 - t1:.1f} s", flush=True)
         if args.verify:
             tv = time.perf_counter()
-            try:
-                from __graft_entry__ import load_oracle
-                zo = load_oracle()
-                data = np.fromfile(args.out, dtype=np.uint8)
-                if zo.have_ref():
-                    code, out_len, rcrc = zo.ref_inflate_stream(data, 31)
-                    who = "unmodified reference zng_inflate (oracle/_ref)"
-                else:
-                    raise ImportError
-            except ImportError:
-                import zlib
-                d = zlib.decompressobj(31); out_len = 0; rcrc = 0
-                with open(args.out, "rb") as f:
-                    while True:
-                        b = f.read(64 << 20)
-                        if not b:
-                            break
-                        o = d.decompress(b); out_len += len(o); rcrc = zlib.crc32(o, rcrc)
-                code = 1 if d.eof else -5
-                who = "CPython zlib"
+            import zlib
+            d = zlib.decompressobj(31); out_len = 0; rcrc = 0
+            with open(args.out, "rb") as f:
+                while True:
+                    b = f.read(64 << 20)
+                    if not b:
+                        break
+                    o = d.decompress(b); out_len += len(o); rcrc = zlib.crc32(o, rcrc)
+            code = 1 if d.eof else -5
+            who = "CPython zlib"
             ok = code == 1 and out_len == n_total and (rcrc & 0xffffffff) == crc
             print(f"verify with {who}: code {code}, {out_len} bytes, crc32 {rcrc & 0xffffffff:08x} -> {'OK' if ok else 'MISMATCH'} ({time.perf_counter() - tv:.1f} s)", flush=True)
             if not ok:
