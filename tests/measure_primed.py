@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Device-resident throughput of zng_b200_deflate_chunks_primed (pigz's dependent mode, level 1) next to the independent-chunk
-path, and the unmodified reference doing the same call sequence on the host cores.  python profiles/measure_primed.py [MiB]"""
+path, and the unmodified reference doing the same call sequence on the host cores.  python tests/measure_primed.py [MiB]   (lives under tests/: it times oracle/_ref as the CPU baseline)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
