@@ -101,3 +101,44 @@ def test_synth_is_deterministic_and_shardable(pkg):
     b = pkg.synth(8 * 65536, offset=12 * 65536)
     assert np.array_equal(a[12 * 65536:], b)
     assert not np.array_equal(pkg.synth(65536, seed=1), pkg.synth(65536, seed=2))
+
+
+def _fuzz_input(rng, n):
+    """Structured random bytes: literals from a small alphabet, runs, copies of earlier substrings at assorted distances."""
+    out = np.empty(n, dtype=np.uint8)
+    pos = 0
+    alphabet = rng.integers(0, 256, size=int(rng.integers(2, 40)), dtype=np.uint8)
+    while pos < n:
+        kind = rng.integers(0, 4)
+        ln = int(min(n - pos, rng.integers(1, 400 if kind else 40)))
+        if kind == 0 or pos == 0:
+            out[pos:pos + ln] = alphabet[rng.integers(0, alphabet.size, size=ln)]
+        elif kind == 1:
+            out[pos:pos + ln] = out[pos - 1]
+        else:
+            dist = int(min(pos, rng.choice([1, 2, 3, 4, 7, 64, 258, 1000, 4096, 32506, 32507, 32768, 40000])))
+            for k in range(ln):
+                out[pos + k] = out[pos + k - dist]
+        pos += ln
+    return out
+
+
+def test_port_matches_reference_on_structured_random_inputs(pkg, zo):
+    """Deterministic fuzz: 120 structured inputs x levels 1-6, fresh stream per chunk (Z_FINISH), plus the same data as
+    primed chunks -- the oracle must reproduce the unmodified reference byte for byte."""
+    if not zo.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(2026)
+    sizes = [int(x) for x in rng.integers(0, 3000, size=80)] + [int(x) for x in rng.integers(60000, 65537, size=30)] + [65536] * 10
+    for n in sizes:
+        d = _fuzz_input(rng, n)
+        for level in (1, 2, 3, 4, 5, 6):
+            a = zo.port_deflate_chunks(d, 65536, level, 4, nthreads=1)
+            b = zo.ref_deflate_chunks(d, 65536, level, 4, nthreads=1)
+            assert len(a[1]) == len(b[1]) and all(a[1][i] == b[1][i] and np.array_equal(a[0][i, : a[1][i]], b[0][i, : b[1][i]]) for i in range(len(a[1]))), (n, level)
+    for n in sizes[-25:]:
+        d = _fuzz_input(rng, 65536 + n)
+        for level in (1, 2, 3, 4, 5, 6):
+            a = zo.port_deflate_chunks_primed(d, 65536, level, 2, nthreads=1)
+            b = zo.ref_deflate_chunks_primed(d, 65536, level, 2, nthreads=1)
+            assert all(a[1][i] == b[1][i] and np.array_equal(a[0][i, : a[1][i]], b[0][i, : b[1][i]]) for i in range(len(a[1]))), ("primed", n, level)
