@@ -1,8 +1,9 @@
-// deflate_fast.cu -- K2: level-2 (deflate_fast) compression of independent <= 64 KiB chunks.
+// deflate_fast.cu -- K2: levels 2 (deflate_fast) and 3-6 (deflate_medium; 5-6 in lazy_parse.cuh) of independent <= 64 KiB chunks.
 //
 // Reference semantics reproduced bit-exactly (files under /root/reference):
 //   deflate_fast.c:19-104         greedy parse: hash_head != 0, longest_match, insert_string for short matches
-//   match_tpl.h:26-280            longest_match, non-SLOW, level-2 parameters {good 4, lazy 4, nice 8, chain 4}
+//   deflate_medium.c:22-278       levels 3-6: insert_match, (5-6) the look-ahead-one branch and fizzle_matches
+//   match_tpl.h:26-280            longest_match, non-SLOW, {nice, chain} of configuration_table (deflate.c:142-168) per level
 //   insert_string_tpl.h:48-104    quick_insert_string / insert_string: head[] + prev[] hash chains
 //   deflate_p.h:61-112            zng_tr_tally_lit/_dist, FLUSH_BLOCK (block full at sym_next == 16383)
 //   trees.c:106-120,151-173,185-270,280-312,322-405   init_block, pqdownheap, gen_bitlen, gen_codes, build_tree
