@@ -100,6 +100,9 @@ struct zng_b200_ctx {
     uint16_t* prevs = nullptr;                 // K2: prev[] slab pool and stale-window images, same (sm, slot) indexing
     uint32_t* vtails = nullptr;
     int chains_per_sm = 24;
+    int k1_cta = 0;                            // level-1 parser: 1 = CTA per chain with L2-resident tables (v5), 0 = warp per chain (env ZNG_B200_K1=warp)
+    int warps_cta = 8;                         // warps per chain of the v5 parser (env ZNG_B200_K1_WARPS: 2, 4, 8)
+    int chains_cta = 4;                        // chains (CTAs) per SM of the v5 parser (env ZNG_B200_K1_CHAINS)
     int chains_per_sm_l2 = 32;                 // measured on B200: 16 -> 12.4, 24 -> 14.4, 32 -> 15.4 GB/s
     Scratch scratch;                           // for the device-resident entry points; users are ordered by k1_done
     cudaEvent_t k1_done = nullptr;
@@ -229,9 +232,14 @@ int run_deflate_chunks(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size
                "block_emit launch");
             continue;
         }
-        CK(launch_quick_parse(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->sm_slots,
-                              grid, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream),
-           "quick_parse launch");
+        if (ctx->k1_cta)
+            CK(launch_quick_parse_cta(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->sm_slots,
+                                      ctx->sms, ctx->chains_cta, ctx->warps_cta, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream),
+               "quick_parse_cta launch");
+        else
+            CK(launch_quick_parse(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->sm_slots,
+                                  grid, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream),
+               "quick_parse launch");
         CK(launch_static_emit(toks, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
                               d_sizes + c0, ctx->sms, stream),
            "static_emit launch");
@@ -367,6 +375,9 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     ctx->sms = prop.multiProcessorCount;
     if (prop.major < 10) { delete ctx; return ZNG_B200_STREAM_ERROR; }       // sm_100a kernels only
     if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm = v; }
+    if (const char* e = getenv("ZNG_B200_K1")) ctx->k1_cta = (strcmp(e, "cta") == 0);
+    if (const char* e = getenv("ZNG_B200_K1_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->chains_cta = v; }
+    if (const char* e = getenv("ZNG_B200_K1_WARPS")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) ctx->warps_cta = v; }
     if (const char* e = getenv("ZNG_B200_SLAB_CHUNKS")) { int v = atoi(e); if (v >= 64 && v <= 16384) ctx->slab_chunks = (uint32_t)v; }
     if (const char* e = getenv("ZNG_B200_STREAMED")) ctx->streamed = atoi(e);
     if (const char* e = getenv("ZNG_B200_STREAM_SHIFT")) { int v = atoi(e); if (v >= 8 && v <= 11) ctx->stream_shift = (uint32_t)v; }
@@ -1241,7 +1252,11 @@ static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t 
     for (uint32_t j = 0; j < nslabs; j++) S.h_done[j] = 0;
     StreamSync sy; sy.ready = S.d_sync; sy.failed = S.d_sync + 1; sy.done = S.d_sync + 4; sy.done_shift = kStreamSlabShift; sy.patience = patience;
     sy.host_done = S.d_h_done;
-    if (level == 1)
+    if (level == 1 && ctx->k1_cta)
+        CK(launch_quick_parse_cta(S.d_in, n, chunk, nch, S.tokens, (uint32_t)tstride, S.ntok, S.d_sync + 2, ctx->heads, ctx->sm_slots,
+                                  ctx->sms, ctx->chains_cta, ctx->warps_cta, nullptr, S.parse, &sy),
+           "quick_parse_cta launch");
+    else if (level == 1)
         CK(launch_quick_parse(S.d_in, n, chunk, nch, S.tokens, (uint32_t)tstride, S.ntok, S.d_sync + 2, ctx->heads, ctx->sm_slots,
                               deflate_quick_grid(nch, ctx->sms, ctx->chains_per_sm), nullptr, S.parse, &sy),
            "quick_parse launch");
