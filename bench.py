@@ -4,6 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (BASELINE metric: level 1)
     python bench.py --impl reference --gpus N --steps K ...  # zlib-ng's own CPU path, all host cores
     python bench.py --workload deflate2..deflate6|checksum|inflate     # the other BASELINE configs (same JSON contract)
+    python bench.py --config 0..4 [--gpus N]                 # BASELINE.json configs[k] at its full size (see CONFIGS below)
 
 Default workload (BASELINE.json configs[0], the configuration the metric is quoted on): per GPU a 1 GiB synthetic
 mixed text/binary buffer = 16,384 independent 64 KiB chunks, deflate_quick (level 1) raw deflate with Z_FULL_FLUSH
@@ -41,8 +42,20 @@ METRICS = {"deflate1": "level1_deflate_input_throughput", "deflate2": "level2_de
            "checksum": "crc32_adler32_input_throughput", "inflate": "inflate_output_throughput"}
 
 
+# BASELINE.json configs[k] -> (workload, total MiB over all GPUs or None = 1 GiB per GPU, scaling).  configs[4] (64 GiB on
+# 8 GPUs) is 8 GiB per GPU: with fewer GPUs the per-GPU size stays 8 GiB (input + slots + packed stream of 64 GiB do not
+# fit one GPU's 180 GB), so it weak-scales; configs[1] defaults to its largest size, --total-gib 1|4 selects the others;
+# configs[2] runs level 2, --level 3 selects deflate_medium.
+CONFIGS = {0: ("deflate1", None, "weak"), 1: ("checksum", 16384, "strong"), 2: ("deflate2", 4096, "strong"),
+           3: ("inflate", 4096, "strong"), 4: ("deflate1", None, "weak")}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=None, choices=sorted(CONFIGS), help="BASELINE.json configs[k] at full size")
+    ap.add_argument("--total-gib", type=int, default=None, help="with --config 1/2/3: total GiB over all GPUs")
+    ap.add_argument("--level", type=int, default=None, choices=[1, 2, 3, 4, 5, 6], help="with --config 2: deflate level (default 2)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the every-chunk comparison with the reference")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -51,7 +64,24 @@ def parse_args():
     ap.add_argument("--mib-per-gpu", type=int, default=1024, help="input (inflate: output) MiB per GPU; default = the 1 GiB BASELINE config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.scaling = "weak"
+    args.config_name = None
+    if args.config is not None:
+        world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+        wl, total, scaling = CONFIGS[args.config]
+        if args.config == 2 and args.level:
+            wl = f"deflate{args.level}"
+        if args.total_gib and total is not None:
+            total = args.total_gib << 10
+        args.workload = wl
+        args.scaling = scaling
+        if args.config == 4:
+            args.mib_per_gpu = 8192
+        elif total is not None:
+            args.mib_per_gpu = max(64, total // max(1, world))
+        args.config_name = f"BASELINE configs[{args.config}]"
+    return args
 
 
 def workload_text(w, mib, ngpu):
@@ -68,6 +98,34 @@ def workload_text(w, mib, ngpu):
         return f"zng_crc32 + zng_adler32 of a flat {mib} MiB buffer per GPU, 64 KiB tiles + combine folds (BASELINE configs[1])"
     return (f"batched inflate of {n // MEMBER} independent 4 KiB gzip members per GPU (bodies = level-1 Z_FINISH streams, minigzip -1 framing), "
             f"output + CRC-32 + ISIZE checked on device (BASELINE configs[3] at {mib} MiB of output per GPU)")
+
+
+def config_dict(args, ngpu):
+    """`config` of the JSON line: the same dict from both arms (the driver compares them)."""
+    wl = args.workload
+    text = workload_text(wl, args.mib_per_gpu, ngpu)
+    if args.config_name:
+        text += f" [{args.config_name} at full size: {args.mib_per_gpu * ngpu} MiB over {ngpu} GPU(s)]"
+    return {"workload": text, "chunk_bytes": CHUNK, "sharding": f"contiguous chunk ranges x{ngpu}",
+            "collective": ("nccl allgather of (size, crc32) per chunk" if wl.startswith("deflate") else
+                           ("nccl allgather of (crc32, adler32) per rank" if wl == "checksum" else "none")) if ngpu > 1 else "none",
+            "l2": f"input {args.mib_per_gpu} MiB per step >> 126 MB L2, no flush needed"}
+
+
+ROOFLINE_NOTES = {
+    "deflate1": "serial-per-chunk LZ77 parse; the hash-head tables of the resident chains exceed L2, so the parser is bound by DRAM "
+                "sector (random access) rate, not by streaming bandwidth (DESIGN.md section 7)",
+    "deflate2": "hash-chain walk (<= 4 links) per position + per-block Huffman tree build: latency bound",
+    "deflate3": "deflate_medium, chain 6 / nice 16, every position of a match inserted: latency bound",
+    "deflate4": "deflate_medium, chain 24 / nice 32: dependent prev[] link loads dominate",
+    "deflate5": "deflate_medium with look-ahead, chain 32: dependent prev[] link loads dominate",
+    "deflate6": "deflate_medium with look-ahead, chain 128 (zlib-ng's default level): dependent prev[] link loads dominate",
+}
+
+
+def synth_mod():
+    from __graft_entry__ import load_synth
+    return load_synth()
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -127,7 +185,7 @@ def make_members(pkg, n_bytes, seed_offset=0):
     ctx = pkg.Context(torch.cuda.current_device())
     n_members = n_bytes // MEMBER
     data = np.empty(n_bytes, dtype=np.uint8)
-    assert pkg.lib().zng_b200_synth_fill(data.ctypes.data, n_bytes, SEED, seed_offset) == 0
+    synth_mod().fill(data.ctypes.data, n_bytes, SEED, seed_offset)
     stride = pkg.deflate_bound(MEMBER)
     parts_sizes = np.zeros(n_members, dtype=np.int64)
     bodies = []
@@ -161,11 +219,11 @@ def make_members(pkg, n_bytes, seed_offset=0):
     return members, in_off, data
 
 
-def make_members_cpu(zo, pkg, n_bytes):
+def make_members_cpu(zo, n_bytes):
     """Same members from the CPU side (reference arm: no GPU needed): refdrv_gzip_members / oracle port."""
     import numpy as np
     n_members = n_bytes // MEMBER
-    data = pkg.synth(n_bytes, SEED)
+    data = synth_mod().synth(n_bytes, SEED)
     out, sizes, crcs, _ = (zo.ref_deflate_chunks if zo.have_ref() else zo.port_deflate_chunks)(data, MEMBER, 1, 4)
     in_off = np.zeros(n_members + 1, dtype=np.uint64)
     in_off[1:] = np.cumsum(sizes.astype(np.int64) + 18).astype(np.uint64)
@@ -188,9 +246,9 @@ def cpu_reference_run(workload: str, n_bytes: int, steps: int, warmup: int):
     """Time the reference's CPU implementation (oracle/_ref when it was built from /root/reference, else the oracle
     port) on the same workload with every host core: one zng_stream per worker thread, one chunk / member per task."""
     import numpy as np
-    from __graft_entry__ import load_oracle, load_package
-    pkg = load_package()
-    zo = load_oracle()
+    from __graft_entry__ import load_oracle
+    zo = load_oracle()          # the reference arm loads oracle/ and the synthetic generator only, never the product library
+    sd = synth_mod()
     cores = host_cores()
     kind = "reference" if zo.have_ref() else "port"
     if kind == "port":
@@ -199,16 +257,16 @@ def cpu_reference_run(workload: str, n_bytes: int, steps: int, warmup: int):
     if workload.startswith("deflate"):
         level = int(workload[-1])
         fn = zo.ref().refdrv_deflate_chunks if kind == "reference" else zo.port().zo_deflate_chunks
-        data = pkg.synth(n_bytes, SEED)
+        data = sd.synth(n_bytes, SEED)
         nch = (n_bytes + CHUNK - 1) // CHUNK
-        stride = pkg.deflate_bound(CHUNK)
+        stride = int(zo.port().zo_deflate_bound(CHUNK))
         out = np.empty(nch * stride, dtype=np.uint8)
         sizes = np.zeros(nch, dtype=np.uint32)
         crcs = np.zeros(nch, dtype=np.uint32)
         call = lambda: fn(data.ctypes.data, n_bytes, CHUNK, level, 3, out.ctypes.data, stride, sizes.ctypes.data, crcs.ctypes.data, None, cores)
         what = f"{n_bytes >> 20} MiB of the same synthetic workload per step ({nch} chunks; zng_deflateReset + zng_deflate(Z_FULL_FLUSH) + zng_crc32 per chunk)"
     elif workload == "checksum":
-        data = pkg.synth(n_bytes, SEED)
+        data = sd.synth(n_bytes, SEED)
         if kind == "reference":
             c, a = ctypes_u32(), ctypes_u32()
             call = lambda: zo.ref().refdrv_checksum_flat(data.ctypes.data, n_bytes, 1 << 20, cores, c, a)
@@ -217,7 +275,7 @@ def cpu_reference_run(workload: str, n_bytes: int, steps: int, warmup: int):
             cores = 1
         what = f"{n_bytes >> 20} MiB flat buffer per step, 1 MiB pieces per thread + combine (zng_crc32_z + zng_adler32_z + *_combine)"
     else:
-        members, in_off, data = make_members_cpu(zo, pkg, n_bytes)
+        members, in_off, data = make_members_cpu(zo, n_bytes)
         nm = len(in_off) - 1
         out = np.empty(n_bytes, dtype=np.uint8)
         out_off = (np.arange(nm + 1, dtype=np.uint64) * MEMBER)
@@ -265,9 +323,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRICS[args.workload], "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_text(args.workload, args.mib_per_gpu, args.gpus), "chunk_bytes": CHUNK,
-                   "sharding": f"chunks x{args.gpus}"},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": config_dict(args, args.gpus),
         "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "compression_ratio": res["ratio"],
@@ -315,6 +372,64 @@ def bind_to_gpu_numa_node(torch, local_rank):
         return None
 
 
+def copy_ceiling(torch, dev, h_src, h2d_bytes, d2h_bytes, barrier, reps):
+    """Seconds (best of reps) to move h2d_bytes host->device in 16 MiB pieces and d2h_bytes device->host in 32 MiB pieces,
+    concurrently on two streams, between pinned host memory and HBM -- the transfers of one e2e step without any kernel."""
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    h2d_bytes = min(int(h2d_bytes), h_src.numel())
+    d_up = torch.empty(max(h2d_bytes, 16), dtype=torch.uint8, device=dev)
+    d_dn = torch.empty(max(int(d2h_bytes), 16), dtype=torch.uint8, device=dev)
+    h_dn = torch.empty(max(int(d2h_bytes), 16), dtype=torch.uint8, pin_memory=True)
+    best = float("inf")
+    for _ in range(reps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_up):
+            for o in range(0, h2d_bytes, 16 << 20):
+                e = min(h2d_bytes, o + (16 << 20))
+                d_up[o:e].copy_(h_src[o:e], non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            for o in range(0, int(d2h_bytes), 32 << 20):
+                e = min(int(d2h_bytes), o + (32 << 20))
+                h_dn[o:e].copy_(d_dn[o:e], non_blocking=True)
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cross_rank_parity(allp, wl, gf):
+    """Rank 0: every rank's verdict plus what only exists across ranks -- the folded CRC-32 of the whole stream and its total
+    packed length (deflate), the combined crc32 / adler32 (checksum) -- against the reference's own combine functions."""
+    from __graft_entry__ import load_oracle
+    zo = load_oracle()
+    bad = [r for r, (_, ok, _) in enumerate(allp) if ok is not True]
+    if bad:
+        return f"MISMATCH or unchecked on ranks {bad}: " + " | ".join(str(allp[r][0]) for r in bad)
+    text = f"{len(allp)} ranks: " + allp[0][0]
+    if gf is None:
+        return text
+    L = zo.ref() if zo.have_ref() else zo.port()
+    ccomb = L.zng_crc32_combine if zo.have_ref() else L.zo_crc32_combine
+    acomb = L.zng_adler32_combine if zo.have_ref() else L.zo_adler32_combine
+    if wl.startswith("deflate"):
+        fold, total = 0, 0
+        for _, _, f in allp:
+            fold = ccomb(fold, f["crc_fold"], f["n"]); total += f["packed"]
+        good = fold == gf["crc_fold"] and total == gf["packed"]
+        return text + (f"; stream crc32 {fold:08x} (crc32_combine over all ranks) and total length {total} equal the device fold / scan" if good
+                       else f"; MISMATCH across ranks: fold {fold:08x} vs {gf['crc_fold']:08x}, length {total} vs {gf['packed']}")
+    if wl == "checksum":
+        c, a = 0, 1
+        for _, _, f in allp:
+            c = ccomb(c, f["crc"], f["n"]); a = acomb(a, f["adler"], f["n"])
+        gc, ga = 0, 1
+        for (rc, ra) in gf["per_rank"]:
+            gc = ccomb(gc, rc, allp[0][2]["n"]); ga = acomb(ga, ra, allp[0][2]["n"])
+        good = (c, a) == (gc, ga)
+        return text + (f"; combined crc32 {c:08x} / adler32 {a:08x} over all ranks equal the allgathered device values" if good else "; MISMATCH of the combined checksums")
+    return text
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -357,7 +472,7 @@ def run_b200(args):
         nch = n // CHUNK
         stride = pkg.deflate_bound(CHUNK)
         h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)        # this rank's shard of the synthetic stream
-        assert pkg.lib().zng_b200_synth_fill(h_in.data_ptr(), n, SEED, rank * n) == 0
+        synth_mod().fill(h_in.data_ptr(), n, SEED, rank * n)
         d_in = h_in.to(dev, non_blocking=True)
         slots = torch.empty(nch * stride, dtype=torch.uint8, device=dev)
         meta = torch.zeros(2, nch, dtype=torch.int32, device=dev)          # row 0 sizes, row 1 crc32
@@ -390,22 +505,51 @@ def run_b200(args):
             ctx.gather_chunks(slots, stride, sizes, offsets, nch, packed)
             launches["n"] += 2
 
-        def parity_check():
+        def parity_check(e2e_out=None):
+            """EVERY chunk of this rank's shard against the unmodified reference (oracle/_ref; the port if it is absent):
+            size and bytes of the device-resident slots, the per-chunk CRC-32, and -- when the e2e leg ran -- the packed
+            host output of zng_b200_deflate_host.  Returns (text, ok, shard facts for the cross-rank check)."""
             from __graft_entry__ import load_oracle
             zo = load_oracle()
+            cores = host_cores() if ngpu == 1 else max(1, host_cores() // ngpu)
             hs = sizes.cpu().numpy().view(np.uint32)
-            hslots = slots.view(-1, stride)
-            pick = np.random.default_rng(0).choice(nch, size=min(64, nch), replace=False)
+            hc = crcs.cpu().numpy().view(np.uint32)
             hin = h_in.numpy()
-            ok = True
-            for ci in pick:
-                exp, es, ec, _ = zo.port_deflate_chunks(hin[ci * CHUNK:(ci + 1) * CHUNK], CHUNK, level, 3, stride, nthreads=1)
-                got = hslots[ci, : int(es[0])].cpu().numpy()
-                ok &= bool(es[0] == hs[ci]) and bool(np.array_equal(got, exp[0, : es[0]]))
-            return "bit-exact vs oracle on 64 sampled chunks" if ok else "MISMATCH vs oracle"
+            piece = 16384
+            bad = bad_crc = bad_e2e = 0
+            first = None
+            fold, eo, kind = 0, 0, "?"
+            comb = zo.ref().zng_crc32_combine if zo.have_ref() else zo.port().zo_crc32_combine
+            for c0 in range(0, nch, piece):
+                c1 = min(nch, c0 + piece)
+                kind, exp, es, ec, _ = zo.best_deflate_chunks(hin[c0 * CHUNK:c1 * CHUNK], CHUNK, level, 3, stride, nthreads=cores)
+                got = slots[c0 * stride:c1 * stride].cpu().numpy()
+                b, f = zo.compare_chunks(got, stride, hs[c0:c1], exp, stride, es)
+                if b and first is None:
+                    first = c0 + f
+                bad += b
+                bad_crc += int((hc[c0:c1] != ec).sum())
+                if e2e_out is not None:
+                    seg = int(es.astype(np.int64).sum())
+                    b2, _ = zo.compare_chunks(e2e_out[eo:eo + seg], 0, es, exp, stride, es)
+                    bad_e2e += b2
+                    eo += seg
+                for k in range(c1 - c0):
+                    fold = comb(fold, int(ec[k]), CHUNK)
+            ok = bad == 0 and bad_crc == 0 and bad_e2e == 0
+            text = (f"all {nch} of {nch} chunks equal {kind}: compressed size + bytes and crc32" if ok else
+                    f"MISMATCH vs {kind}: {bad} of {nch} chunks differ (first {first}), {bad_crc} crc32 differ, {bad_e2e} e2e chunks differ")
+            if ok and e2e_out is not None:
+                text += f"; e2e host output ({eo} bytes) equals the concatenated reference chunks"
+            return text, ok, {"crc_fold": int(fold), "packed": int(hs.astype(np.int64).sum()), "n": n}
 
         def finish():
             return int(offsets[nch].item())
+
+        def global_facts():
+            """What the collective produced on this rank: the fold of every rank's chunk CRCs and the end of the global scan."""
+            u = lambda v: int(v) & 0xffffffff
+            return {"crc_fold": u(res[0].item()), "packed": int(offsets_all[ngpu * nch].item()) if ngpu > 1 else int(offsets[nch].item())}
 
         cap = nch * stride
 
@@ -415,49 +559,69 @@ def run_b200(args):
 
             def call():
                 state["out_len"], _, _ = ctx.deflate_host(h_in, n, CHUNK, level, False, h_out, cap)
-            return call, (lambda: (n, int(state["out_len"]))), ("zng_b200_deflate_host (pinned host in/out; streamed: one persistent parse kernel fed by the copy engine in 16 MiB pieces, emit / gather / D2H per 32 MiB slab)"
-                                                                     if level == 1 else "zng_b200_deflate_host (pinned host in/out, 4 x 128 MiB slabs in flight on separate streams)")
+            api = ("zng_b200_deflate_host (pinned host in/out; streamed: one persistent parse kernel fed by the copy engine in 16 MiB pieces, emit / gather / D2H per 32 MiB slab)"
+                   if level == 1 else "zng_b200_deflate_host (pinned host in/out, 4 x 128 MiB slabs in flight on separate streams)")
+            return call, (lambda: (n, int(state["out_len"]))), api, (lambda: h_out.numpy()[: int(state["out_len"])])
         e2e_fn = make_e2e
         alg_bytes = lambda ob: n + ob                                     # in + out per chunk, x chunks per launch
         kernel_name = "quick_parse_kernel + static_emit_kernel (+ checksum_tiles_kernel)" if level == 1 else f"fast_parse_kernel<{level}> + block_emit_kernel (+ checksum_tiles_kernel)"
-        note = "serial-per-chunk LZ77 parse: latency/issue bound, not HBM bound (see DESIGN.md)"
+        note = ROOFLINE_NOTES[wl]
 
     elif wl == "checksum":
         h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-        assert pkg.lib().zng_b200_synth_fill(h_in.data_ptr(), n, SEED, rank * n) == 0
+        synth_mod().fill(h_in.data_ptr(), n, SEED, rank * n)
         d_in = h_in.to(dev, non_blocking=True)
         res = torch.zeros(4, dtype=torch.int32, device=dev)
         if ngpu > 1:
             gath = torch.zeros(ngpu * 4, dtype=torch.int32, device=dev)
 
+        ntile = (n + CHUNK - 1) // CHUNK
+        t_crc = torch.zeros(ntile, dtype=torch.int32, device=dev)
+        t_adl = torch.zeros(ntile, dtype=torch.int32, device=dev)
+
         def step(i_timed=None):
             if i_timed is not None:
                 k_start[i_timed].record()
-            ctx.crc32(d_in, n, 0, res[0:1])
-            ctx.adler32(d_in, n, 1, res[1:2])
+            ctx.checksum_chunks(d_in, n, CHUNK, t_crc, t_adl)             # ONE pass over the buffer: both checksums per 64 KiB tile
+            ctx.crc32_fold(t_crc, ntile, CHUNK, n, 0, res[0:1])           # crc32_combine / adler32_combine algebra over the tiles
+            ctx.adler32_fold(t_adl, ntile, CHUNK, n, 1, res[1:2])
             if i_timed is not None:
                 k_stop[i_timed].record()
-            launches["n"] += 4
+            launches["n"] += 3
             if ngpu > 1:
                 dist.all_gather_into_tensor(gath, res)                    # G x (crc, adler) -> combined on the host (G values)
 
-        def parity_check():
-            import zlib as pyzlib
+        def parity_check(e2e_out=None):
+            from __graft_entry__ import load_oracle
+            zo = load_oracle()
             r = res.cpu().numpy().view(np.uint32)
-            b = h_in.numpy().tobytes()
-            return "crc32/adler32 equal to an independent CPU implementation" if (int(r[0]) == pyzlib.crc32(b) and int(r[1]) == pyzlib.adler32(b)) else "MISMATCH"
+            hin = h_in.numpy()
+            if zo.have_ref():
+                kind, ec, ea = "oracle/_ref (unmodified zlib-ng 2.2.2)", zo.ref_crc32(hin), zo.ref_adler32(hin)
+            else:
+                kind, ec, ea = "oracle port", zo.port_crc32(hin), zo.port_adler32(hin)
+            ok = int(r[0]) == ec and int(r[1]) == ea
+            if ok and e2e_out is not None:
+                ok = e2e_out == (ec, ea)
+            text = (f"crc32 {ec:08x} and adler32 {ea:08x} of the {n >> 20} MiB shard equal {kind}" + ("; e2e host calls return the same values" if e2e_out is not None else "")) if ok else f"MISMATCH vs {kind}"
+            return text, ok, {"crc": ec, "adler": ea, "n": n}
 
         def finish():
             return 0
 
+        def global_facts():
+            g = gath.cpu().numpy().view(np.uint32).reshape(ngpu, 4) if ngpu > 1 else res.cpu().numpy().view(np.uint32).reshape(1, 4)
+            return {"per_rank": [(int(r[0]), int(r[1])) for r in g]}
+
         def make_e2e():
+            state = {}
+
             def call():
-                ctx.crc32_host(h_in, n, 0)
-                ctx.adler32_host(h_in, n, 1)
-            return call, (lambda: (2 * n, 8)), "zng_b200_crc32_host + zng_b200_adler32_host (what zng_crc32_z / zng_adler32_z call)"
+                state["r"] = (ctx.crc32_host(h_in, n, 0), ctx.adler32_host(h_in, n, 1))
+            return call, (lambda: (2 * n, 8)), "zng_b200_crc32_host + zng_b200_adler32_host (what zng_crc32_z / zng_adler32_z call)", (lambda: state["r"])
         e2e_fn = make_e2e
-        alg_bytes = lambda ob: 2 * n                                      # two passes (crc32, adler32), each reads the buffer once
-        kernel_name = "checksum_tiles_kernel x2 (+ folds)"
+        alg_bytes = lambda ob: n                                          # one fused pass reads the buffer once
+        kernel_name = "checksum_tiles_kernel<crc32 + adler32> (+ folds)"
         note = "table-driven CRC-32 without carry-less multiply: shared-memory lookup bound"
 
     else:  # inflate
@@ -481,10 +645,26 @@ def run_b200(args):
                 k_stop[i_timed].record()
             launches["n"] += 1
 
-        def parity_check():
-            ok = bool((status == 1).all()) and bool((sizes == MEMBER).all())
-            ok &= bool(torch.equal(d_out.cpu(), torch.from_numpy(data)))
-            return "every member Z_STREAM_END (CRC-32 + ISIZE verified on device), output identical to the original buffer" if ok else "MISMATCH"
+        def parity_check(e2e_out=None):
+            """EVERY member against the unmodified reference's zng_inflate(Z_FINISH) (oracle/_ref; the port if absent): return
+            code, output size, CRC-32, output bytes (= the original buffer)."""
+            from __graft_entry__ import load_oracle
+            zo = load_oracle()
+            kind = "oracle/_ref (unmodified zlib-ng 2.2.2)" if zo.have_ref() else "oracle port"
+            fn = zo.ref().refdrv_inflate_members if zo.have_ref() else zo.port().zo_inflate_members
+            r_out = np.empty(n, dtype=np.uint8)
+            r_sizes = np.zeros(nm, dtype=np.uint32); r_crcs = np.zeros(nm, dtype=np.uint32); r_status = np.zeros(nm, dtype=np.int32)
+            u_in = in_off.astype(np.uint64); u_out = out_off.astype(np.uint64)
+            rr = fn(members.ctypes.data, u_in.ctypes.data, nm, r_out.ctypes.data, u_out.ctypes.data, r_sizes.ctypes.data, r_crcs.ctypes.data,
+                    r_status.ctypes.data, host_cores() if ngpu == 1 else max(1, host_cores() // ngpu))
+            g_status = status.cpu().numpy(); g_sizes = sizes.cpu().numpy().view(np.uint32); g_checks = checks.cpu().numpy().view(np.uint32)
+            g_out = d_out.cpu().numpy()
+            bad = int((g_status != r_status).sum()) + int((g_sizes != r_sizes).sum()) + int((g_checks != r_crcs).sum())
+            ok = rr == 0 and bad == 0 and np.array_equal(g_out, r_out) and np.array_equal(r_out, data)
+            if ok and e2e_out is not None:
+                ok = np.array_equal(e2e_out, r_out)
+            text = (f"all {nm} of {nm} members equal {kind}: return code, size, crc32 and output bytes" + ("; e2e host output identical" if e2e_out is not None else "")) if ok else f"MISMATCH vs {kind} ({bad} member fields differ)"
+            return text, ok, {"n": n}
 
         def finish():
             return comp_bytes
@@ -496,7 +676,7 @@ def run_b200(args):
             def call():
                 _, _, st, _, _ = ctx.inflate_members_host(h_members, uin_off, 31, h_out, uout_off)
                 assert int(st.min()) == 1
-            return call, (lambda: (comp_bytes, n)), "zng_b200_inflate_members_host (pinned host in/out, 3 slabs of 32768 members in flight)"
+            return call, (lambda: (comp_bytes, n)), "zng_b200_inflate_members_host (pinned host in/out, 3 slabs of 32768 members in flight)", (lambda: h_out.numpy())
         e2e_fn = make_e2e
         alg_bytes = lambda ob: ob + n                                     # compressed in + raw out
         kernel_name = "inflate_members_kernel"
@@ -506,11 +686,6 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    if rank == 0:
-        try:
-            parity = parity_check()
-        except Exception as e:  # oracle not built: say so, do not guess
-            parity = f"not checked ({e})"
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -534,14 +709,15 @@ def run_b200(args):
     value = ngpu * n / (ms_step * 1e-3) / 1e9
     out_bytes = finish()
 
-    # ---- e2e: host buffers through the C-ABI host call, H2D/D2H inside the timed region
+    # ---- e2e: host buffers through the C-ABI host call, H2D/D2H inside the timed region (every rank at once, max over ranks)
     e2e = None
+    e2e_out = None
     if not args.no_e2e:
-        call, bytes_fn, api = e2e_fn()
+        call, bytes_fn, api, out_fn = e2e_fn()
         for _ in range(2):
             call()
+        e_steps = max(1, steps)
         barrier()
-        e_steps = max(3, min(steps, 5))
         t0 = time.perf_counter()
         for _ in range(e_steps):
             call()
@@ -553,6 +729,33 @@ def run_b200(args):
         dt = float(tt.item())
         h2d, d2h = bytes_fn()
         e2e = {"value": ngpu * n * e_steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps, "api": api}
+        e2e_out = out_fn()
+        # the same bytes over the same pinned buffers with no kernels at all: what the box's host<->device paths allow
+        passes = 2 if wl == "checksum" else 1                      # crc32_host and adler32_host each move the buffer
+        up = h2d // passes
+        scale = min(1.0, float(1 << 30) / max(1, up))               # a bounded sample of the step's transfers (<= 1 GiB up), same ratio
+        ceil = copy_ceiling(torch, dev, h_in if wl != "inflate" else h_members, int(up * scale), int(d2h * scale), barrier, 3)
+        tc = torch.tensor([ceil], dtype=torch.float64, device=dev)
+        if ngpu > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        e2e["copy_ceiling"] = {"value": ngpu * n * scale / (passes * float(tc.item())) / 1e9, "unit": UNIT,
+                               "what": "H2D of the step's input (16 MiB pieces) and D2H of its output (32 MiB pieces) on two streams, same pinned input buffer, no kernels; every rank at once, max over ranks"}
+        e2e["frac_of_copy_ceiling"] = e2e["value"] / e2e["copy_ceiling"]["value"]
+
+    # ---- parity: EVERY unit of every rank's shard against the unmodified reference, then the cross-rank facts
+    ok, facts = None, None
+    if args.no_parity:
+        parity = "skipped (--no-parity)"
+    else:
+        try:
+            parity, ok, facts = parity_check(e2e_out)
+        except Exception as e:  # oracle not built: say so, do not guess
+            parity, ok, facts = f"not checked ({type(e).__name__}: {e})", None, None
+        if ngpu > 1:
+            allp = [None] * ngpu
+            dist.all_gather_object(allp, (parity, ok, facts))
+            if rank == 0:
+                parity = cross_rank_parity(allp, wl, global_facts() if wl != "inflate" else None)
 
     if rank != 0:
         if ngpu > 1:
@@ -588,11 +791,8 @@ def run_b200(args):
 
     line = {
         "metric": METRICS[wl], "value": value, "unit": UNIT, "n_gpus": ngpu, "steps": steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_text(wl, args.mib_per_gpu, ngpu), "chunk_bytes": CHUNK,
-                   "sharding": f"contiguous chunk ranges x{ngpu}",
-                   "collective": ("nccl allgather of (size, crc32) per chunk" if wl.startswith("deflate") else ("nccl allgather of (crc32, adler32) per rank" if wl == "checksum" else "none")) if ngpu > 1 else "none",
-                   "l2": f"input {args.mib_per_gpu} MiB per step >> 126 MB L2, no flush needed"},
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": config_dict(args, ngpu),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["n"], "clocks": clocks, "numa_node": numa,
         "compression_ratio": (out_bytes / n) if wl != "checksum" else None, "parity": parity,
         "pct_hbm_peak_input_only": 100.0 * (value / ngpu) / peak,

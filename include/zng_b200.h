@@ -207,8 +207,6 @@ struct zng_b200_functable {
 };
 const struct zng_b200_functable *zng_b200_functable_get(void);
 
-/* ---- synthetic workload (bench / tests; BASELINE.json "synthetic mixed text/binary") ------- */
-int zng_b200_synth_fill(void *h_buf, size_t n, uint64_t seed, uint64_t offset);
 
 #ifdef __cplusplus
 }

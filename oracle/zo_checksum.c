@@ -122,3 +122,42 @@ uint32_t zo_compare256(const uint8_t *a, const uint8_t *b) {
     while (i < 256 && a[i] == b[i]) i++;
     return i;
 }
+
+/* Test helper (no reference counterpart): compare n chunk outputs byte for byte.  `a` holds chunk i at a + i*stride_a
+ * (stride_a != 0: slots) or packed back to back in chunk order (stride_a == 0); `b` likewise.  Returns the number of
+ * chunks whose size or bytes differ; *first_bad = index of the first one (n if none). */
+#include <string.h>
+size_t zo_compare_chunks(const uint8_t *a, size_t stride_a, const uint32_t *sizes_a,
+                         const uint8_t *b, size_t stride_b, const uint32_t *sizes_b, size_t n, size_t *first_bad) {
+    size_t bad = 0, oa = 0, ob = 0, first = n;
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t *pa = stride_a ? a + i * stride_a : a + oa;
+        const uint8_t *pb = stride_b ? b + i * stride_b : b + ob;
+        if (sizes_a[i] != sizes_b[i] || memcmp(pa, pb, sizes_a[i]) != 0) { if (!bad) first = i; bad++; }
+        oa += sizes_a[i]; ob += sizes_b[i];
+    }
+    if (first_bad) *first_bad = first;
+    return bad;
+}
+
+/* Test helper: wrap n raw-deflate bodies (body i at bodies + i*stride, sizes[i] bytes, CRC-32 crcs[i] of its raw_len[i]
+ * uncompressed bytes) into gzip members as minigzip -1 frames them (deflate.c:902-921 header 1f 8b 08 00 00000000 XFL OS with
+ * XFL 4 for level 1, OS 3; deflate.c:1091-1096 trailer CRC-32, ISIZE), packed back to back.  off[n+1] receives the member
+ * offsets.  Returns the total length (call with out == NULL to size the buffer). */
+size_t zo_frame_gzip_members(const uint8_t *bodies, size_t stride, const uint32_t *sizes, const uint32_t *crcs,
+                             uint32_t raw_len, uint32_t last_raw_len, size_t n, int xfl, uint8_t *out, uint64_t *off) {
+    size_t o = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (off) off[i] = o;
+        if (out) {
+            const uint8_t hdr[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, (uint8_t)xfl, 3};
+            memcpy(out + o, hdr, 10);
+            memcpy(out + o + 10, bodies + i * stride, sizes[i]);
+            uint32_t t[2] = {crcs[i], (i + 1 == n) ? last_raw_len : raw_len};
+            memcpy(out + o + 10 + sizes[i], t, 8);          /* little-endian host (x86-64, the frozen oracle platform) */
+        }
+        o += 18u + sizes[i];
+    }
+    if (off) off[n] = o;
+    return o;
+}

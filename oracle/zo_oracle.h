@@ -39,6 +39,10 @@ uint32_t zo_crc32_combine_gen(int64_t len2);
 uint32_t zo_crc32_combine_op(uint32_t crc1, uint32_t crc2, uint32_t op);
 uint32_t zo_adler32_combine(uint32_t adler1, uint32_t adler2, int64_t len2);
 uint32_t zo_compare256(const uint8_t *a, const uint8_t *b);
+size_t zo_frame_gzip_members(const uint8_t *bodies, size_t stride, const uint32_t *sizes, const uint32_t *crcs,
+                             uint32_t raw_len, uint32_t last_raw_len, size_t n, int xfl, uint8_t *out, uint64_t *off);
+size_t zo_compare_chunks(const uint8_t *a, size_t stride_a, const uint32_t *sizes_a,
+                         const uint8_t *b, size_t stride_b, const uint32_t *sizes_b, size_t n, size_t *first_bad);
 
 /* ---- deflate (zo_deflate.c) ---- */
 /* Upper bound of one chunk's output for the frozen parameters (deflate.c:709-781 analogue,

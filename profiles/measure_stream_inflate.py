@@ -8,7 +8,7 @@ from __graft_entry__ import load_package
 pkg = load_package(); L = pkg.lib()
 n = int(sys.argv[1]) << 20 if len(sys.argv) > 1 else 1 << 30
 h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-assert L.zng_b200_synth_fill(h_in.data_ptr(), n, 0x9E3779B97F4A7C15, 0) == 0
+from __graft_entry__ import load_synth; load_synth().fill(h_in.data_ptr(), n)
 for level in (1, 2):
     s = pkg.ZngStream()
     assert L.zng_deflateInit2(ctypes.byref(s), level, 8, 31, 8, 0) == 0

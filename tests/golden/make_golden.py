@@ -11,7 +11,7 @@ can still check parity.
       Per-chunk (compressed size, crc32 of the compressed bytes, crc32 and adler32 of the input)
       produced by the UNMODIFIED reference (oracle/_ref, zlib-ng 2.2.2, gcc -O3, default build
       flags, x86-64 => OPTIMAL_CMP 64) for seeded inputs of the synthetic generator
-      (zlib-ng_b200/host/synth.c) and a few hand-made edge cases.  Compressed bytes are pinned by
+      (tests/synth.c) and a few hand-made edge cases.  Compressed bytes are pinned by
       no test of the reference, so these digests are the pin.
   inflate_kat.json
       The hand-written bitstreams of test/infcover.c with the return code the reference expects.
@@ -28,6 +28,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference"
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from synthdata import synth  # noqa: E402
 
 
 def c_unescape(lit: str) -> bytes:
@@ -120,16 +122,16 @@ def deflate_digests():
 
     rng = np.random.default_rng(20261018)
     for level in (1, 2, 3, 4, 5, 6):
-        add(f"synth_2MiB_l{level}", pkg.synth(32 * 65536), 65536, level, 3)
-        add(f"synth_ragged_l{level}", pkg.synth(10 * 65536 + 777, seed=12345), 65536, level, 3)
-        add(f"synth_finish_l{level}", pkg.synth(4 * 65536 + 4097, seed=99), 65536, level, 4)
-        add(f"synth_4k_members_l{level}", pkg.synth(64 * 4096, seed=7), 4096, level, 4)
+        add(f"synth_2MiB_l{level}", synth(32 * 65536), 65536, level, 3)
+        add(f"synth_ragged_l{level}", synth(10 * 65536 + 777, seed=12345), 65536, level, 3)
+        add(f"synth_finish_l{level}", synth(4 * 65536 + 4097, seed=99), 65536, level, 4)
+        add(f"synth_4k_members_l{level}", synth(64 * 4096, seed=7), 4096, level, 4)
         add(f"zeros_l{level}", np.zeros(3 * 65536 + 5, dtype=np.uint8), 65536, level, 3)
         add(f"random_l{level}", rng.integers(0, 256, size=2 * 65536 + 100, dtype=np.uint8), 65536, level, 3)
-        add(f"tiny_sizes_l{level}", pkg.synth(65536, seed=3)[:257 * 40], 257, level, 3)
+        add(f"tiny_sizes_l{level}", synth(65536, seed=3)[:257 * 40], 257, level, 3)
         for n in (0, 1, 2, 3, 4, 5, 7, 8, 9, 258, 259, 260, 262, 263):
-            add(f"short_{n}_l{level}", pkg.synth(65536, seed=5)[:n], 65536, level, 3)
-            add(f"short_{n}_finish_l{level}", pkg.synth(65536, seed=5)[:n], 65536, level, 4)
+            add(f"short_{n}_l{level}", synth(65536, seed=5)[:n], 65536, level, 3)
+            add(f"short_{n}_finish_l{level}", synth(65536, seed=5)[:n], 65536, level, 4)
     return cases
 
 
@@ -142,7 +144,7 @@ def primed_digests():
     for seed, n, flush in ((61, 16 * 65536 + 4321, 2), (62, 8 * 65536, 3), (63, 3 * 65536 + 1, 4), (64, 2 * 65536 + 261, 2), (65, 2 * 65536 + 262, 2),
                            (66, 2 * 65536 + 263, 4), (67, 65536 + 32768, 2), (68, 65536 + 32769, 2), (69, 65536 + 65274, 4), (70, 65536 + 65275, 2),
                            (71, 65536 + 65535, 2), (72, 65536 + 3, 2), (73, 4097, 4)):
-        data = pkg.synth(n, seed=seed)
+        data = synth(n, seed=seed)
         for level in (1, 2, 3, 4, 5, 6):
             if level > 1 and n > 9 * 65536:
                 continue
@@ -162,10 +164,10 @@ def main():
     inf = parse_infcover(f"{REF}/test/infcover.c")
     json.dump({"source": "test/infcover.c inf() calls", "vectors": inf}, open(f"{HERE}/inflate_kat.json", "w"), indent=0)
     dd = deflate_digests()
-    json.dump({"source": "oracle/_ref (unmodified zlib-ng 2.2.2) via refdrv_deflate_chunks; inputs from zlib-ng_b200/host/synth.c",
+    json.dump({"source": "oracle/_ref (unmodified zlib-ng 2.2.2) via refdrv_deflate_chunks; inputs from tests/synth.c",
                "cases": dd}, open(f"{HERE}/deflate_digests.json", "w"))
     pd = primed_digests()
-    json.dump({"source": "oracle/_ref (unmodified zlib-ng 2.2.2) via refdrv_deflate_chunks_primed, levels 1-6; inputs pkg.synth(n, seed)",
+    json.dump({"source": "oracle/_ref (unmodified zlib-ng 2.2.2) via refdrv_deflate_chunks_primed, levels 1-6; inputs synth(n, seed)",
                "cases": pd}, open(f"{HERE}/primed_digests.json", "w"))
     print(f"primed digest cases {len(pd)}")
     print(f"crc32 KATs {len(crc)}, adler32 KATs {len(adl)}, infcover vectors {len(inf)}, deflate digest cases {len(dd)}")

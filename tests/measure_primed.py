@@ -6,11 +6,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from __graft_entry__ import load_package, load_oracle
+from synthdata import synth
 pkg = load_package(); zo = load_oracle()
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 n = mib << 20
 ctx = pkg.Context(0)
-data = pkg.synth(n, seed=0x9E3779B97F4A7C15)
+data = synth(n, seed=0x9E3779B97F4A7C15)
 d_in = torch.from_numpy(data).cuda()
 slots, stride, sizes, crcs, _ = ctx.alloc_chunk_outputs(n, 65536)
 for name, fn in (("independent (Z_FULL_FLUSH)", lambda: ctx.deflate_chunks(d_in, n, 65536, 1, 3, slots, stride, sizes, crcs, None)),

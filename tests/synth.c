@@ -7,9 +7,11 @@
  * patterns).  Every 64 KiB unit is generated from (seed, unit index) alone, so each rank of a
  * multi-GPU run can fill its own shard and all ranks agree on the bytes.
  *
- * This is host-side test/bench plumbing, not part of the reference's API.
+ * TEST / BENCH INFRASTRUCTURE ONLY: built into tests/libzng_synth.so (oracle/Makefile target `synth`), loaded by
+ * tests/synthdata.py.  Not part of the product library and not part of the reference's API.
  */
-#include "zng_b200.h"
+#include <stddef.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -127,7 +129,7 @@ static void fill_repetitive(uint8_t *p, uint32_t n, uint64_t st) {
 
 /* Fill buf[0..n) with the bytes of the synthetic stream starting at absolute byte offset
  * `offset` (must be a multiple of 65536).  Deterministic in (seed, offset, n). */
-int zng_b200_synth_fill(void *buf, size_t n, uint64_t seed, uint64_t offset) {
+__attribute__((visibility("default"))) int zng_synth_fill(void *buf, size_t n, uint64_t seed, uint64_t offset) {
     if (offset % SYNTH_UNIT) return -2;
     dict_t *d = (dict_t *)malloc(sizeof(dict_t));
     if (!d) return -4;

@@ -3,6 +3,7 @@ reference's known-answer vectors and the CPU oracle."""
 import zlib as pyzlib
 
 import numpy as np
+from synthdata import synth
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -43,7 +44,7 @@ def test_flat_checksums_vs_oracle(pkg, ctx, zo, n):
 
 def test_unaligned_device_pointer(pkg, ctx, zo):
     import torch
-    data = pkg.synth(4 * 65536, seed=77)
+    data = synth(4 * 65536, seed=77)
     d = torch.from_numpy(data).to(f"cuda:{ctx.device}")
     res = torch.zeros(1, dtype=torch.int32, device=d.device)
     for off in (1, 2, 3, 5, 15):
@@ -55,7 +56,7 @@ def test_unaligned_device_pointer(pkg, ctx, zo):
 def test_chunk_checksums_and_folds(pkg, ctx, zo):
     import torch
     n = 37 * 65536 + 1234
-    data = pkg.synth(n, seed=88)
+    data = synth(n, seed=88)
     dev = f"cuda:{ctx.device}"
     d = torch.from_numpy(data).to(dev)
     for tile in (65536, 4096, 1000):
@@ -80,7 +81,7 @@ def test_crc_of_1GiB_property(pkg, ctx):
     the fold of its two halves and an independent host computation."""
     import torch
     n = 1 << 30
-    data = pkg.synth(n, seed=404)
+    data = synth(n, seed=404)
     d = torch.from_numpy(data).to(f"cuda:{ctx.device}")
     res = torch.zeros(4, dtype=torch.int32, device=d.device)
     ctx.crc32(d, n, 0, res[0:1])
@@ -107,7 +108,7 @@ def test_flat_checksums_at_4GiB_equal_the_combine_of_their_parts(pkg, ctx):
     d = torch.empty(n, dtype=torch.uint8, device=dev)
     h = np.empty(gib, dtype=np.uint8)
     for q in range(4):
-        assert L.zng_b200_synth_fill(h.ctypes.data, gib, 0x9E3779B97F4A7C15, q * gib) == 0
+        h = synth(gib, offset=q * gib)
         d[q * gib:(q + 1) * gib] = torch.from_numpy(h).to(dev)
         if q == 0:
             first = (pyzlib.crc32(h.tobytes()), pyzlib.adler32(h.tobytes()))

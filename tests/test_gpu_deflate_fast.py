@@ -5,6 +5,7 @@ inflater.  Every test runs for every level."""
 import zlib as pyzlib
 
 import numpy as np
+from synthdata import synth
 import pytest
 
 from test_gpu_deflate_quick import assert_parity, gpu_deflate
@@ -18,7 +19,7 @@ def level(request):
 
 
 def test_synthetic_mix_bit_exact(pkg, ctx, zo, level):
-    data = pkg.synth(64 * 65536 + 4321, seed=101)
+    data = synth(64 * 65536 + 4321, seed=101)
     got, sizes = assert_parity(pkg, ctx, zo, data, level=level)
     # every chunk inflates on its own (Z_FULL_FLUSH boundaries) with an independent inflater
     for i in (0, 1, 2, 3, 17, 63, 64):
@@ -28,14 +29,14 @@ def test_synthetic_mix_bit_exact(pkg, ctx, zo, level):
 
 
 def test_each_unit_type(pkg, ctx, zo, level):
-    base = pkg.synth(10 * 65536, seed=202)
+    base = synth(10 * 65536, seed=202)
     for u in range(10):
         assert_parity(pkg, ctx, zo, base[u * 65536:(u + 1) * 65536], level=level)
 
 
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 7, 8, 9, 31, 32, 33, 63, 64, 65, 257, 258, 259, 260, 262, 263, 4095, 4096, 65535])
 def test_short_inputs(pkg, ctx, zo, n, level):
-    data = pkg.synth(65536, seed=5)[:n]
+    data = synth(65536, seed=5)[:n]
     for flush in (3, 4):
         assert_parity(pkg, ctx, zo, data, 65536, flush, level=level)
 
@@ -116,7 +117,7 @@ def test_lookahead_hand_over_and_fizzle(pkg, ctx, zo, level):
     """Many short chunks: every chunk ends in the zone where deflate_medium stops looking ahead (deflate_medium.c:164-172,
     234); low-entropy and periodic data make adjacent matches that fizzle_matches (:84-144) shifts."""
     rng = np.random.default_rng(77)
-    data = pkg.synth(6 * 65536, seed=31)
+    data = synth(6 * 65536, seed=31)
     for chunk in (553, 554, 555, 600, 777, 1024, 2500, 8191):
         assert_parity(pkg, ctx, zo, data[:200 * chunk if 200 * chunk < data.size else data.size], chunk, 3, level=level)
     low = rng.integers(0, 3, size=4 * 65536, dtype=np.uint8)
@@ -132,10 +133,10 @@ def test_lookahead_hand_over_and_fizzle(pkg, ctx, zo, level):
 
 
 def test_small_chunks_and_finish_members(pkg, ctx, zo, level):
-    data = pkg.synth(64 * 4096, seed=7)
+    data = synth(64 * 4096, seed=7)
     assert_parity(pkg, ctx, zo, data, 4096, 4, level=level)
-    assert_parity(pkg, ctx, zo, pkg.synth(65536, seed=3)[:257 * 40], 257, 3, level=level)
-    assert_parity(pkg, ctx, zo, pkg.synth(3 * 65536, seed=9), 1000, 3, level=level)
+    assert_parity(pkg, ctx, zo, synth(65536, seed=3)[:257 * 40], 257, 3, level=level)
+    assert_parity(pkg, ctx, zo, synth(3 * 65536, seed=9), 1000, 3, level=level)
 
 
 def test_golden_digests_of_the_unmodified_reference(pkg, ctx, golden, level):
@@ -155,7 +156,7 @@ def test_golden_digests_of_the_unmodified_reference(pkg, ctx, golden, level):
 def test_host_path_level2_stream(pkg, ctx, zo, level):
     from test_gpu_host_path import oracle_stream
     for n, final in ((5 * 65536 + 99, True), (5 * 65536 + 99, False), ((70 << 20) + 12345, True)):
-        data = pkg.synth(n, seed=n % 1000 + 1)
+        data = synth(n, seed=n % 1000 + 1)
         cap = pkg.deflate_bound(65536) * ((n + 65535) // 65536 + 1)
         out = np.empty(cap, dtype=np.uint8)
         out_len, crc, adler = ctx.deflate_host(data, n, 65536, level, final, out, cap)
@@ -172,7 +173,7 @@ def test_host_path_level2_stream(pkg, ctx, zo, level):
 def test_256MiB_round_trip_and_sampled_parity(pkg, ctx, zo, level):
     import torch
     n = 256 << 20
-    data = pkg.synth(n, seed=404)
+    data = synth(n, seed=404)
     dev = f"cuda:{ctx.device}"
     d_in = torch.from_numpy(data).to(dev)
     slots, stride, sizes, crcs, adlers = ctx.alloc_chunk_outputs(n)

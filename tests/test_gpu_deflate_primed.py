@@ -5,6 +5,7 @@ live, when oracle/_ref travelled) byte for byte, and the concatenation must infl
 import zlib as pyzlib
 
 import numpy as np
+from synthdata import synth
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -38,7 +39,7 @@ def assert_primed_parity(pkg, ctx, zo, data, flush=2):
 
 
 def test_primed_synthetic_mix_and_stream_validity(pkg, ctx, zo):
-    data = pkg.synth(40 * 65536 + 4321, seed=61)
+    data = synth(40 * 65536 + 4321, seed=61)
     got, sizes = assert_primed_parity(pkg, ctx, zo, data, 2)
     stream = b"".join(got[i, : sizes[i]].tobytes() for i in range(len(sizes))) + b"\x03\x00"
     assert pyzlib.decompress(stream, wbits=-15) == data.tobytes()                 # one dependent stream, inflated in order
@@ -64,7 +65,7 @@ def test_primed_data_shapes(pkg, ctx, zo, flush):
 @pytest.mark.parametrize("tail", [0, 1, 2, 3, 4, 5, 100, 261, 262, 263, 300, 32767, 32768, 32769, 33000, 65274, 65275, 65279, 65535])
 def test_primed_last_chunk_lengths(pkg, ctx, zo, tail):
     """The refill / slide schedule of fill_window (deflate.c:1272-1340) depends on the length of the primed chunk."""
-    data = pkg.synth(2 * 65536 + tail, seed=tail)
+    data = synth(2 * 65536 + tail, seed=tail)
     for flush in (2, 4):
         assert_primed_parity(pkg, ctx, zo, data, flush)
     assert_primed_parity(pkg, ctx, zo, data[: 65536 + tail], 2)
@@ -86,7 +87,7 @@ def test_primed_golden_digests_of_the_unmodified_reference(pkg, ctx, golden):
     cases = [c for c in golden("primed_digests.json")["cases"] if c.get("level", 1) == 1]     # the GPU path primes level 1 (levels 2-6: oracle only so far)
     assert len(cases) >= 10
     for c in cases:
-        data = pkg.synth(c["n"], seed=c["seed"])
+        data = synth(c["n"], seed=c["seed"])
         got, sizes, crcs, _, _ = gpu_primed(pkg, ctx, data, c["flush"])
         assert [int(x) for x in sizes] == c["sizes"], c
         assert [int(zlib.crc32(got[i, : sizes[i]].tobytes())) for i in range(len(sizes))] == c["comp_crc32"], c
@@ -95,7 +96,7 @@ def test_primed_golden_digests_of_the_unmodified_reference(pkg, ctx, golden):
 def test_primed_256MiB_round_trip(pkg, ctx, zo):
     import torch
     n = 256 << 20
-    data = pkg.synth(n, seed=2027)
+    data = synth(n, seed=2027)
     d_in = torch.from_numpy(data).to(f"cuda:{ctx.device}")
     slots, stride, sizes, crcs, _ = ctx.alloc_chunk_outputs(n, 65536)
     ctx.deflate_chunks_primed(d_in, n, 65536, 1, 2, slots, stride, sizes, crcs, None)
@@ -117,7 +118,7 @@ def test_primed_stream_inflates_through_the_stream_path(pkg, ctx, zo):
     rng = np.random.default_rng(8)
     words = rng.integers(97, 123, size=(64, 6), dtype=np.uint8)
     text = words[rng.integers(0, 64, size=90000)].reshape(-1)[:7 * 65536 + 999]
-    for data in (text, pkg.synth(6 * 65536 + 5, seed=91)):
+    for data in (text, synth(6 * 65536 + 5, seed=91)):
         got, sizes, _, _, _ = gpu_primed(pkg, ctx, data, 2)
         raw = b"".join(got[i, : sizes[i]].tobytes() for i in range(len(sizes))) + b"\x03\x00"
         assert pyzlib.decompress(raw, wbits=-15) == data.tobytes()

@@ -4,6 +4,7 @@ committed digests of the unmodified reference and size-independent round-trip pr
 import zlib as pyzlib   # independent inflater for round trips / byte-string digests only
 
 import numpy as np
+from synthdata import synth
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -56,19 +57,19 @@ def assert_parity(pkg, ctx, zo, data, chunk=65536, flush=3, level=1):
 
 
 def test_synthetic_mix_bit_exact(pkg, ctx, zo):
-    data = pkg.synth(64 * 65536 + 4321, seed=101)       # every unit type several times + a ragged tail
+    data = synth(64 * 65536 + 4321, seed=101)       # every unit type several times + a ragged tail
     assert_parity(pkg, ctx, zo, data)
 
 
 def test_each_unit_type(pkg, ctx, zo):
-    base = pkg.synth(10 * 65536, seed=202)
+    base = synth(10 * 65536, seed=202)
     for u in range(10):
         assert_parity(pkg, ctx, zo, base[u * 65536:(u + 1) * 65536])
 
 
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 7, 8, 9, 31, 32, 33, 63, 64, 65, 257, 258, 259, 260, 262, 263, 4095, 4096, 65535])
 def test_short_inputs(pkg, ctx, zo, n):
-    data = pkg.synth(65536, seed=5)[:n]
+    data = synth(65536, seed=5)[:n]
     for flush in (3, 4):
         assert_parity(pkg, ctx, zo, data, 65536, flush)
 
@@ -97,10 +98,10 @@ def test_matches_far_and_at_max_dist(pkg, ctx, zo):
 
 
 def test_small_chunks_and_finish_members(pkg, ctx, zo):
-    data = pkg.synth(64 * 4096, seed=7)
+    data = synth(64 * 4096, seed=7)
     assert_parity(pkg, ctx, zo, data, 4096, 4)        # config-4 style members (one Z_FINISH block each)
-    assert_parity(pkg, ctx, zo, pkg.synth(65536, seed=3)[:257 * 40], 257, 3)
-    assert_parity(pkg, ctx, zo, pkg.synth(3 * 65536, seed=9), 1000, 3)
+    assert_parity(pkg, ctx, zo, synth(65536, seed=3)[:257 * 40], 257, 3)
+    assert_parity(pkg, ctx, zo, synth(3 * 65536, seed=9), 1000, 3)
 
 
 def test_golden_digests_of_the_unmodified_reference(pkg, ctx, golden):
@@ -124,7 +125,7 @@ def test_stream_assembly_round_trip_256MiB(pkg, ctx, zo):
     CRC-32s equals the CRC-32 of the whole buffer."""
     import torch
     n = 256 << 20
-    data = pkg.synth(n, seed=303)
+    data = synth(n, seed=303)
     dev = f"cuda:{ctx.device}"
     d_in = torch.from_numpy(data).to(dev)
     slots, stride, sizes, crcs, adlers = ctx.alloc_chunk_outputs(n)

@@ -7,6 +7,7 @@ import struct
 import zlib as pyzlib
 
 import numpy as np
+from synthdata import synth
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -72,7 +73,7 @@ def deflate_via_api(pkg, L, data, level, wb, pieces, out_room=None):
 @pytest.mark.parametrize("wb", [-15, 15, 31])
 @pytest.mark.parametrize("n", [0, 1, 65536, 3 * 65536 + 777, (8 << 20) + 5])
 def test_zng_deflate_one_call_equals_reference_piecewise(pkg, L, zo, n, wb):
-    data = pkg.synth(n, seed=n % 97 + 2)
+    data = synth(n, seed=n % 97 + 2)
     got, adler = deflate_via_api(pkg, L, data, 1, wb, [(n, pkg.Z_FINISH)])
     assert got == expected_stream(zo, data, 1, wb)
     assert pyzlib.decompress(got, wbits=wb) == data.tobytes()
@@ -87,7 +88,7 @@ def test_zng_deflate_every_level(pkg, L, zo, level):
     """Levels 2-6 and Z_DEFAULT_COMPRESSION (= 6, deflate.c:43) through zng_deflateInit2 / zng_deflate, zlib and gzip wrappers
     (the FLEVEL bits of the zlib header follow deflate.c:873-880)."""
     n = 3 * 65536 + 777
-    data = pkg.synth(n, seed=level + 40)
+    data = synth(n, seed=level + 40)
     for wb in (15, 31):
         got, _ = deflate_via_api(pkg, L, data, level, wb, [(n, pkg.Z_FINISH)])
         assert got == expected_stream(zo, data, 6 if level < 0 else level, wb)
@@ -98,7 +99,7 @@ def test_zng_deflateSetDictionary_dependent_chunks(pkg, L, zo):
     """pigz's loop on the library: per chunk zng_deflateReset + zng_deflateSetDictionary(last 32 KiB of the previous chunk) +
     zng_deflate(Z_SYNC_FLUSH / Z_FINISH) -- every chunk equals what the unmodified reference emits for the same calls on a
     fresh stream, and one call over several pieces equals the same pieces joined."""
-    data = pkg.synth(5 * 65536 + 4321, seed=73)
+    data = synth(5 * 65536 + 4321, seed=73)
     n = data.size
     exp, esz, _, _ = (zo.ref_deflate_chunks_primed if zo.have_ref() else zo.port_deflate_chunks_primed)(data, 65536, 1, 2)
     expf, efsz, _, _ = (zo.ref_deflate_chunks_primed if zo.have_ref() else zo.port_deflate_chunks_primed)(data, 65536, 1, 4)
@@ -143,7 +144,7 @@ def test_zng_deflateSetDictionary_dependent_chunks(pkg, L, zo):
 
 def test_zng_deflate_piecewise_and_small_output_windows(pkg, L, zo):
     n = 5 * 65536 + 1234
-    data = pkg.synth(n, seed=11)
+    data = synth(n, seed=11)
     exp = expected_stream(zo, data, 1, 31)
     # the reference's own call sequence: one 64 KiB piece per Z_FULL_FLUSH call, Z_FINISH on the tail
     pieces = [(65536, pkg.Z_FULL_FLUSH)] * 5 + [(1234, pkg.Z_FINISH)]
@@ -187,7 +188,7 @@ def test_zng_inflate_oneshot_matches_oracle(pkg, L, zo):
     rng = np.random.default_rng(5)
     for trial in range(24):
         size = int(rng.integers(0, 200000))
-        data = pkg.synth(size + 10, seed=trial + 3)[:size].tobytes()
+        data = synth(size + 10, seed=trial + 3)[:size].tobytes()
         wb = [-15, 15, 31][trial % 3]
         co = pyzlib.compressobj(int(rng.choice([1, 6])), pyzlib.DEFLATED, wb)
         st = co.compress(data) + co.flush()
@@ -204,7 +205,7 @@ def test_zng_inflate_oneshot_matches_oracle(pkg, L, zo):
 
 
 def test_zng_inflate_incremental(pkg, L):
-    data = pkg.synth(300000, seed=8).tobytes()
+    data = synth(300000, seed=8).tobytes()
     st = pyzlib.compress(data, 6)
     src = np.frombuffer(st, dtype=np.uint8).copy()
     s = pkg.ZngStream()
@@ -225,7 +226,7 @@ def test_zng_inflate_incremental(pkg, L):
 
 
 def test_compress_uncompress_roundtrip(pkg, L, zo):
-    data = pkg.synth(5 * 65536 + 321, seed=21)
+    data = synth(5 * 65536 + 321, seed=21)
     cap = int(L.zng_compressBound(data.size))
     comp = np.zeros(cap, dtype=np.uint8)
     clen = ctypes.c_size_t(cap)
@@ -260,7 +261,7 @@ def test_checksum_api(pkg, L, zo, golden):
         buf = np.frombuffer(bytes.fromhex(v["data_hex"]) + b"\0", dtype=np.uint8).copy()
         assert L.zng_adler32_z(v["init"], buf.ctypes.data, buf.size - 1) == v["expect"], v
     assert L.zng_crc32_z(123, None, 10) == 0 and L.zng_adler32_z(123, None, 10) == 1      # crc32.c:28, adler32_c.c
-    data = pkg.synth(3_000_001, seed=5)
+    data = synth(3_000_001, seed=5)
     a, b = data[:1_234_567], data[1_234_567:]
     ca, cb = L.zng_crc32_z(0, a.ctypes.data, a.size), L.zng_crc32_z(0, b.ctypes.data, b.size)
     assert ca == pyzlib.crc32(a.tobytes()) and L.zng_crc32_combine(ca, cb, b.size) == pyzlib.crc32(data.tobytes())
@@ -281,7 +282,7 @@ def test_minigzip_cli_roundtrip(pkg, zo, tmp_path):
     exe = os.path.join(os.path.dirname(pkg.LIB_PATH), "minigzip_b200")
     if not os.path.exists(exe):
         pytest.skip("minigzip_b200 not built")
-    data = pkg.synth(7 * 65536 + 4321, seed=19)
+    data = synth(7 * 65536 + 4321, seed=19)
     src = tmp_path / "in.bin"
     src.write_bytes(data.tobytes())
     for level in (1, 2, 3, 4, 5, 6):

@@ -3,6 +3,7 @@ K1 -> gather -> D2H, compared with the oracle's concatenated chunk stream."""
 import zlib as pyzlib
 
 import numpy as np
+from synthdata import synth
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -31,7 +32,7 @@ def oracle_stream(zo, data, chunk, level, final):
 @pytest.mark.parametrize("n,final", [(0, True), (0, False), (1, True), (65536, True), (65536, False), (5 * 65536 + 99, True),
                                      (5 * 65536 + 99, False), ((40 << 20) + 12345, True), ((100 << 20), False)])
 def test_deflate_host_matches_oracle_stream(pkg, ctx, zo, n, final):
-    data = pkg.synth(n, seed=n % 1000 + 1)
+    data = synth(n, seed=n % 1000 + 1)
     cap = pkg.deflate_bound(65536) * ((n + 65535) // 65536 + 1)
     out = np.empty(cap, dtype=np.uint8)
     out_len, crc, adler = ctx.deflate_host(data, n, 65536, 1, final, out, cap)
@@ -44,7 +45,7 @@ def test_deflate_host_matches_oracle_stream(pkg, ctx, zo, n, final):
 
 
 def test_deflate_host_output_too_small(pkg, ctx):
-    data = pkg.synth(4 * 65536, seed=3)
+    data = synth(4 * 65536, seed=3)
     out = np.empty(1000, dtype=np.uint8)
     with pytest.raises(pkg.ZngB200Error) as ei:
         ctx.deflate_host(data, data.size, 65536, 1, True, out, 1000)
@@ -57,7 +58,7 @@ def test_more_chunks_than_one_batch(pkg, ctx, zo):
     import torch
     for level, chunk, nch in ((1, 2048, 40000), (2, 2048, 20000), (2, 65536, 16384 + 3)):
         n = chunk * nch - 777
-        data = pkg.synth(n, seed=level * 7 + 1)
+        data = synth(n, seed=level * 7 + 1)
         d_in = torch.from_numpy(data).to(f"cuda:{ctx.device}")
         slots, stride, sizes, crcs, adlers = ctx.alloc_chunk_outputs(n, chunk)
         ctx.deflate_chunks(d_in, n, chunk, level, 3, slots, stride, sizes, crcs, adlers)
@@ -89,7 +90,7 @@ def test_two_host_threads_two_contexts(pkg, zo):
     results = {}
 
     def work(tid):
-        data = pkg.synth((6 + tid) * 65536 + 1000 * tid, seed=40 + tid)
+        data = synth((6 + tid) * 65536 + 1000 * tid, seed=40 + tid)
         for rep in range(3):
             s = pkg.ZngStream()
             assert L.zng_deflateInit2(ctypes.byref(s), 1 + (tid & 1), 8, 31, 8, 0) == 0
@@ -123,7 +124,7 @@ def test_streamed_and_slab_pipelines_agree(pkg, monkeypatch):
     with ZNG_B200_STREAMED=2) and the slab pipeline (ZNG_B200_STREAMED=0) must write the same bytes, checksums included:
     ragged tail, Z_FINISH and flush-only endings, more than one output slab."""
     n = (72 << 20) + 4321
-    data = pkg.synth(n, seed=55)
+    data = synth(n, seed=55)
     cap = n + n // 8 + (n // 65536 + 1) * 8 + 64
     got = {}
     for mode in ("0", "2"):
@@ -147,7 +148,7 @@ def test_streamed_and_slab_pipelines_agree(pkg, monkeypatch):
 def test_streamed_path_output_too_small_then_recovers(pkg, ctx, zo):
     """Z_BUF_ERROR from the streamed path (the output runs out in the middle of the drain) must leave the context usable."""
     n = (40 << 20) + 777
-    data = pkg.synth(n, seed=8)
+    data = synth(n, seed=8)
     small = np.zeros(n // 4, dtype=np.uint8)
     with pytest.raises(pkg.ZngB200Error) as ei:
         ctx.deflate_host(data, n, 65536, 1, True, small, small.size)

@@ -6,6 +6,7 @@ import struct
 import zlib as pyzlib
 
 import numpy as np
+from synthdata import synth
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -99,7 +100,7 @@ def test_random_streams_vs_oracle(pkg, ctx, zo, wb):
     streams, caps, tags = [], [], []
     for trial in range(60):
         size = int(rng.integers(0, 30000))
-        data = pkg.synth(65536 * 2, seed=trial + 1)[int(rng.integers(0, 60000)):][:size].tobytes()
+        data = synth(65536 * 2, seed=trial + 1)[int(rng.integers(0, 60000)):][:size].tobytes()
         lvl = int(rng.choice([0, 1, 6, 9]))
         cwb = 31 if wb == 47 and trial % 2 else (15 if wb == 47 else wb)
         co = pyzlib.compressobj(lvl, pyzlib.DEFLATED, cwb, 8, int(rng.choice([0, 1, 2, 3, 4])))
@@ -120,7 +121,7 @@ def test_random_streams_vs_oracle(pkg, ctx, zo, wb):
 
 def test_large_members_and_overlaps(pkg, ctx, zo):
     """Members far larger than the shared-memory staging limit (direct global path), long overlapping runs."""
-    datas = [pkg.synth(300000, seed=9).tobytes(), b"a" * 200000, bytes(range(256)) * 700, b"ab" * 70000 + b"xyz" * 30000,
+    datas = [synth(300000, seed=9).tobytes(), b"a" * 200000, bytes(range(256)) * 700, b"ab" * 70000 + b"xyz" * 30000,
              np.random.default_rng(1).integers(0, 256, 150000, dtype=np.uint8).tobytes()]
     for lvl in (1, 6):
         streams = [pyzlib.compress(d, lvl) for d in datas]
@@ -146,7 +147,7 @@ def make_l1_members(zo, data, member=4096):
 def test_config4_members_device_resident(pkg, ctx, zo):
     import torch
     n_members = 4096
-    data = pkg.synth(n_members * 4096, seed=4)
+    data = synth(n_members * 4096, seed=4)
     parts = make_l1_members(zo, data)
     assert pyzlib.decompress(parts[7], wbits=31) == data[7 * 4096: 8 * 4096].tobytes()
     in_off = np.zeros(n_members + 1, dtype=np.int64)
@@ -180,7 +181,7 @@ def test_argument_validation(pkg, ctx):
 # ---- parallel inflate of one flush-delimited stream ------------------------------------------
 def _stream_cases(pkg, zo):
     import zlib as z
-    data = pkg.synth(40 * 65536 + 12345, seed=55)
+    data = synth(40 * 65536 + 12345, seed=55)
     raw = data.tobytes()
     cases = []
     for level in (1, 2):
@@ -239,7 +240,7 @@ def test_zng_inflate_large_pigz_stream_roundtrip(pkg, ctx, zo):
     import zlib as z
     L = pkg.lib()
     n = 96 << 20
-    data = pkg.synth(n, seed=77)
+    data = synth(n, seed=77)
     s = pkg.ZngStream()
     assert L.zng_deflateInit2(ctypes.byref(s), 1, 8, 31, 8, 0) == 0
     comp = np.zeros(int(L.zng_deflateBound(ctypes.byref(s), n)) + 64, dtype=np.uint8)

@@ -6,6 +6,7 @@ import ctypes
 import zlib as pyzlib
 
 import numpy as np
+from synthdata import synth
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -44,7 +45,7 @@ def test_functable_host_table(pkg, ctx, zo):
         s2 = s1.copy(); s2[i] = 0
         assert ft.compare256(s1.ctypes.data, s2.ctypes.data) == i
     assert ft.compare256(s1.ctypes.data, s1.ctypes.data) == 256
-    data = pkg.synth(300000, seed=2)
+    data = synth(300000, seed=2)
     assert ft.crc32(0, data.ctypes.data, data.size) == pyzlib.crc32(data.tobytes())
     assert ft.adler32(1, data.ctypes.data, data.size) == pyzlib.adler32(data.tobytes())
     # chunkmemset_safe(out, from, len, left): byte-serial overlap copy, clipped to `left`
@@ -79,7 +80,7 @@ def test_insert_string_and_longest_match_vs_oracle(pkg, ctx, zo):
     import torch
     dev = f"cuda:{ctx.device}"
     rng = np.random.default_rng(3)
-    makers = (lambda: pkg.synth(65536, seed=31)[:60000], lambda: rng.integers(0, 4, size=60000, dtype=np.uint8),
+    makers = (lambda: synth(65536, seed=31)[:60000], lambda: rng.integers(0, 4, size=60000, dtype=np.uint8),
               lambda: np.tile(rng.integers(0, 256, size=37, dtype=np.uint8), 2000)[:60000])
     for trial, maker in enumerate(makers):
         data = np.ascontiguousarray(maker())

@@ -7,6 +7,7 @@ import sys
 import zlib as pyzlib
 
 import numpy as np
+from synthdata import synth
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,7 +25,7 @@ def _worker(rank, world, port, n, level, q):
     st = importlib.util.module_from_spec(spec); spec.loader.exec_module(st)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        data = pkg.synth(n, seed=77)
+        data = synth(n, seed=77)
         nch = (n + st.CHUNK - 1) // st.CHUNK
         lo, hi = st.shard_range(nch, rank, world)
         mine = data[lo * st.CHUNK: min(hi * st.CHUNK, n)]

@@ -5,6 +5,7 @@
 import zlib as pyzlib   # only to digest byte strings (crc32) and to round-trip through an independent inflater
 
 import numpy as np
+from synthdata import synth
 import pytest
 
 
@@ -13,13 +14,13 @@ def _case_input(pkg, name):
     rng = np.random.default_rng(20261018)
     base = name.rsplit("_l", 1)[0]
     if base == "synth_2MiB":
-        return pkg.synth(32 * 65536)
+        return synth(32 * 65536)
     if base == "synth_ragged":
-        return pkg.synth(10 * 65536 + 777, seed=12345)
+        return synth(10 * 65536 + 777, seed=12345)
     if base == "synth_finish":
-        return pkg.synth(4 * 65536 + 4097, seed=99)
+        return synth(4 * 65536 + 4097, seed=99)
     if base == "synth_4k_members":
-        return pkg.synth(64 * 4096, seed=7)
+        return synth(64 * 4096, seed=7)
     if base == "zeros":
         return np.zeros(3 * 65536 + 5, dtype=np.uint8)
     if base == "random":
@@ -30,10 +31,10 @@ def _case_input(pkg, name):
             draw = rng.integers(0, 256, size=2 * 65536 + 100, dtype=np.uint8)
         return draw
     if base == "tiny_sizes":
-        return pkg.synth(65536, seed=3)[:257 * 40]
+        return synth(65536, seed=3)[:257 * 40]
     if base.startswith("short_"):
         n = int(base.split("_")[1])
-        return pkg.synth(65536, seed=5)[:n]
+        return synth(65536, seed=5)[:n]
     raise KeyError(name)
 
 
@@ -59,7 +60,7 @@ def test_port_matches_reference_live(pkg, zo):
     if not zo.have_ref():
         pytest.skip("oracle/_ref not built")
     for seed, n, chunk, flush in ((11, 48 * 65536, 65536, 3), (12, 5 * 65536 + 31000, 65536, 4), (13, 200 * 1000, 1000, 3)):
-        data = pkg.synth(n, seed=seed)
+        data = synth(n, seed=seed)
         for level in (1, 2, 3, 4, 5, 6):
             a = zo.port_deflate_chunks(data, chunk, level, flush)
             # one thread: a short last chunk reads the stale window of the chunk its stream compressed before;
@@ -89,7 +90,7 @@ def test_port_slid_window_position_zero_alias(pkg, zo):
 
 def test_port_output_inflates(pkg, zo):
     # independent check of validity: CPython's zlib inflates the concatenated chunk stream
-    data = pkg.synth(6 * 65536 + 999, seed=21)
+    data = synth(6 * 65536 + 999, seed=21)
     for level in (1, 2, 3, 4, 5, 6):
         out, sizes, _, _ = zo.port_deflate_chunks(data, 65536, level, 3)
         stream = b"".join(out[i, : sizes[i]].tobytes() for i in range(len(sizes))) + b"\x03\x00"
@@ -97,10 +98,10 @@ def test_port_output_inflates(pkg, zo):
 
 
 def test_synth_is_deterministic_and_shardable(pkg):
-    a = pkg.synth(20 * 65536)
-    b = pkg.synth(8 * 65536, offset=12 * 65536)
+    a = synth(20 * 65536)
+    b = synth(8 * 65536, offset=12 * 65536)
     assert np.array_equal(a[12 * 65536:], b)
-    assert not np.array_equal(pkg.synth(65536, seed=1), pkg.synth(65536, seed=2))
+    assert not np.array_equal(synth(65536, seed=1), synth(65536, seed=2))
 
 
 def _fuzz_input(rng, n):

@@ -6,6 +6,7 @@ import struct
 import zlib as pyzlib
 
 import numpy as np
+from synthdata import synth
 import pytest
 
 
@@ -97,7 +98,7 @@ def test_port_vs_reference_live(pkg, zo, golden):
             cmp(bytes(s2), 47, len(payload), "gzip hdr flip")
     for trial in range(120):
         size = int(rng.integers(0, 20000))
-        data = pkg.synth(65536 * 2, seed=trial + 1)[int(rng.integers(0, 60000)):][:size].tobytes()
+        data = synth(65536 * 2, seed=trial + 1)[int(rng.integers(0, 60000)):][:size].tobytes()
         lvl = int(rng.choice([0, 1, 6, 9]))
         wb = [-15, 15, 31, 47][trial % 4]
         cwb = 31 if wb == 47 and trial % 8 < 4 else (15 if wb == 47 else wb)
@@ -114,7 +115,7 @@ def test_port_vs_reference_live(pkg, zo, golden):
             cmp(bytes(s2), wb, size + 10, "flip")
     # what the reference's own deflate produces for the pigz-style call sequence, levels 1 and 2
     for level in (1, 2):
-        data = pkg.synth(3 * 65536 + 777, seed=level)
+        data = synth(3 * 65536 + 777, seed=level)
         for wb in (-15, 15, 31):
             st = zo.ref_deflate_stream(data, 65536, level, wb)
             cmp(st, wb, data.size, "ref stream")

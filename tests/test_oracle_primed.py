@@ -4,6 +4,7 @@ oracle/_ref: fresh zng_deflateInit2 + zng_deflateSetDictionary(32768 bytes in fr
 import zlib as pyzlib
 
 import numpy as np
+from synthdata import synth
 import pytest
 
 
@@ -11,7 +12,7 @@ def test_port_primed_matches_golden_digests(pkg, zo, golden):
     cases = golden("primed_digests.json")["cases"]
     assert len(cases) >= 10
     for c in cases:
-        data = pkg.synth(c["n"], seed=c["seed"])
+        data = synth(c["n"], seed=c["seed"])
         out, sizes, _, _ = zo.port_deflate_chunks_primed(data, 65536, c.get("level", 1), c["flush"])
         assert [int(x) for x in sizes] == c["sizes"], c
         assert [int(pyzlib.crc32(out[i, : sizes[i]].tobytes())) for i in range(len(sizes))] == c["comp_crc32"], c
@@ -21,9 +22,9 @@ def test_port_primed_matches_reference_live(pkg, zo):
     if not zo.have_ref() or not hasattr(zo.ref(), "refdrv_deflate_chunks_primed"):
         pytest.skip("oracle/_ref not built")
     rng = np.random.default_rng(3)
-    inputs = [pkg.synth(12 * 65536 + 777, seed=4), np.zeros(3 * 65536 + 5, dtype=np.uint8), rng.integers(0, 4, size=4 * 65536, dtype=np.uint8),
+    inputs = [synth(12 * 65536 + 777, seed=4), np.zeros(3 * 65536 + 5, dtype=np.uint8), rng.integers(0, 4, size=4 * 65536, dtype=np.uint8),
               np.tile(np.arange(251, dtype=np.uint8), 1100)[:4 * 65536]]
-    inputs += [pkg.synth(2 * 65536 + t, seed=t) for t in (1, 2, 3, 4, 261, 262, 263, 32768, 32769, 65274, 65275, 65535)]
+    inputs += [synth(2 * 65536 + t, seed=t) for t in (1, 2, 3, 4, 261, 262, 263, 32768, 32769, 65274, 65275, 65535)]
     for d in inputs:
         for level in (1, 2, 3, 4, 5, 6):
             for flush in ((2, 3, 4) if level == 1 else (2, 4)):
@@ -43,8 +44,8 @@ def test_window_engine_agrees_with_the_chunk_coordinate_restatement(pkg, zo):
     On fresh streams they must agree byte for byte (and both are pinned to the reference elsewhere)."""
     rng = np.random.default_rng(9)
     words = rng.integers(97, 123, size=(64, 6), dtype=np.uint8)
-    inputs = [pkg.synth(6 * 65536, seed=14), rng.integers(0, 4, size=2 * 65536, dtype=np.uint8), words[rng.integers(0, 64, size=30000)].reshape(-1)[:2 * 65536],
-              pkg.synth(65536, seed=2)[:65300], pkg.synth(65536, seed=3)[:65275], pkg.synth(65536, seed=4)[:300], np.zeros(65536, dtype=np.uint8)]
+    inputs = [synth(6 * 65536, seed=14), rng.integers(0, 4, size=2 * 65536, dtype=np.uint8), words[rng.integers(0, 64, size=30000)].reshape(-1)[:2 * 65536],
+              synth(65536, seed=2)[:65300], synth(65536, seed=3)[:65275], synth(65536, seed=4)[:300], np.zeros(65536, dtype=np.uint8)]
     for d in inputs:
         for level in (2, 3, 4, 5, 6):
             a = zo.port_deflate_chunks_fresh_window(d, 65536, level, 4)
@@ -59,7 +60,7 @@ def test_primed_token_trace_is_consistent(pkg, zo):
     rng = np.random.default_rng(4)
     words = rng.integers(97, 123, size=(64, 6), dtype=np.uint8)
     text = words[rng.integers(0, 64, size=40000)].reshape(-1)[:32768 + 65536]
-    for data in (text, pkg.synth(32768 + 65536, seed=6), pkg.synth(32768 + 1000, seed=7)):
+    for data in (text, synth(32768 + 65536, seed=6), synth(32768 + 1000, seed=7)):
         chunk = data[32768:]
         for level in (1, 2, 6):
             toks = zo.port_tokens_primed(data, level)

@@ -38,6 +38,10 @@ def port():
         L.zo_crc32_combine_op.restype = c_uint32; L.zo_crc32_combine_op.argtypes = [c_uint32, c_uint32, c_uint32]
         L.zo_adler32_combine.restype = c_uint32; L.zo_adler32_combine.argtypes = [c_uint32, c_uint32, c_int64]
         L.zo_compare256.restype = c_uint32; L.zo_compare256.argtypes = [c_void_p, c_void_p]
+        L.zo_frame_gzip_members.restype = c_size_t
+        L.zo_frame_gzip_members.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_uint32, c_uint32, c_size_t, c_int, c_void_p, c_void_p]
+        L.zo_compare_chunks.restype = c_size_t
+        L.zo_compare_chunks.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, POINTER(c_size_t)]
         L.zo_deflate_bound.restype = c_size_t; L.zo_deflate_bound.argtypes = [c_size_t]
         L.zo_deflate_chunk.restype = c_size_t; L.zo_deflate_chunk.argtypes = [c_void_p, c_uint32, c_int, c_int, c_void_p, c_size_t]
         L.zo_deflate_chunks.restype = c_int
@@ -132,6 +136,39 @@ def _deflate_chunks(fn, data, chunk, level, flush, stride, nthreads):
     if r != 0:
         raise RuntimeError(f"oracle deflate_chunks failed: {r}")
     return out[:nch], sizes[:nch], crcs[:nch], adlers[:nch]
+
+
+def gzip_members(data, member=4096, level=1, nthreads=None):
+    """Every `member`-byte slice of data as one gzip member (body = the level-`level` Z_FINISH stream of the slice written by the
+    strongest checker available, framing as minigzip writes it), packed.  Returns (members u8 (+16 bytes of slack), off u64[n+1])."""
+    data = _u8(data)
+    _, out, sizes, crcs, _ = best_deflate_chunks(data, member, level, 4, None, nthreads)
+    nm = sizes.size
+    last = data.size - (nm - 1) * member
+    off = np.zeros(nm + 1, dtype=np.uint64)
+    xfl = 4 if level == 1 else 0
+    total = port().zo_frame_gzip_members(out.ctypes.data, out.shape[1], sizes.ctypes.data, crcs.ctypes.data, member, last, nm, xfl, None, None)
+    buf = np.zeros(total + 16, dtype=np.uint8)
+    port().zo_frame_gzip_members(out.ctypes.data, out.shape[1], sizes.ctypes.data, crcs.ctypes.data, member, last, nm, xfl, buf.ctypes.data, off.ctypes.data)
+    return buf, off
+
+
+def compare_chunks(a, stride_a, sizes_a, b, stride_b, sizes_b):
+    """Every chunk of `a` against `b`, byte for byte (stride 0 = packed back to back).  Returns (bad_count, first_bad)."""
+    a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1); b = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1)
+    sa = np.ascontiguousarray(sizes_a, dtype=np.uint32); sb = np.ascontiguousarray(sizes_b, dtype=np.uint32)
+    assert sa.size == sb.size
+    first = c_size_t(0)
+    bad = port().zo_compare_chunks(_ptr(a), stride_a, sa.ctypes.data, _ptr(b), stride_b, sb.ctypes.data, sa.size, byref(first))
+    return int(bad), int(first.value)
+
+
+def best_deflate_chunks(data, chunk=65536, level=1, flush=3, stride=None, nthreads=None):
+    """The strongest checker available: the unmodified reference when oracle/_ref is present, else the port.
+    Returns (kind, out, sizes, crcs, adlers)."""
+    if have_ref():
+        return ("oracle/_ref (unmodified zlib-ng 2.2.2)",) + ref_deflate_chunks(data, chunk, level, flush, stride, nthreads)
+    return ("oracle port",) + port_deflate_chunks(data, chunk, level, flush, stride, nthreads)
 
 
 def port_deflate_chunks(data, chunk=65536, level=1, flush=3, stride=None, nthreads=None):

@@ -64,7 +64,6 @@ def lib() -> ctypes.CDLL:
         "zng_b200_deflate_host_primed": (c_int, [vp, vp, vp, c_size_t, c_int, vp, c_size_t, POINTER(c_size_t), POINTER(c_uint32), POINTER(c_uint32)]),
         "zng_b200_crc32_host": (c_int, [vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
         "zng_b200_adler32_host": (c_int, [vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
-        "zng_b200_synth_fill": (c_int, [vp, c_size_t, c_uint64, c_uint64]),
         "zng_b200_inflate_members": (c_int, [vp, vp, u64p, c_uint32, c_int, vp, u64p, u32p, u32p, vp, u32p, u32p, vp]),
         "zng_b200_inflate_members_host": (c_int, [vp, vp, u64p, c_uint32, c_int, vp, u64p, u32p, u32p, vp, u32p, u32p]),
         "zng_b200_inflate_msg": (c_char_p, [c_uint32]),
@@ -135,16 +134,6 @@ def inflate_msg(detail: int):
 
 def deflate_bound(chunk_len: int) -> int:
     return int(lib().zng_b200_deflate_bound(chunk_len))
-
-
-def synth(n: int, seed: int = 0x9E3779B97F4A7C15, offset: int = 0):
-    """n bytes of the synthetic mixed text/binary workload (host numpy array)."""
-    import numpy as np
-    buf = np.empty(n, dtype=np.uint8)
-    r = lib().zng_b200_synth_fill(buf.ctypes.data, n, seed, offset)
-    if r != 0:
-        raise ZngB200Error(r, "synth_fill")
-    return buf
 
 
 def _ptr(t) -> int:

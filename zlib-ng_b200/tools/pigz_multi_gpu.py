@@ -30,8 +30,9 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from __graft_entry__ import load_package
+    from __graft_entry__ import load_package, load_synth
     pkg = load_package()
+    sd = load_synth()                  # the synthetic input of BASELINE configs[4] (tests/synthdata.py)
     spec = importlib.util.spec_from_file_location("zstream", os.path.join(ROOT, "zlib-ng_b200", "stream.py"))
     st = importlib.util.module_from_spec(spec); spec.loader.exec_module(st)
 
@@ -54,7 +55,7 @@ def main():
     h = torch.empty(min(piece, n_rank), dtype=torch.uint8, pin_memory=True)
     for o in range(0, n_rank, piece):
         k = min(piece, n_rank - o)
-        assert pkg.lib().zng_b200_synth_fill(h.data_ptr(), k, 0x9E3779B97F4A7C15, rank * n_rank + o) == 0
+        sd.fill(h.data_ptr(), k, sd.SEED, rank * n_rank + o)
         d_in[o:o + k].copy_(h[:k]); torch.cuda.synchronize()
 
     slots = torch.empty(nch * stride, dtype=torch.uint8, device=dev)
