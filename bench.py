@@ -480,10 +480,10 @@ def run_b200(args):
         offsets = torch.zeros(nch + 1, dtype=torch.int64, device=dev)
         packed = torch.empty(nch * stride, dtype=torch.uint8, device=dev)
         res = torch.zeros(4, dtype=torch.int32, device=dev)
-        if ngpu > 1:
-            gathered = torch.zeros(ngpu, 2, nch, dtype=torch.int32, device=dev)
-            offsets_all = torch.zeros(ngpu * nch + 1, dtype=torch.int64, device=dev)
-        k_per_step = 3 if level == 1 else 3                                # parse, emit, checksum tiles
+        comm = pkg.Comm.from_torch(ctx) if ngpu > 1 else None               # zng_b200_comm: NCCL communicator behind the C ABI
+        offsets_g = torch.zeros(nch + 1, dtype=torch.int64, device=dev)     # global stream offsets of this rank's chunks
+        multi = {"end": 0, "crc": 0, "n": 0}
+        k_per_step = 3                                                      # parse, emit, checksum tiles
 
         def step(i_timed=None):
             if i_timed is not None:
@@ -493,11 +493,9 @@ def run_b200(args):
                 k_stop[i_timed].record()
             launches["n"] += k_per_step
             if ngpu > 1:
-                dist.all_gather_into_tensor(gathered.view(-1), meta.view(-1))
-                allm = gathered.permute(1, 0, 2).contiguous()             # [2, ngpu*nch] in global chunk order
-                ctx.chunk_offsets(allm[0].view(-1), ngpu * nch, 0, offsets_all)     # global byte offsets of every chunk
-                ctx.crc32_fold(allm[1].view(-1), ngpu * nch, CHUNK, ngpu * n, 0, res[0:1])
-                launches["n"] += 2
+                # zng_b200_stream_index_multi: ONE ncclAllGather of the (size, crc32) pairs, then scan + crc32_combine fold on every rank
+                multi["end"], multi["crc"], multi["n"] = comm.stream_index(sizes, crcs, nch, CHUNK, n, 10, offsets_g)
+                launches["n"] += 3
             else:
                 ctx.crc32_fold(crcs, nch, CHUNK, n, 0, res[0:1])
                 launches["n"] += 1
@@ -549,7 +547,9 @@ def run_b200(args):
         def global_facts():
             """What the collective produced on this rank: the fold of every rank's chunk CRCs and the end of the global scan."""
             u = lambda v: int(v) & 0xffffffff
-            return {"crc_fold": u(res[0].item()), "packed": int(offsets_all[ngpu * nch].item()) if ngpu > 1 else int(offsets[nch].item())}
+            if ngpu > 1:
+                return {"crc_fold": u(multi["crc"]), "packed": multi["end"] - 10}
+            return {"crc_fold": u(res[0].item()), "packed": int(offsets[nch].item())}
 
         cap = nch * stride
 

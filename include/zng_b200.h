@@ -104,6 +104,41 @@ int zng_b200_chunk_offsets(zng_b200_ctx *ctx, const uint32_t *d_sizes, uint32_t 
 int zng_b200_gather_chunks(zng_b200_ctx *ctx, const void *d_slots, size_t out_stride, const uint32_t *d_sizes,
                            const uint64_t *d_offsets, uint32_t nchunks, void *d_dst, void *stream);
 
+/* ---- multi-GPU stream assembly (csrc/multi.cu) ---------------------------------------------- */
+/* One rank per GPU, each with its own context; rank r owns a contiguous chunk range of one stream.  Replaces, across ranks,
+ * what a single zng_stream accumulates over its zng_deflate(Z_FULL_FLUSH) calls: total_out (deflate.c:789-807), the running
+ * CRC-32 (deflate.c:1021,1092 via crc32_combine, crc32_braid_comb.c:16-24) and the gzip trailer (deflate.c:1091-1096).
+ * The only collective is one NCCL allgather of the per-chunk (compressed size, crc32) pairs, 8 bytes per chunk.
+ * NCCL is bound at run time (libnccl.so.2); without it these entry points return ZNG_B200_STREAM_ERROR. */
+typedef struct zng_b200_comm zng_b200_comm;
+#define ZNG_B200_COMM_ID_BYTES 128
+/* rank 0: a fresh NCCL unique id (128 bytes) that the caller hands to every rank by its own means (MPI, a file, a socket) */
+int  zng_b200_comm_unique_id(void *id, size_t cap);
+/* every rank, collectively: a communicator of `nranks` ranks on the context's device (nranks == 1: no NCCL needed) */
+int  zng_b200_comm_create(zng_b200_ctx *ctx, int nranks, int rank, const void *id, zng_b200_comm **out);
+/* wrap a communicator the application already has (an ncclComm_t passed as void*); it is not destroyed with the wrapper */
+int  zng_b200_comm_adopt(zng_b200_ctx *ctx, void *nccl_comm, zng_b200_comm **out);
+void zng_b200_comm_destroy(zng_b200_comm *comm);
+int  zng_b200_comm_size(const zng_b200_comm *comm);
+int  zng_b200_comm_rank(const zng_b200_comm *comm);
+const char *zng_b200_comm_error(const zng_b200_comm *comm);
+/* Collective.  In: this rank's per-chunk sizes and CRC-32s (device), its chunk count and byte count (every chunk of the stream
+ * but the very last is `chunk` bytes).  Out: d_offsets_local[i] = byte offset of this rank's chunk i in the whole stream,
+ * i in 0..nchunks_local (base + exclusive scan over ALL ranks' chunks); *h_stream_end = base + total compressed bytes;
+ * *h_crc32 = zng_crc32 of the whole input (fold of all chunk CRCs); *h_total_in = input bytes of all ranks. */
+int  zng_b200_stream_index_multi(zng_b200_comm *comm, const uint32_t *d_sizes, const uint32_t *d_crcs, uint32_t nchunks_local,
+                                 uint32_t chunk, size_t n_local, uint64_t base, uint64_t *d_offsets_local,
+                                 uint64_t *h_stream_end, uint32_t *h_crc32, uint64_t *h_total_in, void *stream);
+/* Collective: the whole pigz-style step for this rank's n_local bytes -- chunk compression (64 KiB chunks, Z_FULL_FLUSH ends),
+ * the allgather, scan and fold above, and the gather of this rank's chunks into d_packed.  The gzip file is
+ *   header (10 bytes, rank 0) | rank 0's bytes | rank 1's bytes | ... | "03 00" crc32 isize (10 bytes, at *h_file_bytes - 10)
+ * and this rank's *h_my_bytes packed bytes belong at file offset *h_my_offset.  d_slots / d_sizes / d_crcs as for
+ * zng_b200_deflate_chunks; d_offsets_local: nchunks_local + 1 entries; h_header10 / h_trailer10 are filled on every rank. */
+int  zng_b200_gzip_multi(zng_b200_comm *comm, const void *d_in, size_t n_local, int level,
+                         void *d_slots, size_t out_stride, uint32_t *d_sizes, uint32_t *d_crcs, uint64_t *d_offsets_local,
+                         void *d_packed, size_t packed_cap, uint64_t *h_my_offset, uint64_t *h_my_bytes,
+                         uint64_t *h_file_bytes, uint8_t *h_header10, uint8_t *h_trailer10, void *stream);
+
 /* ---- K3: checksums ------------------------------------------------------------------------ */
 /* Per-tile zng_crc32(0, .) / zng_adler32(1, .) of consecutive tile_bytes-sized pieces (<= 65536). */
 int zng_b200_checksum_chunks(zng_b200_ctx *ctx, const void *d_in, size_t n, uint32_t tile_bytes,
@@ -196,16 +231,70 @@ int zng_b200_op_insert_string(zng_b200_ctx *ctx, const void *d_window, uint16_t 
 /* functable.chunkmemset_safe (chunkset_tpl.h:112-283): d_out[pos + i] = d_out[pos + i - dist] for i in 0..len, byte serial. */
 int zng_b200_op_chunkmemset(zng_b200_ctx *ctx, void *d_out, uint32_t pos, uint32_t dist, uint32_t len, void *stream);
 
-/* The host-callable operator table, shaped like struct functable_s for the operators that have a host-buffer form
- * (functable.h:27,30,31,32,33): each call runs on the GPU through the calling thread's context. */
+/* functable.longest_match for the strategy of `level` 2..6 (configuration_table, deflate.c:142-168: deflate_fast {nice 8, chain 4},
+ * deflate_medium {16,6} {32,24} {32,32} {128,128}); other arguments as zng_b200_op_longest_match (which is level 2).  d_len[i] is
+ * the returned length when it is >= 4, else 0 (the strategies discard shorter results). */
+int zng_b200_op_longest_match_level(zng_b200_ctx *ctx, const void *d_window, uint32_t n, const uint16_t *d_prev,
+                                    const uint32_t *d_pos, const uint32_t *d_cand, uint32_t n_q, int level, uint32_t *d_len,
+                                    uint32_t *d_start, void *stream);
+/* quick_insert_string(s, str) (insert_string_tpl.h:58-75): inserts position str, *d_old_head = the head entry it replaced. */
+int zng_b200_op_quick_insert_string(zng_b200_ctx *ctx, const void *d_window, uint16_t *d_head, uint16_t *d_prev, uint32_t str,
+                                    uint32_t *d_old_head, void *stream);
+/* functable.slide_hash (arch/generic/slide_hash_c.c:15-52): head[65536] and prev[wsize] rebased by wsize, smaller entries -> 0. */
+int zng_b200_op_slide_hash(zng_b200_ctx *ctx, uint16_t *d_head, uint16_t *d_prev, uint32_t wsize, void *stream);
+/* checksum-while-copy (functable.crc32_fold_copy / adler32_fold_copy; read_buf, deflate.c:1190-1212) for host buffers: the bytes
+ * go to the device, are checksummed there and come back into h_dst. */
+int zng_b200_crc32_copy_host(zng_b200_ctx *ctx, void *h_dst, const void *h_src, size_t n, uint32_t init, uint32_t *result);
+int zng_b200_adler32_copy_host(zng_b200_ctx *ctx, void *h_dst, const void *h_src, size_t n, uint32_t init, uint32_t *result);
+
+/* ---- the host-callable operator table: struct functable_s (functable.h:26-42), the same 15 slots in the same order, plus the
+ * three hash callbacks of deflate_state (deflate.h:121-131).  Every slot runs on the GPU through the calling thread's context
+ * (device scratch is owned by the context: no allocation per call); the state arguments are views of the fields the reference's
+ * operators read and write, in HOST memory. */
+struct zng_b200_crc32_fold {           /* crc32.h:8-14: the reference keeps 4 x 128 bits of folding state + value; here the   */
+    uint8_t  fold[64];                 /* state IS the running CRC-32 (fold[] is unused and kept for layout)                  */
+    uint32_t value;
+};
+struct zng_b200_match_state {          /* deflate_state as longest_match / insert_string / slide_hash see it (deflate.h:153-280) */
+    const uint8_t *window;             /* s->window; window_len bytes of data (<= 65536), the rest reads as zeros            */
+    uint32_t window_len;
+    uint16_t *head;                    /* s->head, 65536 entries (HASH_SIZE, deflate.h:81-85)                                 */
+    uint16_t *prev;                    /* s->prev, 32768 entries (w_size)                                                     */
+    uint32_t strstart;                 /* s->strstart                                                                         */
+    uint32_t lookahead;                /* s->lookahead (informative: longest_match uses window_len - strstart)                */
+    uint32_t match_start;              /* out: s->match_start                                                                 */
+    int32_t  level;                    /* 2..6: max_chain_length / nice_match of configuration_table (deflate.c:142-168)      */
+};
 struct zng_b200_functable {
+    void     (*force_init)(void);
     uint32_t (*adler32)(uint32_t adler, const uint8_t *buf, size_t len);
+    uint32_t (*adler32_fold_copy)(uint32_t adler, uint8_t *dst, const uint8_t *src, size_t len);
     uint8_t *(*chunkmemset_safe)(uint8_t *out, uint8_t *from, unsigned len, unsigned left);
     uint32_t (*chunksize)(void);
     uint32_t (*compare256)(const uint8_t *src0, const uint8_t *src1);
     uint32_t (*crc32)(uint32_t crc, const uint8_t *buf, size_t len);
+    void     (*crc32_fold)(struct zng_b200_crc32_fold *crc, const uint8_t *src, size_t len, uint32_t init_crc);
+    void     (*crc32_fold_copy)(struct zng_b200_crc32_fold *crc, uint8_t *dst, const uint8_t *src, size_t len);
+    uint32_t (*crc32_fold_final)(struct zng_b200_crc32_fold *crc);
+    uint32_t (*crc32_fold_reset)(struct zng_b200_crc32_fold *crc);
+    /* inflate_fast(strm, start) (inffast_tpl.h:53): the reference enters it in the middle of a block with its decode tables in
+     * inflate_state; here the slot decodes as far as strm's input and output allow -- one zng_inflate(strm, Z_SYNC_FLUSH) of the
+     * host library (the batched device form is zng_b200_inflate_members).  strm is a zng_stream* (include/zlib-ng.h). */
+    void     (*inflate_fast)(void *strm, uint32_t start);
+    /* returns what the reference returns (match_tpl.h:268-279: best_len, 2 when no candidate improves, clipped to lookahead) for
+     * levels 2..6; s->match_start is written when the result is >= 4 */
+    uint32_t (*longest_match)(struct zng_b200_match_state *s, uint16_t cur_match);
+    /* LONGEST_MATCH_SLOW serves deflate_slow (levels 7-9), outside the hot path: the slot is present, returns 0
+     * and records "longest_match_slow: outside the hot path" in the context (Z_STREAM_ERROR semantics, no CPU fallback) */
+    uint32_t (*longest_match_slow)(struct zng_b200_match_state *s, uint16_t cur_match);
+    void     (*slide_hash)(struct zng_b200_match_state *s);
 };
 const struct zng_b200_functable *zng_b200_functable_get(void);
+/* the hash callbacks (deflate.h:121-131; insert_string.c:11-19): HASH_CALC = (val * 2654435761) >> 16 */
+uint32_t zng_b200_update_hash(uint32_t h, uint32_t val);
+void     zng_b200_insert_string(struct zng_b200_match_state *s, uint32_t str, uint32_t count);
+uint16_t zng_b200_quick_insert_string(struct zng_b200_match_state *s, uint32_t str);
+
 
 
 #ifdef __cplusplus

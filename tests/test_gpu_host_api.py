@@ -225,6 +225,68 @@ def test_zng_inflate_incremental(pkg, L):
     assert L.zng_inflateEnd(ctypes.byref(s)) == 0
 
 
+def test_zng_inflate_incremental_is_not_quadratic(pkg, L):
+    """The common loop "read 64 KiB, zng_inflate(Z_NO_FLUSH)" over a gzip member without flush markers: decode attempts are
+    spaced geometrically (host/zng_inflate.c), so 48 MiB of compressed input costs a dozen attempts, not 768 full decodes."""
+    import time
+    raw = np.random.default_rng(3).integers(0, 256, size=48 << 20, dtype=np.uint8).tobytes()   # incompressible: stored blocks
+    co = pyzlib.compressobj(1, pyzlib.DEFLATED, 31)
+    st = co.compress(raw) + co.flush()
+    src = np.frombuffer(st, dtype=np.uint8).copy()
+    s = pkg.ZngStream()
+    assert L.zng_inflateInit2(ctypes.byref(s), 31) == 0
+    out = np.zeros(len(raw) + 64, dtype=np.uint8)
+    s.next_out = out.ctypes.data; s.avail_out = out.size
+    pos, r, calls = 0, 0, 0
+    t0 = time.perf_counter()
+    while r != 1:
+        take = min(65536, len(st) - pos)
+        s.next_in = src.ctypes.data + pos; s.avail_in = take
+        r = L.zng_inflate(ctypes.byref(s), pkg.Z_NO_FLUSH)
+        assert r in (0, 1), (r, s.msg)
+        pos += take - s.avail_in
+        calls += 1
+        assert calls < 2000
+    dt = time.perf_counter() - t0
+    assert s.total_out == len(raw) and out[: len(raw)].tobytes() == raw and s.total_in == len(st)
+    assert dt < 60, f"{calls} calls took {dt:.1f} s"
+    assert L.zng_inflateEnd(ctypes.byref(s)) == 0
+
+
+def test_uncompress_moves_only_the_bytes_it_produced(pkg, L):
+    """A generous destLen: bytes past the decoded length stay as the caller left them (no stale device bytes travel)."""
+    big = synth(3 << 20, seed=77)
+    comp = pyzlib.compress(big.tobytes(), 1)
+    dst = np.full(4 << 20, 0xA5, dtype=np.uint8)
+    dlen = ctypes.c_size_t(dst.size)
+    assert L.zng_uncompress(dst.ctypes.data, ctypes.byref(dlen), np.frombuffer(comp, dtype=np.uint8).ctypes.data, len(comp)) == 0
+    small = b"tiny payload" * 3
+    comp2 = np.frombuffer(pyzlib.compress(small, 6), dtype=np.uint8).copy()
+    dst = np.full(4 << 20, 0xA5, dtype=np.uint8)
+    dlen = ctypes.c_size_t(dst.size)
+    assert L.zng_uncompress(dst.ctypes.data, ctypes.byref(dlen), comp2.ctypes.data, comp2.size) == 0
+    assert dlen.value == len(small) and dst[: len(small)].tobytes() == small
+    assert (dst[len(small):] == 0xA5).all()
+
+
+@pytest.mark.slow
+def test_adler32_of_a_large_zlib_member(pkg, L):
+    """1.2 GiB of 0xFF in ONE zlib member without flush markers: the position-weighted Adler-32 sums of the member decoder pass
+    2^64 unless they are reduced first (csrc/inflate.cu warp_check)."""
+    n = (1 << 30) + (200 << 20)
+    co = pyzlib.compressobj(1, pyzlib.DEFLATED, 15)
+    piece = b"\xff" * (64 << 20)
+    parts, a = [], 1
+    for _ in range(n // len(piece)):
+        parts.append(co.compress(piece)); a = pyzlib.adler32(piece, a)
+    parts.append(co.flush())
+    st = np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+    dst = np.zeros(n, dtype=np.uint8)
+    dlen = ctypes.c_size_t(n)
+    assert L.zng_uncompress(dst.ctypes.data, ctypes.byref(dlen), st.ctypes.data, st.size) == 0
+    assert dlen.value == n and int(dst.min()) == 0xFF
+
+
 def test_compress_uncompress_roundtrip(pkg, L, zo):
     data = synth(5 * 65536 + 321, seed=21)
     cap = int(L.zng_compressBound(data.size))

@@ -121,3 +121,139 @@ def test_insert_string_and_longest_match_vs_oracle(pkg, ctx, zo):
             else:
                 assert gl[i] == 0, (trial, i)
         assert nmatch > 50
+
+
+# ---- every slot of the 15-slot table against the reference's OWN dispatched variant (oracle/_ref + oracle/ref_ops.c) ------------
+def _need_ref(zo):
+    if not zo.have_ref() or not hasattr(zo.ref(), "refops_longest_match"):
+        pytest.skip("oracle/_ref with ref_ops.c not built")
+    return zo.ref()
+
+
+def test_table_has_the_references_15_slots_in_order(pkg):
+    names = [f[0] for f in pkg.Functable._fields_]
+    assert names == ["force_init", "adler32", "adler32_fold_copy", "chunkmemset_safe", "chunksize", "compare256", "crc32", "crc32_fold",
+                     "crc32_fold_copy", "crc32_fold_final", "crc32_fold_reset", "inflate_fast", "longest_match", "longest_match_slow",
+                     "slide_hash"]                       # functable.h:26-42
+    ft = pkg.functable()
+    ft.force_init()
+    for n in names:
+        assert ctypes.cast(getattr(ft, n), ctypes.c_void_p).value, n
+
+
+def test_fold_slots_vs_reference(pkg, ctx, zo):
+    R = _need_ref(zo)
+    ft = pkg.functable()
+    data = synth(700001, seed=12)
+    for piece in (700001, 65536, 4097, 333):
+        f = pkg.Crc32Fold()
+        assert ft.crc32_fold_reset(ctypes.byref(f)) == 0
+        dst = np.zeros(data.size, dtype=np.uint8)
+        for o in range(0, data.size, piece):
+            k = min(piece, data.size - o)
+            if (o // piece) % 2:
+                ft.crc32_fold(ctypes.byref(f), data.ctypes.data + o, k, 0)
+                dst[o:o + k] = data[o:o + k]
+            else:
+                ft.crc32_fold_copy(ctypes.byref(f), dst.ctypes.data + o, data.ctypes.data + o, k)
+        rdst = np.zeros(data.size, dtype=np.uint8)
+        assert ft.crc32_fold_final(ctypes.byref(f)) == R.refops_crc32_fold(data.ctypes.data, data.size, piece, rdst.ctypes.data)
+        assert np.array_equal(dst, data) and np.array_equal(rdst, data)
+    for init in (1, 0x12345678):
+        dst = np.zeros(data.size, dtype=np.uint8); rdst = np.zeros(data.size, dtype=np.uint8)
+        got = ft.adler32_fold_copy(init, dst.ctypes.data, data.ctypes.data, data.size)
+        assert got == R.refops_adler32_fold_copy(init, rdst.ctypes.data, data.ctypes.data, data.size)
+        assert np.array_equal(dst, data)
+
+
+def test_compare256_chunkmemset_update_hash_vs_reference(pkg, ctx, zo):
+    R = _need_ref(zo)
+    ft = pkg.functable()
+    rng = np.random.default_rng(9)
+    for _ in range(40):
+        a = rng.integers(0, 3, size=256, dtype=np.uint8); b = a.copy()
+        k = int(rng.integers(0, 300))
+        if k < 256:
+            b[k] ^= 1
+        assert ft.compare256(a.ctypes.data, b.ctypes.data) == R.refops_compare256(a.ctypes.data, b.ctypes.data)
+    for dist, ln, left in ((1, 258, 300), (2, 100, 300), (3, 258, 258), (7, 33, 20), (40, 258, 258), (300, 258, 258), (5, 1, 1), (16, 64, 64)):
+        base = np.zeros(1200, dtype=np.uint8); base[:400] = rng.integers(1, 256, size=400, dtype=np.uint8)
+        g = base.copy(); r = base.copy()
+        adv = R.refops_chunkmemset_safe(r.ctypes.data, 400, dist, ln, left)
+        ret = ft.chunkmemset_safe(g.ctypes.data + 400, g.ctypes.data + 400 - dist, ln, left)
+        assert ret - (g.ctypes.data + 400) == adv
+        assert np.array_equal(g[:400 + adv], r[:400 + adv]), (dist, ln, left)       # the reference may scribble past `len` inside `left`
+    for v in (0, 1, 0x61626364, 0xffffffff, 0x9e3779b9):
+        assert pkg.lib().zng_b200_update_hash(0, v) == R.refops_update_hash(0, v)
+
+
+def test_insert_string_quick_insert_slide_hash_vs_reference(pkg, ctx, zo):
+    R = _need_ref(zo)
+    ft = pkg.functable()
+    rng = np.random.default_rng(4)
+    data = np.ascontiguousarray(synth(65536, seed=77)[:50000])
+    head = np.zeros(65536, dtype=np.uint16); prev = np.zeros(32768, dtype=np.uint16)
+    rhead = head.copy(); rprev = prev.copy()
+    st = pkg.MatchState(data.ctypes.data, data.size, head.ctypes.data, prev.ctypes.data, 0, 0, 0, 2)
+    for s0, cnt in ((0, 1), (1, 40), (41, 3000), (20, 64), (3041, 30000)):
+        pkg.lib().zng_b200_insert_string(ctypes.byref(st), s0, cnt)
+        R.refops_insert_string(data.ctypes.data, data.size, rhead.ctypes.data, rprev.ctypes.data, s0, cnt)
+        assert np.array_equal(head, rhead) and np.array_equal(prev, rprev), (s0, cnt)
+    for s0 in (33041, 33042, 100, 40000, 40000):
+        got = pkg.lib().zng_b200_quick_insert_string(ctypes.byref(st), s0)
+        exp = R.refops_insert_string(data.ctypes.data, data.size, rhead.ctypes.data, rprev.ctypes.data, s0, 0)
+        assert got == exp and np.array_equal(head, rhead) and np.array_equal(prev, rprev), s0
+    # slide_hash on the populated tables plus random garbage
+    head[rng.integers(0, 65536, size=3000)] = rng.integers(0, 65536, size=3000).astype(np.uint16)
+    rhead = head.copy(); rprev = prev.copy()
+    ft.slide_hash(ctypes.byref(st))
+    assert R.refops_slide_hash(rhead.ctypes.data, rprev.ctypes.data) == 0
+    assert np.array_equal(head, rhead) and np.array_equal(prev, rprev)
+
+
+@pytest.mark.parametrize("level", [2, 3, 4, 5, 6])
+def test_longest_match_slot_vs_reference_every_level(pkg, ctx, zo, level):
+    """functable.longest_match through the table, one query per call, against the reference's dispatched variant with
+    configuration_table[level]'s chain / nice parameters; the batched device form on the same queries as well."""
+    import torch
+    R = _need_ref(zo)
+    ft = pkg.functable()
+    rng = np.random.default_rng(level)
+    dev = f"cuda:{ctx.device}"
+    for trial, data in enumerate((synth(65536, seed=31)[:40000], rng.integers(0, 3, size=40000, dtype=np.uint8),
+                                  np.tile(rng.integers(0, 256, size=97, dtype=np.uint8), 500)[:40000])):
+        data = np.ascontiguousarray(data)
+        n = data.size
+        head = np.zeros(65536, dtype=np.uint16); prev = np.zeros(32768, dtype=np.uint16)
+        R.refops_insert_string(data.ctypes.data, n, head.ctypes.data, prev.ctypes.data, 0, n - 4)
+        pos = np.concatenate([rng.integers(33000, n - 4, size=24), np.arange(n - 12, n - 3)]).astype(np.int64)
+        cand = prev[pos & 32767].astype(np.int64)
+        ok = (cand != 0) & (cand < pos) & (pos - cand <= 32506)
+        pos, cand = pos[ok], cand[ok]
+        exp = []
+        ms = ctypes.c_uint32(0)
+        for p_, c_ in zip(pos, cand):
+            el = R.refops_longest_match(data.ctypes.data, n, prev.ctypes.data, int(p_), int(c_), level, ctypes.byref(ms))
+            exp.append((el, ms.value))
+        st = pkg.MatchState(data.ctypes.data, n, head.ctypes.data, prev.ctypes.data, 0, 0, 0, level)
+        for (p_, c_), (el, es) in list(zip(zip(pos, cand), exp))[:12]:
+            st.strstart = int(p_); st.lookahead = n - int(p_); st.match_start = 0xffffffff
+            gl = ft.longest_match(ctypes.byref(st), int(c_))
+            assert gl == el, (level, trial, int(p_), int(c_), gl, el)
+            if el >= 4:
+                assert st.match_start == es
+        # batched device form
+        win = np.zeros(n + 600, dtype=np.uint8); win[:n] = data
+        d_win = torch.from_numpy(win).to(dev); d_prev = torch.from_numpy(prev.view(np.int16)).to(dev)
+        d_pos = torch.from_numpy(pos.astype(np.int32)).to(dev); d_cand = torch.from_numpy(cand.astype(np.int32)).to(dev)
+        d_len = torch.zeros(pos.size, dtype=torch.int32, device=dev); d_start = torch.zeros_like(d_len)
+        ctx._check(pkg.lib().zng_b200_op_longest_match_level(ctx._h, d_win.data_ptr(), n, d_prev.data_ptr(), d_pos.data_ptr(), d_cand.data_ptr(),
+                                                            pos.size, level, d_len.data_ptr(), d_start.data_ptr(), 0))
+        torch.cuda.synchronize()
+        gl, gs = d_len.cpu().numpy(), d_start.cpu().numpy()
+        for i, (el, es) in enumerate(exp):
+            if el >= 4:
+                assert gl[i] == el and gs[i] == es, (level, trial, i, int(pos[i]), int(cand[i]), gl[i], el)
+            else:
+                assert gl[i] == 0
+    assert ft.longest_match_slow(ctypes.byref(st), 1) == 0          # levels 7-9: slot present, outside the hot path

@@ -90,6 +90,18 @@ def ref():
         L.refdrv_gzip_members.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_int]
         L.refdrv_inflate_stream.restype = c_int
         L.refdrv_inflate_stream.argtypes = [c_void_p, c_size_t, c_int, c_void_p, c_size_t, POINTER(c_uint64), POINTER(c_uint32)]
+        if hasattr(L, "refops_longest_match"):          # oracle/ref_ops.c: the reference's operators one at a time
+            L.refops_longest_match.restype = c_uint32
+            L.refops_longest_match.argtypes = [c_void_p, c_uint32, c_void_p, c_uint32, c_uint32, c_int, POINTER(c_uint32)]
+            L.refops_insert_string.restype = c_uint32
+            L.refops_insert_string.argtypes = [c_void_p, c_uint32, c_void_p, c_void_p, c_uint32, c_uint32]
+            L.refops_slide_hash.restype = c_int; L.refops_slide_hash.argtypes = [c_void_p, c_void_p]
+            L.refops_update_hash.restype = c_uint32; L.refops_update_hash.argtypes = [c_uint32, c_uint32]
+            L.refops_compare256.restype = c_uint32; L.refops_compare256.argtypes = [c_void_p, c_void_p]
+            L.refops_chunksize.restype = c_uint32; L.refops_chunksize.argtypes = []
+            L.refops_chunkmemset_safe.restype = c_uint32; L.refops_chunkmemset_safe.argtypes = [c_void_p, c_uint32, c_uint32, c_uint32, c_uint32]
+            L.refops_crc32_fold.restype = c_uint32; L.refops_crc32_fold.argtypes = [c_void_p, c_size_t, c_size_t, c_void_p]
+            L.refops_adler32_fold_copy.restype = c_uint32; L.refops_adler32_fold_copy.argtypes = [c_uint32, c_void_p, c_void_p, c_size_t]
         L.refdrv_now.restype = c_double
         L.refdrv_inflate_oneshot.restype = c_int
         L.refdrv_inflate_oneshot.argtypes = [c_void_p, c_size_t, c_int, c_void_p, c_size_t, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_uint32), c_char_p]

@@ -64,6 +64,16 @@ def lib() -> ctypes.CDLL:
         "zng_b200_deflate_host_primed": (c_int, [vp, vp, vp, c_size_t, c_int, vp, c_size_t, POINTER(c_size_t), POINTER(c_uint32), POINTER(c_uint32)]),
         "zng_b200_crc32_host": (c_int, [vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
         "zng_b200_adler32_host": (c_int, [vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
+        "zng_b200_comm_unique_id": (c_int, [vp, c_size_t]),
+        "zng_b200_comm_create": (c_int, [vp, c_int, c_int, vp, POINTER(c_void_p)]),
+        "zng_b200_comm_adopt": (c_int, [vp, vp, POINTER(c_void_p)]),
+        "zng_b200_comm_destroy": (None, [vp]),
+        "zng_b200_comm_size": (c_int, [vp]),
+        "zng_b200_comm_rank": (c_int, [vp]),
+        "zng_b200_comm_error": (c_char_p, [vp]),
+        "zng_b200_stream_index_multi": (c_int, [vp, u32p, u32p, c_uint32, c_uint32, c_size_t, c_uint64, u64p, POINTER(c_uint64), POINTER(c_uint32), POINTER(c_uint64), vp]),
+        "zng_b200_gzip_multi": (c_int, [vp, vp, c_size_t, c_int, vp, c_size_t, u32p, u32p, u64p, vp, c_size_t, POINTER(c_uint64), POINTER(c_uint64),
+                                        POINTER(c_uint64), vp, vp, vp]),
         "zng_b200_inflate_members": (c_int, [vp, vp, u64p, c_uint32, c_int, vp, u64p, u32p, u32p, vp, u32p, u32p, vp]),
         "zng_b200_inflate_members_host": (c_int, [vp, vp, u64p, c_uint32, c_int, vp, u64p, u32p, u32p, vp, u32p, u32p]),
         "zng_b200_inflate_msg": (c_char_p, [c_uint32]),
@@ -73,6 +83,14 @@ def lib() -> ctypes.CDLL:
         "zng_b200_op_insert_string": (c_int, [vp, vp, vp, vp, c_uint32, c_uint32, vp]),
         "zng_b200_op_chunkmemset": (c_int, [vp, vp, c_uint32, c_uint32, c_uint32, vp]),
         "zng_b200_functable_get": (c_void_p, []),
+        "zng_b200_op_longest_match_level": (c_int, [vp, vp, c_uint32, vp, u32p, u32p, c_uint32, c_int, u32p, u32p, vp]),
+        "zng_b200_op_quick_insert_string": (c_int, [vp, vp, vp, vp, c_uint32, u32p, vp]),
+        "zng_b200_op_slide_hash": (c_int, [vp, vp, vp, c_uint32, vp]),
+        "zng_b200_crc32_copy_host": (c_int, [vp, vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
+        "zng_b200_adler32_copy_host": (c_int, [vp, vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
+        "zng_b200_update_hash": (c_uint32, [c_uint32, c_uint32]),
+        "zng_b200_insert_string": (None, [vp, c_uint32, c_uint32]),
+        "zng_b200_quick_insert_string": (ctypes.c_uint16, [vp, c_uint32]),
         # the C11 host library: zlib-ng's own API (include/zlib-ng.h)
         "zlibng_version": (c_char_p, []),
         "zng_deflateInit2": (c_int32, [vp, c_int32, c_int32, c_int32, c_int32, c_int32]),
@@ -106,13 +124,34 @@ def lib() -> ctypes.CDLL:
     return L
 
 
+class Crc32Fold(ctypes.Structure):
+    """struct zng_b200_crc32_fold (crc32.h:8-14 layout)."""
+    _fields_ = [("fold", ctypes.c_uint8 * 64), ("value", c_uint32)]
+
+
+class MatchState(ctypes.Structure):
+    """struct zng_b200_match_state: the deflate_state fields longest_match / insert_string / slide_hash read and write (host memory)."""
+    _fields_ = [("window", c_void_p), ("window_len", c_uint32), ("head", c_void_p), ("prev", c_void_p), ("strstart", c_uint32),
+                ("lookahead", c_uint32), ("match_start", c_uint32), ("level", c_int32)]
+
+
 class Functable(ctypes.Structure):
-    """struct zng_b200_functable (include/zng_b200.h), the host-callable part of the reference's functable_s."""
-    _fields_ = [("adler32", ctypes.CFUNCTYPE(c_uint32, c_uint32, c_void_p, c_size_t)),
+    """struct zng_b200_functable (include/zng_b200.h): the 15 slots of the reference's functable_s, same order."""
+    _fields_ = [("force_init", ctypes.CFUNCTYPE(None)),
+                ("adler32", ctypes.CFUNCTYPE(c_uint32, c_uint32, c_void_p, c_size_t)),
+                ("adler32_fold_copy", ctypes.CFUNCTYPE(c_uint32, c_uint32, c_void_p, c_void_p, c_size_t)),
                 ("chunkmemset_safe", ctypes.CFUNCTYPE(c_void_p, c_void_p, c_void_p, ctypes.c_uint, ctypes.c_uint)),
                 ("chunksize", ctypes.CFUNCTYPE(c_uint32)),
                 ("compare256", ctypes.CFUNCTYPE(c_uint32, c_void_p, c_void_p)),
-                ("crc32", ctypes.CFUNCTYPE(c_uint32, c_uint32, c_void_p, c_size_t))]
+                ("crc32", ctypes.CFUNCTYPE(c_uint32, c_uint32, c_void_p, c_size_t)),
+                ("crc32_fold", ctypes.CFUNCTYPE(None, POINTER(Crc32Fold), c_void_p, c_size_t, c_uint32)),
+                ("crc32_fold_copy", ctypes.CFUNCTYPE(None, POINTER(Crc32Fold), c_void_p, c_void_p, c_size_t)),
+                ("crc32_fold_final", ctypes.CFUNCTYPE(c_uint32, POINTER(Crc32Fold))),
+                ("crc32_fold_reset", ctypes.CFUNCTYPE(c_uint32, POINTER(Crc32Fold))),
+                ("inflate_fast", ctypes.CFUNCTYPE(None, c_void_p, c_uint32)),
+                ("longest_match", ctypes.CFUNCTYPE(c_uint32, POINTER(MatchState), ctypes.c_uint16)),
+                ("longest_match_slow", ctypes.CFUNCTYPE(c_uint32, POINTER(MatchState), ctypes.c_uint16)),
+                ("slide_hash", ctypes.CFUNCTYPE(None, POINTER(MatchState)))]
 
 
 def functable() -> "Functable":
@@ -262,3 +301,62 @@ class Context:
         res = c_uint32(0)
         self._check(lib().zng_b200_adler32_host(self._h, _ptr(h_buf), n, init, byref(res)))
         return int(res.value)
+
+
+class Comm:
+    """One zng_b200_comm (csrc/multi.cu): the NCCL communicator of the multi-GPU stream assembly.  `Comm.from_torch(ctx)`
+    builds it for the ranks of the default torch.distributed process group (the 128-byte NCCL id travels by broadcast)."""
+
+    def __init__(self, ctx: "Context", nranks: int, rank: int, uid: bytes | None):
+        self.ctx = ctx
+        self._h = c_void_p()
+        buf = ctypes.create_string_buffer(uid, 128) if uid is not None else None
+        r = lib().zng_b200_comm_create(ctx._h, nranks, rank, buf, byref(self._h))
+        if r != 0:
+            raise ZngB200Error(r, "zng_b200_comm_create failed (NCCL not loadable, or bad arguments)")
+        self.nranks, self.rank = nranks, rank
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        r = lib().zng_b200_comm_unique_id(buf, 128)
+        if r != 0:
+            raise ZngB200Error(r, "zng_b200_comm_unique_id failed (NCCL not loadable)")
+        return buf.raw
+
+    @classmethod
+    def from_torch(cls, ctx: "Context"):
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return cls(ctx, 1, 0, None)
+        rank, world = dist.get_rank(), dist.get_world_size()
+        t = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{ctx.device}")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return cls(ctx, world, rank, bytes(t.cpu().numpy().tobytes()))
+
+    def close(self):
+        if self._h:
+            lib().zng_b200_comm_destroy(self._h)
+            self._h = c_void_p()
+
+    def _check(self, r: int):
+        if r != 0:
+            raise ZngB200Error(r, lib().zng_b200_comm_error(self._h).decode() or lib().zng_b200_last_error(self.ctx._h).decode())
+
+    def stream_index(self, sizes, crcs, nchunks_local: int, chunk: int, n_local: int, base: int, offsets_local):
+        """Collective.  Returns (stream_end, crc32, total_in); offsets_local (int64 device tensor, nchunks_local + 1) is filled."""
+        end, crc, tin = c_uint64(0), c_uint32(0), c_uint64(0)
+        self._check(lib().zng_b200_stream_index_multi(self._h, _ptr(sizes), _ptr(crcs), nchunks_local, chunk, n_local, base,
+                                                      _ptr(offsets_local), byref(end), byref(crc), byref(tin), Context._stream()))
+        return int(end.value), int(crc.value), int(tin.value)
+
+    def gzip_multi(self, d_in, n_local: int, level: int, slots, stride: int, sizes, crcs, offsets_local, packed, packed_cap: int):
+        """Collective: compress + allgather + scan + fold + pack.  Returns (my_offset, my_bytes, file_bytes, header, trailer)."""
+        off, nb, fb = c_uint64(0), c_uint64(0), c_uint64(0)
+        hdr = ctypes.create_string_buffer(10); trl = ctypes.create_string_buffer(10)
+        self._check(lib().zng_b200_gzip_multi(self._h, _ptr(d_in), n_local, level, _ptr(slots), stride, _ptr(sizes), _ptr(crcs), _ptr(offsets_local),
+                                              _ptr(packed), packed_cap, byref(off), byref(nb), byref(fb), hdr, trl, Context._stream()))
+        return int(off.value), int(nb.value), int(fb.value), hdr.raw, trl.raw

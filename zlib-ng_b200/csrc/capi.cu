@@ -132,6 +132,7 @@ struct zng_b200_ctx {
     uint8_t* d_pbuf = nullptr; size_t pbuf_cap = 0;   // zng_b200_deflate_host_primed: [dictionary | input], slots | packed, sizes | crcs | adlers | offsets
     uint8_t* d_pout = nullptr; size_t pout_cap = 0;
     uint32_t* d_pmeta = nullptr; size_t pmeta_cap = 0;
+    uint8_t* d_arena = nullptr; size_t arena_cap = 0;   // scratch of the host-callable operator table
     uint8_t* d_hostbuf = nullptr;              // staging for *_host checksums
     size_t hostbuf_cap = 0;
     uint32_t x2n[32];
@@ -377,7 +378,7 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm = v; }
     if (const char* e = getenv("ZNG_B200_K1")) ctx->k1_cta = (strcmp(e, "cta") == 0);
     if (const char* e = getenv("ZNG_B200_K1_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->chains_cta = v; }
-    if (const char* e = getenv("ZNG_B200_K1_WARPS")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) ctx->warps_cta = v; }
+    if (const char* e = getenv("ZNG_B200_K1_WARPS")) { int v = atoi(e); if (v == 4 || v == 6 || v == 8 || v == 12) ctx->warps_cta = v; }
     if (const char* e = getenv("ZNG_B200_SLAB_CHUNKS")) { int v = atoi(e); if (v >= 64 && v <= 16384) ctx->slab_chunks = (uint32_t)v; }
     if (const char* e = getenv("ZNG_B200_STREAMED")) ctx->streamed = atoi(e);
     if (const char* e = getenv("ZNG_B200_STREAM_SHIFT")) { int v = atoi(e); if (v >= 8 && v <= 11) ctx->stream_shift = (uint32_t)v; }
@@ -467,6 +468,7 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
         for (auto e : S.slab_done) if (e) cudaEventDestroy(e);
     }
     if (ctx->d_hostbuf) cudaFree(ctx->d_hostbuf);
+    if (ctx->d_arena) cudaFree(ctx->d_arena);
     if (ctx->d_pbuf) cudaFree(ctx->d_pbuf);
     if (ctx->d_pout) cudaFree(ctx->d_pout);
     if (ctx->d_pmeta) cudaFree(ctx->d_pmeta);
@@ -627,6 +629,46 @@ int zng_b200_op_longest_match(zng_b200_ctx* ctx, const void* d_window, uint32_t 
     CK(launch_op_longest_match((const uint8_t*)d_window, n, d_prev, d_pos, d_cand, n_q, d_len, d_start, (cudaStream_t)stream), "longest_match launch");
     return 0;
 }
+int zng_b200_op_longest_match_level(zng_b200_ctx* ctx, const void* d_window, uint32_t n, const uint16_t* d_prev, const uint32_t* d_pos,
+                                    const uint32_t* d_cand, uint32_t n_q, int level, uint32_t* d_len, uint32_t* d_start, void* stream) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    const bool raw = (level & 0x100) != 0;                     // internal: the host operator table wants the reference's raw return value
+    level &= 0xff;
+    if (level < 2 || level > 6) return bad(ctx, "longest_match: levels 2..6 (levels 7-9 use longest_match_slow, outside the hot path)");
+    if (n_q && (!d_window || !d_prev || !d_pos || !d_cand || !d_len || !d_start)) return bad(ctx, "NULL argument");
+    if (n > ZNG_B200_CHUNK_MAX) return bad(ctx, "window larger than 65536");
+    DeviceGuard g(ctx->device);
+    CK(launch_op_longest_match((const uint8_t*)d_window, n, d_prev, d_pos, d_cand, n_q, d_len, d_start, (cudaStream_t)stream, level, raw), "longest_match launch");
+    return 0;
+}
+int zng_b200_op_quick_insert_string(zng_b200_ctx* ctx, const void* d_window, uint16_t* d_head, uint16_t* d_prev, uint32_t str,
+                                    uint32_t* d_old_head, void* stream) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (!d_window || !d_head || !d_prev || !d_old_head) return bad(ctx, "NULL argument");
+    DeviceGuard g(ctx->device);
+    CK(launch_op_insert_string((const uint8_t*)d_window, d_head, d_prev, str, 1, (cudaStream_t)stream, d_old_head), "quick_insert_string launch");
+    return 0;
+}
+int zng_b200_op_slide_hash(zng_b200_ctx* ctx, uint16_t* d_head, uint16_t* d_prev, uint32_t wsize, void* stream) {
+    if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (!d_head || !d_prev) return bad(ctx, "NULL argument");
+    if (wsize == 0 || wsize > 32768u || (wsize & 7u)) return bad(ctx, "slide_hash: wsize must be a multiple of 8 up to 32768");
+    DeviceGuard g(ctx->device);
+    CK(launch_op_slide_hash(d_head, d_prev, wsize, (cudaStream_t)stream), "slide_hash launch");
+    return 0;
+}
+// device scratch of the host-callable operator table (host/zng_functable.c): grow-only, owned by the context -- no allocation per call
+void* zng_b200_ctx_arena(zng_b200_ctx* ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    DeviceGuard g(ctx->device);
+    if (ctx->arena_cap < bytes) {
+        if (ctx->d_arena) { cudaDeviceSynchronize(); cudaFree(ctx->d_arena); ctx->d_arena = nullptr; ctx->arena_cap = 0; }
+        size_t want = bytes < ((size_t)1 << 20) ? ((size_t)1 << 20) : bytes + bytes / 4;
+        if (cudaMalloc(&ctx->d_arena, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        ctx->arena_cap = want;
+    }
+    return ctx->d_arena;
+}
 int zng_b200_op_insert_string(zng_b200_ctx* ctx, const void* d_window, uint16_t* d_head, uint16_t* d_prev, uint32_t str, uint32_t count, void* stream) {
     if (!ctx) return ZNG_B200_STREAM_ERROR;
     if (count && (!d_window || !d_head || !d_prev)) return bad(ctx, "NULL argument");
@@ -745,11 +787,24 @@ int zng_b200_inflate_members_host(zng_b200_ctx* ctx, const void* h_in, const uin
         CK(cudaMemcpyAsync(s.d_off, s.h_off, 2 * ((size_t)cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream), "H2D offsets");
         const size_t cap = s.cnt_cap;
         const int slot = next_slot(ctx);
+        // batched members: the whole output range of the slab goes back in one copy; what a member leaves unwritten inside its
+        // range (it decoded less than its capacity) must not carry bytes of an earlier call on this context
+        if (n_members != 1 && out_bytes) CK(cudaMemsetAsync(s.d_out, 0, out_bytes, s.stream), "cudaMemsetAsync(inflate output)");
         CK(launch_inflate_members(s.d_in, s.d_off, cnt, window_bits, s.d_out, s.d_off + (cnt + 1), s.d_res, s.d_res + cap,
                                   (int32_t*)(s.d_res + 2 * cap), s.d_res + 3 * cap, s.d_res + 4 * cap, ctx->counters + slot, ctx->sms, s.stream),
            "inflate launch");
-        if (out_bytes) CK(cudaMemcpyAsync((uint8_t*)h_out + o0, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream), "D2H output");
-        CK(cudaMemcpyAsync(s.h_res, s.d_res, 5 * cap * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream), "D2H results");
+        if (n_members == 1) {
+            // the one-member call of zng_inflate / zng_uncompress: the capacity is the caller's whole avail_out.  Only the bytes
+            // the decoder produced are moved (the rest of the caller's buffer stays untouched, no stale device bytes travel).
+            CK(cudaMemcpyAsync(s.h_res, s.d_res, 5 * cap * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream), "D2H results");
+            CK(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+            size_t produced = s.h_res[0];
+            if (produced > out_bytes) produced = out_bytes;
+            if (produced) CK(cudaMemcpyAsync((uint8_t*)h_out + o0, s.d_out, produced, cudaMemcpyDeviceToHost, s.stream), "D2H output");
+        } else {
+            if (out_bytes) CK(cudaMemcpyAsync((uint8_t*)h_out + o0, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream), "D2H output");
+            CK(cudaMemcpyAsync(s.h_res, s.d_res, 5 * cap * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream), "D2H results");
+        }
         CK(cudaEventRecord(s.done, s.stream), "event record");
         s.first = m; s.cnt = cnt; s.busy = true;
         m += cnt;
@@ -1054,7 +1109,7 @@ int zng_b200_inflate_stream_host(zng_b200_ctx* ctx, const void* h_in, size_t n, 
 }
 
 // ---------------------------------------------------------------- host-buffer entry points
-static int host_checksum(zng_b200_ctx* ctx, const void* h_buf, size_t n, uint32_t init, uint32_t* result, bool crc) {
+static int host_checksum(zng_b200_ctx* ctx, const void* h_buf, size_t n, uint32_t init, uint32_t* result, bool crc, void* h_copy = nullptr) {
     if (!ctx || !result) return ZNG_B200_STREAM_ERROR;
     if (n && !h_buf) return bad(ctx, "h_buf is NULL");
     DeviceGuard g(ctx->device);
@@ -1077,6 +1132,8 @@ static int host_checksum(zng_b200_ctx* ctx, const void* h_buf, size_t n, uint32_
                     : zng_b200_adler32(ctx, ctx->d_hostbuf, take, cur, ctx->d_result, nullptr);
         if (r) return r;
         CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0), "D2H");
+        // checksum-while-copy (read_buf, deflate.c:1190-1212): the copy is the bytes' trip back from the staging buffer
+        if (h_copy && take) CK(cudaMemcpyAsync((uint8_t*)h_copy + off, ctx->d_hostbuf, take, cudaMemcpyDeviceToHost, 0), "D2H copy");
         CK(cudaStreamSynchronize(0), "sync");
         cur = ctx->h_result[0];
         off += take;
@@ -1090,6 +1147,14 @@ int zng_b200_crc32_host(zng_b200_ctx* ctx, const void* h_buf, size_t n, uint32_t
 }
 int zng_b200_adler32_host(zng_b200_ctx* ctx, const void* h_buf, size_t n, uint32_t init, uint32_t* result) {
     return host_checksum(ctx, h_buf, n, init, result, false);
+}
+int zng_b200_crc32_copy_host(zng_b200_ctx* ctx, void* h_dst, const void* h_src, size_t n, uint32_t init, uint32_t* result) {
+    if (n && !h_dst) return ZNG_B200_STREAM_ERROR;
+    return host_checksum(ctx, h_src, n, init, result, true, h_dst);
+}
+int zng_b200_adler32_copy_host(zng_b200_ctx* ctx, void* h_dst, const void* h_src, size_t n, uint32_t init, uint32_t* result) {
+    if (n && !h_dst) return ZNG_B200_STREAM_ERROR;
+    return host_checksum(ctx, h_src, n, init, result, false, h_dst);
 }
 
 // drain one slab: wait for its kernels, copy the packed bytes out

@@ -121,12 +121,7 @@ __device__ uint32_t fast_parse_warp(const VWindow W, uint32_t n, uint16_t* head,
             __stcs(tok + wr + __popc(V & lt), t);
         }
         wr += __popc(V);
-        if ((I >> lane) & 1u) {                              // insert_string_tpl.h:58-75 for every inserted position
-            const unsigned prior = peers & I & lt;
-            const uint32_t old = prior ? p + (31u - (uint32_t)__clz(prior)) : cand0;
-            __stcg(prev + (q & (kWSize - 1u)), (uint16_t)old);
-            if ((peers & I & ~lt & ~(1u << lane)) == 0u) __stcg(head + h, (uint16_t)q);
-        }
+        insert_lanes(head, prev, h, q, p, cand0, peers, I, lane);    // insert_string_tpl.h:58-75 for every inserted position
         p = next_p; skip = next_skip;
         __syncwarp();
     }

@@ -30,6 +30,7 @@
 // Per-chunk CRC-32 / Adler-32 come from the K3 tile kernel (checksum.cu) launched on the same stream.
 #include "common.cuh"
 #include "kernels.h"
+#include "lz_ops.cuh"
 #include <cstdlib>
 
 namespace zb {
@@ -46,24 +47,8 @@ struct Window {
     __device__ __forceinline__ uint32_t word(uint32_t i) const { return __ldg(w + i); }
 };
 
-// ---------------------------------------------------------------- parser (warp 0)
-// Warp-wide first-mismatch over 256 bytes: lane l compares the 8 bytes at a+8l / b+8l (byte
-// offsets already include the skew).  Returns the number of equal leading bytes (0..256).
-// (compare256 analogue, compare256_c.c:12-43)
-__device__ __forceinline__ uint32_t warp_compare256(const Window& W, uint32_t a, uint32_t b, unsigned lane) {
-    a += 8u * lane; b += 8u * lane;
-    const uint32_t ia = a >> 2, sa = (a & 3u) << 3, ib = b >> 2, sb = (b & 3u) << 3;
-    const uint32_t a0 = W.word(ia), a1 = W.word(ia + 1), a2 = W.word(ia + 2);
-    const uint32_t b0 = W.word(ib), b1 = W.word(ib + 1), b2 = W.word(ib + 2);
-    const uint64_t x = ((uint64_t)__funnelshift_r(a0, a1, sa) | ((uint64_t)__funnelshift_r(a1, a2, sa) << 32)) ^
-                       ((uint64_t)__funnelshift_r(b0, b1, sb) | ((uint64_t)__funnelshift_r(b1, b2, sb) << 32));
-    const unsigned diff = __ballot_sync(ZB_FULL, x != 0ull);
-    if (diff == 0u) return 256u;
-    const unsigned f = __ffs(diff) - 1u;
-    unsigned byte = (unsigned)(__ffsll((long long)x) - 1) >> 3;
-    byte = __shfl_sync(ZB_FULL, byte, f);
-    return 8u * f + byte;
-}
+// ---------------------------------------------------------------- parser
+// compare256 (compare256_c.c:12-43) is lz_ops.cuh:warp_compare_bytes -- the one warp-wide first-mismatch of this library.
 
 // Parse one chunk; tokens go to tok[0..count) in global memory (coalesced: the visited lanes of a
 // window write consecutive slots), followed by the kTokEnd marker.  Returns the token count.
@@ -125,7 +110,7 @@ __device__ uint32_t quick_parse_warp(const Window W, uint32_t n, uint16_t* head,
                 // (checked below) -- a stale long match is cut away before it is used.
                 const uint32_t ck = __shfl_sync(ZB_FULL, cand, k);
                 const uint32_t qk = p + k;
-                len = 12u + warp_compare256(W, qk + 12u + W.skew, ck + 12u + W.skew, lane);
+                len = 12u + warp_compare_bytes(W, qk + 12u + W.skew, ck + 12u + W.skew, 256u, lane);
                 len = min(len, n - qk);
                 len = min(len, kMaxMatch);                   // deflate_quick.c:102-103
                 if (lane == k) slen = len;
@@ -251,7 +236,7 @@ __device__ uint32_t primed_parse_warp(const Window W, uint32_t D, uint32_t N, ui
             if (len >= 12u) {
                 const uint32_t ck = __shfl_sync(ZB_FULL, cand, k);
                 const uint32_t qk = p + k;
-                len = 12u + warp_compare256(W, qk + 12u + W.skew, ck + 12u + W.skew, lane);
+                len = 12u + warp_compare_bytes(W, qk + 12u + W.skew, ck + 12u + W.skew, 256u, lane);
                 len = min(min(len, R - qk), kMaxMatch);
                 if (lane == k) slen = len;
             }

@@ -1,30 +1,33 @@
-// deflate_quick_cta.cu -- K1a v5: level-1 (deflate_quick) parse, one CTA per chunk chain.
+// deflate_quick_cta.cu -- K1a v6: level-1 (deflate_quick) parse, one CTA per chunk chain, producers and walker pipelined.
 //
 // Reference semantics (files under /root/reference), reproduced bit-exactly -- same rules as quick_parse_warp:
 //   deflate_quick.c:47-130        greedy single-probe parse
 //   insert_string_tpl.h:58-75     quick_insert_string: head[] is updated at VISITED positions only
 //   arch/generic/compare256_c.c   first-mismatch compare
 //
-// Why a second parser.  Round 1's warp-per-chain parser walks 32 positions per step and pays, on the dependent chain of every
-// step, two or three trips to L2 / DRAM (head lookup, candidate bytes) and one __match_any_sync (measured on B200: 240..410
-// clocks, profiles/r2_ubench_warp.txt).  It hides that latency with 24 chains per SM, whose 128 KiB head tables + 64 KiB
-// chunks (680 MB) thrash the 126 MB L2: every speculative head lookup becomes a DRAM sector read (ncu: 99 GB read + 17 GB
-// written per GiB of input).  This parser splits the work of one chain over the warps of a CTA:
-//   * PRODUCER phase, all warps, one position per thread, W = 32 x warps positions per window: hash, head lookup in the table
-//     as it stands at the window start, candidate bytes, 12-byte match measurement; plus, from a shared array of the
-//     window's hashes, the distance d to the nearest earlier position of the window (<= 31 back) with the same hash and the
-//     match against THAT position.  One trip to L2 for the lookups and one to L1 / L2 for the candidate bytes per W positions.
-//   * WALK phase, one warp, 32 positions per step, everything from shared memory: ballot / ffs replay of the greedy
-//     decisions; the orbit of the greedy jump function is followed with one shuffle per visited match (every lane
-//     precomputes where a match taken at it leads).
-//   * What the walk inserts is not visible to lookups made at the window start.  A small exact cache in shared memory
-//     (2W sets x 4 ways, tag = the 16-bit hash + the window's epoch) holds every insert of the current window; a lane that
-//     finds its hash there takes that (newer) candidate -- normally position - d, already measured by the producers.  A
-//     visited lane whose hash also belongs to an earlier VISITED lane of its own step (seen from d, no match_any) cuts the
-//     step there: the next step finds the entry in the cache.  If a cache set overflows the window ends at that point; at a
-//     window start the table in global memory is exact.
+// Why.  Round 1's warp-per-chain parser pays, on the dependent chain of every 32-position step, two or three trips to L2 /
+// DRAM (head lookup, candidate bytes) and one __match_any_sync, and hides that with 24 chains per SM whose 128 KiB head
+// tables + 64 KiB chunks (680 MB) thrash the 126 MB L2 (ncu: 99 GB read + 17 GB written per GiB of input).  Here the work
+// of one chain is split over the warps of a CTA and SOFTWARE-PIPELINED, so that the serial part never waits for memory:
+//   * PRODUCER warps (PW of them, one aligned block of 32 positions each, window = 32 x PW positions) work one window
+//     AHEAD of the walker: hash, head lookup in the table as it stands (global memory, L2 resident: few chains per SM),
+//     candidate bytes, match length up to 64 bytes, and the distance d to the nearest earlier position of the block with the
+//     same hash (one __match_any_sync).  They leave one 8-byte record per position in a double-buffered shared ring.
+//   * The WALKER warp replays the greedy decisions of deflate_quick over the records, one aligned block per step, everything
+//     from shared memory: ballot / ffs, and one shuffle per visited match to follow the orbit of the greedy jump function.
+//   * Staleness.  A producer lookup for window w+1 runs while the walker inserts window w, so it may miss inserts of windows
+//     w and w+1.  Every insert therefore also sets one bit (one bit per 16-bit hash value) in the bitmap generation of its
+//     window and leaves its position in a small direct-mapped table last[h & 8191].  A lane whose hash bit is set in either
+//     live generation takes its candidate from last[] (verified against the ring of recent hashes: the newest insert of that
+//     hash) and measures it itself; if the slot was taken over by another hash the lane asks the table in global memory --
+//     exact, because the walker's own inserts are ordered before it (rare: one L2 round trip).  A lane whose bit is clear had no
+//     insert of its hash since the lookup, so the producer's candidate is the reference's.  A visited lane whose hash also
+//     belongs to an earlier VISITED lane of its own step (seen from d) cuts the step there; the next step starts at that lane.
+//   * Two CTA barriers per window: (A) walk w and production of w+1 are done -> every thread wipes the bitmap generation
+//     that window w+1 will insert into (it still holds window w-1) -> (B) -> walk w+1 || production of w+2.
 #include "common.cuh"
 #include "kernels.h"
+#include "lz_ops.cuh"
 
 namespace zb {
 
@@ -41,97 +44,106 @@ struct WindowCA {
     }
 };
 
-__device__ __forceinline__ uint32_t warp_compare256_ca(const WindowCA& W, uint32_t a, uint32_t b, unsigned lane) {
-    a += 8u * lane; b += 8u * lane;
-    const uint32_t ia = a >> 2, sa = (a & 3u) << 3, ib = b >> 2, sb = (b & 3u) << 3;
-    const uint32_t a0 = W.word(ia), a1 = W.word(ia + 1), a2 = W.word(ia + 2);
-    const uint32_t b0 = W.word(ib), b1 = W.word(ib + 1), b2 = W.word(ib + 2);
-    const uint64_t x = ((uint64_t)__funnelshift_r(a0, a1, sa) | ((uint64_t)__funnelshift_r(a1, a2, sa) << 32)) ^
-                       ((uint64_t)__funnelshift_r(b0, b1, sb) | ((uint64_t)__funnelshift_r(b1, b2, sb) << 32));
-    const unsigned diff = __ballot_sync(ZB_FULL, x != 0ull);
-    if (diff == 0u) return 256u;
-    const unsigned f = __ffs(diff) - 1u;
-    unsigned byte = (unsigned)(__ffsll((long long)x) - 1) >> 3;
-    byte = __shfl_sync(ZB_FULL, byte, f);
-    return 8u * f + byte;
-}
+constexpr uint32_t kProdCap = 64u;        // producers measure a match up to this many bytes ("64 or more" beyond)
+constexpr uint32_t kWalkCap = 12u;        // the walker's own measurement of a recent candidate ("12 or more" beyond)
 
-// deflate_quick.c:90-103 for one (position, candidate) pair, up to 12 bytes: 0 = no match, 4..11 exact (already clipped to the
-// lookahead), 12 = "12 or more".  v / x: bytes 0..3 and 4..11 at q.
-__device__ __forceinline__ uint32_t match12(const WindowCA& W, uint32_t q, uint32_t cand, uint32_t v, uint64_t x, uint32_t n) {
-    const uint32_t cb = cand + W.skew, i = cb >> 2, sh = (cb & 3u) << 3;
-    const uint32_t b0 = W.word(i), b1 = W.word(i + 1), b2 = W.word(i + 2), b3 = W.word(i + 3);
-    if (__funnelshift_r(b0, b1, sh) != v) return 0u;
-    const uint64_t y = (uint64_t)__funnelshift_r(b1, b2, sh) | ((uint64_t)__funnelshift_r(b2, b3, sh) << 32);
-    const uint64_t d = x ^ y;
-    uint32_t slen = d ? 4u + ((unsigned)(__ffsll((long long)d) - 1) >> 3) : 12u;
-    if (slen < 12u) slen = min(slen, n - q);
-    return slen;
-}
-
-__device__ __forceinline__ void load12(const WindowCA& W, uint32_t q, uint32_t& v, uint64_t& x) {
+__device__ __forceinline__ void ca_load12(const WindowCA& W, uint32_t q, uint32_t& v, uint64_t& x) {
     const uint32_t qb = q + W.skew, i = qb >> 2, sh = (qb & 3u) << 3;
     const uint32_t a0 = W.word(i), a1 = W.word(i + 1), a2 = W.word(i + 2), a3 = W.word(i + 3);
     v = __funnelshift_r(a0, a1, sh);
     x = (uint64_t)__funnelshift_r(a1, a2, sh) | ((uint64_t)__funnelshift_r(a2, a3, sh) << 32);
 }
 
+__device__ __forceinline__ uint64_t ca_load8(const WindowCA& W, uint32_t pos) {
+    const uint32_t qb = pos + W.skew, i = qb >> 2, sh = (qb & 3u) << 3;
+    const uint32_t a0 = W.word(i), a1 = W.word(i + 1), a2 = W.word(i + 2);
+    return (uint64_t)__funnelshift_r(a0, a1, sh) | ((uint64_t)__funnelshift_r(a1, a2, sh) << 32);
+}
+
+// deflate_quick.c:90-103 for one (position, candidate) pair, measured up to `cap` bytes (12 + 8k): 0 = no match (fewer than 4
+// equal bytes), 4 .. cap-1 exact and already clipped to the lookahead, cap = "cap or more".  v / x: bytes 0..3 and 4..11 at q.
+__device__ __forceinline__ uint32_t match_upto(const WindowCA& W, uint32_t q, uint32_t cand, uint32_t v, uint64_t x, uint32_t n, uint32_t cap) {
+    const uint32_t cb = cand + W.skew, i = cb >> 2, sh = (cb & 3u) << 3;
+    const uint32_t b0 = W.word(i), b1 = W.word(i + 1), b2 = W.word(i + 2), b3 = W.word(i + 3);
+    if (__funnelshift_r(b0, b1, sh) != v) return 0u;
+    const uint64_t y = (uint64_t)__funnelshift_r(b1, b2, sh) | ((uint64_t)__funnelshift_r(b2, b3, sh) << 32);
+    uint64_t d = x ^ y;
+    uint32_t len = 4u;
+    while (d == 0ull) {
+        len += 8u;
+        if (len >= cap) return cap;
+        d = ca_load8(W, q + len) ^ ca_load8(W, cand + len);
+    }
+    len += (unsigned)(__ffsll((long long)d) - 1) >> 3;
+    if (len >= cap) return cap;
+    return min(len, n - q);                                   // deflate_quick.c:100-101 clip to the lookahead
+}
+
 // mask of lanes >= s (s in 0..32 and beyond: clamped)
 __device__ __forceinline__ uint32_t lanes_ge(uint32_t s) { return __funnelshift_lc(0u, 0xffffffffu, s); }
 
-// ring record: x = hash << 16 | table candidate;  y = byte | slen << 8 | act << 12 | d << 16
-template <int WARPS>
-struct __align__(16) CtaSmem {
-    static constexpr int kWin = WARPS * 32;
-    uint32_t bitmap[2048];       // one bit per hash value: inserted by the walk of the current window
-    uint8_t  table[4096];        // [hash & 4095] = window index of the last insert that mapped here (verified against hs[])
-    uint2    ring[kWin];
-    uint32_t hs[kWin + 32];      // the window's hashes behind 32 sentinels (never equal to a hash)
+// ring record: x = hash << 16 | table candidate;  y = byte | slen << 8 (7 bits) | act << 15 | d << 16 (5 bits)
+template <int PW>
+struct __align__(16) PipeSmem {
+    static constexpr int kWin = PW * 32;
+    uint32_t gen[2][2048];       // generation (window & 1): one bit per hash value inserted by the walk of that window
+    uint16_t last[8192];         // [hash & 8191] = position of the last insert that mapped here (verified against hs[])
+    uint2    ring[2][kWin];      // records of window w in ring[w & 1]
+    uint32_t hs[4][kWin];        // hashes of window w in hs[w & 3] (inactive positions: values no hash can take)
     uint32_t ci;                 // chunk index of this round
-    uint32_t adv;                // positions consumed by the walk of the current window
     uint32_t slot;
 };
 
-// One 32-position step of the walker warp at window index `cur`.  Returns the positions consumed; wr (token count) is
-// advanced.  ovf: the insert cache could not answer exactly -> the window must end here (the step is not executed, 0 is returned).
-template <int WARPS>
-__device__ __forceinline__ uint32_t walk_step(const WindowCA& W, CtaSmem<WARPS>& sm, uint32_t p, uint32_t cur, uint32_t nwin, uint32_t n,
-                                              uint16_t* head, uint32_t* __restrict__ tok, uint32_t& wr, bool& ovf, unsigned lane) {
+// One step of the walker: the aligned block `blk` of window w from lane s0 on.  Returns the chunk position where the next step
+// starts; wr (token count) is advanced.
+template <int PW>
+__device__ __forceinline__ uint32_t walk_step(const WindowCA& W, PipeSmem<PW>& sm, uint32_t w, uint32_t blk, uint32_t s0, uint32_t n,
+                                              uint16_t* head, uint32_t* __restrict__ tok, uint32_t& wr, unsigned lane) {
+    constexpr uint32_t kWin = PW * 32;
     const unsigned lt = (1u << lane) - 1u;
-    const uint32_t i = cur + lane;
-    const bool inw = i < nwin;
-    const uint32_t q = p + i;
-    uint2 rec = make_uint2(0u, 0u);
-    if (inw) rec = sm.ring[i];
+    const uint32_t b0 = w * kWin + blk * 32u;                 // chunk position of lane 0
+    const uint32_t q = b0 + lane;
+    const uint32_t nl = min(32u, n - b0);                     // lanes that hold a byte
+    const uint2 rec = sm.ring[w & 1u][blk * 32u + lane];
     const uint32_t h = rec.x >> 16;
     uint32_t cand = rec.x & 0xffffu;
-    uint32_t slen = (rec.y >> 8) & 15u;
-    const bool act = (rec.y >> 12) & 1u;
+    uint32_t slen = (rec.y >> 8) & 127u;
+    uint32_t mcap = kProdCap;                                 // slen == mcap: "mcap or more", the walk measures the rest
+    const bool act = (rec.y >> 15) & 1u;
     const uint32_t d = (rec.y >> 16) & 31u;
-    // ---- has the walk of this window inserted my hash already?  Then that position is the head entry now.
-    const uint32_t bw = sm.bitmap[h >> 5];
-    const bool hit = act && ((bw >> (h & 31u)) & 1u);
+    const bool live = act && lane >= s0;
+    // ---- has the walk inserted my hash since the producers looked it up?  Then that position is the head entry now.
+    const uint32_t bw = sm.gen[0][h >> 5] | sm.gen[1][h >> 5];
+    const bool hit = live && ((bw >> (h & 31u)) & 1u);
     if (__any_sync(ZB_FULL, hit)) {
         bool bad = false;
         if (hit) {
-            const uint32_t j = sm.table[h & 4095u];
-            if (j < i && sm.hs[32u + j] == h) {       // written by a visited lane with my hash; a later insert of it would have replaced it
-                uint32_t v; uint64_t x;
-                load12(W, q, v, x);
-                cand = p + j;
-                slen = match12(W, q, cand, v, x, n);
-            } else bad = true;                        // another hash took the slot since
+            const uint32_t j = sm.last[h & 8191u];
+            // written by a visited position with my hash; a later insert of my hash would have replaced it
+            if (j < q && q - j <= 2u * kWin && sm.hs[(j / kWin) & 3u][j % kWin] == h) cand = j;
+            else bad = true;                                  // another hash took the slot since
         }
-        if (__any_sync(ZB_FULL, bad)) { ovf = true; return 0u; }
+        if (__any_sync(ZB_FULL, bad)) {
+            if (bad) {                                        // the table itself: every earlier insert of this walker is ordered before
+                cand = (uint32_t)__ldcg(head + h);
+                if (q == kWSize + kMaxDist && n < kChunkMax && cand < kWSize) cand = kWSize;   // see quick_parse_warp (slide at 65274)
+            }
+        }
+        if (hit) {
+            uint32_t v; uint64_t x;
+            ca_load12(W, q, v, x);
+            slen = ((q - cand - 1u) < kMaxDist) ? match_upto(W, q, cand, v, x, n, kWalkCap) : 0u;
+            mcap = kWalkCap;
+        }
     }
-    // ---- same hash at an earlier lane of THIS step?  j1 = nearest one; has2: j1 has one as well
-    const bool has1 = act && d != 0u && d <= lane;
+    // ---- same hash at an earlier lane of THIS block?  j1 = nearest one; has2: j1 has one as well
+    // (only lanes from s0 on belong to this step: the first lane of a step never waits for anyone, so every step advances)
+    const bool has1 = live && d != 0u && d + s0 <= lane;
     const uint32_t j1 = (lane - d) & 31u;
     const uint32_t dj = __shfl_sync(ZB_FULL, d, j1);
-    const bool has2 = has1 && dj != 0u && dj <= j1;
-    const unsigned M = __ballot_sync(ZB_FULL, slen != 0u);
-    const unsigned L = __ballot_sync(ZB_FULL, slen == 12u);
-    const unsigned nl = min(32u, nwin - cur);
+    const bool has2 = has1 && dj != 0u && dj + s0 <= j1;
+    const unsigned M = __ballot_sync(ZB_FULL, slen != 0u && live);
+    const unsigned L = __ballot_sync(ZB_FULL, slen == mcap && live);
     // ---- walk 1: the orbit of the greedy jump function.  pack = end << 8 | next match lane at or after end (32: none)
     uint32_t pack;
     {
@@ -145,10 +157,11 @@ __device__ __forceinline__ uint32_t walk_step(const WindowCA& W, CtaSmem<WARPS>&
         if ((L >> k) & 1u) {
             // a long match is measured by the whole warp when the walk reaches it
             const uint32_t ck = __shfl_sync(ZB_FULL, cand, k);
-            const uint32_t qk = p + cur + k;
-            uint32_t len = 12u + warp_compare256_ca(W, qk + 12u + W.skew, ck + 12u + W.skew, lane);
+            const uint32_t mk = __shfl_sync(ZB_FULL, mcap, k);
+            const uint32_t qk = b0 + k;
+            uint32_t len = mk + warp_compare_bytes(W, qk + mk + W.skew, ck + mk + W.skew, kMaxMatch - mk, lane);
             len = min(len, n - qk);
-            len = min(len, kMaxMatch);                   // deflate_quick.c:102-103
+            len = min(len, kMaxMatch);                        // deflate_quick.c:102-103
             if (lane == k) {
                 slen = len;
                 const uint32_t end = lane + len;
@@ -170,9 +183,9 @@ __device__ __forceinline__ uint32_t walk_step(const WindowCA& W, CtaSmem<WARPS>&
         const uint32_t e = __shfl_sync(ZB_FULL, pack, kk) >> 8;
         covered = m != 0u && kk < lane && lane < e;
     }
-    unsigned V = __ballot_sync(ZB_FULL, lane < nl && !covered);
+    unsigned V = __ballot_sync(ZB_FULL, lane >= s0 && lane < nl && !covered);
     // ---- walk 2: the first visited lane that shares its hash with an earlier visited lane of this step cuts the step
-    // (has2: the nearest one is not visited but has a predecessor of its own in the step -- cut as well, the next step's lookup decides)
+    // (has2: the nearest one is not visited but has a predecessor of its own in the block -- cut as well, the next step decides)
     const unsigned S = __ballot_sync(ZB_FULL, ((V >> lane) & 1u) && has1 && (((V >> j1) & 1u) || has2));
     if (S) {
         const unsigned j = __ffs(S) - 1u;
@@ -184,32 +197,62 @@ __device__ __forceinline__ uint32_t walk_step(const WindowCA& W, CtaSmem<WARPS>&
     if (vis && slen) mytok = kTokMatch | (slen << 16) | (q - cand);
     if (vis && act) {
         __stcg(head + h, (uint16_t)q);                        // insert_string_tpl.h:70-73
-        atomicOr(&sm.bitmap[h >> 5], 1u << (h & 31u));        // ... and what later steps of this window must know about it
-        sm.table[h & 4095u] = (uint8_t)i;
+        atomicOr(&sm.gen[w & 1u][h >> 5], 1u << (h & 31u));   // ... and what later lookups of this and the next window must know
+        sm.last[h & 8191u] = (uint16_t)q;
     }
     if (vis) __stcs(tok + wr + __popc(V & lt), mytok);
     wr += __popc(V);
     __syncwarp();
-    return c;
+    return b0 + c;
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1024 / (WARPS * 32))
+// One producer warp: the aligned block `blk` of window w, looked up in the table as it stands.
+template <int PW>
+__device__ __forceinline__ void produce_block(const WindowCA& W, PipeSmem<PW>& sm, uint32_t w, uint32_t blk, uint32_t n,
+                                              const uint16_t* head, unsigned lane) {
+    constexpr uint32_t kWin = PW * 32;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t q = w * kWin + blk * 32u + lane;
+    const bool inw = q < n;
+    const bool act = q + kWantMin <= n;                       // deflate_quick.c:88 lookahead >= WANT_MIN_MATCH
+    uint32_t v = 0; uint64_t x = 0;
+    if (inw) ca_load12(W, q, v, x);
+    const uint32_t h = hash4(v);
+    const uint32_t myh = act ? h : (0x10000u + lane);
+    sm.hs[w & 3u][blk * 32u + lane] = myh;
+    uint32_t cand = 0u;
+    if (act) cand = (uint32_t)__ldcg(head + h);
+    if (lane < 2u) {                                          // the bytes two windows ahead, on their way into L2 / L1
+        const uint32_t pf = (w + 2u) * kWin + blk * 32u + 128u * lane;
+        if ((blk & 7u) == 0u && pf + 128u <= n) asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const uint8_t*>(W.w) + W.skew + pf));
+    }
+    const unsigned peers = __match_any_sync(ZB_FULL, myh);
+    const unsigned low = peers & lt;                          // earlier lanes of this block with my hash
+    const uint32_t d = low ? lane - (31u - (uint32_t)__clz(low)) : 0u;
+    uint32_t slen = 0u;
+    if (act) {
+        // the slide of a 65275..65535-byte chunk at strstart 65274 (deflate.c:1285-1299), see quick_parse_warp
+        if (q == kWSize + kMaxDist && n < kChunkMax && cand < kWSize) cand = kWSize;
+        if ((q - cand - 1u) < kMaxDist) slen = match_upto(W, q, cand, v, x, n, kProdCap);
+    }
+    sm.ring[w & 1u][blk * 32u + lane] = make_uint2((h << 16) | cand, (v & 0xffu) | (slen << 8) | ((uint32_t)act << 15) | (d << 16));
+}
+
+template <int PW>
+__global__ void __launch_bounds__((PW + 1) * 32)
 quick_parse_cta_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                        uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
                        uint32_t* __restrict__ counter, uint16_t* heads, unsigned long long* sm_slots,
                        const uint8_t* tail, uint32_t tail_first, StreamSync sy) {
-    constexpr int kThreads = WARPS * 32;
-    constexpr int kWin = kThreads;
-    __shared__ CtaSmem<WARPS> sm;
+    constexpr int kThreads = (PW + 1) * 32;
+    constexpr uint32_t kWin = PW * 32;
+    __shared__ PipeSmem<PW> sm;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const bool walker = warp == PW;                             // the last warp walks, warps 0..PW-1 produce block `warp` of each window
     if (tid == 0) sm.slot = slot_acquire(sm_slots + smid());
-    for (uint32_t k = tid; k < 2048u; k += kThreads) sm.bitmap[k] = 0u;
-    if (tid < 32u) sm.hs[tid] = 0x20000u + tid;
     __syncthreads();
     const uint32_t slot = sm.slot;
     uint16_t* head = heads + ((size_t)smid() * 64u + slot) * 65536u;
-    const unsigned ww = slot % WARPS;                           // the walker warp: chains of one SM spread over its schedulers
     for (;;) {
         if (tid == 0) {
             const uint32_t ci = atomicAdd(counter, 1u);
@@ -226,10 +269,12 @@ quick_parse_cta_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nch
         __syncthreads();
         const uint32_t ci = sm.ci;
         if (ci >= nchunks) break;
-        {   // CLEAR_HASH (deflate.c:182-184)
+        {   // CLEAR_HASH (deflate.c:182-184), and both bitmap generations
             uint4* h4 = reinterpret_cast<uint4*>(head);
-#pragma unroll 8
+#pragma unroll 4
             for (uint32_t k = tid; k < 65536u * 2u / 16u; k += kThreads) __stcg(h4 + k, make_uint4(0, 0, 0, 0));
+            uint4* g4 = reinterpret_cast<uint4*>(&sm.gen[0][0]);
+            for (uint32_t k = tid; k < 2u * 2048u / 4u; k += kThreads) g4[k] = make_uint4(0, 0, 0, 0);
         }
         const size_t off = (size_t)ci * chunk;
         const uint32_t len = (uint32_t)min((size_t)chunk, n - off);
@@ -238,59 +283,29 @@ quick_parse_cta_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nch
         W.skew = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
         W.w = reinterpret_cast<const uint32_t*>(src - W.skew);
         uint32_t* tok = tokens + (size_t)ci * tok_stride;
-        uint32_t p = 0, wr = 0;
-        uint32_t prev_h = 0;                                    // my position's hash in the previous window: its bitmap word is wiped
+        const uint32_t nwin = (len + kWin - 1u) / kWin;
+        uint32_t cur = 0, wr = 0;                               // walker: next position to parse, tokens written
+        __syncthreads();                                        // the cleared table is what window 0's lookups see
+        if (!walker && nwin) produce_block<PW>(W, sm, 0u, warp, len, head, lane);
         __syncthreads();
-        while (p < len) {
-            // ---- producer phase: every thread looks one position up in the table as it stands at the window start
-            sm.bitmap[prev_h >> 5] = 0u;                        // every insert of the last window belongs to some thread's position
-            const uint32_t q = p + tid;
-            const bool inw = q < len;
-            const bool act = q + kWantMin <= len;               // deflate_quick.c:88 lookahead >= WANT_MIN_MATCH
-            uint32_t v = 0; uint64_t x = 0;
-            if (inw) load12(W, q, v, x);
-            const uint32_t h = hash4(v);
-            const uint32_t myh = act ? h : (0x10000u + tid);
-            sm.hs[32u + tid] = myh;
-            prev_h = h;
-            uint32_t cand = 0u;
-            if (act) cand = (uint32_t)__ldcg(head + h);
-            if (warp == ((ww + 1u) % WARPS) && lane < 6u && p + kWin + 128u * lane + 640u <= len) {
-                // the bytes of the next windows, on their way into L1 while this window is walked
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(reinterpret_cast<const uint8_t*>(W.w) + W.skew + p + kWin + 128u * lane));
-            }
-            __syncthreads();
-            // nearest earlier position of this window (<= 31 back) with my hash; the sentinels in front never match
-            uint32_t d = 0u;
-#pragma unroll
-            for (uint32_t k = 31u; k >= 1u; k--) if (sm.hs[32u + tid - k] == myh) d = k;
-            if (inw) {
-                uint32_t slen = 0u;
-                if (act) {
-                    // the slide of a 65275..65535-byte chunk at strstart 65274 (deflate.c:1285-1299), see quick_parse_warp
-                    if (q == kWSize + kMaxDist && len < kChunkMax && cand < kWSize) cand = kWSize;
-                    if ((q - cand - 1u) < kMaxDist) slen = match12(W, q, cand, v, x, len);
+        for (uint32_t w = 0; w < nwin; w++) {
+            if (walker) {
+                const uint32_t wend = min(len, (w + 1u) * kWin);
+                while (cur < wend) {
+                    const uint32_t rel = cur - w * kWin;
+                    cur = walk_step<PW>(W, sm, w, rel >> 5, rel & 31u, len, head, tok, wr, lane);
                 }
-                sm.ring[tid] = make_uint2((h << 16) | cand, (v & 0xffu) | (slen << 8) | ((uint32_t)act << 12) | (d << 16));
+            } else if (w + 1u < nwin) {
+                produce_block<PW>(W, sm, w + 1u, warp, len, head, lane);
             }
-            __syncthreads();
-            if (warp == ww) {
-                const uint32_t nwin = min((uint32_t)kWin, len - p);
-                uint32_t cur = 0;
-                bool ovf = false;
-                while (cur < nwin) {
-                    cur += walk_step<WARPS>(W, sm, p, cur, nwin, len, head, tok, wr, ovf, lane);
-                    if (ovf) break;
-                }
-                if (lane == 0) sm.adv = cur;
+            __syncthreads();                                    // (A) walk w and window w+1's records are complete
+            {   // window w+1 inserts into generation (w+1)&1, which still holds window w-1: wipe it
+                uint4* g4 = reinterpret_cast<uint4*>(&sm.gen[(w + 1u) & 1u][0]);
+                for (uint32_t k = tid; k < 2048u / 4u; k += kThreads) g4[k] = make_uint4(0, 0, 0, 0);
             }
-            __syncthreads();
-            p += sm.adv;
+            __syncthreads();                                    // (B)
         }
-        {   // the last window's inserts
-            sm.bitmap[prev_h >> 5] = 0u;
-        }
-        if (warp == ww) {
+        if (walker) {
             if (lane == 0) { __stcs(tok + wr, kTokEnd); ntok[ci] = wr; }
             if (sy.done) {                                      // per output slab: how many of its chunks are parsed
                 __threadfence();
@@ -310,12 +325,16 @@ quick_parse_cta_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nch
     if (tid == 0) atomicAnd(sm_slots + smid(), ~(1ull << slot));
 }
 
-template <int WARPS>
+template <int PW>
 static cudaError_t launch_cta(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t* tokens, uint32_t tok_stride,
                               uint32_t* ntok, uint32_t* counter, uint16_t* heads, unsigned long long* sm_slots, uint32_t grid,
-                              const uint8_t* tail, uint32_t tail_first, cudaStream_t stream, const StreamSync& sy) {
-    quick_parse_cta_kernel<WARPS><<<grid, WARPS * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots,
-                                                                    tail, tail_first, sy);
+                              const uint8_t* tail, uint32_t tail_first, cudaStream_t stream, const StreamSync& sy, int chains_per_sm) {
+    // shared memory per chain: ~39 KiB at PW = 8; ask for the split that just holds the chains of one SM (the rest stays L1)
+    int carve = (int)((sizeof(PipeSmem<PW>) + 1024u) * (size_t)chains_per_sm * 100u / (228u * 1024u)) + 1;
+    if (carve > 100) carve = 100;
+    cudaFuncSetAttribute(quick_parse_cta_kernel<PW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    quick_parse_cta_kernel<PW><<<grid, (PW + 1) * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots,
+                                                                   tail, tail_first, sy);
     return cudaGetLastError();
 }
 
@@ -341,10 +360,11 @@ cudaError_t launch_quick_parse_cta(const uint8_t* in, size_t n, uint32_t chunk, 
         if (e != cudaSuccess) return e;
         tl = tail;
     }
-    switch (warps) {
-        case 2:  return launch_cta<2>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy);
-        case 4:  return launch_cta<4>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy);
-        default: return launch_cta<8>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy);
+    switch (warps) {       // producer warps per chain (window = 32 x warps positions); one more warp walks
+        case 4:  return launch_cta<4>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm);
+        case 6:  return launch_cta<6>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm);
+        case 12: return launch_cta<12>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm);
+        default: return launch_cta<8>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm);
     }
 }
 

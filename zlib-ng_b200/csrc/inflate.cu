@@ -24,6 +24,7 @@
 //     stores; their CRC-32 / Adler-32 is computed from shared memory (32 slices + x^(8*after) combine).
 #include "common.cuh"
 #include "kernels.h"
+#include "lz_ops.cuh"
 
 namespace zb {
 
@@ -209,7 +210,9 @@ __device__ uint32_t warp_check(const uint8_t* ob, uint32_t o, bool gz, const Inf
     }
     unsigned long long a = 0, b = 0;
     for (uint32_t i = beg; i < end; i++) { const uint32_t by = ob[i]; a += by; b += (unsigned long long)(end - i) * by; }
-    b += a * after;
+    // reduce before the position weight: a * after passes 2^64 from ~380 MiB of output on (a <= 255 * per, after < 2^32)
+    a %= kAdlerBase; b %= kAdlerBase;
+    b += a * (unsigned long long)(after % kAdlerBase);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(ZB_FULL, a, d); b += __shfl_xor_sync(ZB_FULL, b, d); }
     const uint32_t s1 = (uint32_t)((1ull + a) % kAdlerBase), s2 = (uint32_t)((o + b) % kAdlerBase);
@@ -424,15 +427,8 @@ __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, u
             const uint32_t can = min(len, cap - o);
             // out[i] = out[i - dist] byte-serially (chunkset_tpl.h): waves of min(32, D) bytes from D back, where D is a
             // multiple of dist that doubles while it is below 32 (every copied wave is one more period of the run)
-            uint32_t D = dist, rem = can;
-            if (count) { o += rem; rem = 0; }
-            while (rem) {
-                __syncwarp();                               // earlier stores of other lanes -> visible
-                const uint32_t wave = min(min(D, 32u), rem);
-                if (lane < wave) ob[o + lane] = ob[o - D + lane];
-                o += wave; rem -= wave;
-                if (D < 32u) D += D;
-            }
+            if (!count) wave_copy(ob, o, dist, can, lane);  // lz_ops.cuh: the one chunkmemset of this library
+            o += can;
             if (can < len) INF_MORE_OUT();
         }
     }

@@ -80,8 +80,11 @@ const char* inflate_msg(uint32_t id);
 // operator surface (ops.cu): the device operators of K1/K2/K4 one at a time
 cudaError_t launch_op_compare256(const uint8_t* a, const uint8_t* b, size_t stride, uint32_t n_pairs, uint32_t* out, cudaStream_t s);
 cudaError_t launch_op_longest_match(const uint8_t* window, uint32_t n, const uint16_t* prev, const uint32_t* pos, const uint32_t* cand,
-                                    uint32_t n_q, uint32_t* len, uint32_t* start, cudaStream_t s);
-cudaError_t launch_op_insert_string(const uint8_t* window, uint16_t* head, uint16_t* prev, uint32_t str, uint32_t count, cudaStream_t s);
+                                    uint32_t n_q, uint32_t* len, uint32_t* start, cudaStream_t s, int level = 2,
+                                    bool raw = false);   // raw: lengths below 4 are reported as the reference returns them (2, 3)
+cudaError_t launch_op_insert_string(const uint8_t* window, uint16_t* head, uint16_t* prev, uint32_t str, uint32_t count, cudaStream_t s,
+                                    uint32_t* old_head = nullptr);
+cudaError_t launch_op_slide_hash(uint16_t* head, uint16_t* prev, uint32_t wsize, cudaStream_t s);
 cudaError_t launch_op_chunkmemset(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t len, cudaStream_t s);
 
 // stream assembly (assemble.cu)

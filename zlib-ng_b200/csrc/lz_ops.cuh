@@ -23,20 +23,60 @@ __device__ __forceinline__ void load12(const VWindow& W, uint32_t pos, uint32_t&
     x = (uint64_t)__funnelshift_r(a1, a2, sh) | ((uint64_t)__funnelshift_r(a2, a3, sh) << 32);
 }
 
-// warp-wide compare of 256 bytes at byte offsets a / b (skew included): number of equal leading bytes
-__device__ __forceinline__ uint32_t vwarp_compare256(const VWindow& W, uint32_t a, uint32_t b, unsigned lane) {
-    a += 8u * lane; b += 8u * lane;
-    const uint32_t ia = a >> 2, sa = (a & 3u) << 3, ib = b >> 2, sb = (b & 3u) << 3;
-    const uint32_t a0 = W.word(ia), a1 = W.word(ia + 1), a2 = W.word(ia + 2);
-    const uint32_t b0 = W.word(ib), b1 = W.word(ib + 1), b2 = W.word(ib + 2);
-    const uint64_t x = ((uint64_t)__funnelshift_r(a0, a1, sa) | ((uint64_t)__funnelshift_r(a1, a2, sa) << 32)) ^
-                       ((uint64_t)__funnelshift_r(b0, b1, sb) | ((uint64_t)__funnelshift_r(b1, b2, sb) << 32));
+// functable.compare256 (arch/generic/compare256_c.c:12-43), warp wide: first mismatch of the bytes at byte offsets a / b (skew
+// included), at most `limit` (<= 256) of them -- lane l compares the 8 bytes at +8l, ballot / ffs finds the first differing
+// lane.  Returns the number of equal leading bytes; 256 when all `limit` are equal.  ONE definition for every user: K1's two
+// parsers (deflate_quick.cu, deflate_quick_cta.cu), K2 (deflate_fast.cu, lazy_parse.cuh) and the operator kernel (ops.cu).
+template <class Win>
+__device__ __forceinline__ uint32_t warp_compare_bytes(const Win& W, uint32_t a, uint32_t b, uint32_t limit, unsigned lane) {
+    uint64_t x = 0ull;
+    if (8u * lane < limit) {
+        a += 8u * lane; b += 8u * lane;
+        const uint32_t ia = a >> 2, sa = (a & 3u) << 3, ib = b >> 2, sb = (b & 3u) << 3;
+        const uint32_t a0 = W.word(ia), a1 = W.word(ia + 1), a2 = W.word(ia + 2);
+        const uint32_t b0 = W.word(ib), b1 = W.word(ib + 1), b2 = W.word(ib + 2);
+        x = ((uint64_t)__funnelshift_r(a0, a1, sa) | ((uint64_t)__funnelshift_r(a1, a2, sa) << 32)) ^
+            ((uint64_t)__funnelshift_r(b0, b1, sb) | ((uint64_t)__funnelshift_r(b1, b2, sb) << 32));
+    }
     const unsigned diff = __ballot_sync(ZB_FULL, x != 0ull);
     if (diff == 0u) return 256u;
     const unsigned f = __ffs(diff) - 1u;
     unsigned byte = (unsigned)(__ffsll((long long)x) - 1) >> 3;
     byte = __shfl_sync(ZB_FULL, byte, f);
     return 8u * f + byte;
+}
+template <class Win>
+__device__ __forceinline__ uint32_t vwarp_compare256(const Win& W, uint32_t a, uint32_t b, unsigned lane) {
+    return warp_compare_bytes(W, a, b, 256u, lane);
+}
+
+// insert_string / quick_insert_string (insert_string_tpl.h:58-104) for the lanes of mask I, lane l holding position q = p + l with
+// hash h; `table_head` = head[h] as it stood before this group.  The serial insert order is reproduced: a position's prev[] link
+// is the nearest lower inserted lane with its hash (else the table's entry), and the highest inserted lane of a hash owns head[].
+// peers = __match_any_sync over the hashes.  Used by K2's parsers and by the insert_string operator kernel.
+__device__ __forceinline__ void insert_lanes(uint16_t* head, uint16_t* prev, uint32_t h, uint32_t q, uint32_t p, uint32_t table_head,
+                                             unsigned peers, unsigned I, unsigned lane) {
+    const unsigned lt = (1u << lane) - 1u;
+    if ((I >> lane) & 1u) {
+        const unsigned prior = peers & I & lt;
+        const uint32_t old = prior ? p + (31u - (uint32_t)__clz(prior)) : table_head;
+        if (old != (q & 0xffffu)) __stcg(prev + (q & (kWSize - 1u)), (uint16_t)old);      // insert_string_tpl.h:70-73 head != str
+        if ((peers & I & ~lt & ~(1u << lane)) == 0u) __stcg(head + h, (uint16_t)q);
+    }
+}
+
+// functable.chunkmemset_safe / CHUNKCOPY (chunkset_tpl.h:112-283): out[o + i] = out[o + i - dist] for i in 0..len, byte serial,
+// by one warp: waves of min(32, D) bytes from D back, where D is a multiple of dist that doubles while it is below 32 (every
+// copied wave is one more period of the run).  Used by K4's match copy and by the chunkmemset operator kernel.
+__device__ __forceinline__ void wave_copy(uint8_t* out, uint32_t o, uint32_t dist, uint32_t len, unsigned lane) {
+    uint32_t D = dist, rem = len;
+    while (rem) {
+        __syncwarp();                                       // earlier stores of other lanes -> visible
+        const uint32_t wave = min(min(D, 32u), rem);
+        if (lane < wave) out[o + lane] = out[o - D + lane];
+        o += wave; rem -= wave;
+        if (D < 32u) D += D;
+    }
 }
 
 
@@ -95,7 +135,7 @@ __device__ __forceinline__ uint32_t prefix_len(const VWindow& W, uint32_t q, uin
 // vwarp_compare256 and clip"; mcand = match_start of the returned match.
 template <int LEVEL>
 __device__ __forceinline__ uint32_t longest_match_lane(const VWindow& W, uint32_t q, uint32_t v, uint64_t x, uint32_t z, uint32_t cand0,
-                                                       uint32_t look, const uint16_t* prev, uint32_t& mcand) {
+                                                       uint32_t look, const uint16_t* prev, uint32_t& mcand, uint32_t* raw_best = nullptr) {
     using P = LmParams<LEVEL>;
     constexpr bool kDeep = P::kChain > 6u;                  // worth a 4-byte pre-check at the end of the current best
     uint32_t best = 2, chain = P::kChain, cand = cand0, endw = 0;
@@ -119,6 +159,7 @@ __device__ __forceinline__ uint32_t longest_match_lane(const VWindow& W, uint32_
         cand = link;
         if (cand <= limit) break;                          // match_tpl.h:48-51
     }
+    if (raw_best) *raw_best = best;                        // what the reference returns (2 or 3 when nothing useful was found)
     return best >= kWantMin ? best : 0u;
 }
 

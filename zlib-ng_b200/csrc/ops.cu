@@ -32,8 +32,10 @@ __global__ void op_compare256_kernel(const uint8_t* a, const uint8_t* b, size_t 
 
 // queries q: position pos[q] with hash head cand[q] in a window of n bytes (+ >= 272 readable bytes after it) and its
 // prev[] table -> len[q] (0 when longest_match returns less than 4 ... the reference's caller discards those), start[q]
+template <int LEVEL>
 __global__ void op_longest_match_kernel(const uint8_t* window, uint32_t n, const uint16_t* prev, const uint32_t* pos, const uint32_t* cand,
-                                        uint32_t n_q, uint32_t* len, uint32_t* start) {
+                                        uint32_t n_q, uint32_t* len, uint32_t* start, bool raw) {
+    constexpr uint32_t kCmp = LmParams<LEVEL>::kCmp;
     const unsigned lane = lane_id();
     const uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u;
     if (base >= n_q) return;
@@ -42,28 +44,29 @@ __global__ void op_longest_match_kernel(const uint8_t* window, uint32_t n, const
     W.w = reinterpret_cast<const uint32_t*>(window - W.skew);
     W.tail = W.w; W.tw0 = 0xffffffffu;
     const uint32_t qi = base + lane;
-    uint32_t q = 0, c0 = 0, ml = 0, mc = 0;
+    uint32_t q = 0, c0 = 0, ml = 0, mc = 0, rb = 2;
     if (qi < n_q) {
         q = pos[qi]; c0 = cand[qi];
         uint32_t v; uint64_t x;
         load12(W, q, v, x);
-        if (q + kWantMin <= n && c0 != 0u && (q - c0 - 1u) < kMaxDist) ml = longest_match_lane<2>(W, q, v, x, 0u, c0, n - q, prev, mc);
+        const uint32_t z = kCmp > 12u ? load32(W, q + 12u) : 0u;
+        if (q + kWantMin <= n && c0 != 0u && (q - c0 - 1u) < kMaxDist) ml = longest_match_lane<LEVEL>(W, q, v, x, z, c0, n - q, prev, mc, &rb);
     }
-    unsigned L = __ballot_sync(ZB_FULL, ml >= 12u);
+    unsigned L = __ballot_sync(ZB_FULL, ml >= kCmp);
     while (L) {                                              // long matches: measured by the whole warp, as in K2
         const unsigned j = (unsigned)(__ffs(L) - 1); L &= L - 1u;
         const uint32_t qj = __shfl_sync(ZB_FULL, q, j), cj = __shfl_sync(ZB_FULL, mc, j);
-        uint32_t l = 12u + vwarp_compare256(W, qj + 12u + W.skew, cj + 12u + W.skew, lane);
+        uint32_t l = kCmp + vwarp_compare256(W, qj + kCmp + W.skew, cj + kCmp + W.skew, lane);
         l = min(min(l, kMaxMatch), n - qj);
         if (lane == j) ml = l;
     }
-    if (qi < n_q) { len[qi] = ml; start[qi] = mc; }
+    if (qi < n_q) { len[qi] = raw ? (ml ? ml : rb) : ml; start[qi] = mc; }
 }
 
 // insert_string(str, count) on head[65536] / prev[32768] (one warp; the serial insert order is reproduced with the same
 // nearest-lower-peer rule the parsers use)
-__global__ void op_insert_string_kernel(const uint8_t* window, uint16_t* head, uint16_t* prev, uint32_t str, uint32_t count) {
-    const unsigned lane = lane_id(), lt = (1u << lane) - 1u;
+__global__ void op_insert_string_kernel(const uint8_t* window, uint16_t* head, uint16_t* prev, uint32_t str, uint32_t count, uint32_t* old_head) {
+    const unsigned lane = lane_id();
     for (uint32_t p = str; p < str + count; p += 32u) {
         const uint32_t q = p + lane;
         const bool on = q < str + count;
@@ -71,27 +74,16 @@ __global__ void op_insert_string_kernel(const uint8_t* window, uint16_t* head, u
         if (on) v = (uint32_t)window[q] | ((uint32_t)window[q + 1] << 8) | ((uint32_t)window[q + 2] << 16) | ((uint32_t)window[q + 3] << 24);
         const uint32_t h = hash4(v);
         const unsigned peers = __match_any_sync(ZB_FULL, on ? h : (0x10000u + lane));
-        if (on) {
-            const unsigned prior = peers & lt;
-            const uint32_t old = prior ? p + (31u - (uint32_t)__clz(prior)) : (uint32_t)head[h];
-            if (old != (q & 0xffffu)) prev[q & (kWSize - 1u)] = (uint16_t)old;     // insert_string_tpl.h:70-73
-            if ((peers & ~lt & ~(1u << lane)) == 0u) head[h] = (uint16_t)q;
-        }
+        const unsigned I = __ballot_sync(ZB_FULL, on);
+        if (old_head && q == str) *old_head = (uint32_t)__ldcg(head + h);     // quick_insert_string returns the head it replaced
+        insert_lanes(head, prev, h, q, p, on ? (uint32_t)__ldcg(head + h) : 0u, peers, I, lane);      // the device function K2 runs
         __syncwarp();
     }
 }
 
 // out[pos .. pos+len) = byte-serial copy from dist back (one warp; the doubling wave copy of K4)
 __global__ void op_chunkmemset_kernel(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t len) {
-    const unsigned lane = lane_id();
-    uint32_t D = dist, rem = len, o = pos;
-    while (rem) {
-        __syncwarp();
-        const uint32_t wave = min(min(D, 32u), rem);
-        if (lane < wave) out[o + lane] = out[o - D + lane];
-        o += wave; rem -= wave;
-        if (D < 32u) D += D;
-    }
+    wave_copy(out, pos, dist, len, lane_id());               // the device function K4 runs
 }
 
 cudaError_t launch_op_compare256(const uint8_t* a, const uint8_t* b, size_t stride, uint32_t n_pairs, uint32_t* out, cudaStream_t s) {
@@ -100,14 +92,38 @@ cudaError_t launch_op_compare256(const uint8_t* a, const uint8_t* b, size_t stri
     return cudaGetLastError();
 }
 cudaError_t launch_op_longest_match(const uint8_t* window, uint32_t n, const uint16_t* prev, const uint32_t* pos, const uint32_t* cand,
-                                    uint32_t n_q, uint32_t* len, uint32_t* start, cudaStream_t s) {
+                                    uint32_t n_q, uint32_t* len, uint32_t* start, cudaStream_t s, int level, bool raw) {
     if (!n_q) return cudaSuccess;
-    op_longest_match_kernel<<<(n_q + 127u) / 128u, 128, 0, s>>>(window, n, prev, pos, cand, n_q, len, start);
+    const unsigned g = (n_q + 127u) / 128u;
+    switch (level) {
+        case 2: op_longest_match_kernel<2><<<g, 128, 0, s>>>(window, n, prev, pos, cand, n_q, len, start, raw); break;
+        case 3: op_longest_match_kernel<3><<<g, 128, 0, s>>>(window, n, prev, pos, cand, n_q, len, start, raw); break;
+        case 4: op_longest_match_kernel<4><<<g, 128, 0, s>>>(window, n, prev, pos, cand, n_q, len, start, raw); break;
+        case 5: op_longest_match_kernel<5><<<g, 128, 0, s>>>(window, n, prev, pos, cand, n_q, len, start, raw); break;
+        case 6: op_longest_match_kernel<6><<<g, 128, 0, s>>>(window, n, prev, pos, cand, n_q, len, start, raw); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
-cudaError_t launch_op_insert_string(const uint8_t* window, uint16_t* head, uint16_t* prev, uint32_t str, uint32_t count, cudaStream_t s) {
+cudaError_t launch_op_insert_string(const uint8_t* window, uint16_t* head, uint16_t* prev, uint32_t str, uint32_t count, cudaStream_t s, uint32_t* old_head) {
     if (!count) return cudaSuccess;
-    op_insert_string_kernel<<<1, 32, 0, s>>>(window, head, prev, str, count);
+    op_insert_string_kernel<<<1, 32, 0, s>>>(window, head, prev, str, count, old_head);
+    return cudaGetLastError();
+}
+
+// functable.slide_hash (arch/generic/slide_hash_c.c:15-52): every entry of head[65536] and prev[wsize] is rebased by wsize,
+// entries below it become 0 (NIL).  8 entries per thread as one 16-byte vector, saturating subtract per 16-bit lane.
+__global__ void op_slide_hash_kernel(uint4* head, uint32_t head_vecs, uint4* prev, uint32_t prev_vecs, uint32_t wsize) {
+    const uint32_t w2 = wsize | (wsize << 16);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < head_vecs + prev_vecs; i += gridDim.x * blockDim.x) {
+        uint4* p = i < head_vecs ? head + i : prev + (i - head_vecs);
+        uint4 v = *p;
+        v.x = __vsubus2(v.x, w2); v.y = __vsubus2(v.y, w2); v.z = __vsubus2(v.z, w2); v.w = __vsubus2(v.w, w2);
+        *p = v;
+    }
+}
+cudaError_t launch_op_slide_hash(uint16_t* head, uint16_t* prev, uint32_t wsize, cudaStream_t s) {
+    op_slide_hash_kernel<<<48, 256, 0, s>>>(reinterpret_cast<uint4*>(head), 65536u / 8u, reinterpret_cast<uint4*>(prev), wsize / 8u, wsize);
     return cudaGetLastError();
 }
 cudaError_t launch_op_chunkmemset(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t len, cudaStream_t s) {

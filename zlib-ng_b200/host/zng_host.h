@@ -27,6 +27,8 @@ struct internal_state {
     int header_done, trailer_done, finished;
     /* dependent-chunk mode (zng_deflateSetDictionary on a raw level-1 stream): the 32768 bytes in front of the next piece */
     uint8_t *dict; int have_dict;
+    /* inflate, incremental use: retained bytes at which the next decode attempt is due, and the size of the last piece fed */
+    size_t next_try, last_piece;
     int after_sync;            /* a Z_SYNC_FLUSH closed the (only) piece of a stream without dictionary: nothing may follow but Reset */
 };
 

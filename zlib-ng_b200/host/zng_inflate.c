@@ -13,6 +13,10 @@
  * what the reference returns (code, msg, output, total_in, total_out, adler).  Incremental use (Z_NO_FLUSH with
  * partial input) is accepted: input is retained, output is delivered once the member has been decoded, and
  * next_in/avail_in are wound back to the end of the member so that concatenated members can follow.
+ * A decode attempt over an incomplete member costs the whole retained input, so an ordinary "read 64 KiB, inflate" loop
+ * must not attempt one per call (that is quadratic in the member size): after a failed attempt the next one is due when
+ * the retained input has grown by half, or when the piece fed is shorter than the one before (the last read of a file),
+ * or on Z_FINISH, or on a call without new input.  Output therefore arrives at the end of the member, not piecewise.
  */
 #include "zng_host.h"
 #include <stdlib.h>
@@ -37,6 +41,7 @@ int32_t zng_inflateReset(zng_stream *strm) {
     s->in_len = 0; s->pend_pos = s->pend_len = 0;
     s->finished = 0;
     s->check_len = 0;                                       /* bytes of the member's output already handed out */
+    s->next_try = 0; s->last_piece = 0;
     return Z_OK;
 }
 
@@ -123,6 +128,17 @@ int32_t zng_inflate(zng_stream *strm, int32_t flush) {
     }
     const size_t kept = s->in_len;
 
+    if (flush != Z_FINISH && in0 != 0 && s->next_try && n < s->next_try && in0 >= s->last_piece) {
+        /* not due yet (see the header): keep the bytes, consume them, no device work */
+        if (kept == 0) {
+            if (n > s->in_cap) { uint8_t *p = (uint8_t *)realloc(s->in_buf, n); if (!p) return Z_MEM_ERROR; s->in_buf = p; s->in_cap = n; }
+            memcpy(s->in_buf, src, n);
+        }
+        s->in_len = n; s->last_piece = in0;
+        strm->next_in += in0; strm->total_in += in0; strm->avail_in = 0;
+        return Z_OK;
+    }
+
     uint32_t out_len = 0, in_used = 0, check = 0, detail = 0;
     int r;
     if (kept == 0 && flush == Z_FINISH) {
@@ -162,6 +178,7 @@ int32_t zng_inflate(zng_stream *strm, int32_t flush) {
                 memcpy(s->in_buf, src, n);
             }
             s->in_len = n;
+            s->next_try = n + n / 2 + 1; s->last_piece = in0;
             strm->next_in += in0; strm->total_in += in0; strm->avail_in = 0;
             return in0 ? Z_OK : Z_BUF_ERROR;                /* inflate.c:1197-1199: no progress */
         }
@@ -174,7 +191,7 @@ finish:
         /* wind next_in back to the end of the member */
         const size_t used_now = in_used > kept ? in_used - kept : 0;
         strm->next_in += used_now; strm->avail_in -= (uint32_t)used_now; strm->total_in += used_now;
-        s->in_len = 0;
+        s->in_len = 0; s->next_try = 0; s->last_piece = 0;
         strm->adler = check;
         if (r == Z_NEED_DICT) { s->status = IN_DICT; return Z_NEED_DICT; }
         s->status = IN_DONE;
