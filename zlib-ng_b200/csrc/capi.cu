@@ -101,8 +101,9 @@ struct zng_b200_ctx {
     uint32_t* vtails = nullptr;
     int chains_per_sm = 24;
     int k1_cta = 0;                            // level-1 parser: 1 = CTA per chain with L2-resident tables (v5), 0 = warp per chain (env ZNG_B200_K1=warp)
-    int warps_cta = 8;                         // warps per chain of the v5 parser (env ZNG_B200_K1_WARPS: 2, 4, 8)
-    int chains_cta = 4;                        // chains (CTAs) per SM of the v5 parser (env ZNG_B200_K1_CHAINS)
+    int warps_cta = 3;                         // warps per chain of the v5 parser (env ZNG_B200_K1_WARPS: 2, 4, 8)
+    unsigned long long* k1_stats = nullptr;    // env ZNG_B200_K1_STATS=1: 16 debug counters of the v6 parser, printed when the context goes
+    int chains_cta = 10;                       // chains (CTAs) per SM of the v5 parser (env ZNG_B200_K1_CHAINS)
     int chains_per_sm_l2 = 32;                 // measured on B200: 16 -> 12.4, 24 -> 14.4, 32 -> 15.4 GB/s
     Scratch scratch;                           // for the device-resident entry points; users are ordered by k1_done
     cudaEvent_t k1_done = nullptr;
@@ -235,7 +236,7 @@ int run_deflate_chunks(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size
         }
         if (ctx->k1_cta)
             CK(launch_quick_parse_cta(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->sm_slots,
-                                      ctx->sms, ctx->chains_cta, ctx->warps_cta, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream),
+                                      ctx->sms, ctx->chains_cta, ctx->warps_cta, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream, nullptr, ctx->k1_stats),
                "quick_parse_cta launch");
         else
             CK(launch_quick_parse(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->sm_slots,
@@ -377,8 +378,9 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     if (prop.major < 10) { delete ctx; return ZNG_B200_STREAM_ERROR; }       // sm_100a kernels only
     if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm = v; }
     if (const char* e = getenv("ZNG_B200_K1")) ctx->k1_cta = (strcmp(e, "cta") == 0);
+    if (const char* e = getenv("ZNG_B200_K1_STATS")) { if (atoi(e) && cudaMalloc(&ctx->k1_stats, 16 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(ctx->k1_stats, 0, 16 * sizeof(unsigned long long)); }
     if (const char* e = getenv("ZNG_B200_K1_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->chains_cta = v; }
-    if (const char* e = getenv("ZNG_B200_K1_WARPS")) { int v = atoi(e); if (v == 4 || v == 6 || v == 8 || v == 12) ctx->warps_cta = v; }
+    if (const char* e = getenv("ZNG_B200_K1_WARPS")) { int v = atoi(e); if (v >= 2 && v <= 4) ctx->warps_cta = v; }
     if (const char* e = getenv("ZNG_B200_SLAB_CHUNKS")) { int v = atoi(e); if (v >= 64 && v <= 16384) ctx->slab_chunks = (uint32_t)v; }
     if (const char* e = getenv("ZNG_B200_STREAMED")) ctx->streamed = atoi(e);
     if (const char* e = getenv("ZNG_B200_STREAM_SHIFT")) { int v = atoi(e); if (v >= 8 && v <= 11) ctx->stream_shift = (uint32_t)v; }
@@ -469,6 +471,17 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
     }
     if (ctx->d_hostbuf) cudaFree(ctx->d_hostbuf);
     if (ctx->d_arena) cudaFree(ctx->d_arena);
+    if (ctx->k1_stats) {
+        unsigned long long h[16] = {0};
+        cudaDeviceSynchronize();
+        if (cudaMemcpy(h, ctx->k1_stats, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[0])
+            fprintf(stderr, "[zng_b200 K1 v6] chunks %llu  windows/chunk %.1f  steps/chunk %.1f  walk clk/step %.0f  walker busy %.1f %%  "
+                            "producer(warp0) clk/window %.0f  hit steps %.1f %%  fallback steps %.2f %%  cuts %.2f %%  long compares/step %.3f\n",
+                    h[0], (double)h[9] / h[0], (double)h[1] / h[0], (double)h[2] / (h[1] ? h[1] : 1), 100.0 * h[2] / (h[3] ? h[3] : 1),
+                    (double)h[8] / (h[9] ? h[9] : 1), 100.0 * h[4] / (h[1] ? h[1] : 1), 100.0 * h[5] / (h[1] ? h[1] : 1), 100.0 * h[6] / (h[1] ? h[1] : 1),
+                    (double)h[7] / (h[1] ? h[1] : 1));
+        cudaFree(ctx->k1_stats);
+    }
     if (ctx->d_pbuf) cudaFree(ctx->d_pbuf);
     if (ctx->d_pout) cudaFree(ctx->d_pout);
     if (ctx->d_pmeta) cudaFree(ctx->d_pmeta);
@@ -1319,7 +1332,7 @@ static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t 
     sy.host_done = S.d_h_done;
     if (level == 1 && ctx->k1_cta)
         CK(launch_quick_parse_cta(S.d_in, n, chunk, nch, S.tokens, (uint32_t)tstride, S.ntok, S.d_sync + 2, ctx->heads, ctx->sm_slots,
-                                  ctx->sms, ctx->chains_cta, ctx->warps_cta, nullptr, S.parse, &sy),
+                                  ctx->sms, ctx->chains_cta, ctx->warps_cta, nullptr, S.parse, &sy, ctx->k1_stats),
            "quick_parse_cta launch");
     else if (level == 1)
         CK(launch_quick_parse(S.d_in, n, chunk, nch, S.tokens, (uint32_t)tstride, S.ntok, S.d_sync + 2, ctx->heads, ctx->sm_slots,

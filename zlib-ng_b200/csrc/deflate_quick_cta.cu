@@ -16,9 +16,9 @@
 //   * The WALKER warp replays the greedy decisions of deflate_quick over the records, one aligned block per step, everything
 //     from shared memory: ballot / ffs, and one shuffle per visited match to follow the orbit of the greedy jump function.
 //   * Staleness.  A producer lookup for window w+1 runs while the walker inserts window w, so it may miss inserts of windows
-//     w and w+1.  Every insert therefore also sets one bit (one bit per 16-bit hash value) in the bitmap generation of its
-//     window and leaves its position in a small direct-mapped table last[h & 8191].  A lane whose hash bit is set in either
-//     live generation takes its candidate from last[] (verified against the ring of recent hashes: the newest insert of that
+//     w and w+1.  Every insert therefore also sets one bit (one bit per 16-bit hash value) in a bitmap that holds the inserts
+//     of the previous and the current window, and leaves its position in a small direct-mapped table last[h & 2047].  A lane
+//     whose hash bit is set takes its candidate from last[] (verified against the ring of recent hashes: the newest insert of that
 //     hash) and measures it itself; if the slot was taken over by another hash the lane asks the table in global memory --
 //     exact, because the walker's own inserts are ordered before it (rare: one L2 round trip).  A lane whose bit is clear had no
 //     insert of its hash since the lookup, so the producer's candidate is the reference's.  A visited lane whose hash also
@@ -44,7 +44,10 @@ struct WindowCA {
     }
 };
 
-constexpr uint32_t kProdCap = 64u;        // producers measure a match up to this many bytes ("64 or more" beyond)
+#ifndef ZB_PROD_CAP
+#define ZB_PROD_CAP 20
+#endif
+constexpr uint32_t kProdCap = ZB_PROD_CAP; // producers measure a match up to this many bytes ("cap or more" beyond: the walk measures the rest)
 constexpr uint32_t kWalkCap = 12u;        // the walker's own measurement of a recent candidate ("12 or more" beyond)
 
 __device__ __forceinline__ void ca_load12(const WindowCA& W, uint32_t q, uint32_t& v, uint64_t& x) {
@@ -83,28 +86,37 @@ __device__ __forceinline__ uint32_t match_upto(const WindowCA& W, uint32_t q, ui
 __device__ __forceinline__ uint32_t lanes_ge(uint32_t s) { return __funnelshift_lc(0u, 0xffffffffu, s); }
 
 // ring record: x = hash << 16 | table candidate;  y = byte | slen << 8 (7 bits) | act << 15 | d << 16 (5 bits)
+// Shared memory of one chain, ~16.5 KiB (so that 10+ chains fit one SM): rings are circular in the CHUNK POSITION.
+constexpr uint32_t kRing = 256u;          // records: windows w (walked) and w+1 (produced) -> needs 2 x window <= 256
+constexpr uint32_t kHsRing = 512u;        // hashes: windows w-2 .. w+1 -> needs 4 x window <= 512
+constexpr uint32_t kLast = 2048u;
 template <int PW>
 struct __align__(16) PipeSmem {
     static constexpr int kWin = PW * 32;
-    uint32_t gen[2][2048];       // generation (window & 1): one bit per hash value inserted by the walk of that window
-    uint16_t last[8192];         // [hash & 8191] = position of the last insert that mapped here (verified against hs[])
-    uint2    ring[2][kWin];      // records of window w in ring[w & 1]
-    uint32_t hs[4][kWin];        // hashes of window w in hs[w & 3] (inactive positions: values no hash can take)
+    static_assert(PW * 32 * 2 <= (int)kRing, "window too large for the record ring");
+    uint32_t bits[2048];         // one bit per hash value: inserted by the walk of the previous or the current window
+    uint16_t last[kLast];        // [hash & 2047] = position of the last insert that mapped here (verified against hs[])
+    uint2    ring[kRing];        // record of position q in ring[q & 255]
+    uint32_t hs[kHsRing];        // hash of position q in hs[q & 511] (inactive positions: values no hash can take)
+    uint32_t vis[kHsRing / 32];  // visited mask of the block of position q in vis[(q >> 5) & 15]
     uint32_t ci;                 // chunk index of this round
     uint32_t slot;
 };
+
+struct WalkStats { uint32_t steps, hit_steps, bad_steps, cuts, longs; unsigned long long walk_clk; };
 
 // One step of the walker: the aligned block `blk` of window w from lane s0 on.  Returns the chunk position where the next step
 // starts; wr (token count) is advanced.
 template <int PW>
 __device__ __forceinline__ uint32_t walk_step(const WindowCA& W, PipeSmem<PW>& sm, uint32_t w, uint32_t blk, uint32_t s0, uint32_t n,
-                                              uint16_t* head, uint32_t* __restrict__ tok, uint32_t& wr, unsigned lane) {
+                                              uint16_t* head, uint32_t* __restrict__ tok, uint32_t& wr, unsigned lane, WalkStats& ws) {
     constexpr uint32_t kWin = PW * 32;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t b0 = w * kWin + blk * 32u;                 // chunk position of lane 0
+    ws.steps++;
     const uint32_t q = b0 + lane;
     const uint32_t nl = min(32u, n - b0);                     // lanes that hold a byte
-    const uint2 rec = sm.ring[w & 1u][blk * 32u + lane];
+    const uint2 rec = sm.ring[q & (kRing - 1u)];
     const uint32_t h = rec.x >> 16;
     uint32_t cand = rec.x & 0xffffu;
     uint32_t slen = (rec.y >> 8) & 127u;
@@ -113,17 +125,19 @@ __device__ __forceinline__ uint32_t walk_step(const WindowCA& W, PipeSmem<PW>& s
     const uint32_t d = (rec.y >> 16) & 31u;
     const bool live = act && lane >= s0;
     // ---- has the walk inserted my hash since the producers looked it up?  Then that position is the head entry now.
-    const uint32_t bw = sm.gen[0][h >> 5] | sm.gen[1][h >> 5];
+    const uint32_t bw = sm.bits[h >> 5];
     const bool hit = live && ((bw >> (h & 31u)) & 1u);
     if (__any_sync(ZB_FULL, hit)) {
+        ws.hit_steps++;
         bool bad = false;
         if (hit) {
-            const uint32_t j = sm.last[h & 8191u];
+            const uint32_t j = sm.last[h & (kLast - 1u)];
             // written by a visited position with my hash; a later insert of my hash would have replaced it
-            if (j < q && q - j <= 2u * kWin && sm.hs[(j / kWin) & 3u][j % kWin] == h) cand = j;
+            if (j < q && q - j <= 2u * kWin && sm.hs[j & (kHsRing - 1u)] == h) cand = j;
             else bad = true;                                  // another hash took the slot since
         }
         if (__any_sync(ZB_FULL, bad)) {
+            ws.bad_steps++;
             if (bad) {                                        // the table itself: every earlier insert of this walker is ordered before
                 cand = (uint32_t)__ldcg(head + h);
                 if (q == kWSize + kMaxDist && n < kChunkMax && cand < kWSize) cand = kWSize;   // see quick_parse_warp (slide at 65274)
@@ -155,6 +169,7 @@ __device__ __forceinline__ uint32_t walk_step(const WindowCA& W, PipeSmem<PW>& s
     uint32_t k = M ? (uint32_t)(__ffs(M) - 1) : 32u, lastend = 0;
     while (k < 32u) {
         if ((L >> k) & 1u) {
+            ws.longs++;
             // a long match is measured by the whole warp when the walk reaches it
             const uint32_t ck = __shfl_sync(ZB_FULL, cand, k);
             const uint32_t mk = __shfl_sync(ZB_FULL, mcap, k);
@@ -191,15 +206,17 @@ __device__ __forceinline__ uint32_t walk_step(const WindowCA& W, PipeSmem<PW>& s
         const unsigned j = __ffs(S) - 1u;
         V &= ~lanes_ge(j);
         c = j;
+        ws.cuts++;
     }
     const bool vis = (V >> lane) & 1u;
     uint32_t mytok = rec.y & 0xffu;
     if (vis && slen) mytok = kTokMatch | (slen << 16) | (q - cand);
     if (vis && act) {
         __stcg(head + h, (uint16_t)q);                        // insert_string_tpl.h:70-73
-        atomicOr(&sm.gen[w & 1u][h >> 5], 1u << (h & 31u));   // ... and what later lookups of this and the next window must know
-        sm.last[h & 8191u] = (uint16_t)q;
+        atomicOr(&sm.bits[h >> 5], 1u << (h & 31u));          // ... and what later lookups of this and the next window must know
+        sm.last[h & (kLast - 1u)] = (uint16_t)q;
     }
+    if (lane == 0) sm.vis[(b0 >> 5) & (kHsRing / 32u - 1u)] |= V;             // for the re-seeding of the bitmap at the window's end
     if (vis) __stcs(tok + wr + __popc(V & lt), mytok);
     wr += __popc(V);
     __syncwarp();
@@ -219,7 +236,8 @@ __device__ __forceinline__ void produce_block(const WindowCA& W, PipeSmem<PW>& s
     if (inw) ca_load12(W, q, v, x);
     const uint32_t h = hash4(v);
     const uint32_t myh = act ? h : (0x10000u + lane);
-    sm.hs[w & 3u][blk * 32u + lane] = myh;
+    sm.hs[q & (kHsRing - 1u)] = myh;
+    if (lane == 0) sm.vis[(q >> 5) & (kHsRing / 32u - 1u)] = 0u;
     uint32_t cand = 0u;
     if (act) cand = (uint32_t)__ldcg(head + h);
     if (lane < 2u) {                                          // the bytes two windows ahead, on their way into L2 / L1
@@ -235,15 +253,15 @@ __device__ __forceinline__ void produce_block(const WindowCA& W, PipeSmem<PW>& s
         if (q == kWSize + kMaxDist && n < kChunkMax && cand < kWSize) cand = kWSize;
         if ((q - cand - 1u) < kMaxDist) slen = match_upto(W, q, cand, v, x, n, kProdCap);
     }
-    sm.ring[w & 1u][blk * 32u + lane] = make_uint2((h << 16) | cand, (v & 0xffu) | (slen << 8) | ((uint32_t)act << 15) | (d << 16));
+    sm.ring[q & (kRing - 1u)] = make_uint2((h << 16) | cand, (v & 0xffu) | (slen << 8) | ((uint32_t)act << 15) | (d << 16));
 }
 
 template <int PW>
-__global__ void __launch_bounds__((PW + 1) * 32)
+__global__ void __launch_bounds__((PW + 1) * 32, 1280 / ((PW + 1) * 32))
 quick_parse_cta_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                        uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
                        uint32_t* __restrict__ counter, uint16_t* heads, unsigned long long* sm_slots,
-                       const uint8_t* tail, uint32_t tail_first, StreamSync sy) {
+                       const uint8_t* tail, uint32_t tail_first, StreamSync sy, unsigned long long* stats) {
     constexpr int kThreads = (PW + 1) * 32;
     constexpr uint32_t kWin = PW * 32;
     __shared__ PipeSmem<PW> sm;
@@ -273,8 +291,8 @@ quick_parse_cta_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nch
             uint4* h4 = reinterpret_cast<uint4*>(head);
 #pragma unroll 4
             for (uint32_t k = tid; k < 65536u * 2u / 16u; k += kThreads) __stcg(h4 + k, make_uint4(0, 0, 0, 0));
-            uint4* g4 = reinterpret_cast<uint4*>(&sm.gen[0][0]);
-            for (uint32_t k = tid; k < 2u * 2048u / 4u; k += kThreads) g4[k] = make_uint4(0, 0, 0, 0);
+            uint4* g4 = reinterpret_cast<uint4*>(&sm.bits[0]);
+            for (uint32_t k = tid; k < 2048u / 4u; k += kThreads) g4[k] = make_uint4(0, 0, 0, 0);
         }
         const size_t off = (size_t)ci * chunk;
         const uint32_t len = (uint32_t)min((size_t)chunk, n - off);
@@ -285,25 +303,46 @@ quick_parse_cta_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nch
         uint32_t* tok = tokens + (size_t)ci * tok_stride;
         const uint32_t nwin = (len + kWin - 1u) / kWin;
         uint32_t cur = 0, wr = 0;                               // walker: next position to parse, tokens written
+        WalkStats ws{};                                         // debug counters (ZNG_B200_K1_STATS=1), lane-uniform
+        const long long t_chunk = stats ? clock64() : 0;
         __syncthreads();                                        // the cleared table is what window 0's lookups see
         if (!walker && nwin) produce_block<PW>(W, sm, 0u, warp, len, head, lane);
         __syncthreads();
         for (uint32_t w = 0; w < nwin; w++) {
+            const long long t0 = stats ? clock64() : 0;
             if (walker) {
                 const uint32_t wend = min(len, (w + 1u) * kWin);
                 while (cur < wend) {
                     const uint32_t rel = cur - w * kWin;
-                    cur = walk_step<PW>(W, sm, w, rel >> 5, rel & 31u, len, head, tok, wr, lane);
+                    cur = walk_step<PW>(W, sm, w, rel >> 5, rel & 31u, len, head, tok, wr, lane, ws);
                 }
+                if (stats) ws.walk_clk += (unsigned long long)(clock64() - t0);
             } else if (w + 1u < nwin) {
                 produce_block<PW>(W, sm, w + 1u, warp, len, head, lane);
+                if (stats && warp == 0) ws.walk_clk += (unsigned long long)(clock64() - t0);      // producer warp 0: its production time
             }
             __syncthreads();                                    // (A) walk w and window w+1's records are complete
-            {   // window w+1 inserts into generation (w+1)&1, which still holds window w-1: wipe it
-                uint4* g4 = reinterpret_cast<uint4*>(&sm.gen[(w + 1u) & 1u][0]);
+            if (w + 1u < nwin) {
+                // window w+1 was looked up while window w was walked: its walk must know the inserts of windows w and w+1.  The
+                // bitmap still holds window w-1 as well: wipe it, then set the bits of window w's visited positions again.
+                uint4* g4 = reinterpret_cast<uint4*>(&sm.bits[0]);
                 for (uint32_t k = tid; k < 2048u / 4u; k += kThreads) g4[k] = make_uint4(0, 0, 0, 0);
+                __syncthreads();
+                for (uint32_t t = tid; t < kWin; t += kThreads) {
+                    const uint32_t q = w * kWin + t;
+                    const uint32_t hh = sm.hs[q & (kHsRing - 1u)];
+                    if (hh < 0x10000u && ((sm.vis[(q >> 5) & (kHsRing / 32u - 1u)] >> (q & 31u)) & 1u)) atomicOr(&sm.bits[hh >> 5], 1u << (hh & 31u));
+                }
             }
             __syncthreads();                                    // (B)
+        }
+        if (stats && lane == 0 && (walker || warp == 0)) {
+            if (walker) {
+                atomicAdd(stats + 0, 1ull); atomicAdd(stats + 1, (unsigned long long)ws.steps); atomicAdd(stats + 2, ws.walk_clk);
+                atomicAdd(stats + 3, (unsigned long long)(clock64() - t_chunk)); atomicAdd(stats + 4, (unsigned long long)ws.hit_steps);
+                atomicAdd(stats + 5, (unsigned long long)ws.bad_steps); atomicAdd(stats + 6, (unsigned long long)ws.cuts);
+                atomicAdd(stats + 7, (unsigned long long)ws.longs); atomicAdd(stats + 9, (unsigned long long)nwin);
+            } else atomicAdd(stats + 8, ws.walk_clk);
         }
         if (walker) {
             if (lane == 0) { __stcs(tok + wr, kTokEnd); ntok[ci] = wr; }
@@ -328,20 +367,21 @@ quick_parse_cta_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nch
 template <int PW>
 static cudaError_t launch_cta(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t* tokens, uint32_t tok_stride,
                               uint32_t* ntok, uint32_t* counter, uint16_t* heads, unsigned long long* sm_slots, uint32_t grid,
-                              const uint8_t* tail, uint32_t tail_first, cudaStream_t stream, const StreamSync& sy, int chains_per_sm) {
+                              const uint8_t* tail, uint32_t tail_first, cudaStream_t stream, const StreamSync& sy, int chains_per_sm,
+                              unsigned long long* stats) {
     // shared memory per chain: ~39 KiB at PW = 8; ask for the split that just holds the chains of one SM (the rest stays L1)
     int carve = (int)((sizeof(PipeSmem<PW>) + 1024u) * (size_t)chains_per_sm * 100u / (228u * 1024u)) + 1;
     if (carve > 100) carve = 100;
     cudaFuncSetAttribute(quick_parse_cta_kernel<PW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     quick_parse_cta_kernel<PW><<<grid, (PW + 1) * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots,
-                                                                   tail, tail_first, sy);
+                                                                   tail, tail_first, sy, stats);
     return cudaGetLastError();
 }
 
 cudaError_t launch_quick_parse_cta(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                                    uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
                                    uint16_t* heads, unsigned long long* sm_slots, int num_sms, int chains_per_sm, int warps, uint8_t* tail,
-                                   cudaStream_t stream, const StreamSync* sync) {
+                                   cudaStream_t stream, const StreamSync* sync, unsigned long long* stats) {
     if (nchunks == 0) return cudaSuccess;
     uint32_t grid = (uint32_t)num_sms * (uint32_t)chains_per_sm;
     if (grid > nchunks) grid = nchunks;
@@ -361,10 +401,9 @@ cudaError_t launch_quick_parse_cta(const uint8_t* in, size_t n, uint32_t chunk, 
         tl = tail;
     }
     switch (warps) {       // producer warps per chain (window = 32 x warps positions); one more warp walks
-        case 4:  return launch_cta<4>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm);
-        case 6:  return launch_cta<6>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm);
-        case 12: return launch_cta<12>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm);
-        default: return launch_cta<8>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm);
+        case 2:  return launch_cta<2>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm, stats);
+        case 4:  return launch_cta<4>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm, stats);
+        default: return launch_cta<3>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm, stats);
     }
 }
 

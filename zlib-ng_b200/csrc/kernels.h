@@ -29,12 +29,13 @@ cudaError_t launch_quick_parse(const uint8_t* in, size_t n, uint32_t chunk, uint
                                uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
                                uint16_t* heads, unsigned long long* sm_slots, uint32_t grid, uint8_t* tail, cudaStream_t stream,
                                const StreamSync* sync = nullptr);
-// K1a v5 (deflate_quick_cta.cu): one CTA of 8 warps per chain, 256-position windows, few chains per SM so that the head tables
-// stay in L2.  Same inputs / outputs / slab pool / StreamSync protocol as launch_quick_parse.
+// K1a v6 (deflate_quick_cta.cu): one CTA per chain -- producer warps one window ahead of a walker warp, few chains per SM so that
+// the head tables stay in L2.  Same inputs / outputs / slab pool / StreamSync protocol as launch_quick_parse.
 cudaError_t launch_quick_parse_cta(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                                    uint32_t* tokens, uint32_t tok_stride, uint32_t* ntok, uint32_t* counter,
                                    uint16_t* heads, unsigned long long* sm_slots, int num_sms, int chains_per_sm, int warps, uint8_t* tail,
-                                   cudaStream_t stream, const StreamSync* sync = nullptr);   // warps per CTA: 2, 4 or 8 (window = 32 x warps positions)
+                                   cudaStream_t stream, const StreamSync* sync = nullptr,
+                                   unsigned long long* stats = nullptr);   // warps = producer warps per chain: 4, 6, 8 or 12; stats: 16 debug counters
 // K1 primed (pigz's dependent-chunk mode): every chunk but the stream's first has the 32768 bytes in front of it as its
 // preset dictionary.  heads = deflate_primed_head_bytes() pool of 256 KiB slabs (32-bit absolute positions).
 size_t deflate_primed_head_bytes(uint32_t nsmid);
