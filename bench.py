@@ -372,6 +372,16 @@ def bind_to_gpu_numa_node(torch, local_rank):
         return None
 
 
+def host_memory_allows(n, ngpu):
+    """True when MemAvailable covers the pinned input (already allocated) + output + checker buffers of every rank with 25 % to spare."""
+    try:
+        avail = next(int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable:")) * 1024
+    except Exception:
+        return True
+    need = ngpu * (int(n * 1.2) + (4 << 30))
+    return avail > need * 1.25
+
+
 def copy_ceiling(torch, dev, h_src, h2d_bytes, d2h_bytes, barrier, reps):
     """Seconds (best of reps) to move h2d_bytes host->device in 16 MiB pieces and d2h_bytes device->host in 32 MiB pieces,
     concurrently on two streams, between pinned host memory and HBM -- the transfers of one e2e step without any kernel."""
@@ -552,6 +562,10 @@ def run_b200(args):
             return {"crc_fold": u(res[0].item()), "packed": int(offsets[nch].item())}
 
         cap = nch * stride
+        if n > (2 << 30):
+            # multi-GiB shards (configs[4]: 8 GiB per GPU): the pinned output buffer is sized for this workload's ratio (0.56) with
+            # margin, not for the 1.126 n worst case -- 8 ranks x (8 GiB in + 9.2 GiB out) of pinned memory is what a box may not have
+            cap = int(n * 0.75) + (1 << 20)
 
         def make_e2e():
             h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
@@ -712,6 +726,9 @@ def run_b200(args):
     # ---- e2e: host buffers through the C-ABI host call, H2D/D2H inside the timed region (every rank at once, max over ranks)
     e2e = None
     e2e_out = None
+    if not args.no_e2e and not host_memory_allows(n, ngpu):
+        args.no_e2e = True
+        e2e = {"value": None, "unit": UNIT, "skipped": "not enough free host memory for pinned input + output buffers of every rank"}
     if not args.no_e2e:
         call, bytes_fn, api, out_fn = e2e_fn()
         for _ in range(2):

@@ -102,14 +102,18 @@ __device__ __forceinline__ uint32_t crc_table_entry(uint32_t i, int slice) {
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 
 __device__ __forceinline__ uint32_t slot_acquire(unsigned long long* word) {
-    for (;;) {
+    // 64 slots per SM and at most 64 resident warps: a free bit always exists unless a slot leaked (a kernel that died holding one).
+    // The spin is bounded so that such a leak ends in a trap (a loud CUDA error at the next synchronisation), never in a hang.
+    for (uint32_t tries = 0; tries < (1u << 24); tries++) {
         const unsigned long long m = *(volatile unsigned long long*)word;
         const int b = __ffsll((long long)~m) - 1;
         if (b >= 0) {
             const unsigned long long bit = 1ull << b;
             if (!(atomicOr(word, bit) & bit)) return (uint32_t)b;
-        }
+        } else __nanosleep(200);
     }
+    __trap();
+    return 0;
 }
 
 

@@ -224,8 +224,11 @@ constexpr int L_CODES = 286, D_CODES = 30, BL_CODES = 19, HEAP_SZ = 2 * L_CODES 
 struct alignas(16) BlockWs {
     uint32_t stage[kBStageWords];
     uint32_t lfreq[L_CODES + 2], dfreq[D_CODES + 2], bfreq[BL_CODES + 1];
-    uint16_t wfreq[HEAP_SZ], wdad[HEAP_SZ], wlen[HEAP_SZ];   // the tree under construction (trees.c ct_data)
-    unsigned long long heap64[HEAP_SZ + 1];                  // the priority queue of build_tree (key + node per entry)
+    uint16_t wfreq[L_CODES + 2], wdad[HEAP_SZ], wlen[HEAP_SZ];   // the tree under construction (trees.c ct_data); freq: leaves only
+    // the priority queue of build_tree, 1-based, never more than L_CODES entries (one per leaf): sort keys and node ids in
+    // separate arrays, so that the two children 2k, 2k+1 of a node come with ONE 8-byte load and compare as plain integers
+    alignas(8) uint32_t hkey[L_CODES + 4];
+    uint16_t hid[L_CODES + 4];
     int16_t  heap[HEAP_SZ];                                   // nodes in the order they left the queue
     uint16_t bl_count[MAX_BITS + 1];
     uint16_t lcode[L_CODES + 2], dcode[D_CODES + 2], bcode[BL_CODES + 1];
@@ -295,58 +298,56 @@ struct Emitter {
 // ---- trees.c restated for one lane --------------------------------------------------------------------
 struct TreeKind { int elems, max_len, kind; };          // kind 0 literal/length, 1 distance, 2 bit-length
 
-// Heap entries carry their own sort key so that a comparison needs no second lookup: bits 0..15 node, 16..23 depth,
-// 24..47 frequency.  smaller(n, m) of trees.c:141-143 -- freq[n] < freq[m] || (freq equal && depth[n] <= depth[m]) --
-// is then (entry_n >> 16) <= (entry_m >> 16).
-__device__ __forceinline__ unsigned long long heap_entry(uint32_t freq, uint32_t depth, uint32_t node) {
-    return ((unsigned long long)freq << 24) | ((unsigned long long)depth << 16) | node;
-}
-__device__ __forceinline__ void sift_down(unsigned long long* heap, int k, int heap_len) {   // trees.c:151-173 pqdownheap
-    const unsigned long long v = heap[k];
+// Heap entries carry their own sort key so that a comparison needs no second lookup: key = frequency << 8 | depth.
+// smaller(n, m) of trees.c:141-143 -- freq[n] < freq[m] || (freq equal && depth[n] <= depth[m]) -- is then key_n <= key_m.
+__device__ __forceinline__ uint32_t heap_key(uint32_t freq, uint32_t depth) { return (freq << 8) | depth; }
+__device__ __forceinline__ void sift_down(uint32_t* key, uint16_t* id, int k, int heap_len) {   // trees.c:151-173 pqdownheap
+    const uint32_t vk = key[k];
+    const uint16_t vi = id[k];
     int j = k << 1;
     while (j <= heap_len) {
-        unsigned long long hj = heap[j];
-        if (j < heap_len) { const unsigned long long hj1 = heap[j + 1]; if ((hj1 >> 16) <= (hj >> 16)) { hj = hj1; j++; } }
-        if ((v >> 16) <= (hj >> 16)) break;
-        heap[k] = hj; k = j; j <<= 1;
+        const uint2 kk = *reinterpret_cast<const uint2*>(key + j);          // key[j], key[j+1]: j is even
+        uint32_t kj = kk.x;
+        if (j < heap_len && kk.y <= kj) { kj = kk.y; j++; }
+        if (vk <= kj) break;
+        key[k] = kj; id[k] = id[j]; k = j; j <<= 1;
     }
-    heap[k] = v;
+    key[k] = vk; id[k] = vi;
 }
 
 // build_tree + gen_bitlen + gen_codes (trees.c:185-405).  freq_in -> code_out/len_out; returns max_code.
 __device__ int build_huffman(BlockWs& T, const uint32_t* freq_in, TreeKind tk, uint16_t* code_out, uint16_t* len_out,
                              uint32_t& opt_len, uint32_t& static_len) {
-    unsigned long long* heap = T.heap64;
+    uint32_t* key = T.hkey; uint16_t* id = T.hid;
     int heap_len = 0, heap_max = HEAP_SZ, max_code = -1, node;
     for (int n = 0; n < tk.elems; n++) {
         T.wfreq[n] = (uint16_t)freq_in[n];
-        if (freq_in[n]) { heap[++heap_len] = heap_entry(freq_in[n], 0, (uint32_t)(max_code = n)); }
+        if (freq_in[n]) { ++heap_len; key[heap_len] = heap_key(freq_in[n], 0); id[heap_len] = (uint16_t)(max_code = n); }
         else T.wlen[n] = 0;
     }
     while (heap_len < 2) {                                  // trees.c:352-360: force at least two codes
         node = (max_code < 2 ? ++max_code : 0);
-        heap[++heap_len] = heap_entry(1, 0, (uint32_t)node);
+        ++heap_len; key[heap_len] = heap_key(1, 0); id[heap_len] = (uint16_t)node;
         T.wfreq[node] = 1;
         opt_len--;
         if (tk.kind == 0) static_len -= fx_llen((uint32_t)node); else if (tk.kind == 1) static_len -= 5u;
     }
-    for (int n = heap_len / 2; n >= 1; n--) sift_down(heap, n, heap_len);
+    for (int n = heap_len / 2; n >= 1; n--) sift_down(key, id, n, heap_len);
     node = tk.elems;
     do {
-        const unsigned long long en = heap[1];
-        heap[1] = heap[heap_len--];
-        sift_down(heap, 1, heap_len);
-        const unsigned long long em = heap[1];
-        const int n = (int)(en & 0xffffu), m = (int)(em & 0xffffu);
+        const uint32_t kn = key[1]; const int n = id[1];
+        key[1] = key[heap_len]; id[1] = id[heap_len]; heap_len--;
+        sift_down(key, id, 1, heap_len);
+        const uint32_t km = key[1]; const int m = id[1];
         T.heap[--heap_max] = (int16_t)n;                    // the sorted node list gen_bitlen walks
         T.heap[--heap_max] = (int16_t)m;
-        const uint32_t dn = (uint32_t)(en >> 16) & 0xffu, dm = (uint32_t)(em >> 16) & 0xffu;
+        const uint32_t dn = kn & 0xffu, dm = km & 0xffu;
         T.wdad[n] = T.wdad[m] = (uint16_t)node;
-        heap[1] = heap_entry((uint32_t)(en >> 24) + (uint32_t)(em >> 24), ((dn >= dm ? dn : dm) + 1u) & 0xffu, (uint32_t)node);
+        key[1] = heap_key((kn >> 8) + (km >> 8), ((dn >= dm ? dn : dm) + 1u) & 0xffu); id[1] = (uint16_t)node;
         node++;
-        sift_down(heap, 1, heap_len);
+        sift_down(key, id, 1, heap_len);
     } while (heap_len >= 2);
-    T.heap[--heap_max] = (int16_t)(heap[1] & 0xffffu);
+    T.heap[--heap_max] = (int16_t)id[1];
     // gen_bitlen (trees.c:185-270)
     int overflow = 0, h;
     for (int i = 0; i <= MAX_BITS; i++) T.bl_count[i] = 0;

@@ -44,7 +44,14 @@ constexpr uint32_t kStageSeg     = 256;           // words per flush segment (1 
 struct Window {
     const uint32_t* w;             // 4-byte aligned
     uint32_t skew;                 // 0..3: chunk byte 0 is byte `skew` of w[0]
-    __device__ __forceinline__ uint32_t word(uint32_t i) const { return __ldg(w + i); }
+    // An ordinary cached load (L1 + L2), NOT the non-coherent path: in the streamed host pipeline the copy engine is still writing
+    // other parts of this allocation while the kernel runs (each chunk is released to the parser only after it and its successor
+    // have landed), which is outside the read-only contract of ld.global.nc / __ldg.
+    __device__ __forceinline__ uint32_t word(uint32_t i) const {
+        uint32_t r;
+        asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(r) : "l"(w + i));    // volatile: stays behind the wait for the chunk's delivery
+        return r;
+    }
 };
 
 // ---------------------------------------------------------------- parser
@@ -341,10 +348,10 @@ __global__ void nsmid_kernel(uint32_t* out) { uint32_t r; asm volatile("mov.u32 
 // caller's allocation; every other chunk reads ahead into its successors, whose bytes cannot
 // influence the result (lengths are clipped to the chunk).
 __global__ void __launch_bounds__(kParseWarps * 32, 12)
-quick_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint32_t nchunks,
+quick_parse_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                    uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
                    uint32_t* __restrict__ counter, uint16_t* __restrict__ heads, unsigned long long* __restrict__ sm_slots,
-                   const uint8_t* __restrict__ tail, uint32_t tail_first, StreamSync sy) {
+                   const uint8_t* tail, uint32_t tail_first, StreamSync sy) {
     extern __shared__ uint32_t carve_out_only[];              // never touched: see launch_quick_parse (streamed launches)
     const unsigned lane = lane_id();
     const uint32_t sm = smid();

@@ -198,7 +198,10 @@ struct InfResult { int32_t ret; uint32_t detail, out_len, in_used, check; };
 
 // CRC-32 (gz != 0) or Adler-32 of ob[0..o): 32 contiguous slices, one per lane, then the combine algebra.
 __device__ uint32_t warp_check(const uint8_t* ob, uint32_t o, bool gz, const InfShared& S, unsigned lane) {
-    const uint32_t per = (((o + 31u) >> 5) + 3u) & ~3u;
+    // 32 slices of `per` bytes.  per is an ODD number of words: with the output staged in shared memory, a power-of-two slice
+    // (4 KiB member: 128 bytes = 32 words) puts the 32 lanes' reads on ONE bank -- a 32-way conflict per byte, 1.1 G conflicts per
+    // GiB in the round-1 profile; stride 33 words is conflict free.
+    const uint32_t per = (((o + 127u) >> 7) | 1u) << 2;
     const uint32_t beg = min(lane * per, o), end = min(beg + per, o), after = o - end;
     if (gz) {
         uint32_t c = lane == 0u ? 0xffffffffu : 0u;
