@@ -273,7 +273,7 @@ def test_uncompress_moves_only_the_bytes_it_produced(pkg, L):
 def test_adler32_of_a_large_zlib_member(pkg, L):
     """1.2 GiB of 0xFF in ONE zlib member without flush markers: the position-weighted Adler-32 sums of the member decoder pass
     2^64 unless they are reduced first (csrc/inflate.cu warp_check)."""
-    n = (1 << 30) + (200 << 20)
+    n = 20 * (64 << 20)                     # 1.25 GiB
     co = pyzlib.compressobj(1, pyzlib.DEFLATED, 15)
     piece = b"\xff" * (64 << 20)
     parts, a = [], 1
