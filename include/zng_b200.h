@@ -83,7 +83,9 @@ int zng_b200_deflate_chunks(zng_b200_ctx *ctx, const void *d_in, size_t n, uint3
  * stream bytes in front of the chunk) (deflate.c:456-512) + one zng_deflate(flush) -- pigz's default, dependent-chunk
  * mode: chunks stay independent units of work, but chunk i may reference the last 32 KiB of chunk
  * i-1, so the concatenation (Z_SYNC_FLUSH joins) is one raw-deflate stream that must be inflated in order.  The first
- * chunk of the buffer has no dictionary.  Level 1 and chunk 65536 only; other arguments as zng_b200_deflate_chunks. */
+ * chunk of the buffer has no dictionary.  Levels 1..6, chunk 65536 only; other arguments as zng_b200_deflate_chunks.  Level 1 runs
+ * the speculative warp parser on absolute positions (K1p); levels 2-6 run the reference's own window state per chunk, with its two real
+ * slides and refills (K2w, csrc/deflate_window.cu). */
 int zng_b200_deflate_chunks_primed(zng_b200_ctx *ctx, const void *d_in, size_t n, uint32_t chunk, int level, int flush,
                                    void *d_out, size_t out_stride, uint32_t *d_sizes, uint32_t *d_crcs,
                                    uint32_t *d_adlers, void *stream);
@@ -192,6 +194,10 @@ int zng_b200_deflate_host(zng_b200_ctx *ctx, const void *h_in, size_t n, uint32_
  * marker, final != 0: Z_FINISH on the last one.  Synchronous (not pipelined). */
 int zng_b200_deflate_host_primed(zng_b200_ctx *ctx, const void *h_dict, const void *h_in, size_t n, int final,
                                  void *h_out, size_t out_cap, size_t *out_len, uint32_t *crc32, uint32_t *adler32);
+/* The same for levels 1..6 (deflate_quick / deflate_fast / deflate_medium after zng_deflateSetDictionary): levels 2-6 run on the
+ * reference's own window state per chunk, real slides included (csrc/deflate_window.cu). */
+int zng_b200_deflate_host_primed_level(zng_b200_ctx *ctx, const void *h_dict, const void *h_in, size_t n, int level, int final,
+                                       void *h_out, size_t out_cap, size_t *out_len, uint32_t *crc32, uint32_t *adler32);
 /* Host-buffer form of zng_b200_inflate_members (same arrays, all in host memory; offsets are copied to the
  * device with the data, results come back in the h_ arrays). */
 int zng_b200_inflate_members_host(zng_b200_ctx *ctx, const void *h_in, const uint64_t *h_in_off, uint32_t n_members,

@@ -133,6 +133,8 @@ struct zng_b200_ctx {
     uint8_t* d_pbuf = nullptr; size_t pbuf_cap = 0;   // zng_b200_deflate_host_primed: [dictionary | input], slots | packed, sizes | crcs | adlers | offsets
     uint8_t* d_pout = nullptr; size_t pout_cap = 0;
     uint32_t* d_pmeta = nullptr; size_t pmeta_cap = 0;
+    uint8_t* wins = nullptr;                   // K2w: 64.5 KiB window buffer per (sm, slot)
+    uint8_t* blkflags = nullptr; size_t blkflags_cap = 0;   // K2w: 8 flags per chunk
     uint8_t* d_arena = nullptr; size_t arena_cap = 0;   // scratch of the host-callable operator table
     uint8_t* d_hostbuf = nullptr;              // staging for *_host checksums
     size_t hostbuf_cap = 0;
@@ -268,11 +270,51 @@ int run_deflate_shared(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_
 // pigz's dependent-chunk mode at level 1: as run_deflate_shared, every chunk after the stream's first primed with the 32768
 // bytes in front of it (deflate.c:456-512 deflateSetDictionary on a fresh stream).
 // first0: index of d_in's first chunk in the stream (> 0: the 32768 bytes in front of d_in are its dictionary)
+// levels 2-6: K2w (deflate_window.cu) keeps the reference's own window state per chain; the K2 block writer takes the tokens
+int run_deflate_primed_window(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last, int level,
+                              uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers, cudaStream_t stream,
+                              uint32_t first0) {
+    int r = ensure_heads(ctx);
+    if (r) return r;
+    r = ensure_prevs(ctx);
+    if (r) return r;
+    if (!ctx->wins) CK(cudaMalloc(&ctx->wins, deflate_window_win_bytes(ctx->nsmid)), "cudaMalloc(window buffer pool)");
+    if (ctx->blkflags_cap < (size_t)nchunks * 8u) {
+        if (ctx->blkflags) { cudaDeviceSynchronize(); cudaFree(ctx->blkflags); ctx->blkflags = nullptr; ctx->blkflags_cap = 0; }
+        const size_t want = ((size_t)nchunks < 4096u ? 4096u : (size_t)nchunks) * 8u;
+        CK(cudaMalloc(&ctx->blkflags, want), "cudaMalloc(block flags)");
+        ctx->blkflags_cap = want;
+    }
+    Scratch& sc = ctx->scratch;
+    const uint32_t stride = (chunk + 32u) & ~31u;
+    const uint32_t batch = nchunks < kBatchChunks ? nchunks : kBatchChunks;
+    r = ensure_scratch(ctx, sc, batch, stride, nchunks, true);
+    if (r) return r;
+    for (uint32_t c0 = 0; c0 < nchunks; c0 += batch) {
+        const uint32_t nb = (nchunks - c0) < batch ? (nchunks - c0) : batch;
+        const size_t off = (size_t)c0 * chunk;
+        const size_t nbytes = (c0 + nb == nchunks) ? n - off : (size_t)nb * chunk;
+        const int slot = next_slot(ctx);
+        CK(launch_window_parse(d_in + off, nbytes, chunk, nb, c0 + first0, last, sc.tokens, stride, sc.ntok + c0, ctx->blkflags + (size_t)c0 * 8u,
+                               ctx->counters + slot, ctx->heads, ctx->prevs, ctx->wins, ctx->sm_slots, ctx->sms, 32, level, stream),
+           "window_parse launch");
+        CK(launch_block_emit(d_in + off, sc.tokens, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
+                             d_sizes + c0, ctx->sms, stream, -1, ctx->blkflags + (size_t)c0 * 8u),
+           "block_emit launch");
+    }
+    if (d_crcs || d_adlers)
+        CK(launch_checksum_tiles(d_in, n, chunk, nchunks, d_crcs, d_adlers, ctx->sms, stream), "checksum launch");
+    CK(cudaEventRecord(ctx->k1_done, stream), "cudaEventRecord");
+    ctx->k1_pending = true;
+    return 0;
+}
+
 int run_deflate_primed(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, uint32_t chunk, uint32_t nchunks, int last,
                        uint8_t* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs, uint32_t* d_adlers, cudaStream_t stream,
-                       uint32_t first0 = 0) {
+                       uint32_t first0 = 0, int level = 1) {
     if (nchunks == 0) return 0;
     if (ctx->k1_pending) CK(cudaStreamWaitEvent(stream, ctx->k1_done, 0), "cudaStreamWaitEvent");
+    if (level >= 2) return run_deflate_primed_window(ctx, d_in, n, chunk, nchunks, last, level, d_out, out_stride, d_sizes, d_crcs, d_adlers, stream, first0);
     int r = ensure_heads(ctx);
     if (r) return r;
     r = ensure_primed(ctx);
@@ -471,6 +513,8 @@ void zng_b200_ctx_destroy(zng_b200_ctx* ctx) {
     }
     if (ctx->d_hostbuf) cudaFree(ctx->d_hostbuf);
     if (ctx->d_arena) cudaFree(ctx->d_arena);
+    if (ctx->wins) cudaFree(ctx->wins);
+    if (ctx->blkflags) cudaFree(ctx->blkflags);
     if (ctx->k1_stats) {
         unsigned long long h[16] = {0};
         cudaDeviceSynchronize();
@@ -541,11 +585,11 @@ int zng_b200_deflate_chunks_primed(zng_b200_ctx* ctx, const void* d_in, size_t n
                                    uint32_t* d_adlers, void* stream) {
     int r = check_chunk_args(ctx, d_in, n, chunk, level, flush, d_out, out_stride, d_sizes);
     if (r) return r;
-    if (level != 1 || chunk != 65536u) return bad(ctx, "primed chunks: level 1 and chunk 65536 only");
+    if (level < 1 || level > 6 || chunk != 65536u) return bad(ctx, "primed chunks: levels 1..6 and chunk 65536 only");
     DeviceGuard g(ctx->device);
     const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
     return run_deflate_primed(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
-                              d_sizes, d_crcs, d_adlers, (cudaStream_t)stream);
+                              d_sizes, d_crcs, d_adlers, (cudaStream_t)stream, 0, level);
 }
 
 int zng_b200_chunk_offsets(zng_b200_ctx* ctx, const uint32_t* d_sizes, uint32_t nchunks, uint64_t base,
@@ -1211,7 +1255,13 @@ static int grow(zng_b200_ctx* ctx, T*& p, size_t& cap, size_t want, const char* 
 // first piece has no dictionary).  Pieces end with the sync-flush marker; final: Z_FINISH on the last one.
 int zng_b200_deflate_host_primed(zng_b200_ctx* ctx, const void* h_dict, const void* h_in, size_t n, int final,
                                  void* h_out, size_t out_cap, size_t* out_len, uint32_t* crc32, uint32_t* adler32) {
+    return zng_b200_deflate_host_primed_level(ctx, h_dict, h_in, n, 1, final, h_out, out_cap, out_len, crc32, adler32);
+}
+
+int zng_b200_deflate_host_primed_level(zng_b200_ctx* ctx, const void* h_dict, const void* h_in, size_t n, int level, int final,
+                                       void* h_out, size_t out_cap, size_t* out_len, uint32_t* crc32, uint32_t* adler32) {
     if (!ctx) return ZNG_B200_STREAM_ERROR;
+    if (level < 1 || level > 6) return bad(ctx, "primed chunks: levels 1..6");
     if (!out_len || (n && !h_in) || !h_out) return bad(ctx, "NULL argument");
     if (n > ((size_t)1 << 32)) return bad(ctx, "primed host call: at most 4 GiB per call");
     DeviceGuard g(ctx->device);
@@ -1237,12 +1287,12 @@ int zng_b200_deflate_host_primed(zng_b200_ctx* ctx, const void* h_dict, const vo
     const uint32_t body = final ? nch - 1 : nch;
     const size_t body_bytes = final ? (size_t)body * chunk : n;
     if (body) {
-        r = run_deflate_primed(ctx, d_in, body_bytes, chunk, body, 0, d_slots, stride, d_sizes, d_crcs, d_adlers, st, first0);
+        r = run_deflate_primed(ctx, d_in, body_bytes, chunk, body, 0, d_slots, stride, d_sizes, d_crcs, d_adlers, st, first0, level);
         if (r) return r;
     }
     if (final) {                                             // the Z_FINISH piece (possibly empty: "03 00")
         r = run_deflate_primed(ctx, d_in + body_bytes, n - body_bytes, chunk, 1, 1, d_slots + (size_t)body * stride, stride, d_sizes + body,
-                               d_crcs + body, d_adlers + body, st, first0 + body);
+                               d_crcs + body, d_adlers + body, st, first0 + body, level);
         if (r) return r;
     }
     CK(launch_offsets(d_sizes, nch, 0, d_off, st), "offsets launch");

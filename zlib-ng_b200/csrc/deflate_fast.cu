@@ -461,7 +461,7 @@ __device__ void emit_tokens(Emitter& E, const BlockWs& T, const uint32_t* __rest
 // number of bytes the block covers.  `rest` != 0: this is the flush at the end of the input (the block covers the rest of
 // the chunk, len - bstart bytes, and fill_window has run at lookahead 0); otherwise the block was flushed because it is full.
 __device__ uint32_t flush_block(Emitter& E, BlockWs& T, const uint32_t* __restrict__ tok, uint32_t t0, uint32_t t1,
-                                const uint8_t* src, uint32_t bstart, uint32_t len, bool rest, int last, unsigned lane) {
+                                const uint8_t* src, uint32_t bstart, uint32_t len, bool rest, int last, unsigned lane, int nostore = -1) {
     uint32_t opt_lenb = 0, static_lenb = 0, span = 0;
     int max_blindex = 0, lmax = 0, dmax = 0;
     const uint32_t nsym = t1 - t0;
@@ -522,7 +522,9 @@ __device__ uint32_t flush_block(Emitter& E, BlockWs& T, const uint32_t* __restri
         const uint32_t s_last = bstart + span - ((tl & kTokMatch) ? ((tl >> 16) & 0x1ffu) : 1u);   // parser position before the last symbol
         stored_len = span; slid = s_last >= kSlideAt && len - s_last < 262u;
     }
-    const bool can_store = !(slid && bstart < kWSize);
+    // nostore >= 0: the parser kept the reference's own block_start through its slides (primed chunks, deflate_window.cu) and says
+    // whether this block began before one
+    const bool can_store = nostore >= 0 ? nostore == 0 : !(slid && bstart < kWSize);
     const uint8_t* raw = src + bstart;
     if (stored_len + 4u <= opt_lenb && can_store) {         // zng_tr_stored_block (trees.c:592-609)
         if (lane == 0) {
@@ -568,7 +570,7 @@ __device__ uint32_t flush_block(Emitter& E, BlockWs& T, const uint32_t* __restri
 __global__ void __launch_bounds__(kBlkWarps * 32)
 block_emit_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tokens, uint32_t tok_stride,
                   const uint32_t* __restrict__ ntok, size_t n, uint32_t chunk, uint32_t nchunks, int last,
-                  uint8_t* __restrict__ out, size_t out_stride, uint32_t* __restrict__ sizes) {
+                  uint8_t* __restrict__ out, size_t out_stride, uint32_t* __restrict__ sizes, const uint8_t* __restrict__ blkflags) {
     extern __shared__ __align__(16) unsigned char blk_smem[];
     BlockWs& T = reinterpret_cast<BlockWs*>(blk_smem)[threadIdx.x >> 5];
     const unsigned lane = lane_id();
@@ -581,14 +583,15 @@ block_emit_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ t
         const uint32_t* tok = tokens + (size_t)ci * tok_stride;
         const uint32_t nt = ntok[ci];
         Emitter E{T.stage, out + (size_t)ci * out_stride, 0u, 0u};
-        uint32_t t0 = 0, bstart = 0;
+        uint32_t t0 = 0, bstart = 0, blk = 0;
+        const uint8_t* bf = blkflags ? blkflags + (size_t)ci * 8u : nullptr;
         // deflate_fast.c:93-94: a block is flushed as soon as it holds 16383 symbols
         while (nt - t0 >= kSymEnd) {
-            bstart += flush_block(E, T, tok, t0, t0 + kSymEnd, src, bstart, len, false, 0, lane);
-            t0 += kSymEnd;
+            bstart += flush_block(E, T, tok, t0, t0 + kSymEnd, src, bstart, len, false, 0, lane, bf ? (int)bf[min(blk, 7u)] : -1);
+            t0 += kSymEnd; blk++;
         }
         // deflate_fast.c:96-103: the rest (also an empty last block for Z_FINISH)
-        if (last || nt > t0) flush_block(E, T, tok, t0, nt, src, bstart, len, true, last, lane);
+        if (last || nt > t0) flush_block(E, T, tok, t0, nt, src, bstart, len, true, last, lane, bf ? (int)bf[min(blk, 7u)] : -1);
         if (!last) {                                        // deflate.c:1064-1065 zng_tr_stored_block(NULL, 0, 0)
             if (lane == 0) {
                 E.bitpos += 3;
@@ -635,7 +638,7 @@ cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint3
 
 cudaError_t launch_block_emit(const uint8_t* in, const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n,
                               uint32_t chunk, uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
-                              int num_sms, cudaStream_t stream, int co_carve) {
+                              int num_sms, cudaStream_t stream, int co_carve, const uint8_t* blkflags) {
     if (nchunks == 0) return cudaSuccess;
     const int smem = (int)(sizeof(BlockWs) * kBlkWarps);
     cudaError_t e = cudaFuncSetAttribute(block_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -644,7 +647,7 @@ cudaError_t launch_block_emit(const uint8_t* in, const uint32_t* tokens, uint32_
     uint32_t grid = (uint32_t)num_sms * (uint32_t)((227 * 1024) / (smem + 1024));     // as many CTAs as the shared memory of an SM holds
     const uint32_t need = (nchunks + kBlkWarps - 1u) / kBlkWarps;
     if (grid > need) grid = need;
-    block_emit_kernel<<<grid, kBlkWarps * 32, smem, stream>>>(in, tokens, tok_stride, ntok, n, chunk, nchunks, last, out, out_stride, sizes);
+    block_emit_kernel<<<grid, kBlkWarps * 32, smem, stream>>>(in, tokens, tok_stride, ntok, n, chunk, nchunks, last, out, out_stride, sizes, blkflags);
     return cudaGetLastError();
 }
 

@@ -59,7 +59,14 @@ cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint3
                               const StreamSync* sync = nullptr, int dyn_smem = 0);
 cudaError_t launch_block_emit(const uint8_t* in, const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n,
                               uint32_t chunk, uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
-                              int num_sms, cudaStream_t stream, int co_carve = -1);
+                              int num_sms, cudaStream_t stream, int co_carve = -1,
+                              const uint8_t* blkflags = nullptr);   // blkflags: 8 bytes per chunk, != 0: block k may not be stored (K2w)
+// K2w (deflate_window.cu): dictionary-primed chunks at levels 2-6 on the reference's own window / head / prev state (real slides).
+// Shares the K2 slab pools; wins = deflate_window_win_bytes() of window buffers, blkflags as above (written by the parser).
+size_t deflate_window_win_bytes(uint32_t nsmid);
+cudaError_t launch_window_parse(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t first, int last, uint32_t* tokens,
+                                uint32_t tok_stride, uint32_t* ntok, uint8_t* blkflags, uint32_t* counter, uint16_t* heads, uint16_t* prevs,
+                                uint8_t* wins, unsigned long long* sm_slots, int num_sms, int chains_per_sm, int level, cudaStream_t stream);
 
 // K3: checksums (checksum.cu)
 cudaError_t launch_checksum_tiles(const uint8_t* in, size_t n, uint32_t tile_bytes, uint32_t ntiles,

@@ -97,16 +97,16 @@ int32_t zng_deflateEnd(zng_stream *strm) {
     return busy ? Z_DATA_ERROR : Z_OK;                     /* deflate.c:1125 */
 }
 
-/* deflate.c:456-512.  Supported where the GPU path reproduces the reference bit for bit: a raw (windowBits -15) level-1
- * stream with no input pending and a dictionary of at least one window (the last 32768 bytes are used, :479-488).  The
+/* deflate.c:456-512.  Supported where the GPU path reproduces the reference bit for bit: a raw (windowBits -15) stream of
+ * level 1..6 with no input pending and a dictionary of at least one window (the last 32768 bytes are used, :479-488).  The
  * stream then works in pigz's dependent mode: each 65536-byte piece is compressed exactly as a FRESH stream primed with
  * the 32768 bytes in front of it does (zng_deflateSetDictionary + one zng_deflate per piece), Z_SYNC_FLUSH allowed. */
 int32_t zng_deflateSetDictionary(zng_stream *strm, const uint8_t *dictionary, uint32_t dictLength) {
     if (state_check(strm, 'D') || dictionary == NULL) return Z_STREAM_ERROR;
     struct internal_state *s = strm->state;
     if (s->wrap == 2 || (s->wrap == 1 && s->status != ST_INIT) || s->in_len) return Z_STREAM_ERROR;     /* deflate.c:468-469 */
-    if (s->wrap != 0 || s->level != 1 || dictLength < 32768u) {
-        strm->msg = "unsupported: preset dictionaries on raw level-1 streams, 32768 bytes or more"; return Z_STREAM_ERROR;
+    if (s->wrap != 0 || s->level < 1 || s->level > 6 || dictLength < 32768u) {
+        strm->msg = "unsupported: preset dictionaries on raw streams of level 1..6, 32768 bytes or more"; return Z_STREAM_ERROR;
     }
     if (!s->dict && !(s->dict = (uint8_t *)malloc(32768))) return Z_MEM_ERROR;
     memcpy(s->dict, dictionary + (dictLength - 32768u), 32768);
@@ -181,7 +181,7 @@ static int compress_into_pending(zng_stream *strm, const uint8_t *src, size_t n,
         dst = s->pend + s->pend_len; room = s->pend_cap - s->pend_len;
     }
     if (s->have_dict) {
-        r = zng_b200_deflate_host_primed(ctx, s->dict, src, n, fin, dst, room, &out_len, &crc, &adler);
+        r = zng_b200_deflate_host_primed_level(ctx, s->dict, src, n, s->level, fin, dst, room, &out_len, &crc, &adler);
         if (n >= 32768) memcpy(s->dict, src + n - 32768, 32768);            /* the window in front of the next piece */
         else if (n) { memmove(s->dict, s->dict + n, 32768 - n); memcpy(s->dict + 32768 - n, src, n); }
     } else {
