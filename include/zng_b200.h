@@ -90,6 +90,13 @@ int zng_b200_deflate_chunks_primed(zng_b200_ctx *ctx, const void *d_in, size_t n
                                    void *d_out, size_t out_stride, uint32_t *d_sizes, uint32_t *d_crcs,
                                    uint32_t *d_adlers, void *stream);
 
+/* The same for a buffer that is NOT the start of the stream: have_halo != 0 says the 32768 bytes in front of d_in are readable and
+ * are the stream bytes that precede it, so the first chunk is primed like every other (a rank's shard of a multi-GPU dependent
+ * stream; zng_b200_halo_exchange below delivers those bytes from the previous rank). */
+int zng_b200_deflate_chunks_primed_at(zng_b200_ctx *ctx, const void *d_in, size_t n, uint32_t chunk, int level, int flush, int have_halo,
+                                      void *d_out, size_t out_stride, uint32_t *d_sizes, uint32_t *d_crcs,
+                                      uint32_t *d_adlers, void *stream);
+
 /* Debug aid (ZLIB_DEBUG's Tracevv token trace analogue, deflate_p.h:39-44,72): as above for level 1,
  * additionally writing the LZ77 token stream of chunk i to d_tokens[i*tok_stride ...]: a literal is
  * its byte value, a match is 0x80000000 | len << 16 | dist, the list ends with 0x40000000. */
@@ -131,6 +138,10 @@ const char *zng_b200_comm_error(const zng_b200_comm *comm);
 int  zng_b200_stream_index_multi(zng_b200_comm *comm, const uint32_t *d_sizes, const uint32_t *d_crcs, uint32_t nchunks_local,
                                  uint32_t chunk, size_t n_local, uint64_t base, uint64_t *d_offsets_local,
                                  uint64_t *h_stream_end, uint32_t *h_crc32, uint64_t *h_total_in, void *stream);
+/* Collective, dependent (primed) mode: rank r sends the last 32768 bytes of its shard to rank r+1 and receives rank r-1's into d_halo,
+ * which the caller places directly in front of its input ([d_halo, d_halo + 32768 + n_local) contiguous); then
+ * zng_b200_deflate_chunks_primed_at(..., have_halo = rank > 0, ...) makes the N-GPU dependent stream equal the 1-GPU one. */
+int  zng_b200_halo_exchange(zng_b200_comm *comm, const void *d_in, size_t n_local, void *d_halo, void *stream);
 /* Collective: the whole pigz-style step for this rank's n_local bytes -- chunk compression (64 KiB chunks, Z_FULL_FLUSH ends),
  * the allgather, scan and fold above, and the gather of this rank's chunks into d_packed.  The gzip file is
  *   header (10 bytes, rank 0) | rank 0's bytes | rank 1's bytes | ... | "03 00" crc32 isize (10 bytes, at *h_file_bytes - 10)

@@ -53,3 +53,25 @@ def test_comm_argument_errors(pkg, ctx):
         pkg.Comm(ctx, 2, 5, b"\0" * 128)          # rank out of range
     with pytest.raises(pkg.ZngB200Error):
         pkg.Comm(ctx, 0, 0, None)
+
+
+@pytest.mark.parametrize("level", [1, 2, 5])
+def test_primed_shard_with_halo_equals_the_unsharded_stream(pkg, ctx, zo, level):
+    """A rank's shard of a dependent stream (zng_b200_deflate_chunks_primed_at, have_halo): the 32768 bytes in front of the buffer prime
+    its first chunk, so the shard's chunks equal chunks [k, k + m) of the un-sharded stream.  (The halo's trip between ranks is
+    tests/run_primed_multi.py under torchrun.)"""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    whole = synth(12 * 65536, seed=31 + level)
+    k, m = 5, 7
+    buf = torch.from_numpy(whole[k * 65536 - 32768:(k + m) * 65536].copy()).to(dev)
+    d_in = buf[32768:]
+    stride = pkg.deflate_bound(65536)
+    slots = torch.empty(m * stride, dtype=torch.uint8, device=dev)
+    sizes = torch.zeros(m, dtype=torch.int32, device=dev); crcs = torch.zeros_like(sizes)
+    ctx.deflate_chunks_primed_at(d_in, m * 65536, 65536, level, pkg.Z_SYNC_FLUSH, True, slots, stride, sizes, crcs)
+    torch.cuda.synchronize()
+    fn = zo.ref_deflate_chunks_primed if zo.have_ref() else zo.port_deflate_chunks_primed
+    exp, es, _, _ = fn(whole, 65536, level, 2, stride)
+    bad, first = zo.compare_chunks(slots.cpu().numpy(), stride, sizes.cpu().numpy().view(np.uint32), exp[k:k + m], stride, es[k:k + m])
+    assert bad == 0, (level, bad, first)

@@ -52,6 +52,8 @@ def lib() -> ctypes.CDLL:
         "zng_b200_deflate_bound": (c_size_t, [c_size_t]),
         "zng_b200_deflate_chunks": (c_int, [vp, vp, c_size_t, c_uint32, c_int, c_int, vp, c_size_t, u32p, u32p, u32p, vp]),
         "zng_b200_deflate_chunks_primed": (c_int, [vp, vp, c_size_t, c_uint32, c_int, c_int, vp, c_size_t, u32p, u32p, u32p, vp]),
+        "zng_b200_deflate_chunks_primed_at": (c_int, [vp, vp, c_size_t, c_uint32, c_int, c_int, c_int, vp, c_size_t, u32p, u32p, u32p, vp]),
+        "zng_b200_halo_exchange": (c_int, [vp, vp, c_size_t, vp, vp]),
         "zng_b200_deflate_chunks_trace": (c_int, [vp, vp, c_size_t, c_uint32, c_int, c_int, vp, c_size_t, u32p, u32p, c_uint32, vp]),
         "zng_b200_chunk_offsets": (c_int, [vp, u32p, c_uint32, c_uint64, u64p, vp]),
         "zng_b200_gather_chunks": (c_int, [vp, vp, c_size_t, u32p, u64p, c_uint32, vp, vp]),
@@ -237,6 +239,10 @@ class Context:
         self._check(lib().zng_b200_deflate_chunks_primed(self._h, _ptr(d_in), n, chunk, level, flush, _ptr(slots), stride,
                                                          _ptr(sizes), _ptr(crcs), _ptr(adlers), self._stream()))
 
+    def deflate_chunks_primed_at(self, d_in, n: int, chunk: int, level: int, flush: int, have_halo: bool, slots, stride: int, sizes, crcs=None, adlers=None):
+        self._check(lib().zng_b200_deflate_chunks_primed_at(self._h, _ptr(d_in), n, chunk, level, flush, 1 if have_halo else 0, _ptr(slots), stride,
+                                                            _ptr(sizes), _ptr(crcs), _ptr(adlers), self._stream()))
+
     def deflate_chunks_trace(self, d_in, n: int, chunk: int, level: int, flush: int, slots, stride: int, sizes, tokens, tok_stride: int):
         self._check(lib().zng_b200_deflate_chunks_trace(self._h, _ptr(d_in), n, chunk, level, flush, _ptr(slots), stride,
                                                         _ptr(sizes), _ptr(tokens), tok_stride, self._stream()))
@@ -346,6 +352,10 @@ class Comm:
     def _check(self, r: int):
         if r != 0:
             raise ZngB200Error(r, lib().zng_b200_comm_error(self._h).decode() or lib().zng_b200_last_error(self.ctx._h).decode())
+
+    def halo_exchange(self, d_in, n_local: int, d_halo):
+        """Collective: this rank's last 32 KiB to the next rank, the previous rank's into d_halo (directly in front of d_in)."""
+        self._check(lib().zng_b200_halo_exchange(self._h, _ptr(d_in), n_local, _ptr(d_halo), Context._stream()))
 
     def stream_index(self, sizes, crcs, nchunks_local: int, chunk: int, n_local: int, base: int, offsets_local):
         """Collective.  Returns (stream_end, crc32, total_in); offsets_local (int64 device tensor, nchunks_local + 1) is filled."""

@@ -592,6 +592,18 @@ int zng_b200_deflate_chunks_primed(zng_b200_ctx* ctx, const void* d_in, size_t n
                               d_sizes, d_crcs, d_adlers, (cudaStream_t)stream, 0, level);
 }
 
+int zng_b200_deflate_chunks_primed_at(zng_b200_ctx* ctx, const void* d_in, size_t n, uint32_t chunk, int level, int flush, int have_halo,
+                                      void* d_out, size_t out_stride, uint32_t* d_sizes, uint32_t* d_crcs,
+                                      uint32_t* d_adlers, void* stream) {
+    int r = check_chunk_args(ctx, d_in, n, chunk, level, flush, d_out, out_stride, d_sizes);
+    if (r) return r;
+    if (level < 1 || level > 6 || chunk != 65536u) return bad(ctx, "primed chunks: levels 1..6 and chunk 65536 only");
+    DeviceGuard g(ctx->device);
+    const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
+    return run_deflate_primed(ctx, (const uint8_t*)d_in, n, chunk, nchunks, flush == ZNG_B200_FINISH, (uint8_t*)d_out, out_stride,
+                              d_sizes, d_crcs, d_adlers, (cudaStream_t)stream, have_halo ? 1u : 0u, level);
+}
+
 int zng_b200_chunk_offsets(zng_b200_ctx* ctx, const uint32_t* d_sizes, uint32_t nchunks, uint64_t base,
                            uint64_t* d_offsets, void* stream) {
     if (!ctx || !d_offsets || (nchunks && !d_sizes)) return ZNG_B200_STREAM_ERROR;

@@ -36,6 +36,10 @@ struct NcclApi {
     ncclResult_t (*CommUserRank)(const ncclComm_t, int*) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     bool ok = false;
 };
 
@@ -54,6 +58,10 @@ NcclApi& nccl() {
         api.CommUserRank = (decltype(api.CommUserRank))sym("ncclCommUserRank");
         api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
         api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+        api.Send = (decltype(api.Send))sym("ncclSend");
+        api.Recv = (decltype(api.Recv))sym("ncclRecv");
+        api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
         api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.CommCount && api.CommUserRank && api.AllGather;
     });
     return api;
@@ -243,6 +251,24 @@ int zng_b200_stream_index_multi(zng_b200_comm* c, const uint32_t* d_sizes, const
     if (h_stream_end) *h_stream_end = hh[2 * G + 2];
     if (h_crc32) *h_crc32 = (uint32_t)hh[2 * G + 3];
     if (h_total_in) *h_total_in = n_total;
+    return ZNG_B200_OK;
+}
+
+// Dependent (primed) chunks across ranks: rank r's first chunk is primed with the last 32768 bytes of rank r-1's shard.  Collective:
+// every rank sends its last 32 KiB to its successor and receives its predecessor's into d_halo (which the caller places directly in
+// front of its own input, so that [d_halo, d_halo + 32768 + n_local) is contiguous).  Rank 0 receives nothing.  One ncclSend /
+// ncclRecv pair per neighbour over NVLink; 32 KiB per rank is all the payload that ever crosses it.
+int zng_b200_halo_exchange(zng_b200_comm* c, const void* d_in, size_t n_local, void* d_halo, void* stream) {
+    if (!c || !d_halo || (n_local && !d_in)) return ZNG_B200_STREAM_ERROR;
+    if (c->nranks == 1) return ZNG_B200_OK;
+    if (n_local < 32768u) { snprintf(c->err, sizeof(c->err), "halo exchange: every rank needs at least 32768 bytes of input"); return ZNG_B200_STREAM_ERROR; }
+    if (!nccl().Send || !nccl().Recv || !nccl().GroupStart || !nccl().GroupEnd) return ZNG_B200_STREAM_ERROR;
+    cudaStream_t st = (cudaStream_t)stream;
+    CCK(cudaSetDevice(zng_b200_ctx_device(c->ctx)), "cudaSetDevice");
+    NCK(nccl().GroupStart(), "ncclGroupStart");
+    if (c->rank + 1 < c->nranks) NCK(nccl().Send((const uint8_t*)d_in + n_local - 32768u, 32768u, kNcclUint8, c->rank + 1, c->nc, st), "ncclSend(halo)");
+    if (c->rank > 0) NCK(nccl().Recv(d_halo, 32768u, kNcclUint8, c->rank - 1, c->nc, st), "ncclRecv(halo)");
+    NCK(nccl().GroupEnd(), "ncclGroupEnd");
     return ZNG_B200_OK;
 }
 
