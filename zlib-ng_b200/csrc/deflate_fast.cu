@@ -536,7 +536,12 @@ __device__ uint32_t flush_block(Emitter& E, BlockWs& T, const uint32_t* __restri
         for (uint32_t base = 0; base < stored_len; base += 128u) {
             const uint32_t i = base + 4u * lane;
             uint32_t wv = 0, nby = 0;
-            if (i < stored_len) {
+            if (i + 8u <= stored_len) {                        // interior: two aligned words, funnel-shifted (no read past the block)
+                const uintptr_t a = reinterpret_cast<uintptr_t>(raw + i);
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+                wv = __funnelshift_r(__ldg(wp), __ldg(wp + 1), (uint32_t)(a & 3u) << 3);
+                nby = 4u;
+            } else if (i < stored_len) {
                 nby = min(4u, stored_len - i);
                 for (uint32_t b = 0; b < nby; b++) wv |= (uint32_t)raw[i + b] << (8u * b);
             }
