@@ -1,5 +1,5 @@
-# K1a v6/v7 debug counters per configuration (producer warps, chains per SM): GB/s device-resident + the parser's own counters
-for cfg in ${CFGS:-"3 6" "3 8" "3 10" "2 10" "2 13" "4 8"}; do set -- $cfg; echo "== producers=$1 chains=$2"; ZNG_B200_K1_STATS=1 ZNG_B200_K1=cta ZNG_B200_K1_WARPS=$1 ZNG_B200_K1_CHAINS=$2 timeout 120 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline ${PARITY:---no-parity} 2>&1 | python -c '
+# K1a v7 debug counters per configuration "producer-warps blocks-per-producer-warp chains-per-SM": GB/s device-resident + the parser's own counters
+for cfg in ${CFGS:-"3 1 10" "2 2 11" "2 2 13" "1 4 13" "1 2 13"}; do set -- $cfg; echo "== producers=$1 blocks/producer=$2 chains=$3"; ZNG_B200_K1_STATS=${STATS:-1} ZNG_B200_K1=cta ZNG_B200_K1_WARPS=$1 ZNG_B200_K1_BPW=$2 ZNG_B200_K1_CHAINS=$3 timeout 120 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline ${PARITY:---no-parity} 2>&1 | python -c '
 import sys, json
 for line in sys.stdin:
     if line.startswith("{"):

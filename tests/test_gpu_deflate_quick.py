@@ -185,3 +185,35 @@ def test_slid_window_position_zero_alias(pkg, ctx, zo):
         d[65274:65282] = d[32768:32776] if n >= 65282 else d[32768:32768 + n - 65274]
         for flush in (3, 4):
             assert_parity(pkg, ctx, zo, d, 65536, flush)
+
+
+@pytest.mark.parametrize("knobs", [("3", "1", "10"), ("2", "2", "11"), ("4", "1", "8"), ("1", "4", "6")])
+def test_cta_per_chain_parser_is_bit_exact(pkg, zo, knobs, monkeypatch):
+    """K1a v7 (csrc/deflate_quick_cta.cu, opt-in through ZNG_B200_K1=cta): producer warps one window ahead of a walker warp.  Same
+    inputs as the shipped parser's tests -- the synthetic mix with a ragged tail, every short length class, repetitive data, the
+    post-slide position-0 alias -- compared byte for byte with the oracle, plus 64 MiB against the unmodified reference."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    monkeypatch.setenv("ZNG_B200_K1", "cta")
+    monkeypatch.setenv("ZNG_B200_K1_WARPS", knobs[0]); monkeypatch.setenv("ZNG_B200_K1_BPW", knobs[1]); monkeypatch.setenv("ZNG_B200_K1_CHAINS", knobs[2])
+    c = pkg.Context(0)                                   # the knobs are read when a context is created
+    try:
+        rng = np.random.default_rng(11)
+        inputs = [synth(64 * 65536 + 4321, seed=101), np.zeros(3 * 65536 + 17, dtype=np.uint8), rng.integers(0, 4, size=5 * 65536, dtype=np.uint8),
+                  np.tile(rng.integers(0, 256, size=37, dtype=np.uint8), 8000)[:4 * 65536 + 5], rng.integers(0, 256, size=2 * 65536 + 1, dtype=np.uint8)]
+        inputs += [synth(65536, seed=5)[:n] for n in (0, 1, 3, 4, 5, 31, 32, 33, 95, 96, 97, 127, 128, 129, 255, 256, 257, 4096, 65275, 65279, 65535)]
+        for data in inputs:
+            for flush in (3, 4):
+                assert_parity(pkg, c, zo, data, 65536, flush)
+        assert_parity(pkg, c, zo, synth(64 * 4096, seed=7), 4096, 4)
+        d = rng.integers(0, 256, size=65400, dtype=np.uint8)                     # slid window, position-0 alias (see below)
+        d[32760:32780] = d[1000:1020]; d[65274:65282] = d[32768:32776]
+        assert_parity(pkg, c, zo, d, 65536, 3)
+        big = synth(64 << 20, seed=808)
+        got, sizes, crcs, _, stride = gpu_deflate(pkg, c, big, want_adler=False)
+        _, exp, es, ec, _ = zo.best_deflate_chunks(big, 65536, 1, 3, stride)
+        bad, first = zo.compare_chunks(got, stride, sizes, exp, stride, es)
+        assert bad == 0 and np.array_equal(crcs, ec), (knobs, bad, first)
+    finally:
+        c.close()

@@ -19,7 +19,7 @@ using namespace zb;
 namespace {
 constexpr int kCounters = 64;
 constexpr int kPipeMax = 16;                   // most slabs in flight on the host path (ctx->pipe of them are used)
-constexpr uint32_t kSlabChunksDefault = 2048;  // 128 MiB of input per slab at 64 KiB chunks (ctx->slab_chunks, env ZNG_B200_SLAB_CHUNKS)
+constexpr uint32_t kSlabChunksDefault = 4096;  // 256 MiB of input per slab at 64 KiB chunks (ctx->slab_chunks, env ZNG_B200_SLAB_CHUNKS)
 constexpr uint32_t kBatchChunks = 16384;       // chunks per K1a/K1b launch pair (token scratch: 4 GiB at 64 KiB chunks)
 
 // K1a -> K1b hand-over: LZ77 token lists (4 B per input byte) + token counts
@@ -101,7 +101,7 @@ struct zng_b200_ctx {
     uint32_t* vtails = nullptr;
     int chains_per_sm = 24;
     int k1_cta = 0;                            // level-1 parser: 1 = CTA per chain with L2-resident tables (v5), 0 = warp per chain (env ZNG_B200_K1=warp)
-    int warps_cta = 3;                         // warps per chain of the v5 parser (env ZNG_B200_K1_WARPS: 2, 4, 8)
+    int warps_cta = 31;                        // warps per chain of the v5 parser (env ZNG_B200_K1_WARPS: 2, 4, 8)
     unsigned long long* k1_stats = nullptr;    // env ZNG_B200_K1_STATS=1: 16 debug counters of the v6 parser, printed when the context goes
     int chains_cta = 10;                       // chains (CTAs) per SM of the v5 parser (env ZNG_B200_K1_CHAINS)
     int chains_per_sm_l2 = 32;                 // measured on B200: 16 -> 12.4, 24 -> 14.4, 32 -> 15.4 GB/s
@@ -117,7 +117,7 @@ struct zng_b200_ctx {
     Streamed st;
     int streamed = 1;                          // env ZNG_B200_STREAMED=0: level 1 goes through the slab pipeline as well
     uint32_t stream_shift = 9;                 // log2(chunks per output slab) of the streamed path (env ZNG_B200_STREAM_SHIFT, 8..11)
-    int pipe = 4;                              // slabs in flight (env ZNG_B200_PIPE); measured: 2048 x 4 -> 23.2 GB/s e2e, 1024 x 6 -> 20.6
+    int pipe = 4;                              // slabs in flight (env ZNG_B200_PIPE); round 1, level 1: 2048 x 4 -> 23.2 GB/s e2e, 1024 x 6 -> 20.6; round 2, levels 2-6: 4096 x 4
     uint32_t slab_chunks = kSlabChunksDefault;
     bool slabs_ready = false;
     size_t slab_stride = 0;
@@ -422,7 +422,8 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     if (const char* e = getenv("ZNG_B200_K1")) ctx->k1_cta = (strcmp(e, "cta") == 0);
     if (const char* e = getenv("ZNG_B200_K1_STATS")) { if (atoi(e) && cudaMalloc(&ctx->k1_stats, 16 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(ctx->k1_stats, 0, 16 * sizeof(unsigned long long)); }
     if (const char* e = getenv("ZNG_B200_K1_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->chains_cta = v; }
-    if (const char* e = getenv("ZNG_B200_K1_WARPS")) { int v = atoi(e); if (v >= 2 && v <= 4) ctx->warps_cta = v; }
+    if (const char* e = getenv("ZNG_B200_K1_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 4) ctx->warps_cta = 10 * v + (ctx->warps_cta % 10); }
+    if (const char* e = getenv("ZNG_B200_K1_BPW")) { int v = atoi(e); if (v >= 1 && v <= 4) ctx->warps_cta = 10 * (ctx->warps_cta / 10) + v; }
     if (const char* e = getenv("ZNG_B200_SLAB_CHUNKS")) { int v = atoi(e); if (v >= 64 && v <= 16384) ctx->slab_chunks = (uint32_t)v; }
     if (const char* e = getenv("ZNG_B200_STREAMED")) ctx->streamed = atoi(e);
     if (const char* e = getenv("ZNG_B200_STREAM_SHIFT")) { int v = atoi(e); if (v >= 8 && v <= 11) ctx->stream_shift = (uint32_t)v; }
@@ -1563,6 +1564,9 @@ int zng_b200_deflate_host(zng_b200_ctx* ctx, const void* h_in, size_t n, uint32_
         r = drain_slab(ctx, s, out, out_cap, out_pos, crc, adler);     // the previous occupant's bytes leave first
         if (r) { sync_slabs(ctx); return r; }
         mark(s.stream);                                                 // [4i+0] slab stream free again (behind the old occupant's D2H)
+        // Full slabs only: at the slow levels a slab must hold most of a wave of chains (4 736 on B200) or the GPU idles behind each
+        // slab's stragglers -- 4096 chunks x 4 slabs is the measured optimum at levels 2, 4 and 6; short first / last slabs (to start
+        // and finish early) were tried and lose (profiles/r2_sweep_slab_levels.txt).
         const size_t take = (n - off) < slab_in ? (n - off) : slab_in;
         const bool is_last = (off + take == n);
         const size_t pre = (level >= 2) ? (off < kWSize ? off : (size_t)kWSize) : 0;

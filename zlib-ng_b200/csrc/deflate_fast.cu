@@ -129,6 +129,8 @@ __device__ uint32_t fast_parse_warp(const VWindow W, uint32_t n, uint16_t* head,
     return wr;
 }
 
+// Levels 4-6 walk hash chains of up to 24 / 32 / 128 dependent prev[] links per position and are bound by that latency.  Trading
+// registers for occupancy (40 registers, 48 chains per SM) was measured and gains 0-5 % (profiles/r2_sweep_k2_levels.txt): not kept.
 template <int LEVEL>
 __global__ void __launch_bounds__(kFastWarps * 32, 8)
 fast_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint32_t nchunks,

@@ -90,10 +90,10 @@ __device__ __forceinline__ uint32_t lanes_ge(uint32_t s) { return __funnelshift_
 constexpr uint32_t kRing = 256u;          // records: windows w (walked) and w+1 (produced) -> needs 2 x window <= 256
 constexpr uint32_t kHsRing = 512u;        // hashes: windows w-2 .. w+1 -> needs 4 x window <= 512
 constexpr uint32_t kLast = 2048u;
-template <int PW>
+template <int PW, int BPW>
 struct __align__(16) PipeSmem {
-    static constexpr int kWin = PW * 32;
-    static_assert(PW * 32 * 2 <= (int)kRing, "window too large for the record ring");
+    static constexpr int kWin = PW * BPW * 32;
+    static_assert(PW * BPW * 32 * 2 <= (int)kRing, "window too large for the record ring");
     uint32_t bits[2048];         // one bit per hash value: inserted by the walk of the previous or the current window
     uint16_t last[kLast];        // [hash & 2047] = position of the last insert that mapped here (verified against hs[])
     uint2    ring[kRing];        // record of position q in ring[q & 255]
@@ -107,10 +107,10 @@ struct WalkStats { uint32_t steps, hit_steps, bad_steps, cuts, longs; unsigned l
 
 // One step of the walker: the aligned block `blk` of window w from lane s0 on.  Returns the chunk position where the next step
 // starts; wr (token count) is advanced.
-template <int PW>
-__device__ __forceinline__ uint32_t walk_step(const WindowCA& W, PipeSmem<PW>& sm, uint32_t w, uint32_t blk, uint32_t s0, uint32_t n,
+template <int PW, int BPW>
+__device__ __forceinline__ uint32_t walk_step(const WindowCA& W, PipeSmem<PW, BPW>& sm, uint32_t w, uint32_t blk, uint32_t s0, uint32_t n,
                                               uint16_t* head, uint32_t* __restrict__ tok, uint32_t& wr, unsigned lane, WalkStats& ws) {
-    constexpr uint32_t kWin = PW * 32;
+    constexpr uint32_t kWin = PW * BPW * 32;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t b0 = w * kWin + blk * 32u;                 // chunk position of lane 0
     ws.steps++;
@@ -224,10 +224,10 @@ __device__ __forceinline__ uint32_t walk_step(const WindowCA& W, PipeSmem<PW>& s
 }
 
 // One producer warp: the aligned block `blk` of window w, looked up in the table as it stands.
-template <int PW>
-__device__ __forceinline__ void produce_block(const WindowCA& W, PipeSmem<PW>& sm, uint32_t w, uint32_t blk, uint32_t n,
+template <int PW, int BPW>
+__device__ __forceinline__ void produce_block(const WindowCA& W, PipeSmem<PW, BPW>& sm, uint32_t w, uint32_t blk, uint32_t n,
                                               const uint16_t* head, unsigned lane) {
-    constexpr uint32_t kWin = PW * 32;
+    constexpr uint32_t kWin = PW * BPW * 32;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t q = w * kWin + blk * 32u + lane;
     const bool inw = q < n;
@@ -256,15 +256,15 @@ __device__ __forceinline__ void produce_block(const WindowCA& W, PipeSmem<PW>& s
     sm.ring[q & (kRing - 1u)] = make_uint2((h << 16) | cand, (v & 0xffu) | (slen << 8) | ((uint32_t)act << 15) | (d << 16));
 }
 
-template <int PW>
+template <int PW, int BPW>
 __global__ void __launch_bounds__((PW + 1) * 32, 1280 / ((PW + 1) * 32))
 quick_parse_cta_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks,
                        uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
                        uint32_t* __restrict__ counter, uint16_t* heads, unsigned long long* sm_slots,
                        const uint8_t* tail, uint32_t tail_first, StreamSync sy, unsigned long long* stats) {
     constexpr int kThreads = (PW + 1) * 32;
-    constexpr uint32_t kWin = PW * 32;
-    __shared__ PipeSmem<PW> sm;
+    constexpr uint32_t kWin = PW * BPW * 32;
+    __shared__ PipeSmem<PW, BPW> sm;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const bool walker = warp == PW;                             // the last warp walks, warps 0..PW-1 produce block `warp` of each window
     if (tid == 0) sm.slot = slot_acquire(sm_slots + smid());
@@ -306,7 +306,7 @@ quick_parse_cta_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nch
         WalkStats ws{};                                         // debug counters (ZNG_B200_K1_STATS=1), lane-uniform
         const long long t_chunk = stats ? clock64() : 0;
         __syncthreads();                                        // the cleared table is what window 0's lookups see
-        if (!walker && nwin) produce_block<PW>(W, sm, 0u, warp, len, head, lane);
+        if (!walker && nwin) for (uint32_t b = warp; b < (uint32_t)(PW * BPW); b += PW) produce_block<PW, BPW>(W, sm, 0u, b, len, head, lane);
         __syncthreads();
         for (uint32_t w = 0; w < nwin; w++) {
             const long long t0 = stats ? clock64() : 0;
@@ -314,11 +314,11 @@ quick_parse_cta_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nch
                 const uint32_t wend = min(len, (w + 1u) * kWin);
                 while (cur < wend) {
                     const uint32_t rel = cur - w * kWin;
-                    cur = walk_step<PW>(W, sm, w, rel >> 5, rel & 31u, len, head, tok, wr, lane, ws);
+                    cur = walk_step<PW, BPW>(W, sm, w, rel >> 5, rel & 31u, len, head, tok, wr, lane, ws);
                 }
                 if (stats) ws.walk_clk += (unsigned long long)(clock64() - t0);
             } else if (w + 1u < nwin) {
-                produce_block<PW>(W, sm, w + 1u, warp, len, head, lane);
+                for (uint32_t b = warp; b < (uint32_t)(PW * BPW); b += PW) produce_block<PW, BPW>(W, sm, w + 1u, b, len, head, lane);
                 if (stats && warp == 0) ws.walk_clk += (unsigned long long)(clock64() - t0);      // producer warp 0: its production time
             }
             __syncthreads();                                    // (A) walk w and window w+1's records are complete
@@ -364,16 +364,16 @@ quick_parse_cta_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nch
     if (tid == 0) atomicAnd(sm_slots + smid(), ~(1ull << slot));
 }
 
-template <int PW>
+template <int PW, int BPW>
 static cudaError_t launch_cta(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t* tokens, uint32_t tok_stride,
                               uint32_t* ntok, uint32_t* counter, uint16_t* heads, unsigned long long* sm_slots, uint32_t grid,
                               const uint8_t* tail, uint32_t tail_first, cudaStream_t stream, const StreamSync& sy, int chains_per_sm,
                               unsigned long long* stats) {
     // shared memory per chain: ~39 KiB at PW = 8; ask for the split that just holds the chains of one SM (the rest stays L1)
-    int carve = (int)((sizeof(PipeSmem<PW>) + 1024u) * (size_t)chains_per_sm * 100u / (228u * 1024u)) + 1;
+    int carve = (int)((sizeof(PipeSmem<PW, BPW>) + 1024u) * (size_t)chains_per_sm * 100u / (228u * 1024u)) + 1;
     if (carve > 100) carve = 100;
-    cudaFuncSetAttribute(quick_parse_cta_kernel<PW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    quick_parse_cta_kernel<PW><<<grid, (PW + 1) * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots,
+    cudaFuncSetAttribute(quick_parse_cta_kernel<PW, BPW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    quick_parse_cta_kernel<PW, BPW><<<grid, (PW + 1) * 32, 0, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots,
                                                                    tail, tail_first, sy, stats);
     return cudaGetLastError();
 }
@@ -400,11 +400,13 @@ cudaError_t launch_quick_parse_cta(const uint8_t* in, size_t n, uint32_t chunk, 
         if (e != cudaSuccess) return e;
         tl = tail;
     }
-    switch (warps) {       // producer warps per chain (window = 32 x warps positions); one more warp walks
-        case 2:  return launch_cta<2>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm, stats);
-        case 4:  return launch_cta<4>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm, stats);
-        default: return launch_cta<3>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm, stats);
+    // warps = 10 * (producer warps per chain) + (blocks per producer warp and window); window = 32 x their product <= 128 positions
+#define ZB_CTA(P, B) case 10 * P + B: return launch_cta<P, B>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, sm_slots, grid, tl, tail_first, stream, sy, chains_per_sm, stats)
+    switch (warps) {
+        ZB_CTA(1, 2); ZB_CTA(1, 4); ZB_CTA(2, 1); ZB_CTA(2, 2); ZB_CTA(3, 1); ZB_CTA(4, 1);
+        default: return cudaErrorInvalidValue;
     }
+#undef ZB_CTA
 }
 
 }  // namespace zb
