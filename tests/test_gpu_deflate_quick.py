@@ -187,16 +187,18 @@ def test_slid_window_position_zero_alias(pkg, ctx, zo):
             assert_parity(pkg, ctx, zo, d, 65536, flush)
 
 
-@pytest.mark.parametrize("knobs", [("3", "1", "10"), ("2", "2", "11"), ("4", "1", "8"), ("1", "4", "6")])
-def test_cta_per_chain_parser_is_bit_exact(pkg, zo, knobs, monkeypatch):
-    """K1a v7 (csrc/deflate_quick_cta.cu, opt-in through ZNG_B200_K1=cta): producer warps one window ahead of a walker warp.  Same
+@pytest.mark.parametrize("knobs", [("warp", "", "", ""), ("cta", "3", "1", "10"), ("cta", "2", "2", "11"), ("cta", "4", "1", "8"), ("cta", "1", "4", "6")])
+def test_both_level1_parsers_are_bit_exact(pkg, zo, knobs, monkeypatch):
+    """The two level-1 parsers forced by ZNG_B200_K1: "warp" = K1a v3 (csrc/deflate_quick.cu, one warp per chain), "cta" = K1a v7
+    (csrc/deflate_quick_cta.cu: producer warps one window ahead of a walker warp; several shapes).  Same
     inputs as the shipped parser's tests -- the synthetic mix with a ragged tail, every short length class, repetitive data, the
     post-slide position-0 alias -- compared byte for byte with the oracle, plus 64 MiB against the unmodified reference."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    monkeypatch.setenv("ZNG_B200_K1", "cta")
-    monkeypatch.setenv("ZNG_B200_K1_WARPS", knobs[0]); monkeypatch.setenv("ZNG_B200_K1_BPW", knobs[1]); monkeypatch.setenv("ZNG_B200_K1_CHAINS", knobs[2])
+    monkeypatch.setenv("ZNG_B200_K1", knobs[0])         # default is "auto": v7 up to 8192 chunks per launch, the warp-per-chain parser beyond
+    if knobs[1]:
+        monkeypatch.setenv("ZNG_B200_K1_WARPS", knobs[1]); monkeypatch.setenv("ZNG_B200_K1_BPW", knobs[2]); monkeypatch.setenv("ZNG_B200_K1_CHAINS", knobs[3])
     c = pkg.Context(0)                                   # the knobs are read when a context is created
     try:
         rng = np.random.default_rng(11)

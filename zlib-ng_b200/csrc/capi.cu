@@ -20,6 +20,7 @@ namespace {
 constexpr int kCounters = 64;
 constexpr int kPipeMax = 16;                   // most slabs in flight on the host path (ctx->pipe of them are used)
 constexpr uint32_t kSlabChunksDefault = 4096;  // 256 MiB of input per slab at 64 KiB chunks (ctx->slab_chunks, env ZNG_B200_SLAB_CHUNKS)
+constexpr uint32_t kAutoCtaChunks = 8192;      // ZNG_B200_K1=auto: launches of at most this many chunks take the CTA-per-chain level-1 parser
 constexpr uint32_t kBatchChunks = 16384;       // chunks per K1a/K1b launch pair (token scratch: 4 GiB at 64 KiB chunks)
 
 // K1a -> K1b hand-over: LZ77 token lists (4 B per input byte) + token counts
@@ -100,10 +101,11 @@ struct zng_b200_ctx {
     uint16_t* prevs = nullptr;                 // K2: prev[] slab pool and stale-window images, same (sm, slot) indexing
     uint32_t* vtails = nullptr;
     int chains_per_sm = 24;
-    int k1_cta = 0;                            // level-1 parser: 1 = CTA per chain with L2-resident tables (v5), 0 = warp per chain (env ZNG_B200_K1=warp)
-    int warps_cta = 31;                        // warps per chain of the v5 parser (env ZNG_B200_K1_WARPS: 2, 4, 8)
+    int k1_cta = 2;                            // level-1 parser of the device-resident / slab calls (env ZNG_B200_K1): 0 = warp per chain (K1a v3), 1 = CTA per
+                                               // chain (K1a v7), 2 = auto: v7 up to kAutoCtaChunks chunks per launch, v3 beyond.  The streamed host path keeps v3.
+    int warps_cta = 22;                        // warps per chain of the v5 parser (env ZNG_B200_K1_WARPS: 2, 4, 8)
     unsigned long long* k1_stats = nullptr;    // env ZNG_B200_K1_STATS=1: 16 debug counters of the v6 parser, printed when the context goes
-    int chains_cta = 10;                       // chains (CTAs) per SM of the v5 parser (env ZNG_B200_K1_CHAINS)
+    int chains_cta = 11;                       // chains (CTAs) per SM of the v5 parser (env ZNG_B200_K1_CHAINS)
     int chains_per_sm_l2 = 32;                 // measured on B200: 16 -> 12.4, 24 -> 14.4, 32 -> 15.4 GB/s
     Scratch scratch;                           // for the device-resident entry points; users are ordered by k1_done
     cudaEvent_t k1_done = nullptr;
@@ -236,7 +238,9 @@ int run_deflate_chunks(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size
                "block_emit launch");
             continue;
         }
-        if (ctx->k1_cta)
+        // auto: the CTA-per-chain parser (K1a v7) for batches that leave the warp-per-chain parser's 24 chains per SM under-filled or
+        // barely filled -- it is 5-21 % faster up to ~8 Ki chunks and equal beyond (profiles/r2_latency_small_batches.txt)
+        if (ctx->k1_cta == 1 || (ctx->k1_cta == 2 && nb <= kAutoCtaChunks))
             CK(launch_quick_parse_cta(d_in + off, nbytes, chunk, nb, toks, stride, sc.ntok + c0, ctx->counters + slot, ctx->heads, ctx->sm_slots,
                                       ctx->sms, ctx->chains_cta, ctx->warps_cta, ctx->tails + (size_t)slot * deflate_quick_tail_bytes(), stream, nullptr, ctx->k1_stats),
                "quick_parse_cta launch");
@@ -419,7 +423,7 @@ int zng_b200_ctx_create(zng_b200_ctx** out, int device) {
     ctx->sms = prop.multiProcessorCount;
     if (prop.major < 10) { delete ctx; return ZNG_B200_STREAM_ERROR; }       // sm_100a kernels only
     if (const char* e = getenv("ZNG_B200_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->chains_per_sm = v; }
-    if (const char* e = getenv("ZNG_B200_K1")) ctx->k1_cta = (strcmp(e, "cta") == 0);
+    if (const char* e = getenv("ZNG_B200_K1")) ctx->k1_cta = strcmp(e, "cta") == 0 ? 1 : (strcmp(e, "warp") == 0 ? 0 : 2);
     if (const char* e = getenv("ZNG_B200_K1_STATS")) { if (atoi(e) && cudaMalloc(&ctx->k1_stats, 16 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(ctx->k1_stats, 0, 16 * sizeof(unsigned long long)); }
     if (const char* e = getenv("ZNG_B200_K1_CHAINS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->chains_cta = v; }
     if (const char* e = getenv("ZNG_B200_K1_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 4) ctx->warps_cta = 10 * v + (ctx->warps_cta % 10); }
@@ -1393,7 +1397,7 @@ static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t 
     for (uint32_t j = 0; j < nslabs; j++) S.h_done[j] = 0;
     StreamSync sy; sy.ready = S.d_sync; sy.failed = S.d_sync + 1; sy.done = S.d_sync + 4; sy.done_shift = kStreamSlabShift; sy.patience = patience;
     sy.host_done = S.d_h_done;
-    if (level == 1 && ctx->k1_cta)
+    if (level == 1 && ctx->k1_cta == 1)                                  // only on explicit request: the streamed path is tuned around v3's occupancy
         CK(launch_quick_parse_cta(S.d_in, n, chunk, nch, S.tokens, (uint32_t)tstride, S.ntok, S.d_sync + 2, ctx->heads, ctx->sm_slots,
                                   ctx->sms, ctx->chains_cta, ctx->warps_cta, nullptr, S.parse, &sy, ctx->k1_stats),
            "quick_parse_cta launch");
