@@ -61,3 +61,14 @@ def test_without_a_device_nothing_is_computed_on_the_cpu(pkg, L):
     dl = ctypes.c_size_t(64)
     assert L.zng_compress2(buf.ctypes.data, ctypes.byref(dl), buf.ctypes.data, 10, 1) == pkg.Z_MEM_ERROR
     assert L.zng_b200_device_count() == 0
+
+
+def test_checksum_without_a_device_aborts_instead_of_returning_a_plausible_value(pkg):
+    """zng_crc32 has no way to report an error; a made-up value would end in a corrupt gzip trailer.  No device -> stderr + abort."""
+    import subprocess, sys, torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    code = ("import ctypes, sys; L = ctypes.CDLL(sys.argv[1]); L.zng_crc32.restype = ctypes.c_uint32; "
+            "L.zng_crc32.argtypes = [ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32]; print(L.zng_crc32(0, b'0123456789', 10))")
+    p = subprocess.run([sys.executable, "-c", code, pkg.LIB_PATH], capture_output=True, text=True)
+    assert p.returncode != 0 and "no CPU fallback" in p.stderr and p.stdout.strip() == ""

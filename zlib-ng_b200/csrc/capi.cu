@@ -1428,7 +1428,7 @@ static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t 
     constexpr int kCoCarve = 44;                                         // the split the streamed parse kernel runs with
     int rc = 0;
     uint32_t next_launch = 0, next_drain = 0;
-    const auto t_begin = std::chrono::steady_clock::now();
+    auto t_progress = std::chrono::steady_clock::now();                  // reset whenever a slab is launched or drained
     while (next_drain < nslabs) {
         bool progressed = false;
         if (next_launch < nslabs) {
@@ -1485,8 +1485,9 @@ static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t 
             }
             next_drain++; progressed = true;
         }
+        if (progressed) t_progress = std::chrono::steady_clock::now();
         if (!progressed) {
-            if (std::chrono::steady_clock::now() - t_begin > std::chrono::seconds(30)) {
+            if (std::chrono::steady_clock::now() - t_progress > std::chrono::seconds(30)) {
                 snprintf(ctx->err, sizeof(ctx->err), "streamed pipeline: no progress for 30 s");
                 cudaDeviceSynchronize();
                 return ZNG_B200_CUDA_ERROR;

@@ -7,6 +7,8 @@
  * functions are 32-bit scalar arithmetic on two words and stay on the host, as in the reference.
  */
 #include "zng_host.h"
+#include <stdio.h>
+#include <stdlib.h>
 
 #define POLY 0xedb88320u
 #define BASE 65521u
@@ -61,12 +63,21 @@ uint32_t zng_adler32_combine(uint32_t adler1, uint32_t adler2, z_off64_t len2) {
     return sum1 | (sum2 << 16);
 }
 
+/* zng_crc32 / zng_adler32 cannot report an error (crc32.c:27-41, adler32.c:15-28 return the value), and any value returned after a
+ * failed GPU call would look like a valid checksum -- a caller writing a gzip trailer with it would emit a corrupt stream without
+ * knowing.  There is no CPU implementation to fall back to (north star), so the failure is made impossible to miss: the reason goes
+ * to stderr and the process aborts.  (zng_deflate / zng_inflate report device failures through their return codes instead.) */
+static void checksum_failed(const char *fn, zng_b200_ctx *ctx) {
+    fprintf(stderr, "libzng_b200: %s: %s -- no CPU fallback, aborting\n", fn, ctx ? zng_b200_last_error(ctx) : "no CUDA device / context");
+    abort();
+}
+
 uint32_t zng_crc32_z(uint32_t crc, const uint8_t *buf, size_t len) {
     if (buf == NULL) return 0;                              /* crc32.c:28 */
     if (len == 0) return crc;
     zng_b200_ctx *ctx = zng_b200_thread_ctx();
     uint32_t r = 0;
-    if (!ctx || zng_b200_crc32_host(ctx, buf, len, crc, &r) != ZNG_B200_OK) return 0;   /* no device: no fallback */
+    if (!ctx || zng_b200_crc32_host(ctx, buf, len, crc, &r) != ZNG_B200_OK) checksum_failed("zng_crc32", ctx);
     return r;
 }
 uint32_t zng_crc32(uint32_t crc, const uint8_t *buf, uint32_t len) { return zng_crc32_z(crc, buf, len); }
@@ -76,7 +87,7 @@ uint32_t zng_adler32_z(uint32_t adler, const uint8_t *buf, size_t len) {
     if (len == 0) return adler;
     zng_b200_ctx *ctx = zng_b200_thread_ctx();
     uint32_t r = 1;
-    if (!ctx || zng_b200_adler32_host(ctx, buf, len, adler, &r) != ZNG_B200_OK) return 1;
+    if (!ctx || zng_b200_adler32_host(ctx, buf, len, adler, &r) != ZNG_B200_OK) checksum_failed("zng_adler32", ctx);
     return r;
 }
 uint32_t zng_adler32(uint32_t adler, const uint8_t *buf, uint32_t len) { return zng_adler32_z(adler, buf, len); }

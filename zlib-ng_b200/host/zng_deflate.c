@@ -258,6 +258,7 @@ int32_t zng_deflate(zng_stream *strm, int32_t flush) {
             }
         } else {
             int fin = (flush == Z_FINISH);
+            const size_t kept = s->in_len;                  /* buffered before this call */
             if (s->in_len) {                                /* join buffered bytes with the new input */
                 if (n) { if (in_append(s, src, n)) return Z_MEM_ERROR; }
                 src = s->in_buf; n = s->in_len;
@@ -269,7 +270,10 @@ int32_t zng_deflate(zng_stream *strm, int32_t flush) {
                 static const uint8_t marker[5] = {0, 0, 0, 0xff, 0xff};
                 if (pend_put(s, marker, 5)) return Z_MEM_ERROR;
             }
-            if (r != Z_OK) return r;
+            if (r != Z_OK) {                                /* nothing was consumed: a retry must not see this call's input twice */
+                s->in_len = kept;
+                return r;
+            }
             strm->next_in += took; strm->total_in += took; strm->avail_in = 0; s->in_len = 0;
             if (fin) {
                 s->finished = 1; s->status = ST_FINISH;
