@@ -31,6 +31,7 @@ extern "C" {
 #define ZNG_B200_DATA_ERROR   (-3)
 #define ZNG_B200_MEM_ERROR    (-4)   /* allocation failed (Z_MEM_ERROR) */
 #define ZNG_B200_BUF_ERROR    (-5)   /* output capacity too small (Z_BUF_ERROR) */
+#define ZNG_B200_NOT_RESUMABLE (-6)   /* zng_b200_inflate_stream_feed: a header the resumable decoder leaves to the one-shot path */
 #define ZNG_B200_CUDA_ERROR   (-100) /* a CUDA call failed; see zng_b200_last_error() */
 
 #define ZNG_B200_CHUNK_MAX 65536u
@@ -224,6 +225,20 @@ int zng_b200_inflate_members_host(zng_b200_ctx *ctx, const void *h_in, const uin
  *             (nothing was written) */
 int zng_b200_inflate_stream_host(zng_b200_ctx *ctx, const void *h_in, size_t n, int window_bits, void *h_out, size_t cap,
                                  size_t *out_len, size_t *in_used, uint32_t *check, int32_t *status, uint32_t *detail);
+/* Resumable inflate of ONE stream fed piecewise -- what zng_inflate(Z_NO_FLUSH) of the host library calls (inflate.c:476: the
+ * reference's inflate() is resumable at byte granularity; here the granularity is the deflate block).  Each feed decodes from the last
+ * block boundary the previous one reached to the last boundary inside what has arrived; decoded output is handed over at once,
+ * consumed input is dropped, the check value and the trailer are verified at the end.  Linear work, piecewise output.
+ *   *status    0 fed (more input, or more room in h_out, needed) / 1 stream end and every byte delivered / -3 data error (*detail =
+ *              message id for zng_b200_inflate_msg) / ZNG_B200_NOT_RESUMABLE: FDICT / FHCRC / malformed header -- nothing consumed,
+ *              use zng_b200_inflate_stream_host
+ *   *in_used   bytes of this call's input that belong to the stream (< n only when the stream ended inside them)
+ *   *out_len   bytes written to h_out (at most cap; what does not fit stays pending: call again with n == 0) */
+typedef struct zng_b200_inflate_stream zng_b200_inflate_stream;
+int  zng_b200_inflate_stream_open(zng_b200_ctx *ctx, int window_bits, zng_b200_inflate_stream **out);
+int  zng_b200_inflate_stream_feed(zng_b200_inflate_stream *st, const void *h_in, size_t n, void *h_out, size_t cap,
+                                  size_t *in_used, size_t *out_len, int32_t *status, uint32_t *detail, uint32_t *check);
+void zng_b200_inflate_stream_close(zng_b200_inflate_stream *st);
 int zng_b200_crc32_host(zng_b200_ctx *ctx, const void *h_buf, size_t n, uint32_t init, uint32_t *result);
 int zng_b200_adler32_host(zng_b200_ctx *ctx, const void *h_buf, size_t n, uint32_t init, uint32_t *result);
 

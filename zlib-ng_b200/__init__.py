@@ -65,6 +65,9 @@ def lib() -> ctypes.CDLL:
         "zng_b200_deflate_host": (c_int, [vp, vp, c_size_t, c_uint32, c_int, c_int, vp, c_size_t, POINTER(c_size_t), POINTER(c_uint32), POINTER(c_uint32)]),
         "zng_b200_deflate_host_primed": (c_int, [vp, vp, vp, c_size_t, c_int, vp, c_size_t, POINTER(c_size_t), POINTER(c_uint32), POINTER(c_uint32)]),
         "zng_b200_deflate_host_primed_level": (c_int, [vp, vp, vp, c_size_t, c_int, c_int, vp, c_size_t, POINTER(c_size_t), POINTER(c_uint32), POINTER(c_uint32)]),
+        "zng_b200_inflate_stream_open": (c_int, [vp, c_int, POINTER(c_void_p)]),
+        "zng_b200_inflate_stream_feed": (c_int, [vp, vp, c_size_t, vp, c_size_t, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_int32), POINTER(c_uint32), POINTER(c_uint32)]),
+        "zng_b200_inflate_stream_close": (None, [vp]),
         "zng_b200_crc32_host": (c_int, [vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
         "zng_b200_adler32_host": (c_int, [vp, vp, c_size_t, c_uint32, POINTER(c_uint32)]),
         "zng_b200_comm_unique_id": (c_int, [vp, c_size_t]),

@@ -1182,6 +1182,191 @@ int zng_b200_inflate_stream_host(zng_b200_ctx* ctx, const void* h_in, size_t n, 
     return 0;
 }
 
+// ---------------------------------------------------------------- resumable inflate of ONE stream fed piecewise
+// What zng_inflate(Z_NO_FLUSH / Z_SYNC_FLUSH) of the host library calls.  The member decoder (K4) runs in RESUME mode: each feed decodes
+// from the last block boundary the previous feed reached -- the output so far stays in a device buffer, where back-references
+// reach it -- to the last block boundary inside what has arrived; the bytes decoded for good go to the caller at once and the
+// input behind them is dropped.  Work is linear in the stream (a feed re-decodes at most the one block it could not finish),
+// output arrives piecewise.  The check value (CRC-32 / Adler-32 of all output, K3) and the trailer are verified at the end.
+// Streams this layer does not parse itself (FDICT, FHCRC, header errors) are reported as "not resumable": the caller keeps the
+// one-shot path for them.
+struct zng_b200_inflate_stream {
+    zng_b200_ctx* ctx = nullptr;
+    int window_bits = 15;
+    Wrapper wr; bool header_done = false;
+    std::vector<uint8_t> in;                      // input from the last boundary on (after the header)
+    uint32_t start_bit = 0;
+    uint8_t* d_in = nullptr; size_t d_in_cap = 0;
+    uint8_t* d_out = nullptr; size_t d_out_cap = 0;
+    uint64_t out_total = 0, delivered = 0;        // decoded for good / handed to the caller
+    bool body_done = false, finished = false;
+    uint32_t check = 0;
+    size_t last_try = 0;                          // retained bytes at the last attempt that found no new boundary
+    uint32_t* d_io = nullptr;                     // offsets (u64 x 4) | results (u32 x 8) | resume_io (u32 x 4)
+    uint32_t* h_io = nullptr;
+};
+
+int zng_b200_inflate_stream_open(zng_b200_ctx* ctx, int window_bits, zng_b200_inflate_stream** out) {
+    if (!ctx || !out) return ZNG_B200_STREAM_ERROR;
+    int wb = window_bits;
+    if (wb < 0) { if (wb < -15) return bad(ctx, "windowBits out of range"); wb = -wb; } else if (wb < 48) wb &= 15;
+    if (wb && (wb < 8 || wb > 15)) return bad(ctx, "windowBits out of range");
+    DeviceGuard g(ctx->device);
+    zng_b200_inflate_stream* st = new (std::nothrow) zng_b200_inflate_stream();
+    if (!st) return ZNG_B200_MEM_ERROR;
+    st->ctx = ctx; st->window_bits = window_bits;
+    if (cudaMalloc(&st->d_io, 128) != cudaSuccess || cudaHostAlloc(&st->h_io, 128, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(st->d_io); delete st; return ZNG_B200_MEM_ERROR;
+    }
+    *out = st;
+    return 0;
+}
+
+void zng_b200_inflate_stream_close(zng_b200_inflate_stream* st) {
+    if (!st) return;
+    DeviceGuard g(st->ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(st->d_in); cudaFree(st->d_out); cudaFree(st->d_io); cudaFreeHost(st->h_io);
+    delete st;
+}
+
+// status: 0 = fed, more input (or more room for output) needed; 1 = stream end, every byte delivered; -3 = data error (*detail =
+// message id, zng_b200_inflate_msg); -6 (ZNG_B200_NOT_RESUMABLE) = a header this layer leaves to the one-shot path, nothing consumed.
+// *in_used: bytes of THIS call's input that belong to the stream (less than n only at the stream's end); *out_len: bytes written to h_out.
+int zng_b200_inflate_stream_feed(zng_b200_inflate_stream* st, const void* h_in, size_t n, void* h_out, size_t cap,
+                                 size_t* in_used, size_t* out_len, int32_t* status, uint32_t* detail, uint32_t* check) {
+    if (!st || !in_used || !out_len || !status || (n && !h_in) || (cap && !h_out)) return ZNG_B200_STREAM_ERROR;
+    zng_b200_ctx* ctx = st->ctx;
+    DeviceGuard g(ctx->device);
+    *in_used = n; *out_len = 0; *status = 0;
+    if (detail) *detail = 0;
+    auto deliver = [&]() -> int {
+        const uint64_t avail = st->out_total - st->delivered;
+        const size_t give = (size_t)std::min<uint64_t>(avail, cap - *out_len);
+        if (give) {
+            CK(cudaMemcpy((uint8_t*)h_out + *out_len, st->d_out + st->delivered, give, cudaMemcpyDeviceToHost), "D2H output");
+            st->delivered += give; *out_len += give;
+        }
+        return 0;
+    };
+    if (st->finished) { int r = deliver(); if (r) return r; *in_used = 0; *status = st->delivered == st->out_total ? 1 : 0; if (check) *check = st->check; return 0; }
+    if (n) st->in.insert(st->in.end(), (const uint8_t*)h_in, (const uint8_t*)h_in + n);
+    if (!st->header_done) {
+        const int wrap = st->window_bits < 0 ? 0 : (st->window_bits >> 4) + 5;
+        if (wrap == 0) { st->wr.kind = 0; st->wr.body = 0; st->header_done = true; }
+        else {
+            // Nothing is taken before the header parses: the caller keeps the bytes and passes them again with more.  An incomplete
+            // header waits (a gzip header with names can be long); what parse_wrapper refuses must go to the one-shot path.
+            if (st->in.size() < 2) { st->in.clear(); *in_used = 0; return 0; }
+            const bool gz = (wrap & 2) && st->in[0] == 0x1f && st->in[1] == 0x8b;
+            if (parse_wrapper(st->in.data(), st->in.size(), st->window_bits, st->wr) != 0) {
+                const bool maybe_short = gz && st->in.size() < 4096 && !(st->in.size() >= 4 && (st->in[2] != 8 || (st->in[3] & 0xe2)));
+                st->in.clear(); *in_used = 0;
+                if (!maybe_short) *status = ZNG_B200_NOT_RESUMABLE;
+                return 0;
+            }
+            st->in.erase(st->in.begin(), st->in.begin() + (ptrdiff_t)st->wr.body);
+            st->header_done = true;
+        }
+    }
+    // ---- decode from the last boundary, as far as the input goes
+    // Every call that brings input is an attempt: the bytes after the stream's end must stay with the caller of THIS call (zlib's
+    // next_in / total_in contract), so input is never parked undecoded.  An attempt that crossed no block boundary decodes the
+    // open block again next time: the cost is bounded by (block size / piece size) passes over one block, not over the stream.
+    while (!st->body_done && !st->in.empty() && (st->last_try == 0 || st->in.size() > st->last_try)) {
+        const size_t nin = st->in.size();
+        if (nin > 0xfffffff0ull || st->out_total > 0xe0000000ull) return bad(ctx, "resumable inflate: stream too large for one member decoder");
+        if (st->d_in_cap < nin + 64) {
+            if (st->d_in) cudaFree(st->d_in);
+            st->d_in = nullptr; st->d_in_cap = 0;
+            size_t want = nin + nin / 2 + (1 << 20);
+            CK(cudaMalloc(&st->d_in, want), "cudaMalloc(resumable in)");
+            st->d_in_cap = want;
+        }
+        size_t want_out = (size_t)st->out_total + std::max<size_t>(4 * nin, (size_t)4 << 20) + 65536;
+        if (want_out > 0xfffffff0ull) want_out = 0xfffffff0ull;
+        if (st->d_out_cap < want_out) {
+            uint8_t* nb = nullptr;
+            want_out += want_out / 2;
+            if (want_out > 0xfffffff0ull) want_out = 0xfffffff0ull;
+            CK(cudaMalloc(&nb, want_out), "cudaMalloc(resumable out)");
+            if (st->d_out && st->out_total) CK(cudaMemcpy(nb, st->d_out, (size_t)st->out_total, cudaMemcpyDeviceToDevice), "copy history");
+            cudaFree(st->d_out);
+            st->d_out = nb; st->d_out_cap = want_out;
+        }
+        CK(cudaMemcpyAsync(st->d_in, st->in.data(), nin, cudaMemcpyHostToDevice, 0), "H2D");
+        CK(cudaMemsetAsync(st->d_in + nin, 0, 64, 0), "memset");
+        uint64_t* ho = reinterpret_cast<uint64_t*>(st->h_io);                 // [0..1] in offsets, [2..3] out offsets
+        uint32_t* hr = st->h_io + 8;                                            // [0..4] results, [8..11] resume_io
+        ho[0] = 0; ho[1] = nin; ho[2] = 0; ho[3] = st->d_out_cap;
+        hr[8] = st->start_bit; hr[9] = (uint32_t)st->out_total; hr[10] = 0; hr[11] = 0;
+        CK(cudaMemcpyAsync(st->d_io, st->h_io, 128, cudaMemcpyHostToDevice, 0), "H2D io");
+        uint64_t* d_o = reinterpret_cast<uint64_t*>(st->d_io);
+        uint32_t* d_r = st->d_io + 8;
+        const int slot = next_slot(ctx);
+        CK(launch_inflate_members(st->d_in, d_o, 1, -15, st->d_out, d_o + 2, d_r + 0, d_r + 1, (int32_t*)(d_r + 2), d_r + 3, d_r + 4,
+                                  ctx->counters + slot, ctx->sms, 0, 8, d_r + 8), "inflate launch (resume)");
+        CK(cudaMemcpyAsync(st->h_io, st->d_io, 128, cudaMemcpyDeviceToHost, 0), "D2H io");
+        CK(cudaStreamSynchronize(0), "sync");
+        const uint32_t o_len = hr[0]; const int32_t ret = (int32_t)hr[2]; const uint32_t used = hr[3], det = hr[4];
+        const uint32_t bb_byte = hr[8], bb_bit = hr[9], bb_out = hr[10];
+        if (ret == ZNG_B200_DATA_ERROR) { *status = ZNG_B200_DATA_ERROR; if (detail) *detail = det & 0xffu; int r = 0; st->out_total = bb_out; r = deliver(); return r; }
+        if (ret == 1) {                                                         // the final block is decoded
+            st->out_total = o_len; st->body_done = true;
+            st->in.erase(st->in.begin(), st->in.begin() + (ptrdiff_t)std::min<size_t>(used, st->in.size()));
+            st->start_bit = 0; st->last_try = 0;
+            break;
+        }
+        const bool out_full = (det & 0x100u) && !(det & 0x200u);
+        if (out_full) {                                                          // the output buffer filled up: double it and go on
+            size_t want = st->d_out_cap * 2;
+            if (want > 0xfffffff0ull) { if (st->d_out_cap >= 0xfffffff0ull) return bad(ctx, "resumable inflate: output beyond 4 GiB"); want = 0xfffffff0ull; }
+            uint8_t* nb = nullptr;
+            CK(cudaMalloc(&nb, want), "cudaMalloc(resumable out)");
+            CK(cudaMemcpy(nb, st->d_out, (size_t)bb_out, cudaMemcpyDeviceToDevice), "copy history");
+            cudaFree(st->d_out); st->d_out = nb; st->d_out_cap = want;
+        }
+        st->out_total = bb_out;
+        if (bb_byte) st->in.erase(st->in.begin(), st->in.begin() + (ptrdiff_t)bb_byte);
+        st->start_bit = bb_bit;
+        if (out_full) { st->last_try = 0; continue; }
+        st->last_try = st->in.size();                                            // all of it has been tried: wait for more input
+        break;                                                                   // ran out of input: wait for the next feed
+    }
+    int r = deliver();
+    if (r) return r;
+    if (st->body_done && !st->finished) {
+        const size_t tlen = st->wr.kind == 2 ? 8 : (st->wr.kind == 1 ? 4 : 0);
+        if (st->in.size() >= tlen) {
+            uint32_t chk = 0;
+            if (st->wr.kind) {
+                r = st->wr.kind == 2 ? zng_b200_crc32(ctx, st->d_out, (size_t)st->out_total, 0, ctx->d_result, nullptr)
+                                     : zng_b200_adler32(ctx, st->d_out, (size_t)st->out_total, 1, ctx->d_result, nullptr);
+                if (r) return r;
+                CK(cudaMemcpy(&chk, ctx->d_result, 4, cudaMemcpyDeviceToHost), "D2H check");
+            }
+            st->check = chk;
+            const uint8_t* t = st->in.data();
+            if (st->wr.kind == 2) {
+                const uint32_t c = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24), l = t[4] | (t[5] << 8) | (t[6] << 16) | ((uint32_t)t[7] << 24);
+                if (c != chk) { *status = ZNG_B200_DATA_ERROR; if (detail) *detail = 17; return 0; }
+                if (l != (uint32_t)st->out_total) { *status = ZNG_B200_DATA_ERROR; if (detail) *detail = 18; return 0; }
+            } else if (st->wr.kind == 1) {
+                const uint32_t c = ((uint32_t)t[0] << 24) | (t[1] << 16) | (t[2] << 8) | t[3];
+                if (c != chk) { *status = ZNG_B200_DATA_ERROR; if (detail) *detail = 17; return 0; }
+            }
+            st->in.erase(st->in.begin(), st->in.begin() + (ptrdiff_t)tlen);
+            st->finished = true;
+            // what is left in `in` follows the stream: it came with this call (earlier calls ended inside the stream)
+            const size_t left = st->in.size();
+            *in_used = left <= n ? n - left : 0;
+            st->in.clear();
+        }
+    }
+    if (st->finished) { if (check) *check = st->check; *status = st->delivered == st->out_total ? 1 : 0; }
+    return 0;
+}
+
 // ---------------------------------------------------------------- host-buffer entry points
 static int host_checksum(zng_b200_ctx* ctx, const void* h_buf, size_t n, uint32_t init, uint32_t* result, bool crc, void* h_copy = nullptr) {
     if (!ctx || !result) return ZNG_B200_STREAM_ERROR;

@@ -194,7 +194,7 @@ __device__ __forceinline__ void dist_base(uint32_t ds, uint32_t& base, uint32_t&
     else { ext = (ds >> 1) - 1u; base = 1u + ((2u + (ds & 1u)) << ext); }
 }
 
-struct InfResult { int32_t ret; uint32_t detail, out_len, in_used, check; };
+struct InfResult { int32_t ret; uint32_t detail, out_len, in_used, check, bb_byte, bb_bit, bb_out; };
 
 // CRC-32 (gz != 0) or Adler-32 of ob[0..o): 32 contiguous slices, one per lane, then the combine algebra.
 __device__ uint32_t warp_check(const uint8_t* ob, uint32_t o, bool gz, const InfShared& S, unsigned lane) {
@@ -229,21 +229,29 @@ __device__ uint32_t warp_check(const uint8_t* ob, uint32_t o, bool gz, const Inf
 // mode bit 0 (segment): the input is one flush-delimited piece of a longer raw stream; running out of input exactly at
 // a block boundary is a clean end (ret 0 = Z_OK) instead of Z_BUF_ERROR.  mode bit 1 (count): decode the symbols and add
 // up the lengths only -- nothing is stored, the output capacity is unlimited (the size pass of the parallel stream inflate).
+// mode bit 3 (resume): the input starts at a block boundary inside a raw deflate stream, `start_bit` bits into its first byte, and
+// gout[0 .. out_start) holds the stream's output so far (the history back-references reach into).  No header, no trailer, no staging.
+// Besides the usual results the decoder reports the last block boundary it passed -- (bb_byte, bb_bit) into the input, bb_out = output
+// length there -- so that a caller fed piecewise can drop what is decoded for good and resume there with more input
+// (zng_b200_inflate_stream_feed, what zng_inflate(Z_NO_FLUSH) calls).
 __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, uint8_t* gout, uint32_t cap,
-                               InfShared& S, InfWarp& P, const Code& FL, const Code& FD, InfResult& R, unsigned lane, int mode) {
-    const bool segment = mode & 1, count = mode & 2;
+                               InfShared& S, InfWarp& P, const Code& FL, const Code& FD, InfResult& R, unsigned lane, int mode,
+                               uint32_t start_bit = 0, uint32_t out_start = 0) {
+    const bool segment = mode & 1, count = mode & 2, resume = mode & 8;
     if (count) cap = 0xffffffffu;
     const uint32_t sk0 = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3u);
     const uint32_t* w = reinterpret_cast<const uint32_t*>(in - sk0);
     const uint32_t e = sk0 + n;
-    const bool staged = cap <= kInfStage && !count;
+    const bool staged = cap <= kInfStage && !count && !resume;
     uint8_t* ob = staged ? P.stage : gout;
-    uint32_t o = 0, bp = sk0;
+    uint32_t o = resume ? out_start : 0u, bp = sk0;
+    R.bb_byte = 0; R.bb_bit = start_bit; R.bb_out = o;
     bool gz = false;
     Reader b;
     R.ret = -5; R.detail = 0; R.check = 0;                  // anything that does not reach the end under Z_FINISH: Z_BUF_ERROR
     int wrap, wbits = window_bits;
     if (wbits < 0) { wrap = 0; wbits = -wbits; } else { wrap = (wbits >> 4) + 5; if (wbits < 48) wbits &= 15; }
+    if (resume) wrap = 0;
     b.init(w, e, e);
 
     if (wrap) {                                             // HEAD
@@ -290,8 +298,13 @@ __device__ void inflate_member(const uint8_t* in, uint32_t n, int window_bits, u
         }
     }
     b.init(w, bp, e);
+    if (resume && start_bit) { b.refill(); if (b.bits < start_bit) INF_MORE_IN(); b.drop(start_bit); }
 
     for (bool last = false; !last;) {                       // TYPEDO
+        if (resume) {                                       // a block boundary: everything before it is decoded for good
+            const uint32_t bits_used = 8u * (min(4u * b.wi, b.e) - sk0) - b.bits;
+            R.bb_byte = bits_used >> 3; R.bb_bit = bits_used & 7u; R.bb_out = o;
+        }
         b.refill();
         if (segment && b.bits == 0u) { R.ret = 0; goto done; }   // every byte used, at a block boundary
         if (b.bits < 3u) INF_MORE_IN();
@@ -475,7 +488,7 @@ __global__ void __launch_bounds__(kInfWarps * 32)
 inflate_members_kernel(const uint8_t* __restrict__ in, const uint64_t* __restrict__ in_off, uint32_t n_members, int window_bits,
                        uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off, uint32_t* __restrict__ sizes,
                        uint32_t* __restrict__ checks, int32_t* __restrict__ status, uint32_t* __restrict__ in_used,
-                       uint32_t* __restrict__ detail, uint32_t* __restrict__ counter, int mode) {
+                       uint32_t* __restrict__ detail, uint32_t* __restrict__ counter, int mode, uint32_t* __restrict__ resume_io) {
     extern __shared__ __align__(16) unsigned char inf_smem[];
     InfShared& S = *reinterpret_cast<InfShared*>(inf_smem);
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -506,8 +519,11 @@ inflate_members_kernel(const uint8_t* __restrict__ in, const uint64_t* __restric
         const size_t mi = (mode & 4) ? 2u * (size_t)m : (size_t)m;
         const uint64_t i0 = in_off[mi], i1 = in_off[mi + 1u], o0 = out_off[mi], o1 = out_off[mi + 1u];
         InfResult R;
-        inflate_member(in + i0, (uint32_t)(i1 - i0), window_bits, out + o0, (uint32_t)(o1 - o0), S, P, FL, FD, R, lane, mode);
+        // resume mode: resume_io[4m .. 4m+4) = {start_bit, out_start} in, {bb_byte, bb_bit | bb_out handled below} out
+        const uint32_t sb = (mode & 8) ? resume_io[4u * m] : 0u, os = (mode & 8) ? resume_io[4u * m + 1u] : 0u;
+        inflate_member(in + i0, (uint32_t)(i1 - i0), window_bits, out + o0, (uint32_t)(o1 - o0), S, P, FL, FD, R, lane, mode, sb, os);
         if (lane == 0u) {
+            if (mode & 8) { resume_io[4u * m] = R.bb_byte; resume_io[4u * m + 1u] = R.bb_bit; resume_io[4u * m + 2u] = R.bb_out; }
             status[m] = R.ret; sizes[m] = R.out_len;
             if (checks) checks[m] = R.check;
             if (in_used) in_used[m] = R.in_used;
@@ -518,8 +534,10 @@ inflate_members_kernel(const uint8_t* __restrict__ in, const uint64_t* __restric
 
 cudaError_t launch_inflate_members(const uint8_t* in, const uint64_t* in_off, uint32_t n_members, int window_bits,
                                    uint8_t* out, const uint64_t* out_off, uint32_t* sizes, uint32_t* checks, int32_t* status,
-                                   uint32_t* in_used, uint32_t* detail, uint32_t* counter, int num_sms, cudaStream_t stream, int mode) {
+                                   uint32_t* in_used, uint32_t* detail, uint32_t* counter, int num_sms, cudaStream_t stream, int mode,
+                                   uint32_t* resume_io) {
     if (n_members == 0) return cudaSuccess;
+    if ((mode & 8) && !resume_io) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(inflate_members_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InfShared));
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
@@ -528,7 +546,7 @@ cudaError_t launch_inflate_members(const uint8_t* in, const uint64_t* in_off, ui
     const uint32_t need = (n_members + kInfWarps - 1u) / kInfWarps;
     if (grid > need) grid = need;
     inflate_members_kernel<<<grid, kInfWarps * 32, sizeof(InfShared), stream>>>(in, in_off, n_members, window_bits, out, out_off,
-                                                                                sizes, checks, status, in_used, detail, counter, mode);
+                                                                                sizes, checks, status, in_used, detail, counter, mode, resume_io);
     return cudaGetLastError();
 }
 

@@ -80,7 +80,8 @@ cudaError_t launch_adler32_fold(const uint32_t* adlers, uint32_t ntiles, uint32_
 cudaError_t launch_inflate_members(const uint8_t* in, const uint64_t* in_off, uint32_t n_members, int window_bits,
                                    uint8_t* out, const uint64_t* out_off, uint32_t* sizes, uint32_t* checks, int32_t* status,
                                    uint32_t* in_used, uint32_t* detail, uint32_t* counter, int num_sms, cudaStream_t stream,
-                                   int mode = 0);   // bit 0: flush-delimited segment of a raw stream; bit 1: sizes only; bit 2: (begin, end) offset pairs
+                                   int mode = 0,    // bit 0: flush-delimited segment of a raw stream; bit 1: sizes only; bit 2: (begin, end) offset pairs;
+                                   uint32_t* resume_io = nullptr);   // bit 3: resume at a block boundary: 4 words per member, in {start_bit, out_start}, out {bb_byte, bb_bit, bb_out}
 cudaError_t launch_marker_scan(const uint8_t* in, size_t n, size_t from, unsigned long long* pos, uint32_t cap, uint32_t* count,
                                int num_sms, cudaStream_t stream);
 const char* inflate_msg(uint32_t id);

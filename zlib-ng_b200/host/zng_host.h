@@ -29,6 +29,8 @@ struct internal_state {
     uint8_t *dict; int have_dict;
     /* inflate, incremental use: retained bytes at which the next decode attempt is due, and the size of the last piece fed */
     size_t next_try, last_piece;
+    /* inflate, incremental use: the resumable device decoder (zng_b200_inflate_stream_*); no_resume: its header check sent the stream to the one-shot path */
+    zng_b200_inflate_stream *res; int res_started, no_resume;
     int after_sync;            /* a Z_SYNC_FLUSH closed the (only) piece of a stream without dictionary: nothing may follow but Reset */
 };
 

@@ -13,10 +13,12 @@
  * what the reference returns (code, msg, output, total_in, total_out, adler).  Incremental use (Z_NO_FLUSH with
  * partial input) is accepted: input is retained, output is delivered once the member has been decoded, and
  * next_in/avail_in are wound back to the end of the member so that concatenated members can follow.
- * A decode attempt over an incomplete member costs the whole retained input, so an ordinary "read 64 KiB, inflate" loop
- * must not attempt one per call (that is quadratic in the member size): after a failed attempt the next one is due when
- * the retained input has grown by half, or when the piece fed is shorter than the one before (the last read of a file),
- * or on Z_FINISH, or on a call without new input.  Output therefore arrives at the end of the member, not piecewise.
+ * Piecewise use goes through the resumable device decoder (zng_b200_inflate_stream_feed): every call decodes from the last deflate
+ * block boundary reached so far to the last one inside the input that has arrived, hands the decoded bytes over at once and
+ * drops the input behind them -- linear work, piecewise output, like the reference's resumable inflate() at block granularity.
+ * Streams whose header that decoder does not parse itself (FDICT, FHCRC, malformed) keep the retained-member path, where a
+ * decode attempt costs the whole retained input and is therefore repeated only when the input has grown by half, when the piece
+ * fed is shorter than the one before, on Z_FINISH, or on a call without new input.
  */
 #include "zng_host.h"
 #include <stdlib.h>
@@ -42,6 +44,8 @@ int32_t zng_inflateReset(zng_stream *strm) {
     s->finished = 0;
     s->check_len = 0;                                       /* bytes of the member's output already handed out */
     s->next_try = 0; s->last_piece = 0;
+    if (s->res) { zng_b200_inflate_stream_close(s->res); s->res = NULL; }
+    s->res_started = 0; s->no_resume = 0;
     return Z_OK;
 }
 
@@ -69,6 +73,7 @@ int32_t zng_inflateEnd(zng_stream *strm) {
     if (istate_check(strm)) return Z_STREAM_ERROR;
     struct internal_state *s = strm->state;
     free(s->in_buf); free(s->pend);
+    if (s->res) zng_b200_inflate_stream_close(s->res);
     strm->zfree(strm->opaque, s);
     strm->state = NULL;
     return Z_OK;
@@ -108,6 +113,13 @@ int32_t zng_inflate(zng_stream *strm, int32_t flush) {
     if (s->status == IN_DICT) return Z_NEED_DICT;           /* zng_inflateSetDictionary is outside the hot path */
     const size_t in0 = strm->avail_in, out0 = strm->avail_out;
     if (s->status == IN_DONE) {
+        if (s->res_started) {                               /* output still pending in the resumable decoder */
+            size_t iu = 0, ol = 0; int32_t st = 0;
+            if (zng_b200_inflate_stream_feed(s->res, NULL, 0, strm->next_out, strm->avail_out, &iu, &ol, &st, NULL, NULL) != ZNG_B200_OK) return Z_MEM_ERROR;
+            strm->next_out += ol; strm->avail_out -= (uint32_t)ol; strm->total_out += ol;
+            if (st == 1) return Z_STREAM_END;
+            return flush == Z_FINISH ? Z_BUF_ERROR : Z_OK;
+        }
         deliver(strm);
         if (s->pend_pos == s->pend_len) return Z_STREAM_END;
         return flush == Z_FINISH ? Z_BUF_ERROR : Z_OK;
@@ -127,6 +139,49 @@ int32_t zng_inflate(zng_stream *strm, int32_t flush) {
         src = s->in_buf; n += s->in_len;
     }
     const size_t kept = s->in_len;
+
+    /* ---- piecewise use: the resumable decoder (block-boundary checkpoints on the device): linear work, output as it is decoded.
+     * The one-shot call (a complete stream with Z_FINISH, nothing retained) keeps the path below, whose codes, messages and
+     * total_in are the reference's to the byte. */
+    if (!s->no_resume && (s->res_started || !(kept == 0 && flush == Z_FINISH))) {
+        zng_b200_ctx *ctx = zng_b200_thread_ctx();
+        if (!ctx) { strm->msg = "no CUDA device"; return Z_MEM_ERROR; }
+        if (!s->res && zng_b200_inflate_stream_open(ctx, s->wrap, &s->res) != ZNG_B200_OK) return Z_MEM_ERROR;
+        size_t iu = 0, ol = 0; int32_t st = 0; uint32_t det = 0, chk = 0;
+        if (zng_b200_inflate_stream_feed(s->res, src, n, strm->next_out, strm->avail_out, &iu, &ol, &st, &det, &chk) != ZNG_B200_OK) {
+            strm->msg = zng_b200_last_error(ctx); return Z_MEM_ERROR;
+        }
+        if (st == ZNG_B200_NOT_RESUMABLE) s->no_resume = 1;                   /* FDICT / FHCRC / header errors: the exact path below */
+        else if (iu == 0 && n != 0 && st == 0 && !s->res_started) {
+            /* the header is not complete yet: keep the bytes here and pass them again with the next piece */
+            if (kept == 0) {
+                if (n > s->in_cap) { uint8_t *p = (uint8_t *)realloc(s->in_buf, n); if (!p) return Z_MEM_ERROR; s->in_buf = p; s->in_cap = n; }
+                memcpy(s->in_buf, src, n);
+            }
+            s->in_len = n;
+            strm->next_in += in0; strm->total_in += in0; strm->avail_in = 0;
+            return flush == Z_FINISH ? Z_BUF_ERROR : (in0 ? Z_OK : Z_BUF_ERROR);
+        } else {
+            s->res_started = 1; s->in_len = 0;
+            strm->next_out += ol; strm->avail_out -= (uint32_t)ol; strm->total_out += ol;
+            const size_t used_now = iu > kept ? iu - kept : 0;                  /* of this call's input */
+            strm->next_in += used_now; strm->avail_in -= (uint32_t)used_now; strm->total_in += used_now;
+            if (st == ZNG_B200_DATA_ERROR) {
+                strm->msg = zng_b200_inflate_msg(det);
+                strm->next_in += strm->avail_in; strm->total_in += strm->avail_in; strm->avail_in = 0;
+                s->status = IN_BAD;
+                return Z_DATA_ERROR;
+            }
+            if (st == 1 || (s->res && iu < n)) {                                /* the stream ended (maybe with output still pending) */
+                strm->adler = chk;
+                s->status = IN_DONE;
+                if (st == 1) return Z_STREAM_END;
+                return flush == Z_FINISH ? Z_BUF_ERROR : Z_OK;
+            }
+            if (flush == Z_FINISH) return Z_BUF_ERROR;                          /* incomplete stream, or no room for its output */
+            return (in0 || ol) ? Z_OK : Z_BUF_ERROR;                            /* inflate.c:1197-1199: no progress */
+        }
+    }
 
     if (flush != Z_FINISH && in0 != 0 && s->next_try && n < s->next_try && in0 >= s->last_piece) {
         /* not due yet (see the header): keep the bytes, consume them, no device work */
