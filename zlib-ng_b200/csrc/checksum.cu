@@ -26,11 +26,14 @@ namespace zb {
 constexpr int      kCkWarps  = 32;           // tiles in flight per CTA (one per warp)
 constexpr uint32_t kCkRow    = 512;          // bytes per warp row (32 lanes x 16)
 
-struct X2N { uint32_t v[32]; };            // x^(2^k) mod P, k = 0..31 (crc32_braid_tbl.h:9437-9444 holds the same values)
+constexpr uint32_t kCkBigEntries = 256 + 256 + 512 + 128;                      // fields of 8, 8, 9 and 7 bits
+struct X2N { uint32_t v[32]; };
+// shifts done as multiplies (FMA pipe): R = 32 (128-byte entries): w >> 8, w >> 16, w << 7; R = 1 (4-byte entries): w >> 13, w >> 21, w << 2, w >> 5
+struct CkMul { uint32_t m[7]; };            // x^(2^k) mod P, k = 0..31 (crc32_braid_tbl.h:9437-9444 holds the same values)
 
 template <int R>                             // R = 32: one copy of the tables per lane (conflict free, 128 KiB); R = 1: one shared copy (4 KiB)
 struct CkShared {
-    uint32_t big[4][256][R];                 // the advance-by-512-bytes tables
+    uint32_t big[kCkBigEntries][R];          // the advance-by-512-bytes tables of the four bit fields (see ZB_LK)
     uint32_t t4[4][256];                     // ordinary slicing-by-4 tables (heads / tails)
     uint32_t klast[128];                     // x^(8 * (512 - 16*lane - 4*k)): last-row accumulators -> end of the rows
     uint32_t x2n[32];
@@ -57,7 +60,7 @@ __device__ uint32_t crc_serial(const CkShared<R>& s, uint32_t c, const uint8_t* 
 template <bool kCrc, bool kAdler, int R = 32>
 __global__ void __launch_bounds__(kCkWarps * 32, 1)
 checksum_tiles_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t tile_bytes, uint32_t ntiles,
-                      uint32_t* __restrict__ crcs, uint32_t* __restrict__ adlers, const X2N x2n_host) {
+                      uint32_t* __restrict__ crcs, uint32_t* __restrict__ adlers, const X2N x2n_host, const CkMul mul) {
     extern __shared__ __align__(16) unsigned char ck_smem[];
     CkShared<R>& s = *reinterpret_cast<CkShared<R>*>(ck_smem);
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -67,16 +70,19 @@ checksum_tiles_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t tile_by
         for (unsigned e = tid; e < 1024u; e += blockDim.x) s.t4[e >> 8][e & 255u] = crc_table_entry(e & 255u, (int)(e >> 8));
         __syncthreads();
         const uint32_t adv = x2nmodp(s.x2n, kCkRow, 3);                         // x^(8*512)
-        for (unsigned e = tid; e < 1024u; e += blockDim.x) {
-            const uint32_t v = multmodp(adv, (e & 255u) << (8u * (e >> 8)));      // state with one byte set, 512 bytes later
+        for (unsigned e = tid; e < kCkBigEntries; e += blockDim.x) {
+            // entry e = the word with one field set, 512 bytes later: bits 14..7 | 22..15 | 31..23 | 6..0 (see ZB_LK)
+            const uint32_t word = e < 256u ? e << 7 : (e < 512u ? (e - 256u) << 15 : (e < 1024u ? (e - 512u) << 23 : e - 1024u));
+            const uint32_t v = multmodp(adv, word);
 #pragma unroll 8
-            for (int r = 0; r < R; r++) s.big[e >> 8][e & 255u][r] = v;
+            for (int r = 0; r < R; r++) s.big[e][r] = v;
         }
         if (tid < 128u) s.klast[tid] = x2nmodp(s.x2n, kCkRow - 16u * (tid >> 2) - 4u * (tid & 3u), 3);
         __syncthreads();
     }
-    // byte offsets into `big`: table k at k*1024*R, entry b at b*4*R, (R = 32) this lane's copy at lane*4
-    const unsigned char* bigb = reinterpret_cast<const unsigned char*>(&s.big[0][0][0]) + (R == 32 ? lane * 4u : 0u);
+    // byte offsets into `big`: entry e at e*4*R, (R = 32) this lane's copy at lane*4
+    const unsigned char* bigb = reinterpret_cast<const unsigned char*>(&s.big[0][0]) + (R == 32 ? lane * 4u : 0u);
+    const uint32_t m1 = mul.m[R == 32 ? 0 : 3], m2 = mul.m[R == 32 ? 1 : 4], m3 = mul.m[R == 32 ? 2 : 5];
 
     for (uint32_t ti = blockIdx.x * cta_warps + warp; ti < ntiles; ti += gridDim.x * cta_warps) {
         const size_t off = (size_t)ti * tile_bytes;
@@ -92,16 +98,23 @@ checksum_tiles_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t tile_by
         if (kCrc && lane == 0) c0 = crc_serial(s, 0xffffffffu, src, head);       // pre-inversion + head bytes ride on the first word
         if (rows) {
             // three rows in flight per warp (32 warps x 3 x 512 B = 48 KiB per SM) to cover the HBM latency
-#define ZB_LK(k, w, sh) (*reinterpret_cast<const uint32_t*>(bigb + (k) * (1024u * R) + (R == 32 ? ((sh) >= 7 ? (((w) >> ((sh) - 7)) & 0x7f80u) : (((w) << 7) & 0x7f80u)) \
-                                                                                                  : ((sh) >= 2 ? (((w) >> ((sh) - 2)) & 0x3fcu) : (((w) << 2) & 0x3fcu)))))
+            // The four lookups of a word need not cut it at byte boundaries (CRC is linear in the bits), and the loop is bound by the
+            // ALU pipe (LOP3 / SHF: 84 % busy in profiles/r2_checksum_ncu_summary.txt) while the FMA pipe idles.  So: field 0 = bits
+            // 14..7 sits where the table offset wants it (no shift); fields 1 and 2 = bits 22..15 and 31..23 come down with a
+            // multiply-high, field 3 = bits 6..0 goes up with a multiply -- IMAD on the FMA pipe; the multipliers are kernel
+            // parameters so that they stay multiplies.  One LOP3 per lookup (mask + this lane's table copy) is what the ALU keeps.
+#define ZB_OFF(e0, x, bits) ((e0) * (4u * R) + ((x) & (((1u << (bits)) - 1u) << (R == 32 ? 7 : 2))))
+#define ZB_LKAT(off) (*reinterpret_cast<const uint32_t*>(bigb + (off)))
+#define ZB_CRC_WORD(w) (ZB_LKAT(ZB_OFF(0u, R == 32 ? (w) : __umulhi((w), mul.m[6]), 8)) ^ ZB_LKAT(ZB_OFF(256u, __umulhi((w), m1), 8)) ^ \
+                        ZB_LKAT(ZB_OFF(512u, __umulhi((w), m2), 9)) ^ ZB_LKAT(ZB_OFF(1024u, (w) * m3, 7)))
 #define ZB_FOLD_ROW(v)                                                                                              \
             do {                                                                                                    \
                 if (kCrc) {                                                                                         \
                     const uint32_t w0 = (v).x ^ c0, w1 = (v).y ^ c1, w2 = (v).z ^ c2, w3 = (v).w ^ c3;              \
-                    c0 = ZB_LK(0, w0, 0) ^ ZB_LK(1, w0, 8) ^ ZB_LK(2, w0, 16) ^ ZB_LK(3, w0, 24);                   \
-                    c1 = ZB_LK(0, w1, 0) ^ ZB_LK(1, w1, 8) ^ ZB_LK(2, w1, 16) ^ ZB_LK(3, w1, 24);                   \
-                    c2 = ZB_LK(0, w2, 0) ^ ZB_LK(1, w2, 8) ^ ZB_LK(2, w2, 16) ^ ZB_LK(3, w2, 24);                   \
-                    c3 = ZB_LK(0, w3, 0) ^ ZB_LK(1, w3, 8) ^ ZB_LK(2, w3, 16) ^ ZB_LK(3, w3, 24);                   \
+                    c0 = ZB_CRC_WORD(w0);                   \
+                    c1 = ZB_CRC_WORD(w1);                   \
+                    c2 = ZB_CRC_WORD(w2);                   \
+                    c3 = ZB_CRC_WORD(w3);                   \
                 }                                                                                                   \
                 if (kAdler) {                                                                                       \
                     const uint32_t s0 = __dp4a((v).x, 0x01010101u, 0u), s1 = __dp4a((v).y, 0x01010101u, 0u);        \
@@ -113,16 +126,16 @@ checksum_tiles_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t tile_by
                 }                                                                                                   \
             } while (0)
             const uint32_t adv = rows - 1u;                                      // rows folded through the tables; the last one is multiplied
-            uint4 q0 = __ldg(rowp), q1 = q0, q2 = q0;
-            if (rows > 1u) q1 = __ldg(rowp + 32u);
-            if (rows > 2u) q2 = __ldg(rowp + 64u);
+            // fold a row, THEN refill its registers (no copy of the row on the loop's back edge); the refill address is clamped to
+            // the last row instead of predicated (a few redundant L1 hits at the end of a tile, no 64-bit address arithmetic per row)
+            uint4 q0 = __ldg(rowp), q1 = __ldg(rowp + min(1u, adv) * 32u), q2 = __ldg(rowp + min(2u, adv) * 32u);
             uint32_t r = 0;
             for (; r + 3u <= adv; r += 3u) {
-                uint4 v = q0; if (r + 3u < rows) q0 = __ldg(rowp + (size_t)(r + 3u) * 32u); ZB_FOLD_ROW(v);
-                v = q1;       if (r + 4u < rows) q1 = __ldg(rowp + (size_t)(r + 4u) * 32u); ZB_FOLD_ROW(v);
-                v = q2;       if (r + 5u < rows) q2 = __ldg(rowp + (size_t)(r + 5u) * 32u); ZB_FOLD_ROW(v);
+                ZB_FOLD_ROW(q0); q0 = __ldg(rowp + min(r + 3u, adv) * 32u);
+                ZB_FOLD_ROW(q1); q1 = __ldg(rowp + min(r + 4u, adv) * 32u);
+                ZB_FOLD_ROW(q2); q2 = __ldg(rowp + min(r + 5u, adv) * 32u);
             }
-            const uint32_t rem = adv - r;                                        // 0..2 table rows left; q0, q1, q2 hold rows r, r+1, r+2
+            const uint32_t rem = adv - r;                                        // 0..2 table rows left; q0, q1, q2 hold rows r, r+1, r+2 (clamped)
             if (rem >= 1u) ZB_FOLD_ROW(q0);
             if (rem >= 2u) ZB_FOLD_ROW(q1);
             const uint4 v = rem == 0u ? q0 : (rem == 1u ? q1 : q2);
@@ -249,7 +262,8 @@ static cudaError_t launch_tiles(const uint8_t* in, size_t n, uint32_t tile_bytes
     uint32_t grid = (uint32_t)num_sms * (kCrc ? 1u : 2u);
     const uint32_t need = (ntiles + (uint32_t)cta_warps - 1u) / (uint32_t)cta_warps;
     if (grid > need) grid = need;
-    checksum_tiles_kernel<kCrc, kAdler, R><<<grid, cta_warps * 32, smem, stream>>>(in, n, tile_bytes, ntiles, crcs, adlers, host_x2n());
+    static const CkMul mul = {{1u << 24, 1u << 16, 1u << 7, 1u << 19, 1u << 11, 1u << 2, 1u << 27}};
+    checksum_tiles_kernel<kCrc, kAdler, R><<<grid, cta_warps * 32, smem, stream>>>(in, n, tile_bytes, ntiles, crcs, adlers, host_x2n(), mul);
     return cudaGetLastError();
 }
 
