@@ -234,7 +234,7 @@ int run_deflate_chunks(zng_b200_ctx* ctx, Scratch& sc, const uint8_t* d_in, size
                                  ctx->vtails, ctx->sm_slots, ctx->sms, ctx->chains_per_sm_l2, (c0 > 0 || have_prev) ? 1 : 0, level, stream),
                "fast_parse launch");
             CK(launch_block_emit(d_in + off, toks, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
-                                 d_sizes + c0, ctx->sms, stream),
+                                 d_sizes + c0, ctx->sms, stream, -1, nullptr, ctx->counters + next_slot(ctx)),
                "block_emit launch");
             continue;
         }
@@ -303,7 +303,7 @@ int run_deflate_primed_window(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, 
                                ctx->counters + slot, ctx->heads, ctx->prevs, ctx->wins, ctx->sm_slots, ctx->sms, 32, level, stream),
            "window_parse launch");
         CK(launch_block_emit(d_in + off, sc.tokens, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
-                             d_sizes + c0, ctx->sms, stream, -1, ctx->blkflags + (size_t)c0 * 8u),
+                             d_sizes + c0, ctx->sms, stream, -1, ctx->blkflags + (size_t)c0 * 8u, ctx->counters + next_slot(ctx)),
            "block_emit launch");
     }
     if (d_crcs || d_adlers)
@@ -1630,7 +1630,8 @@ static int deflate_host_streamed(zng_b200_ctx* ctx, const uint8_t* h_in, size_t 
                                               stride, d_sizes + c0 + first, ctx->sms, st, kCoCarve), "static_emit launch");
                     else
                         CK(launch_block_emit(S.d_in + off + (size_t)first * chunk, tk, (uint32_t)tstride, S.ntok + c0 + first, nbytes, chunk, count, last,
-                                             S.d_slots + (size_t)(c0 + first) * stride, stride, d_sizes + c0 + first, ctx->sms, st, k2_carve), "block_emit launch");
+                                             S.d_slots + (size_t)(c0 + first) * stride, stride, d_sizes + c0 + first, ctx->sms, st, k2_carve, nullptr,
+                                             ctx->counters + next_slot(ctx)), "block_emit launch");
                     return 0;
                 };
                 if (final && c0 + nb == nch) {                           // the stream's last chunk is the Z_FINISH chunk

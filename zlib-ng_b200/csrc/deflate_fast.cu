@@ -27,6 +27,7 @@
 //     with shared-memory atomics, the three Huffman trees serially on lane 0 exactly as trees.c orders its
 //     heap, stored / static / dynamic choice by the reference's byte counts, then warp-parallel bit packing
 //     (code lookup, prefix scan of lengths, OR into a staging ring, 128-bit stores).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "lz_ops.cuh"
@@ -318,7 +319,9 @@ __device__ __forceinline__ void sift_down(uint32_t* key, uint16_t* id, int k, in
 }
 
 // build_tree + gen_bitlen + gen_codes (trees.c:185-405).  freq_in -> code_out/len_out; returns max_code.
-__device__ int build_huffman(BlockWs& T, const uint32_t* freq_in, TreeKind tk, uint16_t* code_out, uint16_t* len_out,
+// One copy of this code (not one per tree and call site): the kernel was 15 000 instructions = 240 KiB, and a fifth of the warps' stall
+// samples were instruction fetch (no_instruction 2.25 per issue slot in profiles/r2_block_emit_ncu_summary.txt).
+__device__ __noinline__ int build_huffman(BlockWs& T, const uint32_t* freq_in, TreeKind tk, uint16_t* code_out, uint16_t* len_out,
                              uint32_t& opt_len, uint32_t& static_len) {
     uint32_t* key = T.hkey; uint16_t* id = T.hid;
     int heap_len = 0, heap_max = HEAP_SZ, max_code = -1, node;
@@ -577,13 +580,17 @@ __device__ uint32_t flush_block(Emitter& E, BlockWs& T, const uint32_t* __restri
 __global__ void __launch_bounds__(kBlkWarps * 32)
 block_emit_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tokens, uint32_t tok_stride,
                   const uint32_t* __restrict__ ntok, size_t n, uint32_t chunk, uint32_t nchunks, int last,
-                  uint8_t* __restrict__ out, size_t out_stride, uint32_t* __restrict__ sizes, const uint8_t* __restrict__ blkflags) {
+                  uint8_t* __restrict__ out, size_t out_stride, uint32_t* __restrict__ sizes, const uint8_t* __restrict__ blkflags,
+                  uint32_t* __restrict__ counter) {
     extern __shared__ __align__(16) unsigned char blk_smem[];
     BlockWs& T = reinterpret_cast<BlockWs*>(blk_smem)[threadIdx.x >> 5];
     const unsigned lane = lane_id();
     for (uint32_t i = lane; i < kBStageWords; i += 32u) T.stage[i] = 0u;
     __syncwarp();
-    for (uint32_t ci = blockIdx.x * kBlkWarps + (threadIdx.x >> 5); ci < nchunks; ci += gridDim.x * kBlkWarps) {
+    // chunks are claimed from a counter (stored blocks cost a fraction of dynamic ones: a fixed assignment leaves warps idle at the end)
+    for (uint32_t ci = blockIdx.x * kBlkWarps + (threadIdx.x >> 5);; ci += gridDim.x * kBlkWarps) {
+        if (counter) { if (lane == 0) ci = atomicAdd(counter, 1u); ci = __shfl_sync(ZB_FULL, ci, 0); }
+        if (ci >= nchunks) break;
         const size_t off = (size_t)ci * chunk;
         const uint32_t len = (uint32_t)min((size_t)chunk, n - off);
         const uint8_t* src = in + off;
@@ -592,13 +599,15 @@ block_emit_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ t
         Emitter E{T.stage, out + (size_t)ci * out_stride, 0u, 0u};
         uint32_t t0 = 0, bstart = 0, blk = 0;
         const uint8_t* bf = blkflags ? blkflags + (size_t)ci * 8u : nullptr;
-        // deflate_fast.c:93-94: a block is flushed as soon as it holds 16383 symbols
-        while (nt - t0 >= kSymEnd) {
-            bstart += flush_block(E, T, tok, t0, t0 + kSymEnd, src, bstart, len, false, 0, lane, bf ? (int)bf[min(blk, 7u)] : -1);
+        // deflate_fast.c:93-94: a block is flushed as soon as it holds 16383 symbols; deflate_fast.c:96-103: then the rest (also an
+        // empty last block for Z_FINISH).  One call site: the block writer is inlined once.
+        for (;;) {
+            const bool full = nt - t0 >= kSymEnd;
+            if (!full && !(last || nt > t0)) break;
+            bstart += flush_block(E, T, tok, t0, full ? t0 + kSymEnd : nt, src, bstart, len, !full, full ? 0 : last, lane, bf ? (int)bf[min(blk, 7u)] : -1);
+            if (!full) break;
             t0 += kSymEnd; blk++;
         }
-        // deflate_fast.c:96-103: the rest (also an empty last block for Z_FINISH)
-        if (last || nt > t0) flush_block(E, T, tok, t0, nt, src, bstart, len, true, last, lane, bf ? (int)bf[min(blk, 7u)] : -1);
         if (!last) {                                        // deflate.c:1064-1065 zng_tr_stored_block(NULL, 0, 0)
             if (lane == 0) {
                 E.bitpos += 3;
@@ -645,16 +654,23 @@ cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint3
 
 cudaError_t launch_block_emit(const uint8_t* in, const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n,
                               uint32_t chunk, uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
-                              int num_sms, cudaStream_t stream, int co_carve, const uint8_t* blkflags) {
+                              int num_sms, cudaStream_t stream, int co_carve, const uint8_t* blkflags, uint32_t* counter) {
     if (nchunks == 0) return cudaSuccess;
+    if (counter) { cudaError_t e0 = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream); if (e0 != cudaSuccess) return e0; }
     const int smem = (int)(sizeof(BlockWs) * kBlkWarps);
     cudaError_t e = cudaFuncSetAttribute(block_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
+    // co_carve < 0 (the kernel has the SMs to itself): ask for all of the shared memory.  The driver's default carve-out stops at
+    // 132 KiB = 3 CTAs (12 warps) per SM (sm__warps_active 18 % in profiles/r2_block_emit_ncu_summary.txt); 5 CTAs fit.
+    if (co_carve < 0) {
+        static const int own = [] { const char* e = getenv("ZNG_B200_EMIT_CARVE"); return e ? atoi(e) : 100; }();   // -1 = the driver's default
+        co_carve = own;
+    }
     cudaFuncSetAttribute(block_emit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co_carve);   // see launch_static_emit
     uint32_t grid = (uint32_t)num_sms * (uint32_t)((227 * 1024) / (smem + 1024));     // as many CTAs as the shared memory of an SM holds
     const uint32_t need = (nchunks + kBlkWarps - 1u) / kBlkWarps;
     if (grid > need) grid = need;
-    block_emit_kernel<<<grid, kBlkWarps * 32, smem, stream>>>(in, tokens, tok_stride, ntok, n, chunk, nchunks, last, out, out_stride, sizes, blkflags);
+    block_emit_kernel<<<grid, kBlkWarps * 32, smem, stream>>>(in, tokens, tok_stride, ntok, n, chunk, nchunks, last, out, out_stride, sizes, blkflags, counter);
     return cudaGetLastError();
 }
 

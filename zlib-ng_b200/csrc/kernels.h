@@ -60,7 +60,8 @@ cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint3
 cudaError_t launch_block_emit(const uint8_t* in, const uint32_t* tokens, uint32_t tok_stride, const uint32_t* ntok, size_t n,
                               uint32_t chunk, uint32_t nchunks, int last, uint8_t* out, size_t out_stride, uint32_t* sizes,
                               int num_sms, cudaStream_t stream, int co_carve = -1,
-                              const uint8_t* blkflags = nullptr);   // blkflags: 8 bytes per chunk, != 0: block k may not be stored (K2w)
+                              const uint8_t* blkflags = nullptr,    // blkflags: 8 bytes per chunk, != 0: block k may not be stored (K2w)
+                              uint32_t* counter = nullptr);         // counter: a device word the kernel claims chunks from (zeroed here)
 // K2w (deflate_window.cu): dictionary-primed chunks at levels 2-6 on the reference's own window / head / prev state (real slides).
 // Shares the K2 slab pools; wins = deflate_window_win_bytes() of window buffers, blkflags as above (written by the parser).
 size_t deflate_window_win_bytes(uint32_t nsmid);
