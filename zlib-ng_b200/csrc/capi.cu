@@ -299,8 +299,9 @@ int run_deflate_primed_window(zng_b200_ctx* ctx, const uint8_t* d_in, size_t n, 
         const size_t off = (size_t)c0 * chunk;
         const size_t nbytes = (c0 + nb == nchunks) ? n - off : (size_t)nb * chunk;
         const int slot = next_slot(ctx);
+        static const int k2w_chains = [] { const char* e = getenv("ZNG_B200_CHAINS_K2W"); int v = e ? atoi(e) : 48; return v >= 1 && v <= 48 ? v : 48; }();
         CK(launch_window_parse(d_in + off, nbytes, chunk, nb, c0 + first0, last, sc.tokens, stride, sc.ntok + c0, ctx->blkflags + (size_t)c0 * 8u,
-                               ctx->counters + slot, ctx->heads, ctx->prevs, ctx->wins, ctx->sm_slots, ctx->sms, 32, level, stream),
+                               ctx->counters + slot, ctx->heads, ctx->prevs, ctx->wins, ctx->sm_slots, ctx->sms, k2w_chains, level, stream),
            "window_parse launch");
         CK(launch_block_emit(d_in + off, sc.tokens, stride, sc.ntok + c0, nbytes, chunk, nb, last, d_out + (size_t)c0 * out_stride, out_stride,
                              d_sizes + c0, ctx->sms, stream, -1, ctx->blkflags + (size_t)c0 * 8u, ctx->counters + next_slot(ctx)),

@@ -164,6 +164,24 @@ __device__ uint32_t w_longest_match(WinState& s, uint32_t cand) {
     return best;
 }
 
+// Every step of the serial loops waits for its own loads, and the tables of all resident chains (256 KiB each) are far larger
+// than L2, so most of those loads go to DRAM.  This runs ahead of the loop and only warms L2 -- it changes no state and no result:
+// once per 32 positions lane l reads head[hash] of position strstart + kAheadBy + l (the value is used one batch later, so nobody
+// waits for it) and prefetches the window bytes and the prev[] link of the candidate it found in the previous batch.
+constexpr uint32_t kAheadBy = 8;
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+struct Ahead {
+    uint32_t at = 0, hv = 0xffffffffu;
+    __device__ __forceinline__ void step(const WinState& s, unsigned lane) {
+        if (s.strstart < at && at - s.strstart <= 64u) return;    // (a slide moves strstart back by 32768: start over)
+        if (hv != 0xffffffffu && hv != 0u) { prefetch_l2(s.win + hv); prefetch_l2(s.prev + (hv & (kWSize - 1u))); }
+        const uint32_t q = s.strstart + kAheadBy + lane;
+        hv = 0xffffffffu;
+        if (q + 4u <= s.strstart + s.lookahead) hv = (uint32_t)__ldcg(s.head + hash4(w32(s, q)));
+        at = s.strstart + 32u;
+    }
+};
+
 struct Sink {                                                   // zng_tr_tally_* (deflate_p.h:61-98) + FLUSH_BLOCK bookkeeping
     uint32_t* tok; uint8_t* flags; uint32_t wr, sym, blk;
     __device__ __forceinline__ void put(uint32_t t, unsigned lane) { if (lane == 0) __stcs(tok + wr, t); wr++; sym++; }
@@ -178,8 +196,10 @@ struct Sink {                                                   // zng_tr_tally_
 // deflate_fast (deflate_fast.c:19-104)
 __device__ void w_deflate_fast(WinState& s, Sink& k, int last, unsigned lane) {
     uint32_t match_len = 0;
+    Ahead ah;
     for (;;) {
         if (s.lookahead < 262u) { w_fill(s, lane); if (s.lookahead == 0u) break; }
+        ah.step(s, lane);
         if (s.lookahead >= kWantMin) {
             const uint32_t hh = w_insert(s, s.strstart, lane);
             const int64_t dist = (int64_t)s.strstart - (int64_t)hh;
@@ -245,8 +265,10 @@ template <int LEVEL>
 __device__ void w_deflate_medium(WinState& s, Sink& k, int last, unsigned lane) {
     constexpr bool greedy = LEVEL < 5;
     MMatch cur = {0, 0, 0, 0}, nxt = {0, 0, 0, 0};
+    Ahead ah;
     for (;;) {
         if (s.lookahead < 262u) { w_fill(s, lane); if (s.lookahead == 0u) break; nxt.len = 0; }
+        ah.step(s, lane);
         if (!greedy && nxt.len > 0u) { cur = nxt; nxt.len = 0; }
         else w_find<LEVEL>(s, s.lookahead >= kWantMin ? w_insert(s, s.strstart, lane) : 0u, cur);
         w_insert_match(s, cur, lane);
@@ -265,7 +287,7 @@ __device__ void w_deflate_medium(WinState& s, Sink& k, int last, unsigned lane) 
 }
 
 template <int LEVEL>
-__global__ void __launch_bounds__(kWinWarps * 32, 8)
+__global__ void __launch_bounds__(kWinWarps * 32, 12)
 window_parse_kernel(const uint8_t* in, size_t n, uint32_t chunk, uint32_t nchunks, uint32_t first, int last,
                     uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok, uint8_t* __restrict__ blkflags,
                     uint32_t* __restrict__ counter, uint16_t* heads, uint16_t* prevs, uint8_t* wins, unsigned long long* sm_slots) {
