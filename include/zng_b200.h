@@ -231,8 +231,11 @@ int zng_b200_inflate_stream_host(zng_b200_ctx *ctx, const void *h_in, size_t n, 
  * consumed input is dropped, the check value and the trailer are verified at the end.  Linear work, piecewise output.
  *   *status    0 fed (more input, or more room in h_out, needed) / 1 stream end and every byte delivered / -3 data error (*detail =
  *              message id for zng_b200_inflate_msg) / ZNG_B200_NOT_RESUMABLE: FDICT / FHCRC / malformed header -- nothing consumed,
- *              use zng_b200_inflate_stream_host
- *   *in_used   bytes of this call's input that belong to the stream (< n only when the stream ended inside them)
+ *              use zng_b200_inflate_stream_host / 2: more than the backlog limit (256 MiB, env ZNG_B200_INFLATE_BACKLOG) of decoded
+ *              output is waiting for the caller: some was handed over, NO input was taken (*in_used = 0) -- call again
+ *   The device keeps 32 KiB of history plus the output not yet taken, not the whole output (delivered bytes are dropped in steps of
+ *   64 MiB, env ZNG_B200_INFLATE_COMPACT), so streams of any length work in bounded memory; the check value is carried along.
+ *   *in_used   bytes of this call's input that belong to the stream (< n only when the stream ended inside them, or 0 with status 2)
  *   *out_len   bytes written to h_out (at most cap; what does not fit stays pending: call again with n == 0) */
 typedef struct zng_b200_inflate_stream zng_b200_inflate_stream;
 int  zng_b200_inflate_stream_open(zng_b200_ctx *ctx, int window_bits, zng_b200_inflate_stream **out);

@@ -305,6 +305,28 @@ def test_zng_inflate_piecewise_errors_and_truncation(pkg, L):
     assert r == pkg.Z_DATA_ERROR and msg == "incorrect length check"
 
 
+def test_zng_inflate_piecewise_bounded_memory(pkg, L, monkeypatch):
+    """The resumable decoder keeps 32 KiB of history plus what the caller has not taken yet, not the whole output: delivered output
+    is dropped from the device buffer (threshold lowered here so that it happens many times), the check value is carried from call
+    to call, and a caller who drains slowly is refused more input (like the reference with avail_out == 0) instead of piling up
+    output.  Same bytes, same CRC-32 / Adler-32 / ISIZE verdict, same total_in."""
+    monkeypatch.setenv("ZNG_B200_INFLATE_COMPACT", "65536")
+    monkeypatch.setenv("ZNG_B200_INFLATE_BACKLOG", "262144")
+    data = synth(3 * 1024 * 1024 + 777, seed=91).tobytes()
+    for wb in (31, 15, -15):
+        co = pyzlib.compressobj(6, pyzlib.DEFLATED, wb)
+        st = co.compress(data) + co.flush()
+        chk = 0 if wb < 0 else (pyzlib.adler32(data) if wb == 15 else pyzlib.crc32(data))
+        for piece, room in ((65536, 1 << 22), (30000, 20000), (len(st), 50000), (50000, 3000)):
+            r, got, tin, adler, calls, _, msg = _inflate_pieces(pkg, L, st + b"tail", wb, piece, room)
+            assert r == 1 and got == data and tin == len(st), (wb, piece, room, r, msg, len(got), tin, len(st), calls)
+            if wb >= 0:
+                assert adler == chk
+    co = pyzlib.compressobj(6, pyzlib.DEFLATED, 31); g = bytearray(co.compress(data) + co.flush()); g[-6] ^= 1
+    r, _, _, _, _, _, msg = _inflate_pieces(pkg, L, bytes(g), 31, 65536, 1 << 20)
+    assert r == pkg.Z_DATA_ERROR and msg == "incorrect data check"
+
+
 def test_zng_inflate_incremental_is_not_quadratic(pkg, L):
     """The common loop "read 64 KiB, zng_inflate(Z_NO_FLUSH)" over a gzip member without flush markers: every call resumes at the last
     block boundary (host/zng_inflate.c -> zng_b200_inflate_stream_feed), so 48 MiB of compressed input costs one pass, not 768 full decodes."""

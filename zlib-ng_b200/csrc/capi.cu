@@ -1199,7 +1199,11 @@ struct zng_b200_inflate_stream {
     uint32_t start_bit = 0;
     uint8_t* d_in = nullptr; size_t d_in_cap = 0;
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
-    uint64_t out_total = 0, delivered = 0;        // decoded for good / handed to the caller
+    uint64_t out_total = 0, delivered = 0;        // decoded for good / handed to the caller: offsets into d_out
+    uint64_t base = 0;                            // stream offset of d_out[0]: delivered output older than the 32 KiB of history is dropped
+    uint64_t compact_at = (uint64_t)64 << 20;     // ... once that much of it has piled up (env ZNG_B200_INFLATE_COMPACT, bytes)
+    uint64_t backlog_max = (uint64_t)256 << 20;   // decoded but not yet taken by the caller: beyond this no more input is accepted (env ZNG_B200_INFLATE_BACKLOG)
+    uint32_t run_check = 0;                       // CRC-32 / Adler-32 of the output up to out_total, carried from attempt to attempt
     bool body_done = false, finished = false;
     uint32_t check = 0;
     size_t last_try = 0;                          // retained bytes at the last attempt that found no new boundary
@@ -1216,6 +1220,8 @@ int zng_b200_inflate_stream_open(zng_b200_ctx* ctx, int window_bits, zng_b200_in
     zng_b200_inflate_stream* st = new (std::nothrow) zng_b200_inflate_stream();
     if (!st) return ZNG_B200_MEM_ERROR;
     st->ctx = ctx; st->window_bits = window_bits;
+    if (const char* e = getenv("ZNG_B200_INFLATE_COMPACT")) { const long long v = atoll(e); if (v >= 65536) st->compact_at = (uint64_t)v; }
+    if (const char* e = getenv("ZNG_B200_INFLATE_BACKLOG")) { const long long v = atoll(e); if (v >= 65536) st->backlog_max = (uint64_t)v; }
     if (cudaMalloc(&st->d_io, 128) != cudaSuccess || cudaHostAlloc(&st->h_io, 128, cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError(); cudaFree(st->d_io); delete st; return ZNG_B200_MEM_ERROR;
     }
@@ -1231,7 +1237,8 @@ void zng_b200_inflate_stream_close(zng_b200_inflate_stream* st) {
     delete st;
 }
 
-// status: 0 = fed, more input (or more room for output) needed; 1 = stream end, every byte delivered; -3 = data error (*detail =
+// status: 0 = fed, more input (or more room for output) needed; 1 = stream end, every byte delivered; 2 = too much output is waiting
+// for the caller (more than the backlog limit): some was handed over, NO input was taken, call again; -3 = data error (*detail =
 // message id, zng_b200_inflate_msg); -6 (ZNG_B200_NOT_RESUMABLE) = a header this layer leaves to the one-shot path, nothing consumed.
 // *in_used: bytes of THIS call's input that belong to the stream (less than n only at the stream's end); *out_len: bytes written to h_out.
 int zng_b200_inflate_stream_feed(zng_b200_inflate_stream* st, const void* h_in, size_t n, void* h_out, size_t cap,
@@ -1251,6 +1258,11 @@ int zng_b200_inflate_stream_feed(zng_b200_inflate_stream* st, const void* h_in, 
         return 0;
     };
     if (st->finished) { int r = deliver(); if (r) return r; *in_used = 0; *status = st->delivered == st->out_total ? 1 : 0; if (check) *check = st->check; return 0; }
+    if (!st->body_done && st->out_total - st->delivered > st->backlog_max) {   // like the reference with avail_out == 0: hand over output, take no input
+        int r = deliver(); if (r) return r;
+        *in_used = 0; *status = 2;
+        return 0;
+    }
     if (n) st->in.insert(st->in.end(), (const uint8_t*)h_in, (const uint8_t*)h_in + n);
     if (!st->header_done) {
         const int wrap = st->window_bits < 0 ? 0 : (st->window_bits >> 4) + 5;
@@ -1268,6 +1280,27 @@ int zng_b200_inflate_stream_feed(zng_b200_inflate_stream* st, const void* h_in, 
             }
             st->in.erase(st->in.begin(), st->in.begin() + (ptrdiff_t)st->wr.body);
             st->header_done = true;
+            st->run_check = st->wr.kind == 1 ? 1u : 0u;
+        }
+    }
+    // the check value rides along: bytes [out_total, upto) join it as soon as they are final (a block boundary has been passed)
+    auto extend_check = [&](uint64_t upto) -> int {
+        if (st->wr.kind && upto > st->out_total) {
+            const int rr = st->wr.kind == 2 ? zng_b200_crc32(ctx, st->d_out + st->out_total, (size_t)(upto - st->out_total), st->run_check, ctx->d_result, nullptr)
+                                            : zng_b200_adler32(ctx, st->d_out + st->out_total, (size_t)(upto - st->out_total), st->run_check, ctx->d_result, nullptr);
+            if (rr) return rr;
+            CK(cudaMemcpy(&st->run_check, ctx->d_result, 4, cudaMemcpyDeviceToHost), "D2H check");
+        }
+        st->out_total = upto;
+        return 0;
+    };
+    // drop delivered output that is no longer history (back-references reach 32 KiB): memory stays bounded, offsets stay 32-bit
+    {
+        const uint64_t hist = st->out_total > 32768u ? st->out_total - 32768u : 0u;
+        const uint64_t from = st->delivered < hist ? st->delivered : hist;
+        if (from >= st->compact_at && from >= st->out_total - from) {          // (source and destination do not overlap)
+            if (st->out_total > from) CK(cudaMemcpy(st->d_out, st->d_out + from, (size_t)(st->out_total - from), cudaMemcpyDeviceToDevice), "compact history");
+            st->base += from; st->delivered -= from; st->out_total -= from;
         }
     }
     // ---- decode from the last boundary, as far as the input goes
@@ -1311,9 +1344,10 @@ int zng_b200_inflate_stream_feed(zng_b200_inflate_stream* st, const void* h_in, 
         CK(cudaStreamSynchronize(0), "sync");
         const uint32_t o_len = hr[0]; const int32_t ret = (int32_t)hr[2]; const uint32_t used = hr[3], det = hr[4];
         const uint32_t bb_byte = hr[8], bb_bit = hr[9], bb_out = hr[10];
-        if (ret == ZNG_B200_DATA_ERROR) { *status = ZNG_B200_DATA_ERROR; if (detail) *detail = det & 0xffu; int r = 0; st->out_total = bb_out; r = deliver(); return r; }
+        if (ret == ZNG_B200_DATA_ERROR) { *status = ZNG_B200_DATA_ERROR; if (detail) *detail = det & 0xffu; int r = extend_check(bb_out); if (r) return r; return deliver(); }
         if (ret == 1) {                                                         // the final block is decoded
-            st->out_total = o_len; st->body_done = true;
+            { int r = extend_check(o_len); if (r) return r; }
+            st->body_done = true;
             st->in.erase(st->in.begin(), st->in.begin() + (ptrdiff_t)std::min<size_t>(used, st->in.size()));
             st->start_bit = 0; st->last_try = 0;
             break;
@@ -1327,7 +1361,7 @@ int zng_b200_inflate_stream_feed(zng_b200_inflate_stream* st, const void* h_in, 
             CK(cudaMemcpy(nb, st->d_out, (size_t)bb_out, cudaMemcpyDeviceToDevice), "copy history");
             cudaFree(st->d_out); st->d_out = nb; st->d_out_cap = want;
         }
-        st->out_total = bb_out;
+        { int r = extend_check(bb_out); if (r) return r; }
         if (bb_byte) st->in.erase(st->in.begin(), st->in.begin() + (ptrdiff_t)bb_byte);
         st->start_bit = bb_bit;
         if (out_full) { st->last_try = 0; continue; }
@@ -1339,19 +1373,13 @@ int zng_b200_inflate_stream_feed(zng_b200_inflate_stream* st, const void* h_in, 
     if (st->body_done && !st->finished) {
         const size_t tlen = st->wr.kind == 2 ? 8 : (st->wr.kind == 1 ? 4 : 0);
         if (st->in.size() >= tlen) {
-            uint32_t chk = 0;
-            if (st->wr.kind) {
-                r = st->wr.kind == 2 ? zng_b200_crc32(ctx, st->d_out, (size_t)st->out_total, 0, ctx->d_result, nullptr)
-                                     : zng_b200_adler32(ctx, st->d_out, (size_t)st->out_total, 1, ctx->d_result, nullptr);
-                if (r) return r;
-                CK(cudaMemcpy(&chk, ctx->d_result, 4, cudaMemcpyDeviceToHost), "D2H check");
-            }
+            const uint32_t chk = st->wr.kind ? st->run_check : 0u;
             st->check = chk;
             const uint8_t* t = st->in.data();
             if (st->wr.kind == 2) {
                 const uint32_t c = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24), l = t[4] | (t[5] << 8) | (t[6] << 16) | ((uint32_t)t[7] << 24);
                 if (c != chk) { *status = ZNG_B200_DATA_ERROR; if (detail) *detail = 17; return 0; }
-                if (l != (uint32_t)st->out_total) { *status = ZNG_B200_DATA_ERROR; if (detail) *detail = 18; return 0; }
+                if (l != (uint32_t)(st->base + st->out_total)) { *status = ZNG_B200_DATA_ERROR; if (detail) *detail = 18; return 0; }
             } else if (st->wr.kind == 1) {
                 const uint32_t c = ((uint32_t)t[0] << 24) | (t[1] << 16) | (t[2] << 8) | t[3];
                 if (c != chk) { *status = ZNG_B200_DATA_ERROR; if (detail) *detail = 17; return 0; }

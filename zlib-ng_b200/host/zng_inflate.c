@@ -151,6 +151,11 @@ int32_t zng_inflate(zng_stream *strm, int32_t flush) {
         if (zng_b200_inflate_stream_feed(s->res, src, n, strm->next_out, strm->avail_out, &iu, &ol, &st, &det, &chk) != ZNG_B200_OK) {
             strm->msg = zng_b200_last_error(ctx); return Z_MEM_ERROR;
         }
+        if (st == 2) {                                                        /* output is piling up: some was handed over, no input taken */
+            strm->next_out += ol; strm->avail_out -= (uint32_t)ol; strm->total_out += ol;
+            if (flush == Z_FINISH) return Z_BUF_ERROR;
+            return ol ? Z_OK : Z_BUF_ERROR;
+        }
         if (st == ZNG_B200_NOT_RESUMABLE) s->no_resume = 1;                   /* FDICT / FHCRC / header errors: the exact path below */
         else if (iu == 0 && n != 0 && st == 0 && !s->res_started) {
             /* the header is not complete yet: keep the bytes here and pass them again with the next piece */
@@ -179,7 +184,7 @@ int32_t zng_inflate(zng_stream *strm, int32_t flush) {
                 return flush == Z_FINISH ? Z_BUF_ERROR : Z_OK;
             }
             if (flush == Z_FINISH) return Z_BUF_ERROR;                          /* incomplete stream, or no room for its output */
-            return (in0 || ol) ? Z_OK : Z_BUF_ERROR;                            /* inflate.c:1197-1199: no progress */
+            return (used_now || ol) ? Z_OK : Z_BUF_ERROR;                       /* inflate.c:1197-1199: no progress */
         }
     }
 
