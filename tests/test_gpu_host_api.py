@@ -327,6 +327,62 @@ def test_zng_inflate_piecewise_bounded_memory(pkg, L, monkeypatch):
     assert r == pkg.Z_DATA_ERROR and msg == "incorrect data check"
 
 
+def test_zng_inflate_piecewise_fuzz_against_cpython(pkg, L):
+    """Deterministic fuzz of the piecewise path: valid, truncated and damaged streams (all three wrappers, levels 1 / 6 / 9, stored
+    blocks included) fed in random pieces with random output room, next to CPython's zlib fed the same pieces.  A stream CPython
+    finishes must finish here with the same bytes and the same consumed length; one it rejects must end in Z_DATA_ERROR (or
+    Z_NEED_DICT) here; one it leaves open must stay open (Z_BUF_ERROR when nothing is left to feed) -- and whatever was delivered
+    is a prefix of what CPython produced (whole blocks here, single symbols there)."""
+    rng = np.random.default_rng(20261019)
+    base = synth(400 * 1024, seed=123).tobytes()
+    noise = rng.integers(0, 256, size=70000, dtype=np.uint8).tobytes()
+    n_done = n_err = n_open = 0
+    for case in range(90):
+        wb = (-15, 15, 31)[case % 3]
+        level = (1, 6, 9)[(case // 3) % 3]
+        n = int(rng.integers(0, 200000))
+        o = int(rng.integers(0, len(base) - n))
+        data = base[o:o + n] if case % 7 else (base[o:o + n // 2] + noise[: n // 3])     # every 7th: stored blocks inside
+        co = pyzlib.compressobj(level, pyzlib.DEFLATED, wb)
+        st = bytearray(co.compress(data) + co.flush())
+        kind = case % 5                                                             # 0, 1: intact; 2: truncated; 3: bit flip; 4: bytes overwritten
+        if kind == 2 and len(st) > 4:
+            st = st[: int(rng.integers(1, len(st)))]
+        elif kind == 3 and len(st) > 4:
+            k = int(rng.integers(0, len(st))); st[k] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 4 and len(st) > 12:
+            k = int(rng.integers(2, len(st) - 8)); st[k:k + 4] = bytes(rng.integers(0, 256, size=4, dtype=np.uint8))
+        tail = b"" if kind == 2 else b"bytes behind the stream"
+        stream = bytes(st) + tail
+        hi = int(rng.integers(2, 9000)) if len(stream) < 3000 else int(rng.integers(300, 9000))
+        sizes = [int(x) for x in rng.integers(1, hi, size=4096)]
+        rooms = [int(x) for x in rng.integers(1, 60000, size=4096)]
+        # CPython over the same pieces
+        d = pyzlib.decompressobj(wb)
+        ref_out, ref_err, pos = bytearray(), False, 0
+        try:
+            i = 0
+            while pos < len(stream) and not d.eof:
+                sz = sizes[i % 4096]; i += 1
+                ref_out += d.decompress(stream[pos:pos + sz]); pos += sz
+        except pyzlib.error:
+            ref_err = True
+        r, got, tin, _, calls, _, msg = _inflate_pieces(pkg, L, stream, wb, lambda i: sizes[i % 4096], lambda i: rooms[i % 4096])
+        ctxt = (case, wb, level, kind, len(data), len(stream), r, msg, len(got), tin, calls)
+        if ref_err:
+            assert r in (pkg.Z_DATA_ERROR, pkg.Z_NEED_DICT), ctxt
+            k = min(len(got), len(ref_out))                          # (CPython loses the output of the call that raises)
+            assert got[:k] == bytes(ref_out[:k]), ctxt
+            n_err += 1
+        elif d.eof:
+            assert r == 1 and got == bytes(ref_out) and tin == min(pos, len(stream)) - len(d.unused_data), ctxt
+            n_done += 1
+        else:
+            assert r == pkg.Z_BUF_ERROR and bytes(ref_out).startswith(got), ctxt
+            n_open += 1
+    assert n_done >= 30 and n_err >= 10 and n_open >= 5, (n_done, n_err, n_open)
+
+
 def test_zng_inflate_incremental_is_not_quadratic(pkg, L):
     """The common loop "read 64 KiB, zng_inflate(Z_NO_FLUSH)" over a gzip member without flush markers: every call resumes at the last
     block boundary (host/zng_inflate.c -> zng_b200_inflate_stream_feed), so 48 MiB of compressed input costs one pass, not 768 full decodes."""
