@@ -195,3 +195,16 @@ def test_256MiB_round_trip_and_sampled_parity(pkg, ctx, zo, level):
     for ci in pick:
         exp, es, _, _ = zo.port_deflate_chunks(data[ci * 65536:(ci + 1) * 65536], 65536, level, 3, stride, nthreads=1)
         assert es[0] == hs[ci] and np.array_equal(hslots[ci, : es[0]], exp[0, : es[0]]), f"chunk {ci}"
+
+
+def test_k2c_cta_per_chunk_parser_is_bit_exact():
+    """K2c (deflate_fast.cu: medium_cta_kernel, opt-in with ZNG_B200_K2C=1): inserter / searcher / resolver warps on one chunk, the
+    prev[] ring in shared memory.  The switch is read once per process, so the level-5 and level-6 cases of this file run again in
+    a child process with it set -- same oracle, same digests of the unmodified reference."""
+    import os, subprocess, sys
+    env = dict(os.environ, ZNG_B200_K2C="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_deflate_fast.py"), "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "(level5 or level6) and not 256MiB"], env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-500:]

@@ -218,6 +218,146 @@ fast_parse_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint
     if (lane == 0) atomicAnd(sm_slots + sm, ~(1ull << slot));
 }
 
+// ---------------------------------------------------------------- K2c: one CTA per chunk for the deep-chain levels (5, 6)
+// The warp-per-chain parser above runs at the random-access rate of L2 + DRAM: 256 KiB of tables per chain, thousands of chains, and
+// at level 6 up to 128 dependent prev[] links per position.  Here three chunks share an SM and the hot part of their state is on
+// chip: each CTA keeps its chunk's prev[] ring in shared memory (64 KiB), head[] and the chunks themselves stay L2 / L1 resident
+// (444 chunks in flight instead of 4 736).  While the look-ahead regime lasts every position is inserted in order and the match at a
+// position does not depend on the parse (lazy_parse.cuh), so the work splits three ways:
+//   warp 1       inserter: insert_string for ALL positions below F, 32 per step, in order (also into the global prev[] ring, which
+//                the end zone's serial code continues from); at most kCoopAhead windows ahead of the resolver, because entering
+//                position t overwrites the ring slot of t - 32768, which a searcher at s may still follow while t > s + 262
+//   warps 2..    searchers: claim 32-position windows, wait for their links, walk the chains (longest_match_lane on shared memory),
+//                leave (length, start) per position in a small ring
+//   warp 0       resolver: lazy_parse_warp's walks on the ring's results; from F on (the last ~550 bytes) the unchanged serial path
+constexpr int kCtaWarps = 10;
+struct alignas(16) CtaSmem {
+    uint16_t prevf[kWSize];
+    uint32_t ring[kCoopRing];
+    uint32_t ready[kCoopReady];
+    uint32_t ins_upto, next_win, res_win, ci, slot;
+};
+
+// the image of the window past the data (see fast_parse_kernel), by `nthreads` threads
+__device__ __forceinline__ void build_tail_image(const VWindow& W, const uint8_t* src, uint32_t len, bool stale, uint32_t* tail, unsigned t0, unsigned nthreads) {
+    for (uint32_t t = t0; t < kTailWords; t += nthreads) {
+        uint32_t wv = 0;
+#pragma unroll
+        for (uint32_t b = 0; b < 4u; b++) {
+            const int pos = (int)(4u * (W.tw0 + t) + b) - (int)W.skew;
+            uint32_t by = 0;
+            if (pos >= 0) {
+                uint32_t pp = (uint32_t)pos;
+                if (pp >= kChunkMax) pp -= kWSize;
+                if (pp < len) by = src[pp];
+                else if (stale) by = *(src - (size_t)kWSize + (pp & (kWSize - 1u)));
+            }
+            wv |= by << (8u * b);
+        }
+        __stcg(tail + t, wv);
+    }
+}
+
+template <int LEVEL>
+__global__ void __launch_bounds__(kCtaWarps * 32, 3)
+medium_cta_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint32_t nchunks,
+                  uint32_t* __restrict__ tokens, uint32_t tok_stride, uint32_t* __restrict__ ntok,
+                  uint32_t* __restrict__ counter, uint16_t* __restrict__ heads, uint16_t* __restrict__ prevs,
+                  uint32_t* __restrict__ tails, unsigned long long* __restrict__ sm_slots, int have_prev) {
+    extern __shared__ __align__(16) unsigned char cta_smem[];
+    CtaSmem& S = *reinterpret_cast<CtaSmem*>(cta_smem);
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    const uint32_t sm = smid();
+    if (threadIdx.x == 0) S.slot = slot_acquire(sm_slots + sm);
+    __syncthreads();
+    const size_t slab = (size_t)sm * 64u + S.slot;
+    uint16_t* head = heads + slab * 65536u;
+    uint16_t* prev = prevs + slab * kWSize;
+    uint32_t* tail = tails + slab * kTailWords;
+    for (;;) {
+        if (threadIdx.x == 0) S.ci = atomicAdd(counter, 1u);
+        __syncthreads();
+        const uint32_t ci = S.ci;
+        if (ci >= nchunks) break;
+        const size_t off = (size_t)ci * chunk;
+        const uint32_t len = (uint32_t)min((size_t)chunk, n - off);
+        const uint8_t* src = in + off;
+        VWindow W;
+        W.skew = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+        W.w = reinterpret_cast<const uint32_t*>(src - W.skew);
+        W.tail = tail;
+        W.tw0 = (W.skew + len) >> 2;
+        {   // CLEAR_HASH (deflate.c:182-184) by the whole CTA; prev[] needs no clearing
+            uint4* h4 = reinterpret_cast<uint4*>(head);
+            for (uint32_t i = threadIdx.x; i < 65536u * 2u / 16u; i += blockDim.x) __stcg(h4 + i, make_uint4(0, 0, 0, 0));
+        }
+        const bool stale = chunk == kChunkMax && (ci > 0u || have_prev) && len < kChunkMax;
+        build_tail_image(W, src, len, stale, tail, threadIdx.x, blockDim.x);
+        // F: the first window start (a multiple of 32) that lies in the end zone of lazy_parse_warp; everything below it is the CTA's
+        const uint32_t F = len < kLazyGuard ? 0u : ((len - kLazyGuard) / 32u + 1u) * 32u;
+        if (threadIdx.x < kCoopReady) S.ready[threadIdx.x] = 0u;
+        if (threadIdx.x == 0) { S.ins_upto = 0u; S.next_win = 0u; S.res_win = 0u; }
+        __syncthreads();
+        volatile uint32_t* ins_upto = &S.ins_upto; volatile uint32_t* res_win = &S.res_win; volatile uint32_t* ready = S.ready;
+        if (warp == 0) {
+            CoopView cv{S.ring, ready, res_win, ins_upto, F};
+            const uint32_t cnt = lazy_parse_warp<LEVEL, true>(W, len, head, prev, tokens + (size_t)ci * tok_stride, &cv);
+            if (lane == 0) ntok[ci] = cnt;
+        } else if (warp == 1) {
+            uint32_t vn = F ? load32(W, lane) : 0u;
+            for (uint32_t base = 0; base < F; base += 32u) {
+                const uint32_t q = base + lane, v = vn;
+                if (lane == 0) for (uint32_t tries = 0; (base >> 5) > *res_win + kCoopAhead; tries++) { __nanosleep(64); if (tries > (1u << 26)) __trap(); }
+                __syncwarp();
+                if (base + 32u < F) vn = load32(W, q + 32u);             // the next window's bytes are on their way while this one waits for head[]
+                const uint32_t h = hash4(v);
+                const uint32_t table_head = (uint32_t)__ldcg(head + h);
+                const unsigned peers = __match_any_sync(ZB_FULL, h);
+                const unsigned prior = peers & lt;
+                const uint32_t old = prior ? base + (31u - (uint32_t)__clz(prior)) : table_head;   // insert_string_tpl.h:58-75 in serial order
+                S.prevf[q & (kWSize - 1u)] = (uint16_t)old;
+                __stcg(prev + (q & (kWSize - 1u)), (uint16_t)old);
+                if ((peers & ~lt & ~(1u << lane)) == 0u) __stcg(head + h, (uint16_t)q);
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) *ins_upto = base + 32u;
+            }
+        } else {
+            for (;;) {
+                uint32_t w = 0;
+                if (lane == 0) w = atomicAdd(&S.next_win, 1u);
+                w = __shfl_sync(ZB_FULL, w, 0);
+                if (32u * w >= F) break;
+                if (lane == 0) {
+                    coop_wait(ins_upto, 32u * (w + 1u));
+                    for (uint32_t tries = 0; w >= *res_win + kCoopReady; tries++) { __nanosleep(128); if (tries > (1u << 26)) __trap(); }
+                }
+                __syncwarp();
+                __threadfence_block();
+                const uint32_t q = 32u * w + lane;
+                uint32_t v, z; uint64_t x;
+                {
+                    const uint32_t qb = q + W.skew, i = qb >> 2, sh = (qb & 3u) << 3;
+                    const uint32_t a0 = W.word(i), a1 = W.word(i + 1), a2 = W.word(i + 2), a3 = W.word(i + 3);
+                    v = __funnelshift_r(a0, a1, sh);
+                    x = (uint64_t)__funnelshift_r(a1, a2, sh) | ((uint64_t)__funnelshift_r(a2, a3, sh) << 32);
+                    z = __funnelshift_r(a3, W.word(i + 4), sh);
+                }
+                const uint32_t cand0 = lds_u16(S.prevf, q & (kWSize - 1u));
+                uint32_t mlen = 0, mcand = 0;
+                if (cand0 != 0u && (q - cand0 - 1u) < kMaxDist)
+                    mlen = longest_match_lane<LEVEL, true>(W, q, v, x, z, cand0, 0x7fffffffu, S.prevf, mcand);
+                S.ring[q & (kCoopRing - 1u)] = mlen | (mcand << 16);
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) ready[w & (kCoopReady - 1u)] = w + 1u;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAnd(sm_slots + sm, ~(1ull << S.slot));
+}
+
 // ---------------------------------------------------------------- K2b block writer
 constexpr int      kBlkWarps   = 4;
 constexpr uint32_t kBStageWords = 512;             // 2 KiB staging ring per warp (a block header is <= 141 words)
@@ -633,6 +773,25 @@ cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint3
     if (nchunks == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
+    // levels 5-6, device-resident and slab calls: K2c, one CTA per chunk -- opt-in (env ZNG_B200_K2C=1): bit-exact, but at 2.98 / 5.5 GB/s
+    // (levels 6 / 5) still behind the warp-per-chain parser's 3.24 / 6.8 (profiles/r2_k2c.md says what holds it back)
+    static const int k2c = [] { const char* e = getenv("ZNG_B200_K2C"); return e ? atoi(e) : 0; }();
+    if (level >= 5 && !sync && k2c) {
+        const int smem = (int)sizeof(CtaSmem);
+        const uint32_t g = nchunks < 3u * (uint32_t)num_sms ? nchunks : 3u * (uint32_t)num_sms;
+        if (level == 5) {
+            e = cudaFuncSetAttribute(medium_cta_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            cudaFuncSetAttribute(medium_cta_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            medium_cta_kernel<5><<<g, kCtaWarps * 32, smem, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, prevs, tails, sm_slots, have_prev);
+        } else {
+            e = cudaFuncSetAttribute(medium_cta_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            cudaFuncSetAttribute(medium_cta_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            medium_cta_kernel<6><<<g, kCtaWarps * 32, smem, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, prevs, tails, sm_slots, have_prev);
+        }
+        return cudaGetLastError();
+    }
     uint32_t ctas_per_sm = ((uint32_t)chains_per_sm + kFastWarps - 1u) / kFastWarps;
     uint32_t grid = (uint32_t)num_sms * ctas_per_sm;
     const uint64_t need = ((uint64_t)nchunks + kFastWarps - 1u) / kFastWarps;

@@ -112,12 +112,23 @@ __device__ uint32_t serial_medium(const VWindow& W, uint32_t n, uint16_t* head, 
     return wr;
 }
 
+// K2c (deflate_fast.cu: medium_cta_kernel): the windows below `F` were inserted by the CTA's inserter warp and searched by its searcher
+// warps; this warp only replays the decisions.  ring[q % kCoopRing] = match length | match start << 16 of position q, valid once
+// ready[w % kCoopReady] == w + 1 (w = q / 32); res_win tells the searchers which ring slots are free again.
+constexpr uint32_t kLazyGuard = 32u + kMaxMatch + 262u + 2u;   // a window starting here or later may leave the look-ahead regime
+constexpr uint32_t kCoopRing = 512, kCoopReady = kCoopRing / 32u;   // 16 windows; at most 8 are in flight (kCoopAhead)
+constexpr uint32_t kCoopAhead = 7;
+struct CoopView { const uint32_t* ring; volatile uint32_t* ready; volatile uint32_t* res_win; volatile uint32_t* ins_upto; uint32_t F; };
+__device__ __forceinline__ void coop_wait(volatile uint32_t* word, uint32_t at_least) {     // bounded: a protocol bug traps, it does not hang
+    for (uint32_t tries = 0; *word < at_least; tries++) { __nanosleep(64); if (tries > (1u << 26)) __trap(); }
+}
+
 // Parse one chunk at level 5 or 6; tokens to tok[0..count) + end marker.  Returns the token count.
-template <int LEVEL>
-__device__ uint32_t lazy_parse_warp(const VWindow W, uint32_t n, uint16_t* head, uint16_t* prev, uint32_t* __restrict__ tok) {
+template <int LEVEL, bool kCoop = false>
+__device__ uint32_t lazy_parse_warp(const VWindow W, uint32_t n, uint16_t* head, uint16_t* prev, uint32_t* __restrict__ tok, const CoopView* cv = nullptr) {
     using P = LmParams<LEVEL>;
     constexpr uint32_t kCmp = P::kCmp;
-    constexpr uint32_t kGuard = 32u + kMaxMatch + 262u + 2u;  // a window starting here or later may leave the look-ahead regime
+    constexpr uint32_t kGuard = kLazyGuard;
     const unsigned lane = lane_id();
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t kNoClip = 0x7fffffffu;                     // s->lookahead during a look-ahead search is > 262: it never clips
@@ -131,6 +142,14 @@ __device__ uint32_t lazy_parse_warp(const VWindow W, uint32_t n, uint16_t* head,
     }
     for (;;) {
         const bool endzone = p + kGuard > n;
+        const bool pre = kCoop && !endzone;                   // K2c: this window is inserted and searched already (p is a multiple of 32, p < F)
+        if (kCoop) {
+            if (pre) {          // (also for a window a long match covers entirely: its searcher must be done before its ring slots are given away)
+                if (lane == 0) { const uint32_t w = p >> 5; for (uint32_t tries = 0; cv->ready[w & (kCoopReady - 1u)] != w + 1u; tries++) { __nanosleep(64); if (tries > (1u << 26)) __trap(); } }
+            } else if (!pre) { if (lane == 0) coop_wait(cv->ins_upto, cv->F); }
+            __syncwarp();
+            __threadfence_block();
+        }
         const uint32_t q = p + lane;
         const bool inb = q + kWantMin <= n;                   // only the end zone has lanes past the data; they are never used
         uint32_t v, z; uint64_t x;
@@ -142,11 +161,13 @@ __device__ uint32_t lazy_parse_warp(const VWindow W, uint32_t n, uint16_t* head,
             z = __funnelshift_r(a3, W.word(i + 4), sh);
         }
         const uint32_t h = hash4(v);
-        const uint32_t cand0 = inb ? (uint32_t)__ldcg(head + h) : 0u;
+        const uint32_t cand0 = (inb && !pre) ? (uint32_t)__ldcg(head + h) : 0u;
         uint32_t mlen = 0, mcand = 0;                        // mlen: 0 none, 4..kCmp-1 exact, kCmp = "kCmp or more"
-        if (inb && lane >= skip && (!endzone || lane == skip) && cand0 != 0u && (q - cand0 - 1u) < kMaxDist)
+        if (pre) {
+            if (lane >= skip) { const uint32_t r = lds_u32(cv->ring, q & (kCoopRing - 1u)); mlen = r & 0xffffu; mcand = r >> 16; }
+        } else if (inb && lane >= skip && (!endzone || lane == skip) && cand0 != 0u && (q - cand0 - 1u) < kMaxDist)
             mlen = longest_match_lane<LEVEL>(W, q, v, x, z, cand0, kNoClip, prev, mcand);
-        const unsigned peers = __match_any_sync(ZB_FULL, inb ? h : (0x10000u + lane));
+        const unsigned peers = pre ? 0u : __match_any_sync(ZB_FULL, inb ? h : (0x10000u + lane));   // (pre: the links are exact, nothing is stale)
         const unsigned M = __ballot_sync(ZB_FULL, mlen != 0u);
         // ---- walk 1: the greedy chain of looked-up positions
         unsigned cur = skip, covered = 0;
@@ -223,7 +244,7 @@ __device__ uint32_t lazy_parse_warp(const VWindow W, uint32_t n, uint16_t* head,
             __stcs(tok + wr + __popc(E & lt), t);
         }
         wr += __popc(E);
-        if ((I >> lane) & 1u) {                              // insert_string_tpl.h:58-75 for every inserted position
+        if (!pre && ((I >> lane) & 1u)) {                    // insert_string_tpl.h:58-75 for every inserted position
             const unsigned prior = peers & I & lt;
             const uint32_t old = prior ? p + (31u - (uint32_t)__clz(prior)) : cand0;
             __stcg(prev + (q & (kWSize - 1u)), (uint16_t)old);
@@ -241,6 +262,7 @@ __device__ uint32_t lazy_parse_warp(const VWindow W, uint32_t n, uint16_t* head,
             wr = serial_medium<LEVEL>(W, n, head, prev, tok, wr, nx.at, nx, true, lane);
             break;
         }
+        if (pre && lane == 0) *cv->res_win = (p >> 5) + 1u;   // the searchers may reuse this window's ring slots
         p = next_p; skip = next_skip;
     }
     if (lane == 0) __stcs(tok + wr, kTokEnd);

@@ -133,7 +133,18 @@ __device__ __forceinline__ uint32_t prefix_len(const VWindow& W, uint32_t q, uin
 // passes it without improving ends the search below level 5 (early_exit, :127,261-266) and is skipped from level 5 on.
 // Returns 0 (no match >= 4), 4..kCmp-1 (exact length, clipped to look), or kCmp = "kCmp or more: measure with
 // vwarp_compare256 and clip"; mcand = match_start of the returned match.
-template <int LEVEL>
+// kShared: `prev` is K2c's copy of the 32 Ki-entry prev[] ring in SHARED memory (same index, same links).
+__device__ __forceinline__ uint32_t lds_u16(const uint16_t* base, uint32_t i) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"((uint32_t)__cvta_generic_to_shared(base) + 2u * i));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(const uint32_t* base, uint32_t i) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(base) + 4u * i));
+    return v;
+}
+template <int LEVEL, bool kShared = false>
 __device__ __forceinline__ uint32_t longest_match_lane(const VWindow& W, uint32_t q, uint32_t v, uint64_t x, uint32_t z, uint32_t cand0,
                                                        uint32_t look, const uint16_t* prev, uint32_t& mcand, uint32_t* raw_best = nullptr) {
     using P = LmParams<LEVEL>;
@@ -142,7 +153,7 @@ __device__ __forceinline__ uint32_t longest_match_lane(const VWindow& W, uint32_
     const uint32_t limit = q > kMaxDist ? q - kMaxDist : 0u;
     for (;;) {
         if (kDeep && cand >= q) break;                     // match_tpl.h:131-132 (a re-inserted string can link forward)
-        const uint32_t link = (uint32_t)__ldcg(prev + (cand & (kWSize - 1u)));   // issued before the compare: the two latencies overlap
+        const uint32_t link = kShared ? lds_u16(prev, cand & (kWSize - 1u)) : (uint32_t)__ldcg(prev + (cand & (kWSize - 1u)));   // issued before the compare: the two latencies overlap
         if (!kDeep || best < 3u || load32(W, cand + best - 3u) == endw) {      // bytes best-3..best must match to improve
             const uint32_t cl = prefix_len<P::kCmp>(W, q, cand, v, x, z);
             if (cl > best) {
