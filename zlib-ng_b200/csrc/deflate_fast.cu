@@ -778,16 +778,18 @@ cudaError_t launch_fast_parse(const uint8_t* in, size_t n, uint32_t chunk, uint3
     static const int k2c = [] { const char* e = getenv("ZNG_B200_K2C"); return e ? atoi(e) : 0; }();
     if (level >= 5 && !sync && k2c) {
         const int smem = (int)sizeof(CtaSmem);
-        const uint32_t g = nchunks < 3u * (uint32_t)num_sms ? nchunks : 3u * (uint32_t)num_sms;
+        static const int per_sm = [] { const char* e = getenv("ZNG_B200_K2C_CTAS"); const int v = e ? atoi(e) : 3; return v >= 1 && v <= 3 ? v : 3; }();
+        const int carve = per_sm == 3 ? 100 : (per_sm == 2 ? 64 : 32);            // what is not shared memory is L1 for the chunks' bytes
+        const uint32_t g = nchunks < (uint32_t)(per_sm * num_sms) ? nchunks : (uint32_t)(per_sm * num_sms);
         if (level == 5) {
             e = cudaFuncSetAttribute(medium_cta_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
-            cudaFuncSetAttribute(medium_cta_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(medium_cta_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             medium_cta_kernel<5><<<g, kCtaWarps * 32, smem, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, prevs, tails, sm_slots, have_prev);
         } else {
             e = cudaFuncSetAttribute(medium_cta_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
-            cudaFuncSetAttribute(medium_cta_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(medium_cta_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             medium_cta_kernel<6><<<g, kCtaWarps * 32, smem, stream>>>(in, n, chunk, nchunks, tokens, tok_stride, ntok, counter, heads, prevs, tails, sm_slots, have_prev);
         }
         return cudaGetLastError();
