@@ -330,7 +330,7 @@ medium_cta_kernel(const uint8_t* __restrict__ in, size_t n, uint32_t chunk, uint
                 if (32u * w >= F) break;
                 if (lane == 0) {
                     coop_wait(ins_upto, 32u * (w + 1u));
-                    for (uint32_t tries = 0; w >= *res_win + kCoopReady; tries++) { __nanosleep(128); if (tries > (1u << 26)) __trap(); }
+                    for (uint32_t tries = 0; w >= *res_win + kCoopReady; tries++) { __nanosleep(400); if (tries > (1u << 24)) __trap(); }
                 }
                 __syncwarp();
                 __threadfence_block();

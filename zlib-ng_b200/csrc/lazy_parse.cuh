@@ -119,8 +119,8 @@ constexpr uint32_t kLazyGuard = 32u + kMaxMatch + 262u + 2u;   // a window start
 constexpr uint32_t kCoopRing = 512, kCoopReady = kCoopRing / 32u;   // 16 windows; at most 8 are in flight (kCoopAhead)
 constexpr uint32_t kCoopAhead = 7;
 struct CoopView { const uint32_t* ring; volatile uint32_t* ready; volatile uint32_t* res_win; volatile uint32_t* ins_upto; uint32_t F; };
-__device__ __forceinline__ void coop_wait(volatile uint32_t* word, uint32_t at_least) {     // bounded: a protocol bug traps, it does not hang
-    for (uint32_t tries = 0; *word < at_least; tries++) { __nanosleep(64); if (tries > (1u << 26)) __trap(); }
+__device__ __forceinline__ void coop_wait(volatile uint32_t* word, uint32_t at_least, uint32_t ns = 400) {   // bounded: a protocol bug traps, it does not hang
+    for (uint32_t tries = 0; *word < at_least; tries++) { __nanosleep(ns); if (tries > (1u << 24)) __trap(); }   // (long naps: a spinning warp costs its neighbours issue slots)
 }
 
 // Parse one chunk at level 5 or 6; tokens to tok[0..count) + end marker.  Returns the token count.
